@@ -1,0 +1,186 @@
+/*
+ * mile_b200.h -- C ABI of the B200-native MCLMC ensemble sampling path for MILE.
+ *
+ * The reference (zhiyuan-yang/MILE) is 100% Python on JAX/BlackJAX and has no FFI of
+ * its own; the seams this library sits behind are the Python callables listed in
+ * SURVEY.md section 8(b).  Each entry point below cites the reference interface
+ * (file:line under /root/reference) whose work it performs.  Host code (the Python
+ * shim in mile_b200/, or any other binding) talks to the library only through this
+ * header: plain pointers and sizes, opaque context handle, int status return
+ * (0 = OK, negative = error, text via mile_last_error()).  No exceptions cross the
+ * ABI.  One context per GPU; a context is not thread-safe.
+ *
+ * Pointer naming: *_dev = device pointer, *_host = host pointer.  All float data is
+ * fp32 (the reference computes in fp32: src/flax_building_blocks/basic.py:29).
+ *
+ * Flat parameter layout (theta, u, grad, noise): jax.flatten_util.ravel_pytree order,
+ * i.e. for every layer: bias(out) then kernel(in,out) row-major; the offsets are
+ * given explicitly in mile_model_desc so that any leaf order ('layer10' < 'layer2')
+ * works.
+ */
+#ifndef MILE_B200_H
+#define MILE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MILE_MAX_LAYERS 12
+
+/* src/config/models/base.py:24-37 (flax.linen.<name>) */
+enum mile_activation {
+  MILE_ACT_IDENTITY = 0,
+  MILE_ACT_RELU = 1,
+  MILE_ACT_SIGMOID = 2,
+  MILE_ACT_TANH = 3,
+  MILE_ACT_GELU = 4, /* tanh approximation, flax default */
+  MILE_ACT_LEAKY_RELU = 5
+};
+/* src/config/data.py Task */
+enum mile_task { MILE_TASK_REGRESSION = 0, MILE_TASK_CLASSIFICATION = 1 };
+/* src/training/priors.py:12-56 */
+enum mile_prior { MILE_PRIOR_NORMAL = 0, MILE_PRIOR_LAPLACE = 1 };
+
+/* What `partial(prob_model.log_unnormalized_posterior, x=train_x, y=train_y)` closes
+ * over (src/training/trainer.py:576-580): FCN shape (src/models/tabular/fcn.py:11-28),
+ * task, prior (src/training/probabilistic.py:20-47). */
+typedef struct mile_model_desc {
+  int32_t n_features;
+  int32_t n_layers;                  /* len(hidden_structure), output layer included */
+  int32_t widths[MILE_MAX_LAYERS];   /* hidden_structure */
+  int32_t bias_off[MILE_MAX_LAYERS]; /* offset of layer l bias in the flat vector */
+  int32_t kernel_off[MILE_MAX_LAYERS];
+  int32_t activation;                /* enum mile_activation */
+  int32_t task;                      /* enum mile_task */
+  int32_t prior;                     /* enum mile_prior */
+  float prior_loc;
+  float prior_scale;
+  float n_batches;                   /* probabilistic.py:136, == 1 for full batch */
+} mile_model_desc;
+
+/* Arguments of custom_mclmc_warmup / mclmc_find_L_and_step_size
+ * (src/training/warmup.py:155-228,486-495). */
+typedef struct mile_tune_cfg {
+  int32_t tune1_steps;
+  int32_t tune2_steps;
+  float desired_energy_var_start;
+  float desired_energy_var_end;
+  float trust_in_estimate;
+  float num_effective_samples;
+} mile_tune_cfg;
+
+typedef struct mile_ctx mile_ctx;
+
+const char* mile_last_error(void);
+int mile_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* One context = one ensemble wave on one GPU (reference: one `inference_loop` call,
+ * src/training/sampling.py:32-40, over `len(step_ids)` chains). */
+int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, mile_ctx** out);
+void mile_destroy(mile_ctx* ctx);
+int32_t mile_n_params(const mile_ctx* ctx);
+/* Execution knobs: cluster size of the persistent kernel (0 = auto), refresh variant
+ * (0 = single post-step refresh, blackjax 1.2.2; 1 = half-step refreshes around the
+ * integrator, later blackjax `with_isokinetic_maruyama`). */
+int mile_set_option(mile_ctx* ctx, const char* key, int64_t value);
+int64_t mile_get_option(const mile_ctx* ctx, const char* key);
+
+/* ---- data (closure constants of the log-posterior, trainer.py:576-580) ---------- */
+/* X [N,F] row-major fp32; y fp32[N] (regression) or int32[N] (classification).
+ * Copies into the library's padded HBM layout; the caller keeps ownership. */
+int mile_set_data(mile_ctx* ctx, const float* X_dev, const void* y_dev, int64_t n_rows, void* stream);
+int mile_set_data_host(mile_ctx* ctx, const float* X_host, const void* y_host, int64_t n_rows);
+/* Test split used by the fused posterior-predictive LPPD (src/inference/evaluation.py:378-400). */
+int mile_set_test(mile_ctx* ctx, const float* X_dev, const void* y_dev, int64_t n_rows, void* stream);
+int mile_set_test_host(mile_ctx* ctx, const float* X_host, const void* y_host, int64_t n_rows);
+
+/* ---- a1: value_and_grad of log_unnormalized_posterior --------------------------- */
+/* src/training/probabilistic.py:115-138 differentiated as blackjax does
+ * (jax.value_and_grad).  theta [n,d] -> lp [n], grad [n,d]; n <= n_chains. */
+int mile_logpost_value_and_grad(mile_ctx* ctx, const float* theta_dev, int32_t n,
+                                float* lp_dev, float* grad_dev, void* stream);
+int mile_logpost_value_and_grad_host(mile_ctx* ctx, const float* theta_host, int32_t n,
+                                     float* lp_host, float* grad_host);
+
+/* ---- a14: blackjax.mcmc.mclmc.init (call site warmup.py:539-541) ---------------- */
+/* theta0 [C,d]; z0 [C,d] normal draws for the initial unit momentum, or NULL to draw
+ * them on the device from `seed` (Philox4x32-10). */
+int mile_mclmc_init(mile_ctx* ctx, const float* theta0_dev, const float* z0_dev, uint64_t seed,
+                    void* stream);
+int mile_mclmc_init_host(mile_ctx* ctx, const float* theta0_host, const float* z0_host, uint64_t seed);
+/* Overwrite / read the full chain state (position, momentum, logdensity, logdensity_grad)
+ * = blackjax IntegratorState, [C,d],[C,d],[C],[C,d].  NULL pointers are skipped. */
+int mile_set_state_host(mile_ctx* ctx, const float* theta, const float* u, const float* lp,
+                        const float* grad);
+int mile_get_state_host(mile_ctx* ctx, float* theta, float* u, float* lp, float* grad);
+int mile_get_state(mile_ctx* ctx, float* theta_dev, float* u_dev, float* lp_dev, float* grad_dev,
+                   void* stream);
+
+/* ---- a6/a14: sampler.step scan (sampling.py:134-177; blackjax mclmc kernel) ------ */
+/* Runs n_steps MCLMC steps for every chain with fixed per-chain step_size / L.
+ *   z_dev        [n_steps,C,d] host-supplied normal draws (parity mode) or NULL
+ *                (Philox from `seed`; draws depend on (seed, chain, step_base+i)).
+ *   step_base    index of the first step (the `idx` of sampling.py:150); position i is
+ *                kept when (step_base+i) % n_thinning == 0 (sampling.py:162), written to
+ *                samples_dev[((step_base+i)/n_thinning - sample_base) , c, :].
+ *   samples_dev  [n_slots,C,d] or NULL.   info_dev [n_steps,C,3] = MCLMCInfo
+ *                (logdensity, kinetic_change, energy_change) or NULL.
+ *   lppd         non-zero: fold every kept position into the online test-set
+ *                logsumexp state (needs mile_set_test).
+ */
+int mile_mclmc_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning,
+                      int64_t sample_base, const float* step_size_dev, const float* L_dev,
+                      const float* z_dev, uint64_t seed, float* samples_dev, int64_t n_slots,
+                      float* info_dev, int32_t lppd, void* stream);
+/* Same with host buffers: uploads step_size/L/z, downloads samples/info (the e2e path). */
+int mile_mclmc_sample_host(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning,
+                           const float* step_size_host, const float* L_host, const float* z_host,
+                           uint64_t seed, float* samples_host, int64_t n_slots, float* info_host,
+                           int32_t lppd);
+
+/* ---- a9-a11: make_L_step_size_adaptation (warmup.py:231-405) -------------------- */
+/* Resets the adaptive state: L = max(sqrt(d),15), step_size = step_size_init,
+ * (time, x_average, step_size_max) = (0,0,inf), streaming averages 0 (warmup.py:204-209,358-363). */
+int mile_tune_reset(mile_ctx* ctx, float step_size_init, void* stream);
+/* n_steps iterations of HOT LOOP A starting at iteration `step_base` (phase 1 while
+ * step < tune1_steps, then phase 2): kernel step, handle_nans, step-size predictor,
+ * streaming mean of (x, x^2).  tune_info_dev [n_steps,C,4] = (energy_change after
+ * handle_nans, step_size after update, step_size_max, success) or NULL. */
+int mile_mclmc_tune(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg,
+                    const float* z_dev, uint64_t seed, float* tune_info_dev, void* stream);
+int mile_mclmc_tune_host(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg,
+                         const float* z_host, uint64_t seed, float* tune_info_host);
+/* L = sqrt(sum(E[x^2]-E[x]^2)) (warmup.py:383-390); writes it into the tuning state. */
+int mile_tune_finish_phase2(mile_ctx* ctx, void* stream);
+/* step_size [C], L [C], step_size_max [C], mean_x [C,d], mean_x2 [C,d]; NULLs skipped. */
+int mile_get_tuning_host(mile_ctx* ctx, float* step_size, float* L, float* step_size_max,
+                         float* mean_x, float* mean_x2);
+int mile_set_tuning_host(mile_ctx* ctx, const float* step_size, const float* L);
+/* Device views of the tuned parameters (valid until mile_destroy). */
+int mile_tuning_ptrs(mile_ctx* ctx, float** step_size_dev, float** L_dev);
+
+/* ---- a15: posterior-predictive LPPD (metrics.py:247-312, evaluation.py:378-400) --- */
+int mile_lppd_reset(mile_ctx* ctx, void* stream);
+/* Fold theta [n,d] (n <= C; row c belongs to chain c) into the online state. */
+int mile_lppd_accumulate(mile_ctx* ctx, const float* theta_dev, int32_t n, void* stream);
+/* Running max m [C,Nt], scaled sum s [C,Nt], number of folded samples per chain. */
+int mile_lppd_state_host(mile_ctx* ctx, float* m, float* s, int64_t* count);
+/* Forward pass only: theta [n,d] on the test (which=1) or train (which=0) split -> out [n,N,K]. */
+int mile_predict(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t which, float* out_dev,
+                 void* stream);
+
+/* ---- bookkeeping ----------------------------------------------------------------- */
+/* Number of kernels this library has launched since mile_create (bench `gpu_launches`). */
+int64_t mile_launch_count(const mile_ctx* ctx);
+int mile_synchronize(mile_ctx* ctx);
+/* Measured FP32 CUDA-core peak in TFLOP/s (roofline denominator for the narrow-MLP configs,
+ * SURVEY.md section 8d): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 (FFMA2). */
+int mile_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILE_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of include/mile_b200.h.  The product path: there is no CPU fallback --
+if the CUDA library is missing or no CUDA device is present, calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+MILE_MAX_LAYERS = 12
+ACTIVATIONS = {'identity': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3, 'gelu': 4, 'leaky_relu': 5}
+TASKS = {'regr': 0, 'regression': 0, 'class': 1, 'classification': 1}
+PRIORS = {'normal': 0, 'standardnormal': 0, 'laplace': 1}
+
+# every symbol include/mile_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    'mile_last_error', 'mile_version', 'mile_create', 'mile_destroy', 'mile_n_params', 'mile_set_option',
+    'mile_get_option', 'mile_set_data', 'mile_set_data_host', 'mile_set_test', 'mile_set_test_host',
+    'mile_logpost_value_and_grad', 'mile_logpost_value_and_grad_host', 'mile_mclmc_init', 'mile_mclmc_init_host',
+    'mile_set_state_host', 'mile_get_state_host', 'mile_get_state', 'mile_mclmc_sample', 'mile_mclmc_sample_host',
+    'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
+    'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
+    'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
+]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ('n_features', C.c_int32), ('n_layers', C.c_int32),
+        ('widths', C.c_int32 * MILE_MAX_LAYERS), ('bias_off', C.c_int32 * MILE_MAX_LAYERS),
+        ('kernel_off', C.c_int32 * MILE_MAX_LAYERS),
+        ('activation', C.c_int32), ('task', C.c_int32), ('prior', C.c_int32),
+        ('prior_loc', C.c_float), ('prior_scale', C.c_float), ('n_batches', C.c_float),
+    ]
+
+
+class TuneCfg(C.Structure):
+    _fields_ = [
+        ('tune1_steps', C.c_int32), ('tune2_steps', C.c_int32),
+        ('desired_energy_var_start', C.c_float), ('desired_energy_var_end', C.c_float),
+        ('trust_in_estimate', C.c_float), ('num_effective_samples', C.c_float),
+    ]
+
+
+class MileError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / '_lib' / 'libmile_b200.so'
+
+
+def load():
+    """Load libmile_b200.so (built by mile_b200.build / __graft_entry__.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        raise MileError(f'{p} is missing: run `python -m mile_b200.build` (there is no CPU fallback)')
+    lib = C.CDLL(str(p))
+    vp, i32, i64, u64, fp = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
+    lib.mile_last_error.restype = C.c_char_p
+    lib.mile_version.restype = C.c_int
+    lib.mile_create.argtypes = [C.POINTER(ModelDesc), i32, i32, C.POINTER(vp)]
+    lib.mile_destroy.argtypes = [vp]
+    lib.mile_destroy.restype = None
+    lib.mile_n_params.argtypes = [vp]
+    lib.mile_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.mile_get_option.argtypes = [vp, C.c_char_p]
+    lib.mile_get_option.restype = i64
+    for name in ('mile_set_data', 'mile_set_test'):
+        getattr(lib, name).argtypes = [vp, fp, vp, i64, vp]
+    for name in ('mile_set_data_host', 'mile_set_test_host'):
+        getattr(lib, name).argtypes = [vp, fp, vp, i64]
+    lib.mile_logpost_value_and_grad.argtypes = [vp, fp, i32, fp, fp, vp]
+    lib.mile_logpost_value_and_grad_host.argtypes = [vp, fp, i32, fp, fp]
+    lib.mile_mclmc_init.argtypes = [vp, fp, fp, u64, vp]
+    lib.mile_mclmc_init_host.argtypes = [vp, fp, fp, u64]
+    lib.mile_set_state_host.argtypes = [vp, fp, fp, fp, fp]
+    lib.mile_get_state_host.argtypes = [vp, fp, fp, fp, fp]
+    lib.mile_get_state.argtypes = [vp, fp, fp, fp, fp, vp]
+    lib.mile_mclmc_sample.argtypes = [vp, i32, i64, i32, i64, fp, fp, fp, u64, fp, i64, fp, i32, vp]
+    lib.mile_mclmc_sample_host.argtypes = [vp, i32, i64, i32, fp, fp, fp, u64, fp, i64, fp, i32]
+    lib.mile_tune_reset.argtypes = [vp, C.c_float, vp]
+    lib.mile_mclmc_tune.argtypes = [vp, i32, i64, C.POINTER(TuneCfg), fp, u64, fp, vp]
+    lib.mile_mclmc_tune_host.argtypes = [vp, i32, i64, C.POINTER(TuneCfg), fp, u64, fp]
+    lib.mile_tune_finish_phase2.argtypes = [vp, vp]
+    lib.mile_get_tuning_host.argtypes = [vp, fp, fp, fp, fp, fp]
+    lib.mile_set_tuning_host.argtypes = [vp, fp, fp]
+    lib.mile_tuning_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.mile_lppd_reset.argtypes = [vp, vp]
+    lib.mile_lppd_accumulate.argtypes = [vp, fp, i32, vp]
+    lib.mile_lppd_state_host.argtypes = [vp, fp, fp, C.POINTER(i64)]
+    lib.mile_predict.argtypes = [vp, fp, i32, i32, fp, vp]
+    lib.mile_launch_count.argtypes = [vp]
+    lib.mile_launch_count.restype = i64
+    lib.mile_synchronize.argtypes = [vp]
+    lib.mile_measure_fp32_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+    _LIB = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MileError(load().mile_last_error().decode())
+
+
+def host_ptr(a: np.ndarray | None):
+    if a is None:
+        return None
+    assert a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,609 @@
+// mile_api.cu -- host side of the C ABI declared in include/mile_b200.h.
+// Owns the device buffers of one ensemble wave, plans the shared-memory carve-up and the
+// cluster shape, and launches the persistent kernel of mile_kernel.cuh.  Links cudart only.
+#include "mile_kernel.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+
+static const size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+struct mile_ctx {
+  mile_model_desc desc;
+  DevModel M;
+  int C = 0, device = 0, d = 0;
+  // options
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1;
+  // data
+  float* X = nullptr; void* y = nullptr; long N = 0;
+  float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
+  // state
+  float *theta = nullptr, *u = nullptr, *grad = nullptr, *lp = nullptr;
+  float *t_time = nullptr, *t_xavg = nullptr, *t_epsmax = nullptr, *t_eps = nullptr, *t_L = nullptr,
+        *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
+  float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
+  // staging for the *_host entry points
+  std::vector<std::pair<void*, size_t>> scratch;  // slot -> (ptr, bytes)
+  cudaStream_t own_stream = nullptr;
+  long launches = 0;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static int stride_for(int w) { int p = round_up(w, 4); return (p % 8 == 4) ? p : p + 4; }
+
+static void build_model(mile_ctx* c) {
+  const mile_model_desc& D = c->desc;
+  DevModel& M = c->M;
+  memset(&M, 0, sizeof(M));
+  M.F = D.n_features; M.NL = D.n_layers; M.act = D.activation; M.task = D.task; M.prior = D.prior;
+  M.prior_loc = D.prior_loc; M.prior_scale = D.prior_scale; M.n_batches = D.n_batches;
+  M.dims[0] = D.n_features;
+  for (int l = 0; l < M.NL; ++l) M.dims[l + 1] = D.widths[l];
+  int d = 0, ps = 0;
+  for (int l = 0; l <= M.NL; ++l) { M.dimp[l] = round_up(M.dims[l], 4); M.sA[l] = stride_for(M.dims[l]); }
+  for (int l = 0; l < M.NL; ++l) {
+    M.bias_off[l] = D.bias_off[l]; M.kern_off[l] = D.kernel_off[l];
+    d += M.dims[l + 1] + M.dims[l] * M.dims[l + 1];
+    M.pb_off[l] = ps; ps += M.dimp[l + 1];
+    M.pw_off[l] = ps; ps += M.dimp[l] * M.dimp[l + 1];
+  }
+  M.d = d; M.psize = ps;
+  c->d = d;
+}
+
+struct Plan {
+  int G, TR, resident, rows_res;
+  size_t smem;
+  KParams kp;  // offsets + model filled in
+};
+
+static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl) {
+  DevModel M = c->M;
+  int G = c->opt_cluster;
+  if (G <= 0) {
+    if (n_chains * 8 <= 128) G = 8; else if (n_chains * 4 <= 148) G = 4; else if (n_chains * 2 <= 148) G = 2; else G = 1;
+    while (G > 1 && nrows_for_split / G < 64) G >>= 1;
+  }
+  if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16) return fail("cluster_size must be 1,2,4,8 or 16");
+  const long rows_cta = (nrows_for_split + G - 1) / G;
+  const int dS = round_up(M.d, 4);
+  int S1 = 0;
+  for (int l = 1; l <= M.NL; ++l) S1 += M.sA[l];
+  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + dS + 64;
+  int TR = c->opt_tile_rows > 0 ? round_up(c->opt_tile_rows, 32) : 256;
+  const int want = round_up((int)(rows_cta < 32 ? 32 : (rows_cta > 256 ? 256 : rows_cta)), 32);
+  if (c->opt_tile_rows <= 0 && TR > want) TR = want;
+  for (;; TR -= 32) {
+    if (TR < 32) return fail("model too large for the CUDA-core path (shared memory): use the wide path");
+    size_t tile = (size_t)2 * TR * S1;
+    if (tile < MILE_THREADS * 20) tile = MILE_THREADS * 20;
+    const size_t need = (fixed + tile + (size_t)TR * M.sA[0]) * 4;
+    if (need <= kSmemLimit) break;
+    if (c->opt_tile_rows > 0) return fail("tile_rows does not fit in shared memory");
+  }
+  size_t tile = (size_t)2 * TR * S1;
+  if (tile < MILE_THREADS * 20) tile = MILE_THREADS * 20;
+  M.TR = TR; M.tile_floats = (int)tile;
+  int off = 0;
+  for (int l = 1; l <= M.NL; ++l) { M.a_off[l] = off; off += TR * M.sA[l]; }
+  for (int l = 0; l < M.NL; ++l) { M.d_off[l] = off; off += TR * M.sA[l + 1]; }
+  const int rows_res = (int)((rows_cta + TR - 1) / TR) * TR;
+  size_t base = fixed + tile + (size_t)TR * M.sA[0];
+  int resident = 0;
+  if (want_resident && c->opt_resident != 0 && (base + (size_t)rows_res * M.sA[0]) * 4 <= kSmemLimit) resident = 1;
+  KParams& k = pl.kp;
+  memset(&k, 0, sizeof(k));
+  k.M = M; k.dS = dS;
+  int o = 0;
+  k.off_wp = o; o += round_up(M.psize, 4);
+  k.off_th = o; o += dS; k.off_u = o; o += dS; k.off_g = o; o += dS;
+  k.off_thb = o; o += dS; k.off_ub = o; o += dS; k.off_gb = o; o += dS;
+  k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
+  k.off_gpart = o; o += 2 * (dS + 4);
+  k.off_pmap = o; o += dS;
+  k.off_red = o; o += 64;
+  k.off_tile = o; o += (int)tile + TR * M.sA[0];
+  k.off_x = o; if (resident) o += rows_res * M.sA[0];
+  pl.G = G; pl.TR = TR; pl.resident = resident; pl.rows_res = rows_res;
+  pl.smem = (size_t)o * 4;
+  if (pl.smem > kSmemLimit) return fail("internal: shared-memory plan exceeds the limit");
+  k.G = G; k.resident = resident; k.rows_res = rows_res; k.C = n_chains;
+  for (int l = 0; l < M.NL; ++l)
+    if ((M.dimp[l] / 4) * (M.dimp[l + 1] / 4) > MILE_THREADS)
+      return fail("layer too wide for the CUDA-core path (more than 256 4x4 weight tiles): use the wide path");
+  return 0;
+}
+
+template <int NLMAX>
+static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
+  auto kern = mile_mclmc_kernel<NLMAX>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  if (pl.G > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(n_chains * pl.G), 1, 1);
+  cfg.blockDim = dim3(MILE_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pl.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, pl.kp));
+  return 0;
+}
+
+static int launch(mile_ctx* c, const Plan& pl, int n_chains, cudaStream_t st) {
+  CK(cudaSetDevice(c->device));
+  const int NL = c->M.NL;
+  int rc;
+  if (NL <= 2) rc = launch_t<2>(pl, n_chains, st);
+  else if (NL <= 3) rc = launch_t<3>(pl, n_chains, st);
+  else if (NL <= 4) rc = launch_t<4>(pl, n_chains, st);
+  else if (NL <= 6) rc = launch_t<6>(pl, n_chains, st);
+  else if (NL <= 8) rc = launch_t<8>(pl, n_chains, st);
+  else rc = launch_t<12>(pl, n_chains, st);
+  if (rc == 0) c->launches++;
+  return rc;
+}
+
+static void fill_common(mile_ctx* c, KParams& k) {
+  k.X = c->X; k.y = c->y; k.N = c->N; k.Xt = c->Xt; k.yt = c->yt; k.Nt = c->Nt;
+  k.theta = c->theta; k.u = c->u; k.grad = c->grad; k.lp = c->lp;
+  k.t_time = c->t_time; k.t_xavg = c->t_xavg; k.t_epsmax = c->t_epsmax; k.t_eps = c->t_eps; k.t_L = c->t_L;
+  k.t_wtot = c->t_wtot; k.avg_x = c->avg_x; k.avg_x2 = c->avg_x2;
+  k.lppd_m = c->lppd_m; k.lppd_s = c->lppd_s;
+  k.refresh_mode = c->opt_refresh; k.thin = 1;
+}
+
+// ---- small utility kernels ------------------------------------------------------------------
+__global__ void pad_rows_kernel(const float* __restrict__ X, float* __restrict__ Xp, long N, int F, int sx) {
+  const long total = N * sx;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / sx; const int f = (int)(i % sx);
+    Xp[i] = f < F ? X[r * F + f] : 0.f;
+  }
+}
+__global__ void fill_kernel(float* p, long n, float v) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void tune_L_kernel(const float* __restrict__ ax, const float* __restrict__ ax2, float* L, int d) {
+  // L = sqrt(sum(E[x^2] - E[x]^2))  (warmup.py:387-390); one CTA per chain
+  __shared__ float red[64];
+  int phase = 0;
+  const int c = blockIdx.x;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+    const float m = ax[(long)c * d + i];
+    v[0] += ax2[(long)c * d + i] - m * m;
+  }
+  block_sum<1>(v, red, phase);
+  if (threadIdx.x == 0) L[c] = sqrtf(v[0]);
+}
+
+static void* scratch(mile_ctx* c, int slot, size_t bytes) {
+  if ((int)c->scratch.size() <= slot) c->scratch.resize(slot + 1, {nullptr, 0});
+  auto& s = c->scratch[slot];
+  if (s.second < bytes) {
+    if (s.first) cudaFree(s.first);
+    s.first = nullptr; s.second = 0;
+    if (cudaMalloc(&s.first, bytes) != cudaSuccess) return nullptr;
+    s.second = bytes;
+  }
+  return s.first;
+}
+
+extern "C" {
+
+const char* mile_last_error(void) { return g_err.c_str(); }
+int mile_version(void) { return 100; }
+
+int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, mile_ctx** out) {
+  if (!desc || !out) return fail("null argument");
+  if (desc->n_layers < 1 || desc->n_layers > MILE_MAX_LAYERS) return fail("n_layers out of range");
+  if (n_chains < 1) return fail("n_chains must be >= 1");
+  if (desc->task == MILE_TASK_REGRESSION && desc->widths[desc->n_layers - 1] < 2)
+    return fail("regression needs an output width >= 2 (mean, log-sigma)");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("no such CUDA device (this library has no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 9) return fail("mile_b200 needs thread-block clusters (built for sm_100a)");
+  mile_ctx* c = new mile_ctx();
+  c->desc = *desc; c->C = n_chains; c->device = device;
+  build_model(c);
+  if (c->d < 2) { delete c; return fail("The target distribution must have more than 1 dimension for MCLMC."); }
+  const size_t Cd = (size_t)n_chains * c->d * 4, Cb = (size_t)n_chains * 4;
+  CK(cudaMalloc(&c->theta, Cd)); CK(cudaMalloc(&c->u, Cd)); CK(cudaMalloc(&c->grad, Cd)); CK(cudaMalloc(&c->lp, Cb));
+  CK(cudaMalloc(&c->avg_x, Cd)); CK(cudaMalloc(&c->avg_x2, Cd));
+  CK(cudaMalloc(&c->t_time, Cb)); CK(cudaMalloc(&c->t_xavg, Cb)); CK(cudaMalloc(&c->t_epsmax, Cb));
+  CK(cudaMalloc(&c->t_eps, Cb)); CK(cudaMalloc(&c->t_L, Cb)); CK(cudaMalloc(&c->t_wtot, Cb));
+  CK(cudaMemset(c->theta, 0, Cd)); CK(cudaMemset(c->u, 0, Cd)); CK(cudaMemset(c->grad, 0, Cd)); CK(cudaMemset(c->lp, 0, Cb));
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+
+void mile_destroy(mile_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
+                  c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int32_t mile_n_params(const mile_ctx* c) { return c ? c->d : -1; }
+
+int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
+  if (!c || !key) return fail("null argument");
+  if (!strcmp(key, "cluster_size")) c->opt_cluster = (int)v;
+  else if (!strcmp(key, "tile_rows")) c->opt_tile_rows = (int)v;
+  else if (!strcmp(key, "refresh_mode")) c->opt_refresh = (int)v;
+  else if (!strcmp(key, "resident")) c->opt_resident = (int)v;
+  else return fail(std::string("unknown option ") + key);
+  return 0;
+}
+
+int64_t mile_get_option(const mile_ctx* c, const char* key) {
+  if (!c || !key) return -1;
+  if (!strcmp(key, "cluster_size") || !strcmp(key, "tile_rows") || !strcmp(key, "resident") || !strcmp(key, "smem_bytes")) {
+    Plan pl;
+    if (make_plan(c, c->C, c->N > 0 ? c->N : 1, true, pl)) return -1;
+    if (!strcmp(key, "cluster_size")) return pl.G;
+    if (!strcmp(key, "tile_rows")) return pl.TR;
+    if (!strcmp(key, "resident")) return pl.resident;
+    return (int64_t)pl.smem;
+  }
+  if (!strcmp(key, "refresh_mode")) return c->opt_refresh;
+  if (!strcmp(key, "row_stride")) return c->M.sA[0];
+  return -1;
+}
+
+static int set_split(mile_ctx* c, const float* X_dev, const void* y_dev, long N, cudaStream_t st, float** Xd,
+                     void** yd, long* Nd) {
+  if (N < 0) return fail("n_rows < 0");
+  CK(cudaSetDevice(c->device));
+  if (*Xd) { CK(cudaFree(*Xd)); *Xd = nullptr; }
+  if (*yd) { CK(cudaFree(*yd)); *yd = nullptr; }
+  *Nd = N;
+  if (N == 0) return 0;
+  const int sx = c->M.sA[0];
+  CK(cudaMalloc(Xd, (size_t)N * sx * 4));
+  CK(cudaMalloc(yd, (size_t)N * 4));
+  pad_rows_kernel<<<296, 256, 0, st>>>(X_dev, *Xd, N, c->M.F, sx);
+  CK(cudaGetLastError());
+  c->launches++;
+  CK(cudaMemcpyAsync(*yd, y_dev, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int lppd_alloc(mile_ctx* c, cudaStream_t st) {
+  if (c->lppd_m) { CK(cudaFree(c->lppd_m)); c->lppd_m = nullptr; }
+  if (c->lppd_s) { CK(cudaFree(c->lppd_s)); c->lppd_s = nullptr; }
+  if (c->Nt == 0) return 0;
+  const long n = (long)c->C * c->Nt;
+  CK(cudaMalloc(&c->lppd_m, n * 4)); CK(cudaMalloc(&c->lppd_s, n * 4));
+  fill_kernel<<<148, 256, 0, st>>>(c->lppd_m, n, -INFINITY);
+  fill_kernel<<<148, 256, 0, st>>>(c->lppd_s, n, 0.f);
+  CK(cudaGetLastError());
+  c->launches += 2; c->lppd_count = 0;
+  return 0;
+}
+
+int mile_set_data(mile_ctx* c, const float* X_dev, const void* y_dev, int64_t N, void* stream) {
+  if (!c) return fail("null ctx");
+  return set_split(c, X_dev, y_dev, (long)N, (cudaStream_t)stream, &c->X, &c->y, &c->N);
+}
+int mile_set_test(mile_ctx* c, const float* X_dev, const void* y_dev, int64_t N, void* stream) {
+  if (!c) return fail("null ctx");
+  if (set_split(c, X_dev, y_dev, (long)N, (cudaStream_t)stream, &c->Xt, &c->yt, &c->Nt)) return -1;
+  return lppd_alloc(c, (cudaStream_t)stream);
+}
+
+static int set_split_host(mile_ctx* c, const float* X, const void* y, long N, bool test) {
+  CK(cudaSetDevice(c->device));
+  float* Xd = (float*)scratch(c, 0, (size_t)(N > 0 ? N : 1) * c->M.F * 4);
+  void* yd = scratch(c, 1, (size_t)(N > 0 ? N : 1) * 4);
+  if (!Xd || !yd) return fail("cudaMalloc failed (staging)");
+  CK(cudaMemcpyAsync(Xd, X, (size_t)N * c->M.F * 4, cudaMemcpyHostToDevice, c->own_stream));
+  CK(cudaMemcpyAsync(yd, y, (size_t)N * 4, cudaMemcpyHostToDevice, c->own_stream));
+  int rc = test ? mile_set_test(c, Xd, yd, N, c->own_stream) : mile_set_data(c, Xd, yd, N, c->own_stream);
+  CK(cudaStreamSynchronize(c->own_stream));
+  return rc;
+}
+int mile_set_data_host(mile_ctx* c, const float* X, const void* y, int64_t N) {
+  if (!c) return fail("null ctx");
+  return set_split_host(c, X, y, (long)N, false);
+}
+int mile_set_test_host(mile_ctx* c, const float* X, const void* y, int64_t N) {
+  if (!c) return fail("null ctx");
+  return set_split_host(c, X, y, (long)N, true);
+}
+
+int mile_logpost_value_and_grad(mile_ctx* c, const float* theta_dev, int32_t n, float* lp_dev, float* grad_dev,
+                                void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (n < 1) return fail("n must be >= 1");
+  Plan pl;
+  if (make_plan(c, n, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.C = n; pl.kp.mode = MODE_EVAL; pl.kp.theta_in = theta_dev; pl.kp.lp_out = lp_dev; pl.kp.grad_out = grad_dev;
+  pl.kp.n_eval = n;
+  return launch(c, pl, n, (cudaStream_t)stream);
+}
+
+int mile_logpost_value_and_grad_host(mile_ctx* c, const float* theta, int32_t n, float* lp, float* grad) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const size_t nd = (size_t)n * c->d * 4;
+  float* th = (float*)scratch(c, 2, nd); float* g = (float*)scratch(c, 3, nd); float* l = (float*)scratch(c, 4, (size_t)n * 4);
+  if (!th || !g || !l) return fail("cudaMalloc failed (staging)");
+  CK(cudaMemcpyAsync(th, theta, nd, cudaMemcpyHostToDevice, c->own_stream));
+  if (mile_logpost_value_and_grad(c, th, n, l, g, c->own_stream)) return -1;
+  CK(cudaMemcpyAsync(lp, l, (size_t)n * 4, cudaMemcpyDeviceToHost, c->own_stream));
+  CK(cudaMemcpyAsync(grad, g, nd, cudaMemcpyDeviceToHost, c->own_stream));
+  CK(cudaStreamSynchronize(c->own_stream));
+  return 0;
+}
+
+int mile_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->X) return fail("mile_set_data has not been called");
+  Plan pl;
+  if (make_plan(c, c->C, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.mode = MODE_INIT; pl.kp.theta_in = theta0_dev; pl.kp.z = z0_dev; pl.kp.seed = seed;
+  return launch(c, pl, c->C, (cudaStream_t)stream);
+}
+
+int mile_mclmc_init_host(mile_ctx* c, const float* theta0, const float* z0, uint64_t seed) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  float* th = (float*)scratch(c, 2, Cd); float* z = z0 ? (float*)scratch(c, 3, Cd) : nullptr;
+  if (!th || (z0 && !z)) return fail("cudaMalloc failed (staging)");
+  CK(cudaMemcpyAsync(th, theta0, Cd, cudaMemcpyHostToDevice, c->own_stream));
+  if (z0) CK(cudaMemcpyAsync(z, z0, Cd, cudaMemcpyHostToDevice, c->own_stream));
+  if (mile_mclmc_init(c, th, z, seed, c->own_stream)) return -1;
+  CK(cudaStreamSynchronize(c->own_stream));
+  return 0;
+}
+
+int mile_set_state_host(mile_ctx* c, const float* theta, const float* u, const float* lp, const float* grad) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (theta) CK(cudaMemcpy(c->theta, theta, Cd, cudaMemcpyHostToDevice));
+  if (u) CK(cudaMemcpy(c->u, u, Cd, cudaMemcpyHostToDevice));
+  if (grad) CK(cudaMemcpy(c->grad, grad, Cd, cudaMemcpyHostToDevice));
+  if (lp) CK(cudaMemcpy(c->lp, lp, (size_t)c->C * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+int mile_get_state_host(mile_ctx* c, float* theta, float* u, float* lp, float* grad) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (theta) CK(cudaMemcpy(theta, c->theta, Cd, cudaMemcpyDeviceToHost));
+  if (u) CK(cudaMemcpy(u, c->u, Cd, cudaMemcpyDeviceToHost));
+  if (grad) CK(cudaMemcpy(grad, c->grad, Cd, cudaMemcpyDeviceToHost));
+  if (lp) CK(cudaMemcpy(lp, c->lp, (size_t)c->C * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int mile_get_state(mile_ctx* c, float* theta, float* u, float* lp, float* grad, void* stream) {
+  if (!c) return fail("null ctx");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (theta) CK(cudaMemcpyAsync(theta, c->theta, Cd, cudaMemcpyDeviceToDevice, st));
+  if (u) CK(cudaMemcpyAsync(u, c->u, Cd, cudaMemcpyDeviceToDevice, st));
+  if (grad) CK(cudaMemcpyAsync(grad, c->grad, Cd, cudaMemcpyDeviceToDevice, st));
+  if (lp) CK(cudaMemcpyAsync(lp, c->lp, (size_t)c->C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mile_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
+                      const float* step_size_dev, const float* L_dev, const float* z_dev, uint64_t seed,
+                      float* samples_dev, int64_t n_slots, float* info_dev, int32_t lppd, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (n_steps < 0 || n_thinning < 1) return fail("n_steps must be >= 0 and n_thinning >= 1");
+  if (lppd && !c->Xt) return fail("lppd requested but mile_set_test has not been called");
+  if (!step_size_dev || !L_dev) return fail("step_size / L are required");
+  if (n_steps == 0) return 0;
+  Plan pl;
+  if (make_plan(c, c->C, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  KParams& k = pl.kp;
+  k.mode = MODE_SAMPLE; k.n_steps = n_steps; k.step_base = step_base; k.thin = n_thinning; k.sample_base = sample_base;
+  k.n_slots = n_slots; k.eps = step_size_dev; k.L = L_dev; k.z = z_dev; k.seed = seed; k.samples = samples_dev;
+  k.info = info_dev; k.do_lppd = lppd;
+  if (launch(c, pl, c->C, (cudaStream_t)stream)) return -1;
+  if (lppd) {
+    // kept positions in [step_base, step_base+n_steps)
+    const long first = (step_base + n_thinning - 1) / n_thinning, last = (step_base + n_steps - 1) / n_thinning;
+    c->lppd_count += (last >= first) ? (last - first + 1) : 0;
+  }
+  return 0;
+}
+
+int mile_mclmc_sample_host(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning,
+                           const float* step_size, const float* L, const float* z, uint64_t seed, float* samples,
+                           int64_t n_slots, float* info, int32_t lppd) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->own_stream;
+  const size_t Cb = (size_t)c->C * 4, Cd = (size_t)c->C * c->d * 4;
+  const int nslot = c->opt_refresh ? 2 : 1;
+  float* e = (float*)scratch(c, 5, Cb); float* l = (float*)scratch(c, 6, Cb);
+  float* zd = z ? (float*)scratch(c, 7, (size_t)n_steps * nslot * Cd) : nullptr;
+  float* sd = samples ? (float*)scratch(c, 8, (size_t)n_slots * Cd) : nullptr;
+  float* id = info ? (float*)scratch(c, 9, (size_t)n_steps * c->C * 3 * 4) : nullptr;
+  if (!e || !l || (z && !zd) || (samples && !sd) || (info && !id)) return fail("cudaMalloc failed (staging)");
+  CK(cudaMemcpyAsync(e, step_size, Cb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(l, L, Cb, cudaMemcpyHostToDevice, st));
+  if (z) CK(cudaMemcpyAsync(zd, z, (size_t)n_steps * nslot * Cd, cudaMemcpyHostToDevice, st));
+  const int64_t sample_base = (step_base + n_thinning - 1) / n_thinning;
+  if (mile_mclmc_sample(c, n_steps, step_base, n_thinning, sample_base, e, l, zd, seed, sd, n_slots, id, lppd, st)) return -1;
+  if (samples) CK(cudaMemcpyAsync(samples, sd, (size_t)n_slots * Cd, cudaMemcpyDeviceToHost, st));
+  if (info) CK(cudaMemcpyAsync(info, id, (size_t)n_steps * c->C * 3 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mile_tune_reset(mile_ctx* c, float step_size_init, void* stream) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long C = c->C, Cd = (long)c->C * c->d;
+  fill_kernel<<<8, 256, 0, st>>>(c->t_time, C, 0.f);
+  fill_kernel<<<8, 256, 0, st>>>(c->t_xavg, C, 0.f);
+  fill_kernel<<<8, 256, 0, st>>>(c->t_epsmax, C, INFINITY);
+  fill_kernel<<<8, 256, 0, st>>>(c->t_eps, C, step_size_init);
+  fill_kernel<<<8, 256, 0, st>>>(c->t_L, C, fmaxf(sqrtf((float)c->d), 15.0f));
+  fill_kernel<<<8, 256, 0, st>>>(c->t_wtot, C, 0.f);
+  fill_kernel<<<148, 256, 0, st>>>(c->avg_x, Cd, 0.f);
+  fill_kernel<<<148, 256, 0, st>>>(c->avg_x2, Cd, 0.f);
+  CK(cudaGetLastError());
+  c->launches += 8;
+  return 0;
+}
+
+int mile_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg, const float* z_dev,
+                    uint64_t seed, float* tune_info_dev, void* stream) {
+  if (!c || !cfg) return fail("null argument");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (n_steps <= 0) return 0;
+  Plan pl;
+  if (make_plan(c, c->C, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  KParams& k = pl.kp;
+  k.mode = MODE_TUNE; k.n_steps = n_steps; k.step_base = step_base; k.z = z_dev; k.seed = seed; k.tune_info = tune_info_dev;
+  k.tune1 = cfg->tune1_steps; k.tune2 = cfg->tune2_steps; k.ev_start = cfg->desired_energy_var_start;
+  k.ev_end = cfg->desired_energy_var_end; k.trust = cfg->trust_in_estimate; k.neff = cfg->num_effective_samples;
+  return launch(c, pl, c->C, (cudaStream_t)stream);
+}
+
+int mile_mclmc_tune_host(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg, const float* z,
+                         uint64_t seed, float* tune_info) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->own_stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  const int nslot = c->opt_refresh ? 2 : 1;
+  float* zd = z ? (float*)scratch(c, 7, (size_t)n_steps * nslot * Cd) : nullptr;
+  float* id = tune_info ? (float*)scratch(c, 9, (size_t)n_steps * c->C * 4 * 4) : nullptr;
+  if ((z && !zd) || (tune_info && !id)) return fail("cudaMalloc failed (staging)");
+  if (z) CK(cudaMemcpyAsync(zd, z, (size_t)n_steps * nslot * Cd, cudaMemcpyHostToDevice, st));
+  if (mile_mclmc_tune(c, n_steps, step_base, cfg, zd, seed, id, st)) return -1;
+  if (tune_info) CK(cudaMemcpyAsync(tune_info, id, (size_t)n_steps * c->C * 4 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mile_tune_finish_phase2(mile_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  tune_L_kernel<<<c->C, MILE_THREADS, 0, (cudaStream_t)stream>>>(c->avg_x, c->avg_x2, c->t_L, c->d);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int mile_get_tuning_host(mile_ctx* c, float* step_size, float* L, float* step_size_max, float* mean_x, float* mean_x2) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  const size_t Cb = (size_t)c->C * 4, Cd = (size_t)c->C * c->d * 4;
+  if (step_size) CK(cudaMemcpy(step_size, c->t_eps, Cb, cudaMemcpyDeviceToHost));
+  if (L) CK(cudaMemcpy(L, c->t_L, Cb, cudaMemcpyDeviceToHost));
+  if (step_size_max) CK(cudaMemcpy(step_size_max, c->t_epsmax, Cb, cudaMemcpyDeviceToHost));
+  if (mean_x) CK(cudaMemcpy(mean_x, c->avg_x, Cd, cudaMemcpyDeviceToHost));
+  if (mean_x2) CK(cudaMemcpy(mean_x2, c->avg_x2, Cd, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int mile_set_tuning_host(mile_ctx* c, const float* step_size, const float* L) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const size_t Cb = (size_t)c->C * 4;
+  if (step_size) CK(cudaMemcpy(c->t_eps, step_size, Cb, cudaMemcpyHostToDevice));
+  if (L) CK(cudaMemcpy(c->t_L, L, Cb, cudaMemcpyHostToDevice));
+  return 0;
+}
+int mile_tuning_ptrs(mile_ctx* c, float** step_size_dev, float** L_dev) {
+  if (!c) return fail("null ctx");
+  if (step_size_dev) *step_size_dev = c->t_eps;
+  if (L_dev) *L_dev = c->t_L;
+  return 0;
+}
+
+int mile_lppd_reset(mile_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->Xt) return fail("mile_set_test has not been called");
+  return lppd_alloc(c, (cudaStream_t)stream);
+}
+
+int mile_lppd_accumulate(mile_ctx* c, const float* theta_dev, int32_t n, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->Xt) return fail("mile_set_test has not been called");
+  if (n < 1 || n > c->C) return fail("n must be in [1, n_chains]");
+  Plan pl;
+  if (make_plan(c, c->C, c->Nt, false, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.mode = MODE_LPPD; pl.kp.theta_in = theta_dev;
+  if (launch(c, pl, n, (cudaStream_t)stream)) return -1;
+  c->lppd_count += 1;
+  return 0;
+}
+
+int mile_lppd_state_host(mile_ctx* c, float* m, float* s, int64_t* count) {
+  if (!c) return fail("null ctx");
+  if (!c->Xt) return fail("mile_set_test has not been called");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  const size_t n = (size_t)c->C * c->Nt * 4;
+  if (m) CK(cudaMemcpy(m, c->lppd_m, n, cudaMemcpyDeviceToHost));
+  if (s) CK(cudaMemcpy(s, c->lppd_s, n, cudaMemcpyDeviceToHost));
+  if (count) *count = c->lppd_count;
+  return 0;
+}
+
+int mile_predict(mile_ctx* c, const float* theta_dev, int32_t n, int32_t which, float* out_dev, void* stream) {
+  if (!c) return fail("null ctx");
+  if (which ? !c->Xt : !c->X) return fail("requested split has not been set");
+  if (n < 1) return fail("n must be >= 1");
+  Plan pl;
+  if (make_plan(c, n, which ? c->Nt : c->N, false, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.C = n; pl.kp.mode = MODE_PREDICT; pl.kp.theta_in = theta_dev; pl.kp.pred_out = out_dev; pl.kp.which = which;
+  return launch(c, pl, n, (cudaStream_t)stream);
+}
+
+int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
+int mile_synchronize(mile_ctx* c) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,551 @@
+// mile_kernel.cuh -- the persistent cluster-per-chain MCLMC kernel.
+//
+// One thread-block cluster of G CTAs owns one chain for the whole launch:
+//   * theta / momentum / gradient live replicated in every CTA's shared memory,
+//   * the training rows are split across the G CTAs (X slice resident in shared memory
+//     when it fits, otherwise streamed tile by tile from the padded HBM/L2 copy),
+//   * every gradient evaluation ends in a DSMEM all-reduce of the G partial gradients
+//     (one cluster barrier, fixed summation order => all CTAs hold bit-identical state),
+//   * B/A/B/A/B + partial refresh + energy bookkeeping + tuning statistics + thinned
+//     sample capture + test-set logsumexp run in the same kernel: zero launches per step.
+//
+// Reference call stack replaced: src/training/sampling.py:134-177 (scan of sampler.step),
+// src/training/warmup.py:276-352 (tuning step), blackjax 1.2.2 mclmc kernel.
+#pragma once
+#include "mile_device.cuh"
+#include <float.h>
+
+enum { MODE_EVAL = 0, MODE_INIT = 1, MODE_SAMPLE = 2, MODE_TUNE = 3, MODE_LPPD = 4, MODE_PREDICT = 5 };
+
+struct KParams {
+  DevModel M;
+  // data: padded row-major copies [N][sA[0]]
+  const float* X; const void* y; long N;
+  const float* Xt; const void* yt; long Nt;
+  int C, G, resident, rows_res;   // rows_res: rows of the resident X slice buffer (multiple of TR)
+  // chain state [C,d],[C,d],[C,d],[C]
+  float* theta; float* u; float* grad; float* lp;
+  int mode, n_steps, thin, refresh_mode, do_lppd;
+  long step_base, sample_base, n_slots;
+  const float* eps; const float* L;  // [C]
+  const float* z; unsigned long long seed;
+  float* samples; float* info;
+  float* lppd_m; float* lppd_s;
+  // tuning state [C] / [C,d]
+  float *t_time, *t_xavg, *t_epsmax, *t_eps, *t_L, *t_wtot, *avg_x, *avg_x2, *tune_info;
+  int tune1, tune2; float ev_start, ev_end, trust, neff;
+  // eval / init / lppd / predict io
+  const float* theta_in; float* lp_out; float* grad_out; float* pred_out; int n_eval, which;
+  // shared-memory carve-up (float offsets)
+  int dS, off_wp, off_th, off_u, off_g, off_thb, off_ub, off_gb, off_gpart, off_avgx, off_avgx2,
+      off_pmap, off_red, off_tile, off_x;
+};
+
+struct Ctx {
+  const KParams& P;
+  float *wp, *th, *uu, *gg, *thb, *ub, *gb, *gpart, *avgx, *avgx2, *red, *tile, *xbuf, *xstream;
+  int* pmap;
+  int phase;   // block_sum double-buffer phase
+  int rank, G, chain;
+  __device__ Ctx(const KParams& p) : P(p) {}
+};
+
+// flat element i -> position in the padded parameter image
+__device__ __forceinline__ void build_pmap(const DevModel& M, int* pmap) {
+  for (int l = 0; l < M.NL; ++l) {
+    const int IN = M.dims[l], OUT = M.dims[l + 1], OUTP = M.dimp[l + 1];
+    for (int j = threadIdx.x; j < OUT; j += MILE_THREADS) pmap[M.bias_off[l] + j] = M.pb_off[l] + j;
+    for (int e = threadIdx.x; e < IN * OUT; e += MILE_THREADS)
+      pmap[M.kern_off[l] + e] = M.pw_off[l] + (e / OUT) * OUTP + (e % OUT);
+  }
+}
+
+__device__ __forceinline__ void refresh_wp(Ctx& c) {
+  const int d = c.P.M.d;
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.wp[c.pmap[i]] = c.th[i];
+}
+
+// Copy rows [row0, row0+rows_pad) of the padded global matrix into a shared tile, zero beyond nvalid.
+__device__ __forceinline__ void load_x_tile(float* dst, const float* __restrict__ src, long row0, int nvalid,
+                                            int rows_pad, int sx) {
+  const float4* s4 = reinterpret_cast<const float4*>(src + row0 * sx);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const int nv4 = nvalid * (sx >> 2), np4 = rows_pad * (sx >> 2);
+  for (int i = threadIdx.x; i < np4; i += MILE_THREADS)
+    d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Forward pass of one row tile; returns pointer to the output buffer (stride sA[NL]).
+__device__ __forceinline__ const float* forward_tile(Ctx& c, const float* Xt, int Q) {
+  const DevModel& M = c.P.M;
+  const float* in = Xt;
+  int sin_ = M.sA[0];
+  for (int l = 0; l < M.NL; ++l) {
+    float* out = c.tile + M.a_off[l + 1];
+    fwd_layer(M, l, c.wp, in, sin_, out, c.tile + M.d_off[l], M.sA[l + 1], Q, l == M.NL - 1);
+    __syncthreads();
+    in = out; sin_ = M.sA[l + 1];
+  }
+  return in;
+}
+
+// Full-batch value_and_grad restricted to this CTA's rows [r0, r1): partial gradient (flat
+// layout, likelihood part only) and partial log-likelihood into gpart[0..dS] (ll at [dS]).
+template <int NLMAX>
+__device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
+  const KParams& P = c.P;
+  const DevModel& M = P.M;
+  DwAcc<NLMAX> acc;
+  acc.zero();
+  float llpart = 0.f;
+  const int TR = M.TR;
+  const long nrows = r1 > r0 ? r1 - r0 : 0;
+  const int ntiles = (int)((nrows + TR - 1) / TR);
+  for (int t = 0; t < ntiles; ++t) {
+    const long row0 = r0 + (long)t * TR;
+    const int nvalid = (int)((r1 - row0) < TR ? (r1 - row0) : TR);
+    const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
+    const int rows_pad = Q * 4;
+    const float* Xt;
+    if (P.resident) {
+      Xt = c.xbuf + (long)t * TR * M.sA[0];
+    } else {
+      load_x_tile(c.xbuf, P.X, row0, nvalid, rows_pad, M.sA[0]);
+      __syncthreads();
+      Xt = c.xbuf;
+    }
+    const float* out = forward_tile(c, Xt, Q);
+    llpart += loglik_rows(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], P.y, row0, nvalid, rows_pad);
+    __syncthreads();
+    for (int l = M.NL - 1; l >= 1; --l) {
+      bwd_layer(M, l, c.wp, c.tile + M.d_off[l], M.sA[l + 1], c.tile + M.d_off[l - 1], M.sA[l], Q);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int l = 0; l < NLMAX; ++l)
+      if (l < M.NL)
+        dw_accumulate<NLMAX>(M, l, acc, l, l == 0 ? Xt : c.tile + M.a_off[l], M.sA[l],
+                             c.tile + M.d_off[l], M.sA[l + 1], rows_pad);
+    __syncthreads();
+  }
+  // cross-chunk reduction of the per-thread 4x4 tiles (scratch aliases the tile buffers)
+  float* scr = c.tile;
+  float* scrb = c.tile + MILE_THREADS * 16;
+#pragma unroll
+  for (int l = 0; l < NLMAX; ++l) {
+    if (l < M.NL) {
+      const DwRole R = dw_role(M, l);
+      if (R.active) {
+        float4* s4 = reinterpret_cast<float4*>(scr + (R.chunk * R.ntile + R.tile) * 16);
+        s4[0] = make_float4(acc.w[l][0], acc.w[l][1], acc.w[l][2], acc.w[l][3]);
+        s4[1] = make_float4(acc.w[l][4], acc.w[l][5], acc.w[l][6], acc.w[l][7]);
+        s4[2] = make_float4(acc.w[l][8], acc.w[l][9], acc.w[l][10], acc.w[l][11]);
+        s4[3] = make_float4(acc.w[l][12], acc.w[l][13], acc.w[l][14], acc.w[l][15]);
+        if (R.itl == 0)
+          *reinterpret_cast<float4*>(scrb + (R.chunk * R.ntile + R.tile) * 4) =
+              make_float4(acc.b[l][0], acc.b[l][1], acc.b[l][2], acc.b[l][3]);
+      }
+      __syncthreads();
+      const int IN = M.dims[l], OUT = M.dims[l + 1], njt = M.dimp[l + 1] >> 2;
+      for (int o = threadIdx.x; o < R.ntile * 16; o += MILE_THREADS) {
+        const int tile = o >> 4, e = o & 15;
+        float s = 0.f;
+        for (int ch = 0; ch < R.nch; ++ch) s += scr[(ch * R.ntile + tile) * 16 + e];
+        const int i = (tile / njt) * 4 + (e >> 2), j = (tile % njt) * 4 + (e & 3);
+        if (i < IN && j < OUT) gpart[M.kern_off[l] + i * OUT + j] = s;
+      }
+      for (int o = threadIdx.x; o < njt * 4; o += MILE_THREADS) {
+        const int tile = o >> 2, e = o & 3;   // itl == 0 -> tile == jt
+        float s = 0.f;
+        for (int ch = 0; ch < R.nch; ++ch) s += scrb[(ch * R.ntile + tile) * 4 + e];
+        if (o < OUT) gpart[M.bias_off[l] + o] = s;
+      }
+      __syncthreads();
+    }
+  }
+  float v[1] = {llpart};
+  block_sum<1>(v, c.red, c.phase);
+  if (threadIdx.x == 0) gpart[P.dS] = v[0];
+}
+
+// DSMEM all-reduce of the cluster's partial gradients + prior: afterwards gg = full gradient of
+// the log-posterior (bit-identical in every CTA), returns the log-posterior value.  Also returns
+// sum g^2, sum u.g and the number of non-finite entries of theta for the next B-step / handle_nans.
+__device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float& g2, float& ug, float& nonfinite) {
+  const KParams& P = c.P;
+  const DevModel& M = P.M;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (c.G > 1) cluster.sync(); else __syncthreads();
+  float ll = 0.f;
+  for (int r = 0; r < c.G; ++r) {
+    const float* rp = c.G > 1 ? cluster.map_shared_rank(gpart, r) : gpart;
+    ll += rp[P.dS];
+  }
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
+  for (int i = threadIdx.x; i < M.d; i += MILE_THREADS) {
+    float s = 0.f;
+    for (int r = 0; r < c.G; ++r) {
+      const float* rp = c.G > 1 ? cluster.map_shared_rank(gpart, r) : gpart;
+      s += rp[i];
+    }
+    const float th = c.th[i];
+    float pg, pv;
+    if (M.prior == MILE_PRIOR_NORMAL) {
+      const float dlt = th - loc;
+      pv = (logf(6.283185307179586f * s2) + dlt * dlt / s2) / -2.f;
+      pg = -dlt / s2;
+    } else {
+      const float dlt = th - loc;
+      pv = -logf(2.f * sc) - fabsf(dlt) / sc;
+      pg = -((dlt > 0.f) - (dlt < 0.f)) / sc;
+    }
+    const float g = s + pg;
+    c.gg[i] = g;
+    v[0] += pv; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
+  }
+  block_sum<4>(v, c.red, c.phase);
+  g2 = v[1]; ug = v[2]; nonfinite = v[3];
+  return v[0] + ll;
+}
+
+// ESH momentum update B(coef) (blackjax esh_dynamics_momentum_update_one_step, sqrt_diag_cov = 1).
+// delta-small-safe forms: 1-zeta = -expm1(-delta), log(1+p+(1-p)zeta^2) - ln2 = log1p(-(1-p)(1-zeta^2)/2).
+__device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
+  const int d = c.P.M.d;
+  const float gn = sqrtf(g2);
+  const float ginv = gn > 1e-13f ? 1.f / gn : 1.f;
+  const float p = ug * ginv;
+  const float delta = eps * coef * gn / (float)(d - 1);
+  const float zeta = expf(-delta);
+  const float omz = -expm1f(-delta);
+  const float ce = omz * (1.f + zeta + p * omz);
+  const float cu = 2.f * zeta;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+    const float raw = (c.gg[i] * ginv) * ce + cu * c.uu[i];
+    c.uu[i] = raw;
+    v[0] += raw * raw;
+  }
+  block_sum<1>(v, c.red, c.phase);
+  const float rn = sqrtf(v[0]);
+  const float rinv = rn > 1e-13f ? 1.f / rn : 1.f;
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.uu[i] *= rinv;
+  const float omz2 = -expm1f(-2.f * delta);
+  return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
+}
+
+// A(coef): theta += eps*coef*u and refresh the padded weight image.
+__device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
+  const int d = c.P.M.d;
+  const float s = eps * coef;
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+    const float t = c.th[i] + s * c.uu[i];
+    c.th[i] = t;
+    c.wp[c.pmap[i]] = t;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float noise_at(const KParams& P, int chain, long step_local, int slot, int nslot, int i) {
+  if (P.z) return P.z[(((long)step_local * nslot + slot) * P.C + chain) * P.M.d + i];
+  return philox_normal(P.seed, (uint32_t)chain, (uint64_t)(P.step_base + step_local), (uint32_t)slot + 1u, (uint32_t)i);
+}
+
+// partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
+__device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, long step_local, int slot, int nslot,
+                                                 float& ug_out) {
+  const KParams& P = c.P;
+  const int d = P.M.d;
+  if (isinf(L)) {
+    float v[1] = {0.f};
+    for (int i = threadIdx.x; i < d; i += MILE_THREADS) v[0] += c.uu[i] * c.gg[i];
+    block_sum<1>(v, c.red, c.phase);
+    ug_out = v[0];
+    return;
+  }
+  const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
+  float v[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+    const float w = c.uu[i] + nu * noise_at(P, c.chain, step_local, slot, nslot, i);
+    c.uu[i] = w;
+    v[0] += w * w; v[1] += w * c.gg[i];
+  }
+  block_sum<2>(v, c.red, c.phase);
+  const float inv = 1.f / sqrtf(v[0]);
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.uu[i] *= inv;
+  ug_out = v[1] * inv;
+}
+
+__device__ __forceinline__ float nan_to_num(float x) {
+  if (isnan(x)) return 0.f;
+  if (isinf(x)) return x > 0.f ? FLT_MAX : -FLT_MAX;
+  return x;
+}
+
+// Online logsumexp over the test split for the current theta (weights already in c.wp).
+__device__ __forceinline__ void lppd_fold(Ctx& c, int chain) {
+  const KParams& P = c.P;
+  const DevModel& M = P.M;
+  const int TR = M.TR;
+  const long per = (P.Nt + c.G - 1) / c.G;
+  const long r0 = per * c.rank, r1 = (r0 + per) < P.Nt ? (r0 + per) : P.Nt;
+  for (long row0 = r0; row0 < r1; row0 += TR) {
+    const int nvalid = (int)((r1 - row0) < TR ? (r1 - row0) : TR);
+    const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
+    float* xt = c.xstream;
+    load_x_tile(xt, P.Xt, row0, nvalid, Q * 4, M.sA[0]);
+    __syncthreads();
+    const float* out = forward_tile(c, xt, Q);
+    for (int r = threadIdx.x; r < nvalid; r += MILE_THREADS) {
+      const float lp = pointwise_lppd_row(M, out + r * M.sA[M.NL], P.yt, row0 + r);
+      const long idx = (long)chain * P.Nt + row0 + r;
+      const float m = P.lppd_m[idx], s = P.lppd_s[idx];
+      const float nm = fmaxf(m, lp);
+      const float safe = isfinite(nm) ? nm : 0.f;
+      P.lppd_m[idx] = nm;
+      P.lppd_s[idx] = s * expf((isfinite(m) ? m : -INFINITY) - safe) + expf(lp - safe);
+    }
+    __syncthreads();
+  }
+}
+
+template <int NLMAX>
+__global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = P.M;
+  cg::cluster_group cluster = cg::this_cluster();
+  Ctx c(P);
+  c.G = P.G;
+  c.rank = c.G > 1 ? (int)cluster.block_rank() : 0;
+  c.chain = blockIdx.x / c.G;
+  c.phase = 0;
+  c.wp = smem + P.off_wp; c.th = smem + P.off_th; c.uu = smem + P.off_u; c.gg = smem + P.off_g;
+  c.thb = smem + P.off_thb; c.ub = smem + P.off_ub; c.gb = smem + P.off_gb; c.gpart = smem + P.off_gpart;
+  c.avgx = smem + P.off_avgx; c.avgx2 = smem + P.off_avgx2; c.pmap = reinterpret_cast<int*>(smem + P.off_pmap);
+  c.red = smem + P.off_red; c.tile = smem + P.off_tile;
+  c.xstream = c.tile + M.tile_floats;              // one streamed X tile [TR][sA[0]]
+  c.xbuf = P.resident ? smem + P.off_x : c.xstream;  // resident slice or the streamed tile
+  const int d = M.d, ch = c.chain;
+  const int tid = threadIdx.x;
+
+  // ---- prologue: parameter image, state, resident X slice --------------------------------
+  for (int i = tid; i < M.psize; i += MILE_THREADS) c.wp[i] = 0.f;
+  build_pmap(M, c.pmap);
+  const bool from_input = (P.mode == MODE_EVAL || P.mode == MODE_INIT || P.mode == MODE_LPPD || P.mode == MODE_PREDICT);
+  const float* th_src = from_input ? P.theta_in + (long)ch * d : P.theta + (long)ch * d;
+  for (int i = tid; i < d; i += MILE_THREADS) {
+    c.th[i] = th_src[i];
+    if (!from_input) { c.uu[i] = P.u[(long)ch * d + i]; c.gg[i] = P.grad[(long)ch * d + i]; }
+    else { c.uu[i] = 0.f; c.gg[i] = 0.f; }
+  }
+  __syncthreads();
+  refresh_wp(c);
+  const long per = (P.N + c.G - 1) / c.G;
+  const long r0 = per * c.rank < P.N ? per * c.rank : P.N;
+  const long r1 = (r0 + per) < P.N ? (r0 + per) : P.N;
+  const bool needs_train = (P.mode == MODE_EVAL || P.mode == MODE_INIT || P.mode == MODE_SAMPLE || P.mode == MODE_TUNE);
+  if (P.resident && needs_train) {
+    const int sx = M.sA[0];
+    const long nv4 = (r1 - r0) * (sx >> 2), np4 = (long)P.rows_res * (sx >> 2);
+    const float4* s4 = reinterpret_cast<const float4*>(P.X + r0 * sx);
+    float4* d4 = reinterpret_cast<float4*>(c.xbuf);
+    for (long i = tid; i < np4; i += MILE_THREADS) d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  if (P.mode == MODE_PREDICT) {
+    // forward only: out [n, Nrows, K]
+    const float* Xsrc = P.which ? P.Xt : P.X;
+    const long Nr = P.which ? P.Nt : P.N;
+    const int K = M.dims[M.NL];
+    const long pr = (Nr + c.G - 1) / c.G;
+    const long a0 = pr * c.rank, a1 = (a0 + pr) < Nr ? (a0 + pr) : Nr;
+    for (long row0 = a0; row0 < a1; row0 += M.TR) {
+      const int nvalid = (int)((a1 - row0) < M.TR ? (a1 - row0) : M.TR);
+      const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
+      float* xt = c.xstream;
+      load_x_tile(xt, Xsrc, row0, nvalid, Q * 4, M.sA[0]);
+      __syncthreads();
+      const float* out = forward_tile(c, xt, Q);
+      for (int e = tid; e < nvalid * K; e += MILE_THREADS)
+        P.pred_out[((long)ch * Nr + row0 + e / K) * K + e % K] = out[(e / K) * M.sA[M.NL] + e % K];
+      __syncthreads();
+    }
+    if (c.G > 1) cluster.sync();
+    return;
+  }
+  if (P.mode == MODE_LPPD) {
+    lppd_fold(c, ch);
+    if (c.G > 1) cluster.sync();
+    return;
+  }
+
+  int ev = 0;  // gradient-evaluation parity (gpart double buffer)
+  float g2 = 0.f, ug = 0.f, nf = 0.f;
+  if (P.mode == MODE_EVAL || P.mode == MODE_INIT) {
+    float* gp = c.gpart + (ev & 1) * (P.dS + 4);
+    grad_eval<NLMAX>(c, r0, r1, gp);
+    const float lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+    if (P.mode == MODE_EVAL) {
+      if (c.rank == 0) {
+        for (int i = tid; i < d; i += MILE_THREADS) P.grad_out[(long)ch * d + i] = c.gg[i];
+        if (tid == 0) P.lp_out[ch] = lp;
+      }
+    } else {
+      // generate_unit_vector: u = z / |z|
+      float v[1] = {0.f};
+      for (int i = tid; i < d; i += MILE_THREADS) {
+        const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+        c.uu[i] = zz; v[0] += zz * zz;
+      }
+      block_sum<1>(v, c.red, c.phase);
+      const float inv = 1.f / sqrtf(v[0]);
+      if (c.rank == 0) {
+        for (int i = tid; i < d; i += MILE_THREADS) {
+          P.theta[(long)ch * d + i] = c.th[i];
+          P.u[(long)ch * d + i] = c.uu[i] * inv;
+          P.grad[(long)ch * d + i] = c.gg[i];
+        }
+        if (tid == 0) P.lp[ch] = lp;
+      }
+    }
+    if (c.G > 1) cluster.sync();
+    return;
+  }
+
+  // ---- MODE_SAMPLE / MODE_TUNE: the step loop -----------------------------------------------
+  const bool tune = P.mode == MODE_TUNE;
+  float lp = P.lp[ch];
+  float eps = tune ? P.t_eps[ch] : P.eps[ch];
+  float Lc = tune ? P.t_L[ch] : P.L[ch];
+  float t_time = 0.f, t_xavg = 0.f, t_epsmax = INFINITY, t_wtot = 0.f;
+  if (tune) {
+    t_time = P.t_time[ch]; t_xavg = P.t_xavg[ch]; t_epsmax = P.t_epsmax[ch]; t_wtot = P.t_wtot[ch];
+    for (int i = tid; i < d; i += MILE_THREADS) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
+  }
+  const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
+  const int nslot = P.refresh_mode ? 2 : 1;
+  {  // cached gradient: sum g^2 and u.g for the first B-step
+    float v[2] = {0.f, 0.f};
+    for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+    block_sum<2>(v, c.red, c.phase);
+    g2 = v[0]; ug = v[1];
+  }
+  for (int s = 0; s < P.n_steps; ++s) {
+    const float lp_old = lp;
+    if (tune) {
+      for (int i = tid; i < d; i += MILE_THREADS) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+    }
+    if (P.refresh_mode) refresh_momentum(c, 0.5f * eps, Lc, s, 0, nslot, ug);
+    float dK = esh_update(c, eps, b1, g2, ug);
+    position_update(c, eps, 0.5f);
+    float* gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
+    grad_eval<NLMAX>(c, r0, r1, gp);
+    lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+    dK += esh_update(c, eps, b2, g2, ug);
+    position_update(c, eps, 0.5f);
+    gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
+    grad_eval<NLMAX>(c, r0, r1, gp);
+    lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+    dK += esh_update(c, eps, b1, g2, ug);
+    refresh_momentum(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
+    float dE = dK - lp + lp_old;
+
+    if (!tune) {
+      if (P.info && c.rank == 0 && tid == 0) {
+        float* o = P.info + ((long)s * P.C + ch) * 3;
+        o[0] = lp; o[1] = dK; o[2] = dE;
+      }
+    } else {
+      // handle_nans (warmup.py:468-483)
+      const bool success = nf == 0.f;
+      if (!success) {
+        for (int i = tid; i < d; i += MILE_THREADS) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; c.wp[c.pmap[i]] = c.thb[i]; }
+        lp = lp_old;
+        t_epsmax = eps * 0.8f;
+        dE = 0.f;
+        float v[2] = {0.f, 0.f};
+        for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+        block_sum<2>(v, c.red, c.phase);
+        g2 = v[0]; ug = v[1];
+      } else {
+        bool changed = false;
+        for (int i = tid; i < d; i += MILE_THREADS) {
+          const float u0 = c.uu[i], g0 = c.gg[i];
+          const float u1 = nan_to_num(u0), g1 = nan_to_num(g0);
+          if (u1 != u0 || g1 != g0 || isnan(u0) || isnan(g0)) { c.uu[i] = u1; c.gg[i] = g1; changed = true; }
+        }
+        lp = nan_to_num(lp);
+        t_epsmax = nan_to_num(t_epsmax);
+        dE = nan_to_num(dE);
+        if (__syncthreads_or(changed)) {
+          float v[2] = {0.f, 0.f};
+          for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+          block_sum<2>(v, c.red, c.phase);
+          g2 = v[0]; ug = v[1];
+        }
+      }
+      // step-size predictor (warmup.py:302-322)
+      const long it = P.step_base + s;
+      const float total = (float)(P.tune1 + P.tune2 + 1);
+      float target;
+      if (P.ev_start > 2.0f) {
+        const float ex = expf(-(float)it / (total / 4.f));
+        target = P.ev_start * ex + P.ev_end * (1.f - ex);
+      } else {
+        const float progress = fminf((float)it / total, 1.f);
+        target = P.ev_start - (P.ev_start - P.ev_end) * progress;
+      }
+      const float decay = (P.neff - 1.f) / (P.neff + 1.f);
+      const float xi = dE * dE / ((float)d * target) + 1e-8f;
+      const float lx = logf(xi) / (6.f * P.trust);
+      const float wgt = expf(-0.5f * lx * lx);
+      t_xavg = decay * t_xavg + wgt * (xi / powf(eps, 6.f));
+      t_time = decay * t_time + wgt;
+      float eps_new = powf(t_xavg / t_time, -1.f / 6.f);
+      eps_new = (eps_new < t_epsmax ? eps_new : 0.f) + (eps_new > t_epsmax ? t_epsmax : 0.f);
+      // streaming average of (x, x^2) in phase 2 (warmup.py:341-348); phase 1 keeps it at 0
+      if (it >= P.tune1) {
+        const float w = (success ? 1.f : 0.f) * eps_new;
+        const float denom = t_wtot + w;
+        for (int i = tid; i < d; i += MILE_THREADS) {
+          const float x = c.th[i];
+          c.avgx[i] = (t_wtot * c.avgx[i] + w * x) / denom;
+          c.avgx2[i] = (t_wtot * c.avgx2[i] + w * (x * x)) / denom;
+        }
+        t_wtot += w;
+      }
+      if (P.tune_info && c.rank == 0 && tid == 0) {
+        float* o = P.tune_info + ((long)s * P.C + ch) * 4;
+        o[0] = dE; o[1] = eps_new; o[2] = t_epsmax; o[3] = success ? 1.f : 0.f;
+      }
+      eps = eps_new;
+      __syncthreads();
+    }
+    // thinned sample capture (sampling.py:152-164) + fused posterior-predictive fold
+    if (!tune) {
+      const long idx = P.step_base + s;
+      if (idx % P.thin == 0) {
+        const long slot = idx / P.thin - P.sample_base;
+        if (P.samples && c.rank == 0 && slot >= 0 && slot < P.n_slots)
+          for (int i = tid; i < d; i += MILE_THREADS) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
+        if (P.do_lppd) lppd_fold(c, ch);
+      }
+    }
+  }
+  // ---- epilogue: write state back ------------------------------------------------------------
+  if (c.rank == 0) {
+    for (int i = tid; i < d; i += MILE_THREADS) {
+      P.theta[(long)ch * d + i] = c.th[i];
+      P.u[(long)ch * d + i] = c.uu[i];
+      P.grad[(long)ch * d + i] = c.gg[i];
+      if (tune) { P.avg_x[(long)ch * d + i] = c.avgx[i]; P.avg_x2[(long)ch * d + i] = c.avgx2[i]; }
+    }
+    if (tid == 0) {
+      P.lp[ch] = lp;
+      if (tune) { P.t_time[ch] = t_time; P.t_xavg[ch] = t_xavg; P.t_epsmax[ch] = t_epsmax; P.t_eps[ch] = eps; P.t_wtot[ch] = t_wtot; }
+    }
+  }
+  if (c.G > 1) cluster.sync();
+}

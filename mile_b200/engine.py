@@ -1,0 +1,306 @@
+"""Thin object wrapper around the C ABI: one `Ensemble` = one `mile_ctx` = one ensemble wave
+on one GPU.  Host arrays are numpy; device arrays are torch CUDA tensors (torch is only the
+allocator / stream owner here, all compute happens in libmile_b200.so)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass(frozen=True)
+class FCNSpec:
+    """What `partial(prob_model.log_unnormalized_posterior, x=..., y=...)` closes over
+    (src/training/trainer.py:576-580): FCN shape (src/models/tabular/fcn.py:11-28, the
+    hidden_structure INCLUDES the output width), task, prior."""
+
+    n_features: int
+    widths: tuple
+    activation: str = 'relu'
+    task: str = 'regr'
+    prior: str = 'normal'
+    prior_loc: float = 0.0
+    prior_scale: float = 1.0
+    n_batches: float = 1.0
+    layer_order: tuple = field(default=None)
+
+    def __post_init__(self):
+        object.__setattr__(self, 'widths', tuple(int(w) for w in self.widths))
+        if self.layer_order is None:
+            # ravel_pytree flattens dicts in sorted key order ('layer10' < 'layer2')
+            object.__setattr__(self, 'layer_order',
+                               tuple(sorted(range(len(self.widths)), key=lambda i: f'layer{i}')))
+        if self.activation not in capi.ACTIVATIONS:
+            raise NotImplementedError(f'activation {self.activation!r} is not supported by the CUDA path')
+        if len(self.widths) > capi.MILE_MAX_LAYERS:
+            raise NotImplementedError(f'at most {capi.MILE_MAX_LAYERS} layers')
+
+    @property
+    def dims(self):
+        return (self.n_features,) + self.widths
+
+    @property
+    def n_params(self):
+        d = self.dims
+        return sum(d[i] * d[i + 1] + d[i + 1] for i in range(len(self.widths)))
+
+    def offsets(self):
+        d = self.dims
+        nl = len(self.widths)
+        bias_off, kern_off, off = [0] * nl, [0] * nl, 0
+        for l in self.layer_order:
+            bias_off[l] = off
+            off += d[l + 1]
+            kern_off[l] = off
+            off += d[l] * d[l + 1]
+        return bias_off, kern_off
+
+    def to_desc(self) -> capi.ModelDesc:
+        m = capi.ModelDesc()
+        m.n_features = self.n_features
+        m.n_layers = len(self.widths)
+        b, k = self.offsets()
+        for l, w in enumerate(self.widths):
+            m.widths[l], m.bias_off[l], m.kernel_off[l] = w, b[l], k[l]
+        m.activation = capi.ACTIVATIONS[self.activation]
+        m.task = capi.TASKS[self.task]
+        m.prior = capi.PRIORS[self.prior.lower()]
+        m.prior_loc, m.prior_scale, m.n_batches = self.prior_loc, self.prior_scale, self.n_batches
+        return m
+
+    # --- pytree <-> flat (ravel_pytree order) ----------------------------------------
+    def ravel(self, tree: dict) -> np.ndarray:
+        """{'fcn': {'layer{i}': {'bias','kernel'}}} with optional leading batch axes -> [..., d]."""
+        inner = tree['fcn'] if 'fcn' in tree else tree
+        d = self.dims
+        parts = []
+        for l in self.layer_order:
+            lay = inner[f'layer{l}']
+            b = np.asarray(lay['bias'], dtype=np.float32)
+            k = np.asarray(lay['kernel'], dtype=np.float32)
+            lead = b.shape[:-1]
+            parts.append(b.reshape(lead + (d[l + 1],)))
+            parts.append(k.reshape(lead + (d[l] * d[l + 1],)))
+        return np.ascontiguousarray(np.concatenate(parts, axis=-1))
+
+    def unravel(self, theta: np.ndarray) -> dict:
+        b_off, k_off = self.offsets()
+        d = self.dims
+        lead = theta.shape[:-1]
+        out = {}
+        for l in range(len(self.widths)):
+            out[f'layer{l}'] = {
+                'bias': np.array(theta[..., b_off[l]:b_off[l] + d[l + 1]]),
+                'kernel': np.array(theta[..., k_off[l]:k_off[l] + d[l] * d[l + 1]]).reshape(lead + (d[l], d[l + 1])),
+            }
+        return {'fcn': out}
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor (contiguous) -> void*; None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'device tensors must be contiguous CUDA tensors'
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Ensemble:
+    """One ensemble wave of `n_chains` chains on one GPU."""
+
+    def __init__(self, spec: FCNSpec, n_chains: int, device: int = 0, **options):
+        self.spec, self.n_chains, self.device = spec, int(n_chains), int(device)
+        self.lib = capi.load()
+        h = C.c_void_p()
+        desc = spec.to_desc()
+        capi.check(self.lib.mile_create(C.byref(desc), self.n_chains, self.device, C.byref(h)))
+        self.h = h
+        self.d = self.lib.mile_n_params(self.h)
+        assert self.d == spec.n_params
+        self.n_train = self.n_test = 0
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.mile_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        capi.check(self.lib.mile_set_option(self.h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        return int(self.lib.mile_get_option(self.h, key.encode()))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mile_launch_count(self.h))
+
+    def synchronize(self):
+        capi.check(self.lib.mile_synchronize(self.h))
+
+    # ---- data ---------------------------------------------------------------------------
+    def _y(self, y):
+        return np.ascontiguousarray(y, dtype=np.int32 if self.spec.task.startswith('class') else np.float32)
+
+    def set_data(self, X, y):
+        X, y = _f32(X), self._y(y)
+        assert X.ndim == 2 and X.shape[1] == self.spec.n_features and y.shape == (X.shape[0],)
+        capi.check(self.lib.mile_set_data_host(self.h, capi.host_ptr(X), capi.host_ptr(y), X.shape[0]))
+        self.n_train = X.shape[0]
+
+    def set_test(self, X, y):
+        X, y = _f32(X), self._y(y)
+        assert X.ndim == 2 and X.shape[1] == self.spec.n_features and y.shape == (X.shape[0],)
+        capi.check(self.lib.mile_set_test_host(self.h, capi.host_ptr(X), capi.host_ptr(y), X.shape[0]))
+        self.n_test = X.shape[0]
+
+    # ---- a1: value_and_grad -------------------------------------------------------------
+    def value_and_grad(self, theta):
+        theta = _f32(theta).reshape(-1, self.d)
+        n = theta.shape[0]
+        lp = np.empty(n, np.float32)
+        g = np.empty((n, self.d), np.float32)
+        capi.check(self.lib.mile_logpost_value_and_grad_host(self.h, capi.host_ptr(theta), n, capi.host_ptr(lp),
+                                                             capi.host_ptr(g)))
+        return lp, g
+
+    # ---- state --------------------------------------------------------------------------
+    def init(self, theta0, z0=None, seed: int = 0):
+        theta0 = _f32(theta0).reshape(self.n_chains, self.d)
+        z0 = None if z0 is None else _f32(z0).reshape(self.n_chains, self.d)
+        capi.check(self.lib.mile_mclmc_init_host(self.h, capi.host_ptr(theta0), capi.host_ptr(z0), seed))
+
+    def get_state(self):
+        C_, d = self.n_chains, self.d
+        th, u, g = (np.empty((C_, d), np.float32) for _ in range(3))
+        lp = np.empty(C_, np.float32)
+        capi.check(self.lib.mile_get_state_host(self.h, capi.host_ptr(th), capi.host_ptr(u), capi.host_ptr(lp),
+                                                capi.host_ptr(g)))
+        return th, u, lp, g
+
+    def set_state(self, theta=None, u=None, lp=None, grad=None):
+        capi.check(self.lib.mile_set_state_host(self.h, capi.host_ptr(_f32(theta)), capi.host_ptr(_f32(u)),
+                                                capi.host_ptr(_f32(lp)), capi.host_ptr(_f32(grad))))
+
+    # ---- sampling -----------------------------------------------------------------------
+    def sample(self, n_steps, step_size, L, *, step_base=0, n_thinning=1, z=None, seed=0, keep=True, info=False,
+               lppd=False):
+        """Host-buffer sampling call (the e2e path): returns (samples [S,C,d] | None, info [n,C,3] | None)."""
+        C_, d = self.n_chains, self.d
+        eps = _f32(np.broadcast_to(step_size, (C_,)))
+        Ls = _f32(np.broadcast_to(L, (C_,)))
+        first = -(-step_base // n_thinning)
+        last = (step_base + n_steps - 1) // n_thinning
+        n_slots = max(0, last - first + 1) if keep and n_steps > 0 else 0
+        samples = np.empty((n_slots, C_, d), np.float32) if keep else None
+        inf = np.empty((n_steps, C_, 3), np.float32) if info else None
+        z = None if z is None else _f32(z)
+        capi.check(self.lib.mile_mclmc_sample_host(self.h, n_steps, step_base, n_thinning, capi.host_ptr(eps),
+                                                   capi.host_ptr(Ls), capi.host_ptr(z), seed, capi.host_ptr(samples),
+                                                   n_slots, capi.host_ptr(inf), int(lppd)))
+        return samples, inf
+
+    def sample_device(self, n_steps, step_size_dev, L_dev, *, step_base=0, n_thinning=1, sample_base=0, z_dev=None,
+                      seed=0, samples_dev=None, n_slots=0, info_dev=None, lppd=False):
+        """Device-buffer sampling call on torch's current stream (no host transfer, asynchronous)."""
+        capi.check(self.lib.mile_mclmc_sample(self.h, n_steps, step_base, n_thinning, sample_base,
+                                              _dev_ptr(step_size_dev), _dev_ptr(L_dev), _dev_ptr(z_dev), seed,
+                                              _dev_ptr(samples_dev), n_slots, _dev_ptr(info_dev), int(lppd),
+                                              _stream_ptr()))
+
+    # ---- tuning -------------------------------------------------------------------------
+    @staticmethod
+    def tune_cfg(tune1, tune2, desired_energy_var_start, desired_energy_var_end, trust_in_estimate,
+                 num_effective_samples) -> capi.TuneCfg:
+        return capi.TuneCfg(int(tune1), int(tune2), desired_energy_var_start, desired_energy_var_end,
+                            trust_in_estimate, float(num_effective_samples))
+
+    def tune_reset(self, step_size_init: float):
+        capi.check(self.lib.mile_tune_reset(self.h, step_size_init, None))
+        self.synchronize()
+
+    def tune(self, n_steps, step_base, cfg: capi.TuneCfg, z=None, seed=0, info=False):
+        inf = np.empty((n_steps, self.n_chains, 4), np.float32) if info else None
+        z = None if z is None else _f32(z)
+        capi.check(self.lib.mile_mclmc_tune_host(self.h, n_steps, step_base, C.byref(cfg), capi.host_ptr(z), seed,
+                                                 capi.host_ptr(inf)))
+        return inf
+
+    def tune_finish_phase2(self):
+        capi.check(self.lib.mile_tune_finish_phase2(self.h, None))
+        self.synchronize()
+
+    def get_tuning(self, moments=False):
+        C_, d = self.n_chains, self.d
+        eps, L, emax = (np.empty(C_, np.float32) for _ in range(3))
+        mx = np.empty((C_, d), np.float32) if moments else None
+        mx2 = np.empty((C_, d), np.float32) if moments else None
+        capi.check(self.lib.mile_get_tuning_host(self.h, capi.host_ptr(eps), capi.host_ptr(L), capi.host_ptr(emax),
+                                                 capi.host_ptr(mx), capi.host_ptr(mx2)))
+        return (eps, L, emax, mx, mx2) if moments else (eps, L, emax)
+
+    def set_tuning(self, step_size=None, L=None):
+        C_ = self.n_chains
+        e = None if step_size is None else _f32(np.broadcast_to(step_size, (C_,)))
+        l = None if L is None else _f32(np.broadcast_to(L, (C_,)))
+        capi.check(self.lib.mile_set_tuning_host(self.h, capi.host_ptr(e), capi.host_ptr(l)))
+
+    # ---- LPPD / predict -----------------------------------------------------------------
+    def lppd_reset(self):
+        capi.check(self.lib.mile_lppd_reset(self.h, None))
+        self.synchronize()
+
+    def lppd_accumulate(self, theta):
+        """theta host [n,d] (row c -> chain c) folded into the online logsumexp state."""
+        import torch
+        theta = _f32(theta).reshape(-1, self.d)
+        t = torch.from_numpy(theta).to(f'cuda:{self.device}')
+        capi.check(self.lib.mile_lppd_accumulate(self.h, _dev_ptr(t), theta.shape[0], _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def lppd_state(self):
+        m = np.empty((self.n_chains, self.n_test), np.float32)
+        s = np.empty((self.n_chains, self.n_test), np.float32)
+        cnt = C.c_int64()
+        capi.check(self.lib.mile_lppd_state_host(self.h, capi.host_ptr(m), capi.host_ptr(s), C.byref(cnt)))
+        return m, s, cnt.value
+
+    def predict(self, theta, which='test'):
+        import torch
+        theta = _f32(theta).reshape(-1, self.d)
+        n = theta.shape[0]
+        N = self.n_test if which == 'test' else self.n_train
+        K = self.spec.widths[-1]
+        t = torch.from_numpy(theta).to(f'cuda:{self.device}')
+        out = torch.empty((n, N, K), dtype=torch.float32, device=t.device)
+        capi.check(self.lib.mile_predict(self.h, _dev_ptr(t), n, 1 if which == 'test' else 0, _dev_ptr(out),
+                                         _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy()
+
+
+def lppd_from_state(m: np.ndarray, s: np.ndarray, total_samples: int) -> float:
+    """Merge per-chain online (max, sum-exp) states into LPPD = mean_n logsumexp_{c,s}(lp) - log(C*S)
+    (src/inference/metrics.py:296-312)."""
+    M = m.max(axis=0)
+    safe = np.where(np.isfinite(M), M, 0.0)
+    tot = (s.astype(np.float64) * np.exp(m.astype(np.float64) - safe)).sum(axis=0)
+    return float((safe + np.log(tot / total_samples)).mean())

@@ -1,0 +1,286 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the numpy oracle on the
+same seeded inputs.  Tolerances follow the north star: 1e-5 relative in fp32 for single-step
+positions / momenta / energies (energies relative to |logdensity|)."""
+import numpy as np
+import pytest
+
+from oracle import mile_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ['airfoil_3x16', 'airfoil_2x16', 'bikesharing_2x16', 'protein_2x16', 'covertype_ref']
+
+
+def make(name, C, n_train=None, n_test=None, **opts):
+    from mile_b200 import Ensemble, FCNSpec
+    ospec = o.make_spec(name)
+    X, y, Xt, yt = o.synthetic_data(name, n_train=n_train, n_test=n_test)
+    ens = Ensemble(FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task), C, **opts)
+    ens.set_data(X, y)
+    return ospec, ens, X, y, Xt, yt
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize('name', CONFIGS)
+@pytest.mark.parametrize('G', [1, 2, 8])
+def test_value_and_grad_matches_oracle(name, G):
+    C = 3
+    ospec, ens, X, y, _, _ = make(name, C, cluster_size=G)
+    th = o.synthetic_theta0(ospec, C)
+    lp, g = ens.value_and_grad(th)
+    lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
+    lp32, g32 = o.logpost_batch(ospec, th, X, y)
+    for c in range(C):
+        assert abs(lp[c] - lp64[c]) <= 1e-5 * abs(lp64[c])
+        assert rel(g[c], g64[c]) <= 1e-5
+        assert rel(g[c], g32[c]) <= 1e-5
+    ens.close()
+
+
+@pytest.mark.parametrize('act', ['relu', 'sigmoid', 'tanh', 'gelu', 'leaky_relu', 'identity'])
+@pytest.mark.parametrize('task,prior', [('regr', 'normal'), ('class', 'laplace')])
+def test_value_and_grad_activations_tasks_priors(act, task, prior):
+    from mile_b200 import Ensemble, FCNSpec
+    K = 2 if task == 'regr' else 5
+    kw = dict(prior_loc=0.1, prior_scale=1.7)
+    ospec = o.ModelSpec(7, (9, 6, K), act, task, prior, **kw)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((333, 7)).astype(np.float32)
+    y = rng.standard_normal(333).astype(np.float32) if task == 'regr' else rng.integers(0, K, 333).astype(np.int32)
+    th = (rng.standard_normal((2, ospec.n_params)) * 0.4).astype(np.float32)
+    ens = Ensemble(FCNSpec(7, (9, 6, K), act, task, prior, **kw), 2)
+    ens.set_data(X, y)
+    lp, g = ens.value_and_grad(th)
+    lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
+    for c in range(2):
+        assert abs(lp[c] - lp64[c]) <= 1e-5 * abs(lp64[c])
+        assert rel(g[c], g64[c]) <= 1e-5
+    ens.close()
+
+
+def test_ragged_and_tiny_row_counts():
+    """Edge cases: N not a multiple of anything, N smaller than a tile, N = 1."""
+    for N in (1, 3, 31, 33, 257, 1000):
+        ospec, ens, X, y, _, _ = make('airfoil_2x16', 2, n_train=N)
+        th = o.synthetic_theta0(ospec, 2)
+        lp, g = ens.value_and_grad(th)
+        lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
+        for c in range(2):
+            assert abs(lp[c] - lp64[c]) <= 1e-5 * abs(lp64[c]), N
+            assert rel(g[c], g64[c]) <= 1e-5, N
+        ens.close()
+
+
+def test_deep_narrow_network():
+    """feasibility/feas.yaml is 9x16 + head (10 layers): exercises NLMAX=12 and the
+    lexicographic leaf order ('layer10' < 'layer2' does not occur at 10 layers, does at 12)."""
+    from mile_b200 import Ensemble, FCNSpec
+    widths = (8,) * 11 + (2,)
+    ospec = o.ModelSpec(5, widths, 'tanh', 'regr')
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((200, 5)).astype(np.float32)
+    y = rng.standard_normal(200).astype(np.float32)
+    th = (rng.standard_normal((2, ospec.n_params)) * 0.4).astype(np.float32)
+    ens = Ensemble(FCNSpec(5, widths, 'tanh', 'regr'), 2)
+    ens.set_data(X, y)
+    lp, g = ens.value_and_grad(th)
+    lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
+    for c in range(2):
+        assert abs(lp[c] - lp64[c]) <= 1e-5 * abs(lp64[c])
+        assert rel(g[c], g64[c]) <= 2e-5
+    ens.close()
+
+
+@pytest.mark.parametrize('name,G', [('airfoil_3x16', 1), ('airfoil_3x16', 8), ('bikesharing_2x16', 8),
+                                    ('covertype_ref', 4), ('protein_2x16', 8)])
+def test_single_step_parity(name, G):
+    """The north-star criterion: identical (theta,u,l,g,eps,L,z) in -> (theta',u',l',dK,dE) within 1e-5."""
+    C = 3
+    ospec, ens, X, y, _, _ = make(name, C, cluster_size=G)
+    d = ospec.n_params
+    th0 = o.synthetic_theta0(ospec, C)
+    rng = np.random.default_rng(11)
+    z0 = rng.standard_normal((C, d)).astype(np.float32)
+    z = rng.standard_normal((1, C, d)).astype(np.float32)
+    eps, L = 0.01, float(np.sqrt(d))
+    ens.init(th0, z0)
+    th_i, u_i, lp_i, g_i = ens.get_state()
+    _, info = ens.sample(1, eps, L, z=z, keep=False, info=True)
+    th, u, lp, g = ens.get_state()
+    f64 = lambda t: o.logpost_value_and_grad(ospec, t, X.astype(np.float64), y)
+    f32 = lambda t: o.logpost_value_and_grad(ospec, t, X, y)
+    for c in range(C):
+        s64 = o.mclmc_init(f64, th0[c].astype(np.float64), z0[c].astype(np.float64))
+        assert rel(u_i[c], s64.momentum) <= 1e-6
+        assert rel(g_i[c], s64.logdensity_grad) <= 1e-5
+        n64, i64 = o.mclmc_step(f64, s64, eps, L, z[0, c].astype(np.float64))
+        s32 = o.mclmc_init(f32, th0[c], z0[c])
+        n32, i32 = o.mclmc_step(f32, s32, eps, L, z[0, c])
+        scale = abs(n64.logdensity)
+        for ref, inf in ((n64, i64), (n32, i32)):
+            assert rel(th[c], ref.position) <= 1e-5
+            assert rel(u[c], ref.momentum) <= 1e-5
+            assert abs(lp[c] - ref.logdensity) <= 1e-5 * scale
+            assert rel(g[c], ref.logdensity_grad) <= 1e-4
+            assert abs(info[0, c, 0] - ref.logdensity) <= 1e-5 * scale
+        # energies: compare with the fp64 twin, relative to the energy scale |l|
+        assert abs(info[0, c, 1] - i64.kinetic_change) <= 1e-5 * scale
+        assert abs(info[0, c, 2] - i64.energy_change) <= 1e-5 * scale
+    ens.close()
+
+
+def test_multi_step_trajectory_and_thinning():
+    """20 steps with host noise: trajectory tracks the fp64 oracle; kept positions obey idx % n_thinning == 0."""
+    name, C, n, thin = 'airfoil_3x16', 2, 20, 4
+    ospec, ens, X, y, _, _ = make(name, C)
+    d = ospec.n_params
+    th0 = o.synthetic_theta0(ospec, C)
+    rng = np.random.default_rng(5)
+    z0 = rng.standard_normal((C, d)).astype(np.float32)
+    z = rng.standard_normal((n, C, d)).astype(np.float32)
+    ens.init(th0, z0)
+    samples, info = ens.sample(n, 0.02, 20.0, z=z, n_thinning=thin, info=True)
+    assert samples.shape == (5, C, d)
+    f64 = lambda t: o.logpost_value_and_grad(ospec, t, X.astype(np.float64), y)
+    for c in range(C):
+        st = o.mclmc_init(f64, th0[c].astype(np.float64), z0[c].astype(np.float64))
+        st, kept, idxs, des = o.run_sampling(f64, st, 0.02, 20.0, z[:, c].astype(np.float64), n_thinning=thin)
+        assert idxs == [0, 4, 8, 12, 16]
+        for k in range(5):
+            assert rel(samples[k, c], kept[k]) <= 2e-5
+        assert np.max(np.abs(info[:, c, 2] - des)) <= 2e-5 * abs(st.logdensity)
+    # split launches == one launch (step_base bookkeeping)
+    ens.init(th0, z0)
+    s1, _ = ens.sample(7, 0.02, 20.0, z=z[:7], n_thinning=thin, step_base=0)
+    s2, _ = ens.sample(13, 0.02, 20.0, z=z[7:], n_thinning=thin, step_base=7)
+    np.testing.assert_array_equal(np.concatenate([s1, s2]), samples)
+    ens.close()
+
+
+def test_cluster_sizes_agree_bitwise_on_state_layout():
+    """Different cluster sizes change the summation order only: results agree to fp32 rounding."""
+    name, C = 'bikesharing_2x16', 2
+    outs = []
+    for G in (1, 2, 4, 8):
+        ospec, ens, X, y, _, _ = make(name, C, cluster_size=G)
+        th0 = o.synthetic_theta0(ospec, C)
+        rng = np.random.default_rng(1)
+        z0 = rng.standard_normal((C, ospec.n_params)).astype(np.float32)
+        z = rng.standard_normal((3, C, ospec.n_params)).astype(np.float32)
+        ens.init(th0, z0)
+        ens.sample(3, 0.01, 22.0, z=z, keep=False)
+        outs.append(ens.get_state())
+        ens.close()
+    for k in range(1, 4):
+        assert rel(outs[k][0], outs[0][0]) <= 1e-6
+        assert rel(outs[k][1], outs[0][1]) <= 1e-5
+
+
+def test_tuning_matches_oracle():
+    """HOT LOOP A (warmup.py:276-352): eps trajectory, streaming moments and L against the oracle."""
+    name, C = 'airfoil_3x16', 2
+    ospec, ens, X, y, _, _ = make(name, C)
+    d = ospec.n_params
+    th0 = o.synthetic_theta0(ospec, C)
+    rng = np.random.default_rng(9)
+    z0 = rng.standard_normal((C, d)).astype(np.float32)
+    t1, t2 = 24, 16
+    z = rng.standard_normal((t1 + t2, C, d)).astype(np.float32)
+    cfg = o.TuneConfig(t1, t2, 0, 0.5, 0.1, 1.5, 100, 0.01)
+    ens.init(th0, z0)
+    ens.tune_reset(0.01)
+    tc = ens.tune_cfg(t1, t2, 0.5, 0.1, 1.5, 100)
+    info_a = ens.tune(10, 0, tc, z=z[:10], info=True)
+    info_b = ens.tune(t1 + t2 - 10, 10, tc, z=z[10:], info=True)
+    info = np.concatenate([info_a, info_b])
+    ens.tune_finish_phase2()
+    eps, L, emax, mx, mx2 = ens.get_tuning(moments=True)
+    f64 = lambda t: o.logpost_value_and_grad(ospec, t, X.astype(np.float64), y)
+    for c in range(C):
+        st = o.mclmc_init(f64, th0[c].astype(np.float64), z0[c].astype(np.float64))
+        ts = o.tune_init(cfg, d, np.float64)
+        for i in range(t1 + t2):
+            st, ts, inf, ok = o.tune_step(f64, cfg, st, ts, z[i, c].astype(np.float64), i)
+            assert info[i, c, 3] == 1.0 and ok
+            assert abs(info[i, c, 1] - ts.step_size) <= 2e-3 * ts.step_size, (i, info[i, c, 1], ts.step_size)
+        ts = o.tune_finish_phase2(cfg, ts)
+        assert abs(eps[c] - ts.step_size) <= 2e-3 * ts.step_size
+        assert rel(mx[c], ts.avg_x) <= 1e-4
+        assert rel(mx2[c], ts.avg_x2) <= 1e-4
+        assert abs(L[c] - ts.L) <= 1e-2 * ts.L
+    ens.close()
+
+
+def test_lppd_and_predict_match_oracle():
+    name, C, S = 'airfoil_3x16', 3, 4
+    ospec, ens, X, y, Xt, yt = make(name, C)
+    ens.set_test(Xt, yt)
+    rng = np.random.default_rng(2)
+    thetas = (rng.standard_normal((S, C, ospec.n_params)) * 0.3).astype(np.float32)
+    out = ens.predict(thetas[0], 'test')
+    ref = np.stack([o.forward(ospec, thetas[0, c].astype(np.float64), Xt.astype(np.float64)) for c in range(C)])
+    assert rel(out, ref) <= 1e-5
+    for s in range(S):
+        ens.lppd_accumulate(thetas[s])
+    m, sst, cnt = ens.lppd_state()
+    assert cnt == S
+    from mile_b200 import lppd_from_state
+    got = lppd_from_state(m, sst, C * S)
+    lv = np.stack([[o.forward(ospec, thetas[s, c].astype(np.float64), Xt.astype(np.float64)) for s in range(S)]
+                   for c in range(C)])
+    want = o.lppd(o.pointwise_lppd(ospec, lv, yt.astype(np.float64)))
+    assert abs(got - want) <= 1e-5 * abs(want)
+    ens.close()
+
+
+def test_fused_lppd_during_sampling_equals_posthoc():
+    name, C = 'airfoil_2x16', 2
+    ospec, ens, X, y, Xt, yt = make(name, C)
+    ens.set_test(Xt, yt)
+    th0 = o.synthetic_theta0(ospec, C)
+    ens.init(th0, seed=3)
+    samples, _ = ens.sample(40, 0.02, 20.0, n_thinning=10, seed=7, lppd=True)
+    m, s, cnt = ens.lppd_state()
+    assert cnt == 4 and samples.shape[0] == 4
+    from mile_b200 import lppd_from_state
+    got = lppd_from_state(m, s, C * 4)
+    lv = np.stack([[o.forward(ospec, samples[k, c].astype(np.float64), Xt.astype(np.float64)) for k in range(4)]
+                   for c in range(C)])
+    want = o.lppd(o.pointwise_lppd(ospec, lv, yt.astype(np.float64)))
+    assert abs(got - want) <= 1e-5 * abs(want)
+    ens.close()
+
+
+def test_philox_noise_statistics_gaussian_target():
+    """Perf-mode noise (in-kernel Philox): a linear 'network' with a flat likelihood is a pure
+    N(0,1) prior target -> sample mean ~ 0, variance ~ 1 (debug.ipynb cell 8 style check)."""
+    from mile_b200 import Ensemble, FCNSpec
+    spec = FCNSpec(3, (4, 2), 'identity', 'regr', n_batches=0.0)   # likelihood switched off
+    ens = Ensemble(spec, 8)
+    ens.set_data(np.zeros((4, 3), np.float32), np.zeros(4, np.float32))
+    d = spec.n_params
+    ens.init(np.random.default_rng(0).standard_normal((8, d)).astype(np.float32), seed=1)
+    samples, _ = ens.sample(20000, 0.5, 3.0, n_thinning=5, seed=2)
+    xs = samples[400:].reshape(-1, d)
+    assert np.all(np.abs(xs.mean(0)) < 0.06)
+    assert np.all(np.abs(xs.var(0) - 1) < 0.08)
+    ens.close()
+
+
+def test_errors_are_loud():
+    from mile_b200 import Ensemble, FCNSpec
+    from mile_b200.capi import MileError
+    ens = Ensemble(FCNSpec(5, (16, 2)), 2)
+    with pytest.raises(MileError):
+        ens.value_and_grad(np.zeros((2, ens.d), np.float32))   # no data yet
+    with pytest.raises(MileError):
+        ens.set_option('no_such_option', 1)
+    ens.close()
+    wide = Ensemble(FCNSpec(5, (512, 512, 2)), 2)
+    wide.set_data(np.zeros((8, 5), np.float32), np.zeros(8, np.float32))
+    with pytest.raises(MileError):
+        wide.value_and_grad(np.zeros((2, wide.d), np.float32))   # too wide for the CUDA-core path
+    wide.close()
