@@ -35,6 +35,7 @@ struct mile_ctx {
   float *t_time = nullptr, *t_xavg = nullptr, *t_epsmax = nullptr, *t_eps = nullptr, *t_L = nullptr,
         *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
   float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
+  float* carry = nullptr; int carry_valid = 0;
   // staging for the *_host entry points
   std::vector<std::pair<void*, size_t>> scratch;  // slot -> (ptr, bytes)
   cudaStream_t own_stream = nullptr;
@@ -166,6 +167,7 @@ static void fill_common(mile_ctx* c, KParams& k) {
   k.t_time = c->t_time; k.t_xavg = c->t_xavg; k.t_epsmax = c->t_epsmax; k.t_eps = c->t_eps; k.t_L = c->t_L;
   k.t_wtot = c->t_wtot; k.avg_x = c->avg_x; k.avg_x2 = c->avg_x2;
   k.lppd_m = c->lppd_m; k.lppd_s = c->lppd_s;
+  k.carry = c->carry; k.carry_valid = c->carry_valid;
   k.refresh_mode = c->opt_refresh; k.thin = 1;
 }
 
@@ -233,6 +235,7 @@ int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, m
   CK(cudaMalloc(&c->avg_x, Cd)); CK(cudaMalloc(&c->avg_x2, Cd));
   CK(cudaMalloc(&c->t_time, Cb)); CK(cudaMalloc(&c->t_xavg, Cb)); CK(cudaMalloc(&c->t_epsmax, Cb));
   CK(cudaMalloc(&c->t_eps, Cb)); CK(cudaMalloc(&c->t_L, Cb)); CK(cudaMalloc(&c->t_wtot, Cb));
+  CK(cudaMalloc(&c->carry, 2 * Cb));
   CK(cudaMemset(c->theta, 0, Cd)); CK(cudaMemset(c->u, 0, Cd)); CK(cudaMemset(c->grad, 0, Cd)); CK(cudaMemset(c->lp, 0, Cb));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   *out = c;
@@ -244,7 +247,7 @@ void mile_destroy(mile_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
-                  c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s};
+                  c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -373,6 +376,7 @@ int mile_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, u
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
   pl.kp.mode = MODE_INIT; pl.kp.theta_in = theta0_dev; pl.kp.z = z0_dev; pl.kp.seed = seed;
+  c->carry_valid = 0;
   return launch(c, pl, c->C, (cudaStream_t)stream);
 }
 
@@ -393,6 +397,7 @@ int mile_set_state_host(mile_ctx* c, const float* theta, const float* u, const f
   if (!c) return fail("null ctx");
   CK(cudaSetDevice(c->device));
   const size_t Cd = (size_t)c->C * c->d * 4;
+  c->carry_valid = 0;
   if (theta) CK(cudaMemcpy(c->theta, theta, Cd, cudaMemcpyHostToDevice));
   if (u) CK(cudaMemcpy(c->u, u, Cd, cudaMemcpyHostToDevice));
   if (grad) CK(cudaMemcpy(c->grad, grad, Cd, cudaMemcpyHostToDevice));
@@ -438,6 +443,7 @@ int mile_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n
   k.n_slots = n_slots; k.eps = step_size_dev; k.L = L_dev; k.z = z_dev; k.seed = seed; k.samples = samples_dev;
   k.info = info_dev; k.do_lppd = lppd;
   if (launch(c, pl, c->C, (cudaStream_t)stream)) return -1;
+  c->carry_valid = 1;
   if (lppd) {
     // kept positions in [step_base, step_base+n_steps)
     const long first = (step_base + n_thinning - 1) / n_thinning, last = (step_base + n_steps - 1) / n_thinning;
@@ -500,7 +506,9 @@ int mile_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_
   k.mode = MODE_TUNE; k.n_steps = n_steps; k.step_base = step_base; k.z = z_dev; k.seed = seed; k.tune_info = tune_info_dev;
   k.tune1 = cfg->tune1_steps; k.tune2 = cfg->tune2_steps; k.ev_start = cfg->desired_energy_var_start;
   k.ev_end = cfg->desired_energy_var_end; k.trust = cfg->trust_in_estimate; k.neff = cfg->num_effective_samples;
-  return launch(c, pl, c->C, (cudaStream_t)stream);
+  if (launch(c, pl, c->C, (cudaStream_t)stream)) return -1;
+  c->carry_valid = 1;
+  return 0;
 }
 
 int mile_mclmc_tune_host(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg, const float* z,

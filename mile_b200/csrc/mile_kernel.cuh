@@ -31,6 +31,7 @@ struct KParams {
   const float* z; unsigned long long seed;
   float* samples; float* info;
   float* lppd_m; float* lppd_s;
+  float* carry; int carry_valid;   // [C,2] (sum g^2, u.g) carried across launches so chunking is bit-exact
   // tuning state [C] / [C,d]
   float *t_time, *t_xavg, *t_epsmax, *t_eps, *t_L, *t_wtot, *avg_x, *avg_x2, *tune_info;
   int tune1, tune2; float ev_start, ev_end, trust, neff;
@@ -426,7 +427,9 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
   }
   const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
   const int nslot = P.refresh_mode ? 2 : 1;
-  {  // cached gradient: sum g^2 and u.g for the first B-step
+  if (P.carry_valid) {
+    g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
+  } else {  // cached gradient: sum g^2 and u.g for the first B-step
     float v[2] = {0.f, 0.f};
     for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
     block_sum<2>(v, c.red, c.phase);
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
     }
     if (tid == 0) {
       P.lp[ch] = lp;
+      P.carry[2 * ch] = g2; P.carry[2 * ch + 1] = ug;
       if (tune) { P.t_time[ch] = t_time; P.t_xavg[ch] = t_xavg; P.t_epsmax[ch] = t_epsmax; P.t_eps[ch] = eps; P.t_wtot[ch] = t_wtot; }
     }
   }

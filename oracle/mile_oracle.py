@@ -444,18 +444,18 @@ def tune_init(cfg: TuneConfig, d: int, dt=np.float32) -> TuneState:
                      dt(max(math.sqrt(d), 15.0)), dt(0), np.zeros(d, dt), np.zeros(d, dt))
 
 
-def tune_step(logdensity_and_grad, cfg: TuneConfig, state: IntegratorState, ts: TuneState,
-              z, step_number: int, refresh='post'):
-    """One iteration of HOT LOOP A: warmup.py:276-352 (`predictor` + `step`)."""
-    dt = state.position.dtype.type
-    d = state.position.shape[0]
+def tune_update(cfg: TuneConfig, ts: TuneState, x: np.ndarray, de, success: bool, step_number: int):
+    """The adaptive part of one HOT LOOP A iteration, after the dynamics and handle_nans:
+    energy-variance step-size predictor (warmup.py:302-322) and the streaming average of
+    (x, x^2) (warmup.py:341-348, blackjax.util.streaming_average_update).  `ts.step_size_max`
+    must already hold the value handle_nans returned."""
+    dt = x.dtype.type
+    d = x.shape[0]
     decay = dt((cfg.num_effective_samples - 1.0) / (cfg.num_effective_samples + 1.0))
-    new, info = mclmc_step(logdensity_and_grad, state, ts.step_size, ts.L, z, refresh=refresh)
-    success, state, step_size_max, de = handle_nans(state, new, ts.step_size, ts.step_size_max,
-                                                    info.energy_change)
     target = desired_energy_var(cfg, step_number, dt)
+    step_size_max = ts.step_size_max
     with np.errstate(divide='ignore', over='ignore', invalid='ignore'):
-        xi = np.square(de) / (dt(d) * target) + dt(1e-8)
+        xi = np.square(dt(de)) / (dt(d) * target) + dt(1e-8)
         weight = np.exp(dt(-0.5) * np.square(np.log(xi) / dt(6.0 * cfg.trust_in_estimate)))
         x_average = decay * ts.x_average + weight * (xi / np.power(ts.step_size, dt(6.0)))
         time = decay * ts.time + weight
@@ -464,14 +464,22 @@ def tune_step(logdensity_and_grad, cfg: TuneConfig, state: IntegratorState, ts: 
     step_size = dt(step_size < step_size_max) * step_size + dt(step_size > step_size_max) * step_size_max
     mask = 1.0 if step_number < cfg.tune1 else 0.0  # warmup.py:376
     w = dt((1.0 - mask) * float(success)) * step_size
-    x = state.position
-    # blackjax.util.streaming_average_update (zero_prevention = mask)
     denom = ts.w_total + w + dt(mask)
-    avg_x = (ts.w_total * ts.avg_x + w * x) / denom
-    avg_x2 = (ts.w_total * ts.avg_x2 + w * np.square(x)) / denom
-    ts = TuneState(dt(time), dt(x_average), dt(step_size_max), dt(step_size), ts.L,
-                   dt(ts.w_total + w), avg_x.astype(x.dtype), avg_x2.astype(x.dtype))
-    return state, ts, info, success
+    with np.errstate(divide='ignore', invalid='ignore'):
+        avg_x = (ts.w_total * ts.avg_x + w * x) / denom
+        avg_x2 = (ts.w_total * ts.avg_x2 + w * np.square(x)) / denom
+    return TuneState(dt(time), dt(x_average), dt(step_size_max), dt(step_size), ts.L,
+                     dt(ts.w_total + w), avg_x.astype(x.dtype), avg_x2.astype(x.dtype))
+
+
+def tune_step(logdensity_and_grad, cfg: TuneConfig, state: IntegratorState, ts: TuneState,
+              z, step_number: int, refresh='post'):
+    """One iteration of HOT LOOP A: warmup.py:276-352 (`predictor` + `step`)."""
+    new, info = mclmc_step(logdensity_and_grad, state, ts.step_size, ts.L, z, refresh=refresh)
+    success, state, step_size_max, de = handle_nans(state, new, ts.step_size, ts.step_size_max,
+                                                    info.energy_change)
+    ts = tune_update(cfg, ts._replace(step_size_max=step_size_max), state.position, de, success, step_number)
+    return state, ts, info._replace(energy_change=de), success
 
 
 def tune_finish_phase2(cfg: TuneConfig, ts: TuneState) -> TuneState:
