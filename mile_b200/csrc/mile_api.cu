@@ -43,7 +43,7 @@ struct mile_ctx {
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-static int stride_for(int w) { int p = round_up(w, 4); return (p % 8 == 4) ? p : p + 4; }
+static int stride_for(int w) { return round_up(w, 4); }  // dense rows: see DevModel comment
 
 static void build_model(mile_ctx* c) {
   const mile_model_desc& D = c->desc;
@@ -60,6 +60,7 @@ static void build_model(mile_ctx* c) {
     d += M.dims[l + 1] + M.dims[l] * M.dims[l + 1];
     M.pb_off[l] = ps; ps += M.dimp[l + 1];
     M.pw_off[l] = ps; ps += M.dimp[l] * M.dimp[l + 1];
+    if (l >= 1) { M.pwt_off[l] = ps; ps += M.dimp[l] * M.dimp[l + 1]; } else M.pwt_off[l] = M.pw_off[l];
   }
   M.d = d; M.psize = ps;
   c->d = d;
@@ -83,7 +84,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   const int dS = round_up(M.d, 4);
   int S1 = 0;
   for (int l = 1; l <= M.NL; ++l) S1 += M.sA[l];
-  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + dS + 64;
+  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 64;
   int TR = c->opt_tile_rows > 0 ? round_up(c->opt_tile_rows, 32) : 256;
   const int want = round_up((int)(rows_cta < 32 ? 32 : (rows_cta > 256 ? 256 : rows_cta)), 32);
   if (c->opt_tile_rows <= 0 && TR > want) TR = want;
@@ -114,7 +115,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   k.off_thb = o; o += dS; k.off_ub = o; o += dS; k.off_gb = o; o += dS;
   k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
   k.off_gpart = o; o += 2 * (dS + 4);
-  k.off_pmap = o; o += dS;
+  k.off_pmap = o; o += 2 * dS;
   k.off_red = o; o += 64;
   k.off_tile = o; o += (int)tile + TR * M.sA[0];
   k.off_x = o; if (resident) o += rows_res * M.sA[0];
@@ -605,6 +606,15 @@ int mile_predict(mile_ctx* c, const float* theta_dev, int32_t n, int32_t which, 
   pl.kp.C = n; pl.kp.mode = MODE_PREDICT; pl.kp.theta_in = theta_dev; pl.kp.pred_out = out_dev; pl.kp.which = which;
   return launch(c, pl, n, (cudaStream_t)stream);
 }
+
+#ifdef MILE_PROFILE
+int mile_debug_read_profile(unsigned long long* out32, int reset) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out32, g_prof, sizeof(unsigned long long) * 32));
+  if (reset) { unsigned long long z[32] = {0}; CK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
+  return 0;
+}
+#endif
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
 int mile_synchronize(mile_ctx* c) {

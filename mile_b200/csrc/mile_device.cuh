@@ -15,14 +15,31 @@
 
 namespace cg = cooperative_groups;
 
+// Optional phase timers (build with -DMILE_PROFILE; tools/phase_profile.py): thread 0 of CTA 0
+// accumulates clock64() deltas per phase into g_prof[].
+#ifdef MILE_PROFILE
+__device__ unsigned long long g_prof[32];
+#define PROF_DECL long long prof_t_ = clock64()
+#define PROF(i)                                                                            \
+  do {                                                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {                                             \
+      long long n_ = clock64(); g_prof[i] += (unsigned long long)(n_ - prof_t_); prof_t_ = n_; \
+    }                                                                                      \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#endif
+
 #define MILE_THREADS 256
 #define MILE_NWARPS (MILE_THREADS / 32)
 
 // ------------------------------------------------------------------------------------
 // Device-side model description (kernel parameter, lives in the constant bank).
 // Activations and deltas are kept row-major in shared memory: buffer l holds
-// [rows][stride_l] floats with stride_l = 4 (mod 8) so that the 8 distinct rows a warp
-// touches per LDS.128 fall into distinct bank groups.
+// [rows][stride_l] floats, stride_l = width padded to 4.  128-bit shared accesses are served
+// per quarter-warp (8 lanes = 4 neuron tiles x 2 rows in the tile GEMMs), so dense rows of
+// <= 16 floats never conflict (measured: tools/lds_microbench.cu, profiles/r1_*).
 // ------------------------------------------------------------------------------------
 struct DevModel {
   int F, NL, act, task, prior, d;
@@ -32,7 +49,8 @@ struct DevModel {
   int bias_off[MILE_MAX_LAYERS];   // flat-vector offsets
   int kern_off[MILE_MAX_LAYERS];
   int pb_off[MILE_MAX_LAYERS];     // padded shared-memory parameter image: bias[OUTP]
-  int pw_off[MILE_MAX_LAYERS];     //                                       W[IN][OUTP]
+  int pw_off[MILE_MAX_LAYERS];     //                                       W[INP][OUTP]
+  int pwt_off[MILE_MAX_LAYERS];    //                                       W^T[OUTP][INP] (layers >= 1, for the backward pass)
   int psize;                       // floats in the padded image
   int sA[MILE_MAX_LAYERS + 1];     // row stride of activation buffer l (l=0: X)
   int a_off[MILE_MAX_LAYERS + 1];  // float offset of activation buffer l inside a tile (l>=1)
@@ -181,12 +199,13 @@ __device__ __forceinline__ void fwd_layer(const DevModel& M, int l, const float*
   }
 }
 
-// D_{l-1} <- D_{l-1}(=act') * (D_l W_l^T): reduction over the (contiguous) out index j.
+// D_{l-1} <- D_{l-1}(=act') * (D_l W_l^T), using the transposed weight image W^T[OUTP][INP] so that
+// the 4 input-neuron tiles of a quarter-warp read one contiguous 64 B segment (no bank conflicts).
 __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float* __restrict__ Wp,
                                           const float* __restrict__ Dl, int sl,
                                           float* __restrict__ Dprev, int sp, int Q) {
   const int OUTP = M.dimp[l + 1], INP = M.dimp[l], nit = INP >> 2;
-  const float* __restrict__ W = Wp + M.pw_off[l];
+  const float* __restrict__ WT = Wp + M.pwt_off[l];
   for (int it = threadIdx.x; it < Q * nit; it += MILE_THREADS) {
     const int itl = it % nit, q = it / nit;
     float acc[4][4];
@@ -195,7 +214,7 @@ __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float*
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
     const float* dp = Dl + q * sl;
-    const float* wp = W + (itl * 4) * OUTP;
+    const float* wp = WT + itl * 4;
     const int rstep = Q * sl;
 #pragma unroll 2
     for (int j = 0; j < OUTP; j += 4) {
@@ -203,16 +222,18 @@ __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float*
 #pragma unroll
       for (int r = 0; r < 4; ++r) dd[r] = *reinterpret_cast<const float4*>(dp + r * rstep + j);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wp + i * OUTP + j);
+      for (int jj = 0; jj < 4; ++jj) w[jj] = *reinterpret_cast<const float4*>(wp + (j + jj) * INP);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 4; ++r) {
+        const float dv[4] = {dd[r].x, dd[r].y, dd[r].z, dd[r].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[r][i] = fmaf(dd[r].x, w[i].x, acc[r][i]);
-          acc[r][i] = fmaf(dd[r].y, w[i].y, acc[r][i]);
-          acc[r][i] = fmaf(dd[r].z, w[i].z, acc[r][i]);
-          acc[r][i] = fmaf(dd[r].w, w[i].w, acc[r][i]);
+        for (int jj = 0; jj < 4; ++jj) {
+          acc[r][0] = fmaf(dv[jj], w[jj].x, acc[r][0]);
+          acc[r][1] = fmaf(dv[jj], w[jj].y, acc[r][1]);
+          acc[r][2] = fmaf(dv[jj], w[jj].z, acc[r][2]);
+          acc[r][3] = fmaf(dv[jj], w[jj].w, acc[r][3]);
         }
+      }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

@@ -51,19 +51,31 @@ struct Ctx {
   __device__ Ctx(const KParams& p) : P(p) {}
 };
 
-// flat element i -> position in the padded parameter image
-__device__ __forceinline__ void build_pmap(const DevModel& M, int* pmap) {
+// flat element i -> position in the padded parameter image (pmap) and in the transposed image
+// (pmap + dS; biases and layer 0, which need no transpose, point at their pmap slot again)
+__device__ __forceinline__ void build_pmap(const DevModel& M, int* pmap, int dS) {
   for (int l = 0; l < M.NL; ++l) {
-    const int IN = M.dims[l], OUT = M.dims[l + 1], OUTP = M.dimp[l + 1];
-    for (int j = threadIdx.x; j < OUT; j += MILE_THREADS) pmap[M.bias_off[l] + j] = M.pb_off[l] + j;
-    for (int e = threadIdx.x; e < IN * OUT; e += MILE_THREADS)
-      pmap[M.kern_off[l] + e] = M.pw_off[l] + (e / OUT) * OUTP + (e % OUT);
+    const int IN = M.dims[l], OUT = M.dims[l + 1], OUTP = M.dimp[l + 1], INP = M.dimp[l];
+    for (int j = threadIdx.x; j < OUT; j += MILE_THREADS) {
+      pmap[M.bias_off[l] + j] = M.pb_off[l] + j;
+      pmap[dS + M.bias_off[l] + j] = M.pb_off[l] + j;
+    }
+    for (int e = threadIdx.x; e < IN * OUT; e += MILE_THREADS) {
+      const int i = e / OUT, j = e % OUT;
+      pmap[M.kern_off[l] + e] = M.pw_off[l] + i * OUTP + j;
+      pmap[dS + M.kern_off[l] + e] = l >= 1 ? M.pwt_off[l] + j * INP + i : M.pw_off[l] + i * OUTP + j;
+    }
   }
+}
+
+__device__ __forceinline__ void store_param(Ctx& c, int i, float t) {
+  c.wp[c.pmap[i]] = t;
+  c.wp[c.pmap[c.P.dS + i]] = t;
 }
 
 __device__ __forceinline__ void refresh_wp(Ctx& c) {
   const int d = c.P.M.d;
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.wp[c.pmap[i]] = c.th[i];
+  for (int i = threadIdx.x; i < d; i += MILE_THREADS) store_param(c, i, c.th[i]);
 }
 
 // Copy rows [row0, row0+rows_pad) of the padded global matrix into a shared tile, zero beyond nvalid.
@@ -93,12 +105,13 @@ __device__ __forceinline__ const float* forward_tile(Ctx& c, const float* Xt, in
 // Full-batch value_and_grad restricted to this CTA's rows [r0, r1): partial gradient (flat
 // layout, likelihood part only) and partial log-likelihood into gpart[0..dS] (ll at [dS]).
 template <int NLMAX>
-__device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
+__device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
   const KParams& P = c.P;
   const DevModel& M = P.M;
   DwAcc<NLMAX> acc;
   acc.zero();
   float llpart = 0.f;
+  PROF_DECL;
   const int TR = M.TR;
   const long nrows = r1 > r0 ? r1 - r0 : 0;
   const int ntiles = (int)((nrows + TR - 1) / TR);
@@ -115,19 +128,24 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
       __syncthreads();
       Xt = c.xbuf;
     }
+    PROF(0);
     const float* out = forward_tile(c, Xt, Q);
+    PROF(1);
     llpart += loglik_rows(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], P.y, row0, nvalid, rows_pad);
     __syncthreads();
+    PROF(2);
     for (int l = M.NL - 1; l >= 1; --l) {
       bwd_layer(M, l, c.wp, c.tile + M.d_off[l], M.sA[l + 1], c.tile + M.d_off[l - 1], M.sA[l], Q);
       __syncthreads();
     }
+    PROF(3);
 #pragma unroll
     for (int l = 0; l < NLMAX; ++l)
       if (l < M.NL)
         dw_accumulate<NLMAX>(M, l, acc, l, l == 0 ? Xt : c.tile + M.a_off[l], M.sA[l],
                              c.tile + M.d_off[l], M.sA[l + 1], rows_pad);
     __syncthreads();
+    PROF(4);
   }
   // cross-chunk reduction of the per-thread 4x4 tiles (scratch aliases the tile buffers)
   float* scr = c.tile;
@@ -167,6 +185,7 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
   float v[1] = {llpart};
   block_sum<1>(v, c.red, c.phase);
   if (threadIdx.x == 0) gpart[P.dS] = v[0];
+  PROF(5);
 }
 
 // DSMEM all-reduce of the cluster's partial gradients + prior: afterwards gg = full gradient of
@@ -243,7 +262,7 @@ __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
   for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
     const float t = c.th[i] + s * c.uu[i];
     c.th[i] = t;
-    c.wp[c.pmap[i]] = t;
+    store_param(c, i, t);
   }
   __syncthreads();
 }
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
 
   // ---- prologue: parameter image, state, resident X slice --------------------------------
   for (int i = tid; i < M.psize; i += MILE_THREADS) c.wp[i] = 0.f;
-  build_pmap(M, c.pmap);
+  build_pmap(M, c.pmap, P.dS);
   const bool from_input = (P.mode == MODE_EVAL || P.mode == MODE_INIT || P.mode == MODE_LPPD || P.mode == MODE_PREDICT);
   const float* th_src = from_input ? P.theta_in + (long)ch * d : P.theta + (long)ch * d;
   for (int i = tid; i < d; i += MILE_THREADS) {
@@ -441,18 +460,24 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       for (int i = tid; i < d; i += MILE_THREADS) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
     }
     if (P.refresh_mode) refresh_momentum(c, 0.5f * eps, Lc, s, 0, nslot, ug);
-    float dK = esh_update(c, eps, b1, g2, ug);
-    position_update(c, eps, 0.5f);
-    float* gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
-    grad_eval<NLMAX>(c, r0, r1, gp);
-    lp = cluster_reduce_grad(c, gp, g2, ug, nf);
-    dK += esh_update(c, eps, b2, g2, ug);
-    position_update(c, eps, 0.5f);
-    gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
-    grad_eval<NLMAX>(c, r0, r1, gp);
-    lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+    float dK = 0.f;
+    PROF_DECL;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {   // B(b1) A(1/2) grad | B(1-2 b1) A(1/2) grad
+      dK += esh_update(c, eps, h == 0 ? b1 : b2, g2, ug);
+      PROF(8);
+      position_update(c, eps, 0.5f);
+      PROF(9);
+      float* gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
+      grad_eval<NLMAX>(c, r0, r1, gp);
+      PROF(10);
+      lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+      PROF(11);
+    }
     dK += esh_update(c, eps, b1, g2, ug);
+    PROF(8);
     refresh_momentum(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
+    PROF(12);
     float dE = dK - lp + lp_old;
 
     if (!tune) {
@@ -464,7 +489,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       // handle_nans (warmup.py:468-483)
       const bool success = nf == 0.f;
       if (!success) {
-        for (int i = tid; i < d; i += MILE_THREADS) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; c.wp[c.pmap[i]] = c.thb[i]; }
+        for (int i = tid; i < d; i += MILE_THREADS) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; store_param(c, i, c.thb[i]); }
         lp = lp_old;
         t_epsmax = eps * 0.8f;
         dE = 0.f;

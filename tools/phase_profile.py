@@ -1,0 +1,37 @@
+"""Phase-level cycle breakdown of the persistent kernel (developer tool, not part of the product).
+Builds a -DMILE_PROFILE variant of the library into tools/_prof/ and runs a short sampling launch."""
+import ctypes, subprocess, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+out = ROOT / 'tools' / '_prof'
+out.mkdir(exist_ok=True)
+lib = out / 'libmile_b200.so'
+src = ROOT / 'mile_b200' / 'csrc'
+subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-DMILE_PROFILE',
+                '-shared', '-Xcompiler', '-fPIC', '-o', str(lib), str(src / 'mile_api.cu'), str(src / 'mile_microbench.cu')], check=True)
+if len(sys.argv) > 1 and sys.argv[1] == 'build':
+    sys.exit(0)
+from mile_b200 import capi
+capi.lib_path = lambda: lib
+from mile_b200 import Ensemble, FCNSpec
+from oracle import mile_oracle as o
+NAMES = {0: 'x-tile/loop', 1: 'forward', 2: 'loglik', 3: 'backward', 4: 'dW accumulate', 5: 'cross-chunk reduce',
+         8: 'esh_update (B)', 9: 'position_update (A)', 10: 'grad_eval total (outer)', 11: 'cluster reduce', 12: 'refresh'}
+for name, C, steps, opts in [('airfoil_3x16', 12, 200, {}), ('bikesharing_2x16', 10, 50, {}), ('airfoil_3x16', 1024, 20, {})]:
+    ospec = o.make_spec(name)
+    X, y, _, _ = o.synthetic_data(name)
+    ens = Ensemble(FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task), C, **opts)
+    ens.set_data(X, y)
+    ens.init(o.synthetic_theta0(ospec, C), seed=1)
+    prof = (ctypes.c_ulonglong * 32)()
+    ens.lib.mile_debug_read_profile(prof, 1)
+    ens.sample(steps, 0.02, float(np.sqrt(ospec.n_params)), keep=False, seed=3)
+    ens.lib.mile_debug_read_profile(prof, 1)
+    tot = sum(prof[i] for i in (8, 9, 10, 11, 12))
+    print(f'--- {name} C={C} G={ens.get_option("cluster_size")} TR={ens.get_option("tile_rows")} '
+          f'resident={ens.get_option("resident")}: {tot / steps:.0f} cycles/step')
+    for i, n in NAMES.items():
+        print(f'  {n:28s} {prof[i] / steps:10.0f} cycles/step  {100 * prof[i] / tot:5.1f}%')
+    ens.close()
