@@ -1,7 +1,7 @@
 // mile_api.cu -- host side of the C ABI declared in include/mile_b200.h.
 // Owns the device buffers of one ensemble wave, plans the shared-memory carve-up and the
 // cluster shape, and launches the persistent kernel of mile_kernel.cuh.  Links cudart only.
-#include "mile_kernel.cuh"
+#include "mile_fast.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -26,7 +26,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1;
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1;
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -67,7 +67,7 @@ static void build_model(mile_ctx* c) {
 }
 
 struct Plan {
-  int G, TR, resident, rows_res;
+  int G, TR, resident, rows_res, fast = 0, fast_fp = 0;
   size_t smem;
   KParams kp;  // offsets + model filled in
 };
@@ -84,7 +84,46 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   const int dS = round_up(M.d, 4);
   int S1 = 0;
   for (int l = 1; l <= M.NL; ++l) S1 += M.sA[l];
-  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 64;
+  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 128;
+  // ---- fast path: warp-specialised pipeline (mile_fast.cuh) for hidden width 16 + Gaussian head ----
+  {
+    bool ok = want_resident && c->opt_fast && M.task == MILE_TASK_REGRESSION &&
+              M.dims[M.NL] == 2 && (M.NL == 3 || M.NL == 4) && M.act == MILE_ACT_RELU &&
+              (M.dimp[0] == 8 || M.dimp[0] == 12);
+    for (int l = 1; ok && l < M.NL; ++l) ok = M.dims[l] == 16;
+    if (ok) {
+      const int T = M.NL == 3 ? 64 : 32, depth = 2 * M.NL - 1, nbuf = 2 * (M.NL - 1);
+      const int TRg = 64;  // tile of the generic forward used by the fused lppd fold inside the fast kernel
+      size_t ring = (size_t)depth * nbuf * T * 16, gen = (size_t)2 * TRg * S1;
+      size_t tile = ring > gen ? ring : gen;
+      const int rows_res = (int)((rows_cta + T - 1) / T) * T;
+      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0]) * 4;
+      const int res = (c->opt_resident != 0 && base_need + (size_t)rows_res * M.sA[0] * 4 <= kSmemLimit) ? 1 : 0;
+      if (base_need <= kSmemLimit) {
+        M.TR = TRg; M.tile_floats = (int)tile;
+        int off = 0;
+        for (int l = 1; l <= M.NL; ++l) { M.a_off[l] = off; off += TRg * M.sA[l]; }
+        for (int l = 0; l < M.NL; ++l) { M.d_off[l] = off; off += TRg * M.sA[l + 1]; }
+        KParams& k = pl.kp;
+        memset(&k, 0, sizeof(k));
+        k.M = M; k.dS = dS;
+        int o = 0;
+        k.off_wp = o; o += round_up(M.psize, 4);
+        k.off_th = o; o += dS; k.off_u = o; o += dS; k.off_g = o; o += dS;
+        k.off_thb = o; o += dS; k.off_ub = o; o += dS; k.off_gb = o; o += dS;
+        k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
+        k.off_gpart = o; o += 2 * (dS + 4);
+        k.off_pmap = o; o += 2 * dS;
+        k.off_red = o; o += 128;
+        k.off_tile = o; o += (int)tile + TRg * M.sA[0];
+        k.off_x = o; if (res) o += rows_res * M.sA[0];
+        pl.G = G; pl.TR = T; pl.resident = res; pl.rows_res = rows_res; pl.fast = 1; pl.fast_fp = M.dimp[0];
+        pl.smem = (size_t)o * 4;
+        k.G = G; k.resident = res; k.rows_res = rows_res; k.C = n_chains;
+        return 0;
+      }
+    }
+  }
   int TR = c->opt_tile_rows > 0 ? round_up(c->opt_tile_rows, 32) : 256;
   const int want = round_up((int)(rows_cta < 32 ? 32 : (rows_cta > 256 ? 256 : rows_cta)), 32);
   if (c->opt_tile_rows <= 0 && TR > want) TR = want;
@@ -116,7 +155,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
   k.off_gpart = o; o += 2 * (dS + 4);
   k.off_pmap = o; o += 2 * dS;
-  k.off_red = o; o += 64;
+  k.off_red = o; o += 128;
   k.off_tile = o; o += (int)tile + TR * M.sA[0];
   k.off_x = o; if (resident) o += rows_res * M.sA[0];
   pl.G = G; pl.TR = TR; pl.resident = resident; pl.rows_res = rows_res;
@@ -129,15 +168,15 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   return 0;
 }
 
-template <int NLMAX>
+template <class GE>
 static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
-  auto kern = mile_mclmc_kernel<NLMAX>;
+  auto kern = mile_mclmc_kernel<GE>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   if (pl.G > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(n_chains * pl.G), 1, 1);
-  cfg.blockDim = dim3(MILE_THREADS, 1, 1);
+  cfg.blockDim = dim3(GE::NT, 1, 1);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -152,12 +191,18 @@ static int launch(mile_ctx* c, const Plan& pl, int n_chains, cudaStream_t st) {
   CK(cudaSetDevice(c->device));
   const int NL = c->M.NL;
   int rc;
-  if (NL <= 2) rc = launch_t<2>(pl, n_chains, st);
-  else if (NL <= 3) rc = launch_t<3>(pl, n_chains, st);
-  else if (NL <= 4) rc = launch_t<4>(pl, n_chains, st);
-  else if (NL <= 6) rc = launch_t<6>(pl, n_chains, st);
-  else if (NL <= 8) rc = launch_t<8>(pl, n_chains, st);
-  else rc = launch_t<12>(pl, n_chains, st);
+  if (pl.fast) {
+    if (NL == 3 && pl.fast_fp == 8) rc = launch_t<FastGE<3, 8, MILE_ACT_RELU>>(pl, n_chains, st);
+    else if (NL == 3) rc = launch_t<FastGE<3, 12, MILE_ACT_RELU>>(pl, n_chains, st);
+    else if (pl.fast_fp == 8) rc = launch_t<FastGE<4, 8, MILE_ACT_RELU>>(pl, n_chains, st);
+    else rc = launch_t<FastGE<4, 12, MILE_ACT_RELU>>(pl, n_chains, st);
+  }
+  else if (NL <= 2) rc = launch_t<GenericGE<2>>(pl, n_chains, st);
+  else if (NL <= 3) rc = launch_t<GenericGE<3>>(pl, n_chains, st);
+  else if (NL <= 4) rc = launch_t<GenericGE<4>>(pl, n_chains, st);
+  else if (NL <= 6) rc = launch_t<GenericGE<6>>(pl, n_chains, st);
+  else if (NL <= 8) rc = launch_t<GenericGE<8>>(pl, n_chains, st);
+  else rc = launch_t<GenericGE<12>>(pl, n_chains, st);
   if (rc == 0) c->launches++;
   return rc;
 }
@@ -193,7 +238,7 @@ __global__ void tune_L_kernel(const float* __restrict__ ax, const float* __restr
     const float m = ax[(long)c * d + i];
     v[0] += ax2[(long)c * d + i] - m * m;
   }
-  block_sum<1>(v, red, phase);
+  block_sum<1, MILE_THREADS>(v, red, phase);
   if (threadIdx.x == 0) L[c] = sqrtf(v[0]);
 }
 
@@ -263,18 +308,21 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "tile_rows")) c->opt_tile_rows = (int)v;
   else if (!strcmp(key, "refresh_mode")) c->opt_refresh = (int)v;
   else if (!strcmp(key, "resident")) c->opt_resident = (int)v;
+  else if (!strcmp(key, "fast")) c->opt_fast = (int)v;
   else return fail(std::string("unknown option ") + key);
   return 0;
 }
 
 int64_t mile_get_option(const mile_ctx* c, const char* key) {
   if (!c || !key) return -1;
-  if (!strcmp(key, "cluster_size") || !strcmp(key, "tile_rows") || !strcmp(key, "resident") || !strcmp(key, "smem_bytes")) {
+  if (!strcmp(key, "cluster_size") || !strcmp(key, "tile_rows") || !strcmp(key, "resident") || !strcmp(key, "smem_bytes") ||
+      !strcmp(key, "fast")) {
     Plan pl;
     if (make_plan(c, c->C, c->N > 0 ? c->N : 1, true, pl)) return -1;
     if (!strcmp(key, "cluster_size")) return pl.G;
     if (!strcmp(key, "tile_rows")) return pl.TR;
     if (!strcmp(key, "resident")) return pl.resident;
+    if (!strcmp(key, "fast")) return pl.fast;
     return (int64_t)pl.smem;
   }
   if (!strcmp(key, "refresh_mode")) return c->opt_refresh;

@@ -31,8 +31,7 @@ __device__ unsigned long long g_prof[32];
 #define PROF(i)
 #endif
 
-#define MILE_THREADS 256
-#define MILE_NWARPS (MILE_THREADS / 32)
+#define MILE_THREADS 256            // block size of the generic kernel (the fast kernel uses 512)
 
 // ------------------------------------------------------------------------------------
 // Device-side model description (kernel parameter, lives in the constant bank).
@@ -69,10 +68,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Deterministic block-wide sum of NV values; every thread returns the same totals.
-// scratch: [2][NV_MAX=4][MILE_NWARPS] floats, phase toggles between the two halves so
+// scratch: [2][NV_MAX=4][NT/32] floats, phase toggles between the two halves so
 // that a single __syncthreads per reduction suffices.
-template <int NV>
+template <int NV, int NT>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch, int& phase) {
+  constexpr int MILE_NWARPS = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* buf = scratch + phase * (4 * MILE_NWARPS);
 #pragma unroll
@@ -144,6 +144,7 @@ __device__ __forceinline__ void act_eval(int act, float z, float& a, float& da) 
 // ------------------------------------------------------------------------------------
 
 // Z = A_in W + b ; hidden layers: A_out = act(Z), D_out = act'(Z) ; last layer: A_out = Z.
+template <int NT>
 __device__ __forceinline__ void fwd_layer(const DevModel& M, int l, const float* __restrict__ Wp,
                                           const float* __restrict__ Ain, int sin_,
                                           float* __restrict__ Aout, float* __restrict__ Dout,
@@ -152,7 +153,7 @@ __device__ __forceinline__ void fwd_layer(const DevModel& M, int l, const float*
   const float* __restrict__ W = Wp + M.pw_off[l];
   const float* __restrict__ B = Wp + M.pb_off[l];
   const int act = M.act;
-  for (int it = threadIdx.x; it < Q * njt; it += MILE_THREADS) {
+  for (int it = threadIdx.x; it < Q * njt; it += NT) {
     const int jt = it % njt, q = it / njt;
     const float4 b4 = *reinterpret_cast<const float4*>(B + jt * 4);
     float acc[4][4];
@@ -201,12 +202,13 @@ __device__ __forceinline__ void fwd_layer(const DevModel& M, int l, const float*
 
 // D_{l-1} <- D_{l-1}(=act') * (D_l W_l^T), using the transposed weight image W^T[OUTP][INP] so that
 // the 4 input-neuron tiles of a quarter-warp read one contiguous 64 B segment (no bank conflicts).
+template <int NT>
 __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float* __restrict__ Wp,
                                           const float* __restrict__ Dl, int sl,
                                           float* __restrict__ Dprev, int sp, int Q) {
   const int OUTP = M.dimp[l + 1], INP = M.dimp[l], nit = INP >> 2;
   const float* __restrict__ WT = Wp + M.pwt_off[l];
-  for (int it = threadIdx.x; it < Q * nit; it += MILE_THREADS) {
+  for (int it = threadIdx.x; it < Q * nit; it += NT) {
     const int itl = it % nit, q = it / nit;
     float acc[4][4];
 #pragma unroll
@@ -248,12 +250,13 @@ __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float*
 // Per-row log-likelihood and d/d(out) (probabilistic.py:93-109).  Writes the output-layer
 // delta (scaled by n_batches; zero for padded rows / NaN rows) and returns the thread's
 // partial sum of log-likelihood terms.
+template <int NT>
 __device__ __forceinline__ float loglik_rows(const DevModel& M, const float* __restrict__ Out,
                                              float* __restrict__ Dout, int so, const void* __restrict__ y,
                                              long row0, int nvalid, int rows_pad) {
   const int K = M.dims[M.NL], KP = M.dimp[M.NL];
   float part = 0.f;
-  for (int r = threadIdx.x; r < rows_pad; r += MILE_THREADS) {
+  for (int r = threadIdx.x; r < rows_pad; r += NT) {
     const float* o = Out + r * so;
     float* dd = Dout + r * so;
     if (r >= nvalid) {
@@ -333,11 +336,12 @@ struct DwAcc {
 
 struct DwRole { int ntile, nch, tile, chunk, itl, jt; bool active; };
 
+template <int NT>
 __device__ __forceinline__ DwRole dw_role(const DevModel& M, int l) {
   DwRole r;
   const int nit = M.dimp[l] >> 2, njt = M.dimp[l + 1] >> 2;
   r.ntile = nit * njt;
-  r.nch = MILE_THREADS / r.ntile;          // host guarantees ntile <= MILE_THREADS
+  r.nch = NT / r.ntile;          // host guarantees ntile <= NT
   if (r.nch > 1) r.nch &= ~1;              // even, so that chunk pairs cover 8-row groups
   r.tile = threadIdx.x % r.ntile;
   r.chunk = threadIdx.x / r.ntile;
@@ -348,11 +352,11 @@ __device__ __forceinline__ DwRole dw_role(const DevModel& M, int l) {
 }
 
 // dW_l += A_{l}^T D_l over the rows of the current tile (rows_pad = 4Q rows, invalid rows have D = 0).
-template <int NLMAX>
+template <int NLMAX, int NT>
 __device__ __forceinline__ void dw_accumulate(const DevModel& M, int l, DwAcc<NLMAX>& acc, int la,
                                               const float* __restrict__ A, int sa,
                                               const float* __restrict__ D, int sd, int rows_pad) {
-  const DwRole R = dw_role(M, l);
+  const DwRole R = dw_role<NT>(M, l);
   if (!R.active) return;
   const float* ap = A + R.itl * 4;
   const float* dp = D + R.jt * 4;

@@ -53,14 +53,15 @@ struct Ctx {
 
 // flat element i -> position in the padded parameter image (pmap) and in the transposed image
 // (pmap + dS; biases and layer 0, which need no transpose, point at their pmap slot again)
+template <int NT>
 __device__ __forceinline__ void build_pmap(const DevModel& M, int* pmap, int dS) {
   for (int l = 0; l < M.NL; ++l) {
     const int IN = M.dims[l], OUT = M.dims[l + 1], OUTP = M.dimp[l + 1], INP = M.dimp[l];
-    for (int j = threadIdx.x; j < OUT; j += MILE_THREADS) {
+    for (int j = threadIdx.x; j < OUT; j += NT) {
       pmap[M.bias_off[l] + j] = M.pb_off[l] + j;
       pmap[dS + M.bias_off[l] + j] = M.pb_off[l] + j;
     }
-    for (int e = threadIdx.x; e < IN * OUT; e += MILE_THREADS) {
+    for (int e = threadIdx.x; e < IN * OUT; e += NT) {
       const int i = e / OUT, j = e % OUT;
       pmap[M.kern_off[l] + e] = M.pw_off[l] + i * OUTP + j;
       pmap[dS + M.kern_off[l] + e] = l >= 1 ? M.pwt_off[l] + j * INP + i : M.pw_off[l] + i * OUTP + j;
@@ -73,29 +74,32 @@ __device__ __forceinline__ void store_param(Ctx& c, int i, float t) {
   c.wp[c.pmap[c.P.dS + i]] = t;
 }
 
+template <int NT>
 __device__ __forceinline__ void refresh_wp(Ctx& c) {
   const int d = c.P.M.d;
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) store_param(c, i, c.th[i]);
+  for (int i = threadIdx.x; i < d; i += NT) store_param(c, i, c.th[i]);
 }
 
 // Copy rows [row0, row0+rows_pad) of the padded global matrix into a shared tile, zero beyond nvalid.
+template <int NT>
 __device__ __forceinline__ void load_x_tile(float* dst, const float* __restrict__ src, long row0, int nvalid,
                                             int rows_pad, int sx) {
   const float4* s4 = reinterpret_cast<const float4*>(src + row0 * sx);
   float4* d4 = reinterpret_cast<float4*>(dst);
   const int nv4 = nvalid * (sx >> 2), np4 = rows_pad * (sx >> 2);
-  for (int i = threadIdx.x; i < np4; i += MILE_THREADS)
+  for (int i = threadIdx.x; i < np4; i += NT)
     d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Forward pass of one row tile; returns pointer to the output buffer (stride sA[NL]).
+template <int NT>
 __device__ __forceinline__ const float* forward_tile(Ctx& c, const float* Xt, int Q) {
   const DevModel& M = c.P.M;
   const float* in = Xt;
   int sin_ = M.sA[0];
   for (int l = 0; l < M.NL; ++l) {
     float* out = c.tile + M.a_off[l + 1];
-    fwd_layer(M, l, c.wp, in, sin_, out, c.tile + M.d_off[l], M.sA[l + 1], Q, l == M.NL - 1);
+    fwd_layer<NT>(M, l, c.wp, in, sin_, out, c.tile + M.d_off[l], M.sA[l + 1], Q, l == M.NL - 1);
     __syncthreads();
     in = out; sin_ = M.sA[l + 1];
   }
@@ -104,7 +108,7 @@ __device__ __forceinline__ const float* forward_tile(Ctx& c, const float* Xt, in
 
 // Full-batch value_and_grad restricted to this CTA's rows [r0, r1): partial gradient (flat
 // layout, likelihood part only) and partial log-likelihood into gpart[0..dS] (ll at [dS]).
-template <int NLMAX>
+template <int NLMAX, int NT>
 __device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
   const KParams& P = c.P;
   const DevModel& M = P.M;
@@ -124,36 +128,36 @@ __device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
     if (P.resident) {
       Xt = c.xbuf + (long)t * TR * M.sA[0];
     } else {
-      load_x_tile(c.xbuf, P.X, row0, nvalid, rows_pad, M.sA[0]);
+      load_x_tile<NT>(c.xbuf, P.X, row0, nvalid, rows_pad, M.sA[0]);
       __syncthreads();
       Xt = c.xbuf;
     }
     PROF(0);
-    const float* out = forward_tile(c, Xt, Q);
+    const float* out = forward_tile<NT>(c, Xt, Q);
     PROF(1);
-    llpart += loglik_rows(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], P.y, row0, nvalid, rows_pad);
+    llpart += loglik_rows<NT>(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], P.y, row0, nvalid, rows_pad);
     __syncthreads();
     PROF(2);
     for (int l = M.NL - 1; l >= 1; --l) {
-      bwd_layer(M, l, c.wp, c.tile + M.d_off[l], M.sA[l + 1], c.tile + M.d_off[l - 1], M.sA[l], Q);
+      bwd_layer<NT>(M, l, c.wp, c.tile + M.d_off[l], M.sA[l + 1], c.tile + M.d_off[l - 1], M.sA[l], Q);
       __syncthreads();
     }
     PROF(3);
 #pragma unroll
     for (int l = 0; l < NLMAX; ++l)
       if (l < M.NL)
-        dw_accumulate<NLMAX>(M, l, acc, l, l == 0 ? Xt : c.tile + M.a_off[l], M.sA[l],
+        dw_accumulate<NLMAX, NT>(M, l, acc, l, l == 0 ? Xt : c.tile + M.a_off[l], M.sA[l],
                              c.tile + M.d_off[l], M.sA[l + 1], rows_pad);
     __syncthreads();
     PROF(4);
   }
   // cross-chunk reduction of the per-thread 4x4 tiles (scratch aliases the tile buffers)
   float* scr = c.tile;
-  float* scrb = c.tile + MILE_THREADS * 16;
+  float* scrb = c.tile + NT * 16;
 #pragma unroll
   for (int l = 0; l < NLMAX; ++l) {
     if (l < M.NL) {
-      const DwRole R = dw_role(M, l);
+      const DwRole R = dw_role<NT>(M, l);
       if (R.active) {
         float4* s4 = reinterpret_cast<float4*>(scr + (R.chunk * R.ntile + R.tile) * 16);
         s4[0] = make_float4(acc.w[l][0], acc.w[l][1], acc.w[l][2], acc.w[l][3]);
@@ -166,14 +170,14 @@ __device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
       }
       __syncthreads();
       const int IN = M.dims[l], OUT = M.dims[l + 1], njt = M.dimp[l + 1] >> 2;
-      for (int o = threadIdx.x; o < R.ntile * 16; o += MILE_THREADS) {
+      for (int o = threadIdx.x; o < R.ntile * 16; o += NT) {
         const int tile = o >> 4, e = o & 15;
         float s = 0.f;
         for (int ch = 0; ch < R.nch; ++ch) s += scr[(ch * R.ntile + tile) * 16 + e];
         const int i = (tile / njt) * 4 + (e >> 2), j = (tile % njt) * 4 + (e & 3);
         if (i < IN && j < OUT) gpart[M.kern_off[l] + i * OUT + j] = s;
       }
-      for (int o = threadIdx.x; o < njt * 4; o += MILE_THREADS) {
+      for (int o = threadIdx.x; o < njt * 4; o += NT) {
         const int tile = o >> 2, e = o & 3;   // itl == 0 -> tile == jt
         float s = 0.f;
         for (int ch = 0; ch < R.nch; ++ch) s += scrb[(ch * R.ntile + tile) * 4 + e];
@@ -183,7 +187,7 @@ __device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
     }
   }
   float v[1] = {llpart};
-  block_sum<1>(v, c.red, c.phase);
+  block_sum<1, NT>(v, c.red, c.phase);
   if (threadIdx.x == 0) gpart[P.dS] = v[0];
   PROF(5);
 }
@@ -191,6 +195,7 @@ __device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
 // DSMEM all-reduce of the cluster's partial gradients + prior: afterwards gg = full gradient of
 // the log-posterior (bit-identical in every CTA), returns the log-posterior value.  Also returns
 // sum g^2, sum u.g and the number of non-finite entries of theta for the next B-step / handle_nans.
+template <int NT>
 __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float& g2, float& ug, float& nonfinite) {
   const KParams& P = c.P;
   const DevModel& M = P.M;
@@ -203,7 +208,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   }
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
-  for (int i = threadIdx.x; i < M.d; i += MILE_THREADS) {
+  for (int i = threadIdx.x; i < M.d; i += NT) {
     float s = 0.f;
     for (int r = 0; r < c.G; ++r) {
       const float* rp = c.G > 1 ? cluster.map_shared_rank(gpart, r) : gpart;
@@ -224,13 +229,14 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
     c.gg[i] = g;
     v[0] += pv; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   }
-  block_sum<4>(v, c.red, c.phase);
+  block_sum<4, NT>(v, c.red, c.phase);
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
   return v[0] + ll;
 }
 
 // ESH momentum update B(coef) (blackjax esh_dynamics_momentum_update_one_step, sqrt_diag_cov = 1).
 // delta-small-safe forms: 1-zeta = -expm1(-delta), log(1+p+(1-p)zeta^2) - ln2 = log1p(-(1-p)(1-zeta^2)/2).
+template <int NT>
 __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
   const int d = c.P.M.d;
   const float gn = sqrtf(g2);
@@ -242,24 +248,25 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const float ce = omz * (1.f + zeta + p * omz);
   const float cu = 2.f * zeta;
   float v[1] = {0.f};
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+  for (int i = threadIdx.x; i < d; i += NT) {
     const float raw = (c.gg[i] * ginv) * ce + cu * c.uu[i];
     c.uu[i] = raw;
     v[0] += raw * raw;
   }
-  block_sum<1>(v, c.red, c.phase);
+  block_sum<1, NT>(v, c.red, c.phase);
   const float rn = sqrtf(v[0]);
   const float rinv = rn > 1e-13f ? 1.f / rn : 1.f;
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.uu[i] *= rinv;
+  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= rinv;
   const float omz2 = -expm1f(-2.f * delta);
   return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
 }
 
 // A(coef): theta += eps*coef*u and refresh the padded weight image.
+template <int NT>
 __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
   const int d = c.P.M.d;
   const float s = eps * coef;
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+  for (int i = threadIdx.x; i < d; i += NT) {
     const float t = c.th[i] + s * c.uu[i];
     c.th[i] = t;
     store_param(c, i, t);
@@ -273,27 +280,28 @@ __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step
 }
 
 // partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
+template <int NT>
 __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, long step_local, int slot, int nslot,
                                                  float& ug_out) {
   const KParams& P = c.P;
   const int d = P.M.d;
   if (isinf(L)) {
     float v[1] = {0.f};
-    for (int i = threadIdx.x; i < d; i += MILE_THREADS) v[0] += c.uu[i] * c.gg[i];
-    block_sum<1>(v, c.red, c.phase);
+    for (int i = threadIdx.x; i < d; i += NT) v[0] += c.uu[i] * c.gg[i];
+    block_sum<1, NT>(v, c.red, c.phase);
     ug_out = v[0];
     return;
   }
   const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
   float v[2] = {0.f, 0.f};
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) {
+  for (int i = threadIdx.x; i < d; i += NT) {
     const float w = c.uu[i] + nu * noise_at(P, c.chain, step_local, slot, nslot, i);
     c.uu[i] = w;
     v[0] += w * w; v[1] += w * c.gg[i];
   }
-  block_sum<2>(v, c.red, c.phase);
+  block_sum<2, NT>(v, c.red, c.phase);
   const float inv = 1.f / sqrtf(v[0]);
-  for (int i = threadIdx.x; i < d; i += MILE_THREADS) c.uu[i] *= inv;
+  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= inv;
   ug_out = v[1] * inv;
 }
 
@@ -304,6 +312,7 @@ __device__ __forceinline__ float nan_to_num(float x) {
 }
 
 // Online logsumexp over the test split for the current theta (weights already in c.wp).
+template <int NT>
 __device__ __forceinline__ void lppd_fold(Ctx& c, int chain) {
   const KParams& P = c.P;
   const DevModel& M = P.M;
@@ -314,10 +323,10 @@ __device__ __forceinline__ void lppd_fold(Ctx& c, int chain) {
     const int nvalid = (int)((r1 - row0) < TR ? (r1 - row0) : TR);
     const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
     float* xt = c.xstream;
-    load_x_tile(xt, P.Xt, row0, nvalid, Q * 4, M.sA[0]);
+    load_x_tile<NT>(xt, P.Xt, row0, nvalid, Q * 4, M.sA[0]);
     __syncthreads();
-    const float* out = forward_tile(c, xt, Q);
-    for (int r = threadIdx.x; r < nvalid; r += MILE_THREADS) {
+    const float* out = forward_tile<NT>(c, xt, Q);
+    for (int r = threadIdx.x; r < nvalid; r += NT) {
       const float lp = pointwise_lppd_row(M, out + r * M.sA[M.NL], P.yt, row0 + r);
       const long idx = (long)chain * P.Nt + row0 + r;
       const float m = P.lppd_m[idx], s = P.lppd_s[idx];
@@ -330,8 +339,17 @@ __device__ __forceinline__ void lppd_fold(Ctx& c, int chain) {
   }
 }
 
+// Gradient-evaluation policy of the generic kernel: 4x4 register tiles, runtime layer shapes.
 template <int NLMAX>
-__global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __grid_constant__ KParams P) {
+struct GenericGE {
+  static constexpr int NT = 256;
+  static __device__ __forceinline__ void prepare(Ctx&) {}
+  static __device__ __forceinline__ void run(Ctx& c, long r0, long r1, float* gp) { grad_eval<NLMAX, NT>(c, r0, r1, gp); }
+};
+
+template <class GE>
+__global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_constant__ KParams P) {
+  constexpr int NT = GE::NT;
   extern __shared__ __align__(16) float smem[];
   const DevModel& M = P.M;
   cg::cluster_group cluster = cg::this_cluster();
@@ -350,17 +368,17 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
   const int tid = threadIdx.x;
 
   // ---- prologue: parameter image, state, resident X slice --------------------------------
-  for (int i = tid; i < M.psize; i += MILE_THREADS) c.wp[i] = 0.f;
-  build_pmap(M, c.pmap, P.dS);
+  for (int i = tid; i < M.psize; i += NT) c.wp[i] = 0.f;
+  build_pmap<NT>(M, c.pmap, P.dS);
   const bool from_input = (P.mode == MODE_EVAL || P.mode == MODE_INIT || P.mode == MODE_LPPD || P.mode == MODE_PREDICT);
   const float* th_src = from_input ? P.theta_in + (long)ch * d : P.theta + (long)ch * d;
-  for (int i = tid; i < d; i += MILE_THREADS) {
+  for (int i = tid; i < d; i += NT) {
     c.th[i] = th_src[i];
     if (!from_input) { c.uu[i] = P.u[(long)ch * d + i]; c.gg[i] = P.grad[(long)ch * d + i]; }
     else { c.uu[i] = 0.f; c.gg[i] = 0.f; }
   }
   __syncthreads();
-  refresh_wp(c);
+  refresh_wp<NT>(c);
   const long per = (P.N + c.G - 1) / c.G;
   const long r0 = per * c.rank < P.N ? per * c.rank : P.N;
   const long r1 = (r0 + per) < P.N ? (r0 + per) : P.N;
@@ -370,7 +388,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
     const long nv4 = (r1 - r0) * (sx >> 2), np4 = (long)P.rows_res * (sx >> 2);
     const float4* s4 = reinterpret_cast<const float4*>(P.X + r0 * sx);
     float4* d4 = reinterpret_cast<float4*>(c.xbuf);
-    for (long i = tid; i < np4; i += MILE_THREADS) d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long i = tid; i < np4; i += NT) d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
 
@@ -385,10 +403,10 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       const int nvalid = (int)((a1 - row0) < M.TR ? (a1 - row0) : M.TR);
       const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
       float* xt = c.xstream;
-      load_x_tile(xt, Xsrc, row0, nvalid, Q * 4, M.sA[0]);
+      load_x_tile<NT>(xt, Xsrc, row0, nvalid, Q * 4, M.sA[0]);
       __syncthreads();
-      const float* out = forward_tile(c, xt, Q);
-      for (int e = tid; e < nvalid * K; e += MILE_THREADS)
+      const float* out = forward_tile<NT>(c, xt, Q);
+      for (int e = tid; e < nvalid * K; e += NT)
         P.pred_out[((long)ch * Nr + row0 + e / K) * K + e % K] = out[(e / K) * M.sA[M.NL] + e % K];
       __syncthreads();
     }
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
     return;
   }
   if (P.mode == MODE_LPPD) {
-    lppd_fold(c, ch);
+    lppd_fold<NT>(c, ch);
     if (c.G > 1) cluster.sync();
     return;
   }
@@ -405,24 +423,24 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
   float g2 = 0.f, ug = 0.f, nf = 0.f;
   if (P.mode == MODE_EVAL || P.mode == MODE_INIT) {
     float* gp = c.gpart + (ev & 1) * (P.dS + 4);
-    grad_eval<NLMAX>(c, r0, r1, gp);
-    const float lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+    GE::run(c, r0, r1, gp);
+    const float lp = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
     if (P.mode == MODE_EVAL) {
       if (c.rank == 0) {
-        for (int i = tid; i < d; i += MILE_THREADS) P.grad_out[(long)ch * d + i] = c.gg[i];
+        for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * d + i] = c.gg[i];
         if (tid == 0) P.lp_out[ch] = lp;
       }
     } else {
       // generate_unit_vector: u = z / |z|
       float v[1] = {0.f};
-      for (int i = tid; i < d; i += MILE_THREADS) {
+      for (int i = tid; i < d; i += NT) {
         const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
         c.uu[i] = zz; v[0] += zz * zz;
       }
-      block_sum<1>(v, c.red, c.phase);
+      block_sum<1, NT>(v, c.red, c.phase);
       const float inv = 1.f / sqrtf(v[0]);
       if (c.rank == 0) {
-        for (int i = tid; i < d; i += MILE_THREADS) {
+        for (int i = tid; i < d; i += NT) {
           P.theta[(long)ch * d + i] = c.th[i];
           P.u[(long)ch * d + i] = c.uu[i] * inv;
           P.grad[(long)ch * d + i] = c.gg[i];
@@ -442,7 +460,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
   float t_time = 0.f, t_xavg = 0.f, t_epsmax = INFINITY, t_wtot = 0.f;
   if (tune) {
     t_time = P.t_time[ch]; t_xavg = P.t_xavg[ch]; t_epsmax = P.t_epsmax[ch]; t_wtot = P.t_wtot[ch];
-    for (int i = tid; i < d; i += MILE_THREADS) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
+    for (int i = tid; i < d; i += NT) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
   }
   const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
   const int nslot = P.refresh_mode ? 2 : 1;
@@ -450,33 +468,33 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
     g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
   } else {  // cached gradient: sum g^2 and u.g for the first B-step
     float v[2] = {0.f, 0.f};
-    for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-    block_sum<2>(v, c.red, c.phase);
+    for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+    block_sum<2, NT>(v, c.red, c.phase);
     g2 = v[0]; ug = v[1];
   }
   for (int s = 0; s < P.n_steps; ++s) {
     const float lp_old = lp;
     if (tune) {
-      for (int i = tid; i < d; i += MILE_THREADS) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+      for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
     }
-    if (P.refresh_mode) refresh_momentum(c, 0.5f * eps, Lc, s, 0, nslot, ug);
+    if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, s, 0, nslot, ug);
     float dK = 0.f;
     PROF_DECL;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {   // B(b1) A(1/2) grad | B(1-2 b1) A(1/2) grad
-      dK += esh_update(c, eps, h == 0 ? b1 : b2, g2, ug);
+      dK += esh_update<NT>(c, eps, h == 0 ? b1 : b2, g2, ug);
       PROF(8);
-      position_update(c, eps, 0.5f);
+      position_update<NT>(c, eps, 0.5f);
       PROF(9);
       float* gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
-      grad_eval<NLMAX>(c, r0, r1, gp);
+      GE::run(c, r0, r1, gp);
       PROF(10);
-      lp = cluster_reduce_grad(c, gp, g2, ug, nf);
+      lp = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
       PROF(11);
     }
-    dK += esh_update(c, eps, b1, g2, ug);
+    dK += esh_update<NT>(c, eps, b1, g2, ug);
     PROF(8);
-    refresh_momentum(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
+    refresh_momentum<NT>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
     PROF(12);
     float dE = dK - lp + lp_old;
 
@@ -489,17 +507,17 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       // handle_nans (warmup.py:468-483)
       const bool success = nf == 0.f;
       if (!success) {
-        for (int i = tid; i < d; i += MILE_THREADS) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; store_param(c, i, c.thb[i]); }
+        for (int i = tid; i < d; i += NT) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; store_param(c, i, c.thb[i]); }
         lp = lp_old;
         t_epsmax = eps * 0.8f;
         dE = 0.f;
         float v[2] = {0.f, 0.f};
-        for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-        block_sum<2>(v, c.red, c.phase);
+        for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+        block_sum<2, NT>(v, c.red, c.phase);
         g2 = v[0]; ug = v[1];
       } else {
         bool changed = false;
-        for (int i = tid; i < d; i += MILE_THREADS) {
+        for (int i = tid; i < d; i += NT) {
           const float u0 = c.uu[i], g0 = c.gg[i];
           const float u1 = nan_to_num(u0), g1 = nan_to_num(g0);
           if (u1 != u0 || g1 != g0 || isnan(u0) || isnan(g0)) { c.uu[i] = u1; c.gg[i] = g1; changed = true; }
@@ -509,8 +527,8 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
         dE = nan_to_num(dE);
         if (__syncthreads_or(changed)) {
           float v[2] = {0.f, 0.f};
-          for (int i = tid; i < d; i += MILE_THREADS) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-          block_sum<2>(v, c.red, c.phase);
+          for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+          block_sum<2, NT>(v, c.red, c.phase);
           g2 = v[0]; ug = v[1];
         }
       }
@@ -537,7 +555,7 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       if (it >= P.tune1) {
         const float w = (success ? 1.f : 0.f) * eps_new;
         const float denom = t_wtot + w;
-        for (int i = tid; i < d; i += MILE_THREADS) {
+        for (int i = tid; i < d; i += NT) {
           const float x = c.th[i];
           c.avgx[i] = (t_wtot * c.avgx[i] + w * x) / denom;
           c.avgx2[i] = (t_wtot * c.avgx2[i] + w * (x * x)) / denom;
@@ -557,14 +575,14 @@ __global__ void __launch_bounds__(MILE_THREADS, 1) mile_mclmc_kernel(const __gri
       if (idx % P.thin == 0) {
         const long slot = idx / P.thin - P.sample_base;
         if (P.samples && c.rank == 0 && slot >= 0 && slot < P.n_slots)
-          for (int i = tid; i < d; i += MILE_THREADS) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
-        if (P.do_lppd) lppd_fold(c, ch);
+          for (int i = tid; i < d; i += NT) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
+        if (P.do_lppd) lppd_fold<NT>(c, ch);
       }
     }
   }
   // ---- epilogue: write state back ------------------------------------------------------------
   if (c.rank == 0) {
-    for (int i = tid; i < d; i += MILE_THREADS) {
+    for (int i = tid; i < d; i += NT) {
       P.theta[(long)ch * d + i] = c.th[i];
       P.u[(long)ch * d + i] = c.uu[i];
       P.grad[(long)ch * d + i] = c.gg[i];
