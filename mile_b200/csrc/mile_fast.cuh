@@ -301,7 +301,7 @@ struct FastGE {
   }
 
   // ---- one gradient evaluation over this CTA's rows [r0, r1) ----------------------------------------
-  static __device__ __noinline__ void run(Ctx& c, long r0, long r1, float* gpart) {
+  static __device__ __forceinline__ void run(Ctx& c, long r0, long r1, float* gpart) {
     const KParams& P = c.P;
     const DevModel& M = P.M;
     float* ring = c.tile;

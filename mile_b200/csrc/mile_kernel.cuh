@@ -109,7 +109,7 @@ __device__ __forceinline__ const float* forward_tile(Ctx& c, const float* Xt, in
 // Full-batch value_and_grad restricted to this CTA's rows [r0, r1): partial gradient (flat
 // layout, likelihood part only) and partial log-likelihood into gpart[0..dS] (ll at [dS]).
 template <int NLMAX, int NT>
-__device__ __noinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
+__device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart) {
   const KParams& P = c.P;
   const DevModel& M = P.M;
   DwAcc<NLMAX> acc;
@@ -201,28 +201,38 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   const DevModel& M = P.M;
   cg::cluster_group cluster = cg::this_cluster();
   if (c.G > 1) cluster.sync(); else __syncthreads();
+  // rank loops are unrolled to the maximum cluster size with predication so that all remote (DSMEM)
+  // loads of an element are in flight together (~200 cycles each when serialised)
+  const float* rp[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) rp[r] = (c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
   float ll = 0.f;
-  for (int r = 0; r < c.G; ++r) {
-    const float* rp = c.G > 1 ? cluster.map_shared_rank(gpart, r) : gpart;
-    ll += rp[P.dS];
+  {
+    float t[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ll += t[r];
   }
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
+  const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
   for (int i = threadIdx.x; i < M.d; i += NT) {
+    float t[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
     float s = 0.f;
-    for (int r = 0; r < c.G; ++r) {
-      const float* rp = c.G > 1 ? cluster.map_shared_rank(gpart, r) : gpart;
-      s += rp[i];
-    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s += t[r];
     const float th = c.th[i];
     float pg, pv;
     if (M.prior == MILE_PRIOR_NORMAL) {
       const float dlt = th - loc;
-      pv = (logf(6.283185307179586f * s2) + dlt * dlt / s2) / -2.f;
+      pv = (lognorm + dlt * dlt / s2) / -2.f;
       pg = -dlt / s2;
     } else {
       const float dlt = th - loc;
-      pv = -logf(2.f * sc) - fabsf(dlt) / sc;
+      pv = -lognorm - fabsf(dlt) / sc;
       pg = -((dlt > 0.f) - (dlt < 0.f)) / sc;
     }
     const float g = s + pg;
@@ -243,8 +253,8 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const float ginv = gn > 1e-13f ? 1.f / gn : 1.f;
   const float p = ug * ginv;
   const float delta = eps * coef * gn / (float)(d - 1);
-  const float zeta = expf(-delta);
-  const float omz = -expm1f(-delta);
+  const float omz = -expm1f(-delta);   // 1 - zeta without cancellation
+  const float zeta = 1.f - omz;
   const float ce = omz * (1.f + zeta + p * omz);
   const float cu = 2.f * zeta;
   float v[1] = {0.f};
@@ -257,7 +267,7 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const float rn = sqrtf(v[0]);
   const float rinv = rn > 1e-13f ? 1.f / rn : 1.f;
   for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= rinv;
-  const float omz2 = -expm1f(-2.f * delta);
+  const float omz2 = omz * (1.f + zeta);   // 1 - zeta^2
   return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
 }
 
@@ -419,79 +429,85 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     return;
   }
 
-  int ev = 0;  // gradient-evaluation parity (gpart double buffer)
-  float g2 = 0.f, ug = 0.f, nf = 0.f;
-  if (P.mode == MODE_EVAL || P.mode == MODE_INIT) {
-    float* gp = c.gpart + (ev & 1) * (P.dS + 4);
-    GE::run(c, r0, r1, gp);
-    const float lp = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
-    if (P.mode == MODE_EVAL) {
-      if (c.rank == 0) {
-        for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * d + i] = c.gg[i];
-        if (tid == 0) P.lp_out[ch] = lp;
-      }
-    } else {
-      // generate_unit_vector: u = z / |z|
-      float v[1] = {0.f};
-      for (int i = tid; i < d; i += NT) {
-        const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
-        c.uu[i] = zz; v[0] += zz * zz;
-      }
-      block_sum<1, NT>(v, c.red, c.phase);
-      const float inv = 1.f / sqrtf(v[0]);
-      if (c.rank == 0) {
-        for (int i = tid; i < d; i += NT) {
-          P.theta[(long)ch * d + i] = c.th[i];
-          P.u[(long)ch * d + i] = c.uu[i] * inv;
-          P.grad[(long)ch * d + i] = c.gg[i];
-        }
-        if (tid == 0) P.lp[ch] = lp;
-      }
-    }
-    if (c.G > 1) cluster.sync();
-    return;
-  }
-
-  // ---- MODE_SAMPLE / MODE_TUNE: the step loop -----------------------------------------------
+  // ---- one loop over gradient evaluations: 1 for EVAL / INIT, 2 per MCLMC step otherwise.  A single
+  //      call site keeps GE::run inlined exactly once (shared address space stays visible to ptxas).
+  const bool stepping = P.mode == MODE_SAMPLE || P.mode == MODE_TUNE;
   const bool tune = P.mode == MODE_TUNE;
-  float lp = P.lp[ch];
-  float eps = tune ? P.t_eps[ch] : P.eps[ch];
-  float Lc = tune ? P.t_L[ch] : P.L[ch];
+  float g2 = 0.f, ug = 0.f, nf = 0.f;
+  float lp = 0.f, eps = 0.f, Lc = 0.f;
   float t_time = 0.f, t_xavg = 0.f, t_epsmax = INFINITY, t_wtot = 0.f;
-  if (tune) {
-    t_time = P.t_time[ch]; t_xavg = P.t_xavg[ch]; t_epsmax = P.t_epsmax[ch]; t_wtot = P.t_wtot[ch];
-    for (int i = tid; i < d; i += NT) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
-  }
   const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
   const int nslot = P.refresh_mode ? 2 : 1;
-  if (P.carry_valid) {
-    g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
-  } else {  // cached gradient: sum g^2 and u.g for the first B-step
-    float v[2] = {0.f, 0.f};
-    for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-    block_sum<2, NT>(v, c.red, c.phase);
-    g2 = v[0]; ug = v[1];
-  }
-  for (int s = 0; s < P.n_steps; ++s) {
-    const float lp_old = lp;
+  if (stepping) {
+    lp = P.lp[ch];
+    eps = tune ? P.t_eps[ch] : P.eps[ch];
+    Lc = tune ? P.t_L[ch] : P.L[ch];
     if (tune) {
-      for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+      t_time = P.t_time[ch]; t_xavg = P.t_xavg[ch]; t_epsmax = P.t_epsmax[ch]; t_wtot = P.t_wtot[ch];
+      for (int i = tid; i < d; i += NT) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
     }
-    if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, s, 0, nslot, ug);
-    float dK = 0.f;
-    PROF_DECL;
+    if (P.carry_valid) {
+      g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
+    } else {  // cached gradient: sum g^2 and u.g for the first B-step
+      float v[2] = {0.f, 0.f};
+      for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+      block_sum<2, NT>(v, c.red, c.phase);
+      g2 = v[0]; ug = v[1];
+    }
+  }
+  const int n_evals = stepping ? 2 * P.n_steps : 1;
+  float lp_old = 0.f, dK = 0.f;
+  PROF_DECL;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {   // B(b1) A(1/2) grad | B(1-2 b1) A(1/2) grad
+  for (int e = 0; e < n_evals; ++e) {
+    const int h = e & 1, s = e >> 1;   // half-step h of MCLMC step s
+    if (stepping) {
+      if (h == 0) {
+        lp_old = lp; dK = 0.f;
+        if (tune) for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+        if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, s, 0, nslot, ug);
+      }
+      // B(b1) A(1/2) grad | B(1-2 b1) A(1/2) grad
       dK += esh_update<NT>(c, eps, h == 0 ? b1 : b2, g2, ug);
       PROF(8);
       position_update<NT>(c, eps, 0.5f);
       PROF(9);
-      float* gp = c.gpart + (ev & 1) * (P.dS + 4); ++ev;
-      GE::run(c, r0, r1, gp);
-      PROF(10);
-      lp = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
-      PROF(11);
     }
+    float* gp = c.gpart + (e & 1) * (P.dS + 4);
+    GE::run(c, r0, r1, gp);
+    PROF(10);
+    const float lp_new = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
+    PROF(11);
+    if (!stepping) {
+      if (P.mode == MODE_EVAL) {
+        if (c.rank == 0) {
+          for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * d + i] = c.gg[i];
+          if (tid == 0) P.lp_out[ch] = lp_new;
+        }
+      } else {
+        // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
+        float v[1] = {0.f};
+        for (int i = tid; i < d; i += NT) {
+          const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+          c.uu[i] = zz; v[0] += zz * zz;
+        }
+        block_sum<1, NT>(v, c.red, c.phase);
+        const float inv = 1.f / sqrtf(v[0]);
+        if (c.rank == 0) {
+          for (int i = tid; i < d; i += NT) {
+            P.theta[(long)ch * d + i] = c.th[i];
+            P.u[(long)ch * d + i] = c.uu[i] * inv;
+            P.grad[(long)ch * d + i] = c.gg[i];
+          }
+          if (tid == 0) P.lp[ch] = lp_new;
+        }
+      }
+      if (c.G > 1) cluster.sync();
+      return;
+    }
+    lp = lp_new;
+    if (h == 0) continue;
+    // ---- end of MCLMC step s: last B, partial refresh, energy bookkeeping --------------------------
     dK += esh_update<NT>(c, eps, b1, g2, ug);
     PROF(8);
     refresh_momentum<NT>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
