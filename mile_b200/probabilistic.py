@@ -1,0 +1,96 @@
+"""ProbabilisticModel (mirror of src/training/probabilistic.py:17-138).  `log_unnormalized_posterior`
+keeps the reference signature; its value -- and, for the samplers, its gradient -- is computed by the fused
+CUDA value_and_grad kernel (mile_logpost_value_and_grad).  No host / CPU evaluation path exists."""
+from __future__ import annotations
+
+import functools
+import logging
+import weakref
+
+import numpy as np
+
+from .engine import Ensemble, FCNSpec
+from .models import FCN
+from .priors import Prior
+
+logger = logging.getLogger(__name__)
+
+_TASKS = {'regr': 'regr', 'regression': 'regr', 'class': 'class', 'classification': 'class'}
+
+
+class ProbabilisticModel:
+    """Convert a frequentist FCN description into the Bayesian log-posterior the samplers use."""
+
+    def __init__(self, module: FCN, params: dict, prior: Prior, task, n_batches: int = 1):
+        self.task = _TASKS[str(getattr(task, 'value', task)).lower()]
+        self.module = module
+        self.prior = prior
+        self.n_batches = n_batches
+        inner = params['fcn'] if 'fcn' in params else params
+        k0 = np.asarray(inner['layer0']['kernel'])
+        self.n_features = int(k0.shape[-2])
+        self.n_params = int(sum(np.asarray(v).size for lay in inner.values() for v in lay.values())
+                            // max(1, int(np.prod(k0.shape[:-2]))))
+        self._engines = weakref.WeakValueDictionary()
+        self._test = None
+        logger.info(f'Initialized ProbModelBuilder for {self.task} task')
+
+    def __str__(self):
+        return (f'{self.__class__.__name__}:\n | Task: {self.task}\n | Params: {self.n_params}'
+                f' | Batches: {self.n_batches}\n | Prior: {self.prior.name}')
+
+    @property
+    def minibatch(self):
+        return self.n_batches > 1
+
+    @property
+    def spec(self) -> FCNSpec:
+        return FCNSpec(self.n_features, self.module.hidden_structure, self.module.activation, self.task,
+                       self.prior.kind, self.prior.loc, self.prior.scale, float(self.n_batches))
+
+    def attach_test_split(self, x, y):
+        """Optional: test split for the fused posterior-predictive LPPD (src/inference/evaluation.py:378-400)."""
+        self._test = (np.asarray(x, np.float32), np.asarray(y))
+
+    def log_prior(self, params):
+        return self.prior.log_prior(params)
+
+    # ---- engine management ---------------------------------------------------------------------
+    def make_ensemble(self, n_chains: int, x, y, device: int | None = None, **options) -> Ensemble:
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        ens = Ensemble(self.spec, n_chains, device=device, **options)
+        ens.set_data(np.asarray(x, np.float32), np.asarray(y))
+        if self._test is not None:
+            ens.set_test(*self._test)
+        return ens
+
+    def log_unnormalized_posterior(self, position, x, y, **kwargs):
+        """probabilistic.py:115-138.  position: ParamTree (optionally with a leading chain axis)."""
+        spec = self.spec
+        theta = spec.ravel(position)
+        batched = theta.ndim == 2
+        theta = theta.reshape(-1, spec.n_params)
+        ens = self.make_ensemble(theta.shape[0], x, y)
+        try:
+            lp, _ = ens.value_and_grad(theta)
+        finally:
+            ens.close()
+        return lp if batched else lp[0]
+
+
+def unwrap_posterior(fn):
+    """Recognise `partial(prob_model.log_unnormalized_posterior, x=train_x, y=train_y)`
+    (src/training/trainer.py:576-580) and return (prob_model, x, y).  Anything else cannot be routed to the
+    fused CUDA kernel and is rejected loudly (there is no tracing / CPU fallback)."""
+    if isinstance(fn, functools.partial):
+        target = fn.func
+        owner = getattr(target, '__self__', None)
+        if isinstance(owner, ProbabilisticModel) and getattr(target, '__name__', '') == 'log_unnormalized_posterior':
+            kw = fn.keywords or {}
+            if 'x' in kw and 'y' in kw:
+                return owner, kw['x'], kw['y']
+    raise TypeError('mile_b200 samplers need `functools.partial(prob_model.log_unnormalized_posterior, x=..., y=...)` '
+                    'of a mile_b200.probabilistic.ProbabilisticModel: arbitrary Python log-densities cannot run on '
+                    'the CUDA path and there is no CPU fallback')

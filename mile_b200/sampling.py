@@ -1,0 +1,98 @@
+"""Sampler driver (mirror of src/training/sampling.py:32-292): inference_loop / warmup_mclmc with the
+reference's call signatures and on-disk side effects (warmup_params.txt, samples/{id}/sample_{n}.npz,
+samples/info.pkl).  All chains of the wave run in ONE persistent CUDA kernel instead of one XLA-CPU device
+per chain."""
+from __future__ import annotations
+
+import logging
+import pickle
+from pathlib import Path
+
+import numpy as np
+
+from .callbacks import SampleWriter
+from .config import Sampler, SamplerConfig
+from .engine import lppd_from_state
+from .probabilistic import unwrap_posterior
+from .types import key_to_seed, split
+from .warmup import run_warmup
+
+logger = logging.getLogger(__name__)
+
+CHUNK = 1000  # MCLMC steps per sampling launch (rounded to a multiple of n_thinning)
+
+
+def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_params: dict, step_ids,
+                   saving_path: Path, saving_path_warmup: Path | None = None):
+    """sampling.py:32-216: warmup -> warmup_params.txt -> n_samples steps with thinned saves -> info.pkl."""
+    info = {}
+    step_ids = [int(s) for s in np.atleast_1d(np.asarray(step_ids))]
+    n_devices = len(step_ids)
+    rng_key, warmup_key, sample_key = split(rng_key, 3)                      # sampling.py:65
+    assert config.warmup_steps > 0, 'Number of warmup steps must be greater than 0.'
+    if config.name != Sampler.MCLMC:
+        raise NotImplementedError(f'{config.name} does not have a warmup implemented.')
+    saving_path = Path(saving_path)
+    model, x, y = unwrap_posterior(unnorm_log_posterior)
+    spec = model.spec
+    theta0 = spec.ravel(init_params).reshape(-1, spec.n_params)
+    if theta0.shape[0] != n_devices:
+        raise ValueError(f'init_params carry {theta0.shape[0]} chains but step_ids has {n_devices}')
+    ens = model.make_ensemble(n_devices, x, y)
+    try:
+        logger.info('> Starting Warmup sampling...')
+        eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens)
+        saving_path.mkdir(parents=True, exist_ok=True)
+        with open(saving_path.parent / 'warmup_params.txt', 'w') as f:      # sampling.py:92-97
+            f.write(','.join(str(np.float32(v)) for v in eps) + '\n')
+            f.write(','.join(str(np.float32(v)) for v in L) + '\n')
+        logger.info('> Warmup sampling completed successfully.')
+
+        logger.info(f'> Starting {config.name.value} Sampling...')
+        thin = int(config.n_thinning)
+        chunk = max(thin, CHUNK // thin * thin)
+        writer = SampleWriter(spec, saving_path, step_ids)
+        fused_lppd = ens.n_test > 0
+        if fused_lppd:
+            ens.lppd_reset()
+        seed = key_to_seed(sample_key)
+        done = 0
+        while done < config.n_samples:                                       # HOT LOOP C, sampling.py:134-177
+            n = min(chunk, config.n_samples - done)
+            samples, _ = ens.sample(n, eps, L, step_base=done, n_thinning=thin, seed=seed, lppd=fused_lppd)
+            first = -(-done // thin)
+            writer.submit(samples, [(first + k) * thin for k in range(samples.shape[0])])
+            done += n
+        writer.close()
+        if fused_lppd:
+            m, s, cnt = ens.lppd_state()
+            info['lppd'] = lppd_from_state(m, s, n_devices * cnt)
+            np.savez_compressed(saving_path.parent / f'lppd_state_{step_ids[0]}.npz', m=m, s=s, count=cnt,
+                                chains=np.asarray(step_ids))
+            logger.info(f"> fused posterior-predictive LPPD over {n_devices} chains x {cnt} samples: {info['lppd']:.5f}")
+        logger.info(f'> {config.name.value} Sampling completed successfully.')
+    finally:
+        ens.close()
+    with open(saving_path / 'info.pkl', 'wb') as f:                          # sampling.py:213-215
+        pickle.dump({k: v for k, v in info.items() if k != 'lppd'}, f)
+    return info
+
+
+def warmup_mclmc(config: SamplerConfig, rng_key, init_params: dict, unnorm_log_posterior, n_devices: int,
+                 _ensemble=None):
+    """sampling.py:258-292.  Returns (step_size [n_devices], L [n_devices]); the warmed-up chain state stays
+    in the ensemble (`use_warmup_as_init`) when one is passed in, else (state, parameters) like the reference."""
+    model, x, y = unwrap_posterior(unnorm_log_posterior)
+    spec = model.spec
+    theta0 = spec.ravel(init_params).reshape(-1, spec.n_params)
+    kw = dict(desired_energy_var_start=config.desired_energy_var_start,
+              desired_energy_var_end=config.desired_energy_var_end, trust_in_estimate=config.trust_in_estimate,
+              num_effective_samples=config.num_effective_samples, step_size_init=config.step_size_init)
+    if config.diagonal_preconditioning:
+        raise NotImplementedError('diagonal_preconditioning is not implemented on the CUDA path')
+    if _ensemble is not None:
+        return run_warmup(_ensemble, theta0, rng_key, config.warmup_steps, **kw)
+    from .warmup import custom_mclmc_warmup
+    res = custom_mclmc_warmup(unnorm_log_posterior, diagonal_preconditioning=False, **kw).run(
+        rng_key, init_params, config.warmup_steps)
+    return res.state, {'step_size': res.parameters.step_size, 'L': res.parameters.L}

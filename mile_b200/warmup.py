@@ -1,0 +1,104 @@
+"""MCLMC warmup (mirror of src/training/warmup.py:155-568: custom_mclmc_warmup, mclmc_find_L_and_step_size,
+make_L_step_size_adaptation, make_adaptation_L, handle_nans).  Phases 1+2 (HOT LOOP A) run inside the
+persistent CUDA kernel (mile_mclmc_tune); phase 3 (HOT LOOP B) is the sampling kernel capturing every
+position into an HBM buffer, followed by one FFT-based ESS (diagnostics.effective_sample_size)."""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .engine import Ensemble
+from .probabilistic import unwrap_posterior
+from .types import AdaptationAlgorithm, AdaptationResults, IntegratorState, MCLMCAdaptationState, key_to_seed, split
+
+logger = logging.getLogger(__name__)
+
+PHASE_RATIO = (0.8, 0.1, 0.1)      # warmup.py:543
+LFACTOR = 0.4                      # warmup.py:224
+CHUNK = 10000                      # MCLMC steps per kernel launch
+
+
+def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, desired_energy_var_start,
+               desired_energy_var_end, trust_in_estimate, num_effective_samples, step_size_init,
+               fft_params_limit: int = 2000, fft_samples_limit: int = 10000):
+    """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C])."""
+    import torch
+    from .diagnostics import effective_sample_size
+    seed = key_to_seed(rng_key)
+    tune1, tune2, tune3 = (int(num_steps * r) for r in PHASE_RATIO)        # warmup.py:555-557
+    # blackjax.mcmc.mclmc.init with the SAME key as the tuning (warmup.py:539-541,552)
+    ens.init(theta0, seed=seed)
+    part1_key, part2_key = split(seed, 2)                                  # warmup.py:210
+    ens.tune_reset(step_size_init)                                         # warmup.py:204-209
+    cfg = ens.tune_cfg(tune1, tune2, desired_energy_var_start, desired_energy_var_end, trust_in_estimate,
+                       num_effective_samples)
+    done = 0
+    while done < tune1 + tune2:                                            # HOT LOOP A
+        n = min(CHUNK, tune1 + tune2 - done)
+        ens.tune(n, done, cfg, seed=part1_key)
+        done += n
+    if tune2 != 0:
+        ens.tune_finish_phase2()                                           # L = sqrt(sum var), warmup.py:387-390
+    eps, L, _ = ens.get_tuning()
+    if tune3 != 0:                                                         # HOT LOOP B, warmup.py:408-465
+        dev = torch.device(f'cuda:{ens.device}')
+        C, d = ens.n_chains, ens.d
+        pos = torch.empty((tune3, C, d), dtype=torch.float32, device=dev)
+        eps_d, L_d = torch.from_numpy(eps).to(dev), torch.from_numpy(L).to(dev)
+        with torch.cuda.device(dev):
+            done = 0
+            while done < tune3:
+                n = min(CHUNK, tune3 - done)
+                ens.sample_device(n, eps_d, L_d, step_base=done, n_thinning=1, sample_base=0, seed=part2_key,
+                                  samples_dev=pos, n_slots=tune3)
+                done += n
+            torch.cuda.synchronize(dev)
+            flat = pos
+            if d > fft_params_limit:                                       # warmup.py:442-449
+                g = torch.Generator(device='cpu').manual_seed(part2_key & ((1 << 63) - 1))
+                perm = torch.randperm(d, generator=g)[:fft_params_limit].to(dev)
+                flat = flat[:, :, perm]
+            if tune3 > fft_samples_limit:                                  # warmup.py:450-456
+                idx = torch.linspace(0, tune3 - 1, fft_samples_limit).to(torch.int64).to(dev)
+                flat = flat[idx]
+            n_eff_steps = float(tune3)
+            Ls = []
+            for c in range(C):
+                ess = effective_sample_size(flat[:, c][None])              # [1, samples, dim]
+                Ls.append(LFACTOR * float(eps[c]) * float(torch.mean(n_eff_steps / ess)))
+            L = np.asarray(Ls, np.float32)
+        ens.set_tuning(L=L)
+        del pos
+    return eps.astype(np.float32), L.astype(np.float32)
+
+
+def custom_mclmc_warmup(logdensity_fn, diagonal_preconditioning: bool = True, desired_energy_var_start: float = 5e-4,
+                        desired_energy_var_end: float = 5e-4, trust_in_estimate: float = 1.5,
+                        num_effective_samples: int = 100, step_size_init: float = 0.005) -> AdaptationAlgorithm:
+    """warmup.py:486-568 (same argument names and defaults)."""
+    if diagonal_preconditioning:
+        raise NotImplementedError('diagonal_preconditioning=True is off in every MCLMC YAML of the reference and is '
+                                  'not implemented on the CUDA path (SURVEY.md section 3.2)')
+    model, x, y = unwrap_posterior(logdensity_fn)
+    spec = model.spec
+
+    def run(rng_key, position, num_steps: int = 1000):
+        theta0 = spec.ravel(position)
+        batched = theta0.ndim == 2
+        theta0 = theta0.reshape(-1, spec.n_params)
+        ens = model.make_ensemble(theta0.shape[0], x, y)
+        try:
+            eps, L = run_warmup(ens, theta0, rng_key, num_steps, desired_energy_var_start=desired_energy_var_start,
+                                desired_energy_var_end=desired_energy_var_end, trust_in_estimate=trust_in_estimate,
+                                num_effective_samples=num_effective_samples, step_size_init=step_size_init)
+            th, u, lp, g = ens.get_state()
+        finally:
+            ens.close()
+        un = (lambda a: spec.unravel(a)) if batched else (lambda a: spec.unravel(a[0]))
+        state = IntegratorState(un(th), un(u), lp if batched else lp[0], un(g))
+        params = MCLMCAdaptationState(L if batched else L[0], eps if batched else eps[0],
+                                      np.ones(spec.n_params, np.float32))
+        return AdaptationResults(state, params)
+
+    return AdaptationAlgorithm(run)
