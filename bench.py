@@ -206,6 +206,7 @@ def run_ours(args):
     if args.tile_rows:
         ens.set_option('tile_rows', args.tile_rows)
     ens.set_data(X, y)
+    ens.set_test(Xt, yt)          # fused posterior-predictive LPPD fold at every kept sample
     th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * rank)
     ens.init(th0, seed=17 + rank)
     # short tuning run -> frozen (eps, L); fallback eps=0.02, L=sqrt(d)
@@ -227,7 +228,7 @@ def run_ours(args):
 
     def one_step(i):
         ens.sample_device(inner, eps_d, L_d, step_base=i * inner, n_thinning=N_THINNING,
-                          sample_base=i * n_slots, seed=1234, samples_dev=samples_d, n_slots=n_slots)
+                          sample_base=i * n_slots, seed=1234, samples_dev=samples_d, n_slots=n_slots, lppd=True)
 
     def barrier():
         if world > 1:
@@ -238,6 +239,7 @@ def run_ours(args):
         flush.zero_()
         one_step(i)
     barrier()
+    ens.lppd_reset()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = ens.launches
@@ -263,6 +265,12 @@ def run_ours(args):
         t_dev = float(t.item())
     chain_steps = world * C * inner * args.steps
     value = chain_steps / t_dev
+    # the one exchange step of the path: merge the per-chain online logsumexp states (NCCL all-gather)
+    from mile_b200.distributed import merge_lppd_states
+    t0 = time.perf_counter()
+    m_, s_, cnt_ = ens.lppd_state()
+    lppd_val, lppd_total = merge_lppd_states(m_, s_, cnt_, device=dev)
+    lppd_ms = 1e3 * (time.perf_counter() - t0)
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside) --------
     st = ens.get_state()
@@ -275,7 +283,7 @@ def run_ours(args):
     for i in range(e2e_steps):
         ens.set_data(Xp, y)
         ens.set_state(*st)
-        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i)
+        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=True)
         st = ens.get_state()
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -312,6 +320,8 @@ def run_ours(args):
                        'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()), 'parallelism': f'chains x{world}'},
             'grad_evals_per_s': 2 * value,
             'samples_finite': finite,
+            'lppd': {'value': lppd_val, 'samples': int(lppd_total), 'merge_ms': lppd_ms,
+                     'note': 'test-set logsumexp folded in-kernel at every kept sample; merged across ranks after the timed region'},
             'wall_s_timed_region': t_wall,
             'gpu_launches': int(launches),
             'clocks': clk,
