@@ -9,7 +9,8 @@ A bench "step" is ONE launch of the persistent sampler kernel: `inner` MCLMC ste
 chain of the ensemble wave (two full-batch gradient evaluations per chain-step), thinned samples
 captured in HBM.  Workload (N=1): BASELINE.json configs[1] -- UCI bikesharing shape, FCN 2x16,
 10 chains per split on one B200, synthetic data.  With --gpus N every rank
-runs its own 10-chain split (weak scaling; chains/splits shard with no data-path collective).
+runs its own block of 10 chains on the same split (weak scaling: the ensemble shards by chain with no
+data-path collective; the per-chain test-set logsumexp states are merged once at the end over NCCL).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -197,7 +198,7 @@ def run_ours(args):
     if args.inner:
         inner = args.inner
     ospec = o.make_spec(key)
-    X, y, Xt, yt = o.synthetic_data(key, seed=1234 + rank)   # every rank = its own split
+    X, y, Xt, yt = o.synthetic_data(key, seed=1234)   # same split on every rank; the CHAINS are what shards
     d = ospec.n_params
     spec = FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task)
     ens = Ensemble(spec, C, device=local)
