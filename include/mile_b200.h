@@ -172,6 +172,23 @@ int mile_lppd_state_host(mile_ctx* ctx, float* m, float* s, int64_t* count);
 int mile_predict(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t which, float* out_dev,
                  void* stream);
 
+/* ---- data-sharded variant (covertype, rows split across the GPUs of one box) -------- */
+/* Every rank holds ALL chains and 1/world of the training rows (mile_set_data with the local shard).  Each
+ * gradient evaluation = local value_and_grad (prior weighted 1/world) + ncclAllReduce(sum) of the packed
+ * [C, d+1] (gradient | log-density) buffer + an integrator-only kernel; all ranks apply identical updates, so
+ * the chain state stays replicated bit-identically.  The reference has no counterpart (it replicates the data on
+ * every virtual device, src/training/sampling.py:181-184); the arithmetic per step is the same as
+ * mile_mclmc_sample / mile_mclmc_tune.  NCCL is resolved with dlopen at run time. */
+int mile_nccl_unique_id(void* out128);   /* rank 0: 128-byte ncclUniqueId to broadcast to the other ranks */
+int mile_shard_init(mile_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world);
+int mile_shard_mclmc_init(mile_ctx* ctx, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream);
+int mile_shard_mclmc_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning,
+                            int64_t sample_base, const float* step_size_dev, const float* L_dev,
+                            const float* z_dev, uint64_t seed, float* samples_dev, int64_t n_slots,
+                            float* info_dev, void* stream);
+int mile_shard_mclmc_tune(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg,
+                          const float* z_dev, uint64_t seed, float* tune_info_dev, void* stream);
+
 /* ---- bookkeeping ----------------------------------------------------------------- */
 /* Number of kernels this library has launched since mile_create (bench `gpu_launches`). */
 int64_t mile_launch_count(const mile_ctx* ctx);

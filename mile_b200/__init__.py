@@ -5,7 +5,7 @@ Only the hot path named by BASELINE.json:north_star lives here: the C-ABI CUDA l
 Python seams (sampling.inference_loop, kernels.KERNELS['mclmc'], warmup.custom_mclmc_warmup,
 probabilistic.ProbabilisticModel, ...).  There is no CPU fallback.
 """
-from .engine import Ensemble, FCNSpec, lppd_from_state  # noqa: F401
+from .engine import Ensemble, FCNSpec, ShardedEnsemble, lppd_from_state  # noqa: F401
 from .config import PriorConfig, Sampler, SamplerConfig  # noqa: F401
 from .kernels import KERNELS, mclmc  # noqa: F401
 from .models import FCN  # noqa: F401
@@ -14,5 +14,5 @@ from .probabilistic import ProbabilisticModel  # noqa: F401
 from .sampling import inference_loop, warmup_mclmc  # noqa: F401
 from .warmup import custom_mclmc_warmup  # noqa: F401
 
-__all__ = ['Ensemble', 'FCNSpec', 'lppd_from_state', 'PriorConfig', 'Sampler', 'SamplerConfig', 'KERNELS', 'mclmc',
+__all__ = ['Ensemble', 'FCNSpec', 'ShardedEnsemble', 'lppd_from_state', 'PriorConfig', 'Sampler', 'SamplerConfig', 'KERNELS', 'mclmc',
            'FCN', 'Prior', 'PriorDist', 'ProbabilisticModel', 'inference_loop', 'warmup_mclmc', 'custom_mclmc_warmup']

@@ -10,7 +10,7 @@ CSRC = PKG / 'csrc'
 LIBDIR = PKG / '_lib'
 LIB = LIBDIR / 'libmile_b200.so'
 SOURCES = ['mile_api.cu', 'mile_microbench.cu']
-HEADERS = ['mile_device.cuh', 'mile_kernel.cuh', '../../include/mile_b200.h']
+HEADERS = ['mile_device.cuh', 'mile_kernel.cuh', 'mile_fast.cuh', 'mile_sharded.cuh', '../../include/mile_b200.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     LIBDIR.mkdir(exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, '-o', str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, '-o', str(LIB), *[str(CSRC / s) for s in SOURCES], '-ldl']
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, capture_output=True, text=True)

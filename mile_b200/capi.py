@@ -21,6 +21,7 @@ SYMBOLS = [
     'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
+    'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
 ]
 
 
@@ -100,6 +101,11 @@ def load():
     lib.mile_launch_count.restype = i64
     lib.mile_synchronize.argtypes = [vp]
     lib.mile_measure_fp32_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+    lib.mile_nccl_unique_id.argtypes = [vp]
+    lib.mile_shard_init.argtypes = [vp, vp, i32, i32]
+    lib.mile_shard_mclmc_init.argtypes = [vp, fp, fp, u64, vp]
+    lib.mile_shard_mclmc_sample.argtypes = [vp, i32, i64, i32, i64, fp, fp, fp, u64, fp, i64, fp, vp]
+    lib.mile_shard_mclmc_tune.argtypes = [vp, i32, i64, C.POINTER(TuneCfg), fp, u64, fp, vp]
     _LIB = lib
     return lib
 

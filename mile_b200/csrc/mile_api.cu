@@ -2,6 +2,10 @@
 // Owns the device buffers of one ensemble wave, plans the shared-memory carve-up and the
 // cluster shape, and launches the persistent kernel of mile_kernel.cuh.  Links cudart only.
 #include "mile_fast.cuh"
+#include "mile_sharded.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <math.h>
 #include <stdio.h>
@@ -21,6 +25,31 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 
 static const size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 
+// ---- data-sharded variant: NCCL resolved at run time (dlopen) so the library links cudart only ----
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.ok) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);   // the copy torch already loaded, else the system one
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(std::string("cannot load libnccl: ") + dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return fail("libnccl lacks required symbols");
+  g_nccl.ok = true;
+  return 0;
+}
+
 struct mile_ctx {
   mile_model_desc desc;
   DevModel M;
@@ -36,6 +65,9 @@ struct mile_ctx {
         *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
   float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
   float* carry = nullptr; int carry_valid = 0;
+  // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
+  void* nccl_comm = nullptr; int world = 1, rank = 0;
+  float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
   // staging for the *_host entry points
   std::vector<std::pair<void*, size_t>> scratch;  // slot -> (ptr, bytes)
   cudaStream_t own_stream = nullptr;
@@ -215,6 +247,7 @@ static void fill_common(mile_ctx* c, KParams& k) {
   k.lppd_m = c->lppd_m; k.lppd_s = c->lppd_s;
   k.carry = c->carry; k.carry_valid = c->carry_valid;
   k.refresh_mode = c->opt_refresh; k.thin = 1;
+  k.out_stride = c->d; k.prior_weight = 1.f;
 }
 
 // ---- small utility kernels ------------------------------------------------------------------
@@ -293,9 +326,11 @@ void mile_destroy(mile_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
-                  c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry};
+                  c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
+                  c->gl, c->scal, c->thb, c->ub, c->gb};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
+  if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -663,6 +698,141 @@ int mile_debug_read_profile(unsigned long long* out32, int reset) {
   return 0;
 }
 #endif
+
+
+#define NCK(call)                                                                                         \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
+int mile_nccl_unique_id(void* out128) {
+  if (!out128) return fail("null argument");
+  if (nccl_load()) return -1;
+  ncclUniqueId id;
+  NCK(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int mile_shard_init(mile_ctx* c, const void* unique_id128, int32_t rank, int32_t world) {
+  if (!c) return fail("null ctx");
+  if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+  CK(cudaSetDevice(c->device));
+  c->world = world; c->rank = rank;
+  if (world > 1) {
+    if (!unique_id128) return fail("unique id required for world > 1");
+    if (nccl_load()) return -1;
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, 128);
+    ncclComm_t comm;
+    NCK(g_nccl.CommInitRank(&comm, world, id, rank));
+    c->nccl_comm = comm;
+  }
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (!c->gl) {
+    CK(cudaMalloc(&c->gl, (size_t)c->C * (c->d + 1) * 4)); CK(cudaMalloc(&c->scal, (size_t)c->C * 16));
+    CK(cudaMalloc(&c->thb, Cd)); CK(cudaMalloc(&c->ub, Cd)); CK(cudaMalloc(&c->gb, Cd));
+    CK(cudaMemset(c->scal, 0, (size_t)c->C * 16));
+  }
+  return 0;
+}
+
+// local value_and_grad of the rank's row shard into the packed buffer, then all-reduce over the ranks
+static int shard_eval(mile_ctx* c, cudaStream_t st) {
+  Plan pl;
+  if (make_plan(c, c->C, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.mode = MODE_EVAL; pl.kp.theta_in = c->theta; pl.kp.grad_out = c->gl; pl.kp.lp_out = c->gl + c->d;
+  pl.kp.out_stride = c->d + 1; pl.kp.prior_weight = 1.f / (float)c->world; pl.kp.n_eval = c->C;
+  if (launch(c, pl, c->C, st)) return -1;
+  if (c->world > 1)
+    NCK(g_nccl.AllReduce(c->gl, c->gl, (size_t)c->C * (c->d + 1), ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, st));
+  return 0;
+}
+
+static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
+  S.stage = stage; S.s_local = s_local;
+  const size_t smem = ((size_t)8 * S.K.dS + 128) * 4;
+  auto kern = mile_integrator_kernel<256>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  if (smem > kSmemLimit) return fail("model too large for the integrator kernel");
+  kern<<<c->C, 256, smem, st>>>(S);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+static int shard_params(mile_ctx* c, ShardParams& S) {
+  memset(&S, 0, sizeof(S));
+  S.K.M = c->M; S.K.dS = round_up(c->d, 4); S.K.C = c->C;
+  fill_common(c, S.K);
+  S.gl = c->gl; S.scal = c->scal; S.thb = c->thb; S.ub = c->ub; S.gb = c->gb;
+  return 0;
+}
+
+int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (!c->gl) return fail("mile_shard_init has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  CK(cudaMemcpyAsync(c->theta, theta0_dev, Cd, cudaMemcpyDeviceToDevice, st));
+  if (shard_eval(c, st)) return -1;
+  // unit momentum: reuse MODE_INIT's generator by running the fused init on a zero-row problem is not possible;
+  // instead: INIT on the local shard (u only depends on z / seed), then overwrite (lp, grad) with the reduced ones
+  Plan pl;
+  if (make_plan(c, c->C, c->N, true, pl)) return -1;
+  fill_common(c, pl.kp);
+  pl.kp.mode = MODE_INIT; pl.kp.theta_in = theta0_dev; pl.kp.z = z0_dev; pl.kp.seed = seed;
+  if (launch(c, pl, c->C, st)) return -1;
+  CK(cudaMemcpy2DAsync(c->grad, (size_t)c->d * 4, c->gl, (size_t)(c->d + 1) * 4, (size_t)c->d * 4, c->C, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpy2DAsync(c->lp, 4, c->gl + c->d, (size_t)(c->d + 1) * 4, 4, c->C, cudaMemcpyDeviceToDevice, st));
+  c->carry_valid = 0;
+  return 0;
+}
+
+static int shard_run(mile_ctx* c, ShardParams& S, int n_steps, cudaStream_t st) {
+  for (int s = 0; s < n_steps; ++s) {
+    if (shard_integ(c, S, SH_BEGIN, s, st)) return -1;
+    if (shard_eval(c, st)) return -1;
+    if (shard_integ(c, S, SH_MID, s, st)) return -1;
+    if (shard_eval(c, st)) return -1;
+    if (shard_integ(c, S, SH_END, s, st)) return -1;
+  }
+  c->carry_valid = 0;
+  return 0;
+}
+
+int mile_shard_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
+                            const float* step_size_dev, const float* L_dev, const float* z_dev, uint64_t seed,
+                            float* samples_dev, int64_t n_slots, float* info_dev, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->gl) return fail("mile_shard_init has not been called");
+  if (!step_size_dev || !L_dev) return fail("step_size / L are required");
+  ShardParams S;
+  shard_params(c, S);
+  KParams& k = S.K;
+  k.n_steps = n_steps; k.step_base = step_base; k.thin = n_thinning; k.sample_base = sample_base; k.n_slots = n_slots;
+  k.eps = step_size_dev; k.L = L_dev; k.z = z_dev; k.seed = seed; k.samples = samples_dev; k.info = info_dev;
+  S.tune = 0;
+  return shard_run(c, S, n_steps, (cudaStream_t)stream);
+}
+
+int mile_shard_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg, const float* z_dev,
+                          uint64_t seed, float* tune_info_dev, void* stream) {
+  if (!c || !cfg) return fail("null argument");
+  if (!c->gl) return fail("mile_shard_init has not been called");
+  ShardParams S;
+  shard_params(c, S);
+  KParams& k = S.K;
+  k.n_steps = n_steps; k.step_base = step_base; k.z = z_dev; k.seed = seed; k.tune_info = tune_info_dev;
+  k.tune1 = cfg->tune1_steps; k.tune2 = cfg->tune2_steps; k.ev_start = cfg->desired_energy_var_start;
+  k.ev_end = cfg->desired_energy_var_end; k.trust = cfg->trust_in_estimate; k.neff = cfg->num_effective_samples;
+  S.tune = 1;
+  return shard_run(c, S, n_steps, (cudaStream_t)stream);
+}
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
 int mile_synchronize(mile_ctx* c) {

@@ -37,6 +37,8 @@ struct KParams {
   int tune1, tune2; float ev_start, ev_end, trust, neff;
   // eval / init / lppd / predict io
   const float* theta_in; float* lp_out; float* grad_out; float* pred_out; int n_eval, which;
+  int out_stride;        // row stride of grad_out / lp_out (d, or d+1 for the packed [C,d+1] all-reduce buffer)
+  float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)
   int dS, off_wp, off_th, off_u, off_g, off_thb, off_ub, off_gb, off_gpart, off_avgx, off_avgx2,
       off_pmap, off_red, off_tile, off_x;
@@ -235,9 +237,9 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
       pv = -lognorm - fabsf(dlt) / sc;
       pg = -((dlt > 0.f) - (dlt < 0.f)) / sc;
     }
-    const float g = s + pg;
+    const float g = s + pg * P.prior_weight;
     c.gg[i] = g;
-    v[0] += pv; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
+    v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   }
   block_sum<4, NT>(v, c.red, c.phase);
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
@@ -319,6 +321,83 @@ __device__ __forceinline__ float nan_to_num(float x) {
   if (isnan(x)) return 0.f;
   if (isinf(x)) return x > 0.f ? FLT_MAX : -FLT_MAX;
   return x;
+}
+
+// Per-chain scalars of the adaptive state (warmup.py:358-363) carried in registers (uniform across the block).
+struct TuneRegs { float time, xavg, epsmax, wtot; };
+
+// End of a tuning iteration (warmup.py:293-350): handle_nans, energy-variance step-size predictor, streaming
+// average of (x, x^2).  Returns the new step size; lp / dE / g2 / ug are updated in place.
+template <int NT, bool HAS_WP>
+__device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, float lp_old, float nf, long s_local,
+                                               float& lp, float& dE, float& g2, float& ug) {
+  const KParams& P = c.P;
+  const int d = P.M.d, tid = threadIdx.x, ch = c.chain;
+  float& t_time = t.time; float& t_xavg = t.xavg; float& t_epsmax = t.epsmax; float& t_wtot = t.wtot;
+  const long s = s_local;
+      // handle_nans (warmup.py:468-483)
+      const bool success = nf == 0.f;
+      if (!success) {
+        for (int i = tid; i < d; i += NT) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; if (HAS_WP) store_param(c, i, c.thb[i]); }
+        lp = lp_old;
+        t_epsmax = eps * 0.8f;
+        dE = 0.f;
+        float v[2] = {0.f, 0.f};
+        for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+        block_sum<2, NT>(v, c.red, c.phase);
+        g2 = v[0]; ug = v[1];
+      } else {
+        bool changed = false;
+        for (int i = tid; i < d; i += NT) {
+          const float u0 = c.uu[i], g0 = c.gg[i];
+          const float u1 = nan_to_num(u0), g1 = nan_to_num(g0);
+          if (u1 != u0 || g1 != g0 || isnan(u0) || isnan(g0)) { c.uu[i] = u1; c.gg[i] = g1; changed = true; }
+        }
+        lp = nan_to_num(lp);
+        t_epsmax = nan_to_num(t_epsmax);
+        dE = nan_to_num(dE);
+        if (__syncthreads_or(changed)) {
+          float v[2] = {0.f, 0.f};
+          for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+          block_sum<2, NT>(v, c.red, c.phase);
+          g2 = v[0]; ug = v[1];
+        }
+      }
+      // step-size predictor (warmup.py:302-322)
+      const long it = P.step_base + s;
+      const float total = (float)(P.tune1 + P.tune2 + 1);
+      float target;
+      if (P.ev_start > 2.0f) {
+        const float ex = expf(-(float)it / (total / 4.f));
+        target = P.ev_start * ex + P.ev_end * (1.f - ex);
+      } else {
+        const float progress = fminf((float)it / total, 1.f);
+        target = P.ev_start - (P.ev_start - P.ev_end) * progress;
+      }
+      const float decay = (P.neff - 1.f) / (P.neff + 1.f);
+      const float xi = dE * dE / ((float)d * target) + 1e-8f;
+      const float lx = logf(xi) / (6.f * P.trust);
+      const float wgt = expf(-0.5f * lx * lx);
+      t_xavg = decay * t_xavg + wgt * (xi / powf(eps, 6.f));
+      t_time = decay * t_time + wgt;
+      float eps_new = powf(t_xavg / t_time, -1.f / 6.f);
+      eps_new = (eps_new < t_epsmax ? eps_new : 0.f) + (eps_new > t_epsmax ? t_epsmax : 0.f);
+      // streaming average of (x, x^2) in phase 2 (warmup.py:341-348); phase 1 keeps it at 0
+      if (it >= P.tune1) {
+        const float w = (success ? 1.f : 0.f) * eps_new;
+        const float denom = t_wtot + w;
+        for (int i = tid; i < d; i += NT) {
+          const float x = c.th[i];
+          c.avgx[i] = (t_wtot * c.avgx[i] + w * x) / denom;
+          c.avgx2[i] = (t_wtot * c.avgx2[i] + w * (x * x)) / denom;
+        }
+        t_wtot += w;
+      }
+      if (P.tune_info && c.rank == 0 && tid == 0) {
+        float* o = P.tune_info + ((long)s * P.C + ch) * 4;
+        o[0] = dE; o[1] = eps_new; o[2] = t_epsmax; o[3] = success ? 1.f : 0.f;
+      }
+  return eps_new;
 }
 
 // Online logsumexp over the test split for the current theta (weights already in c.wp).
@@ -481,8 +560,8 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     if (!stepping) {
       if (P.mode == MODE_EVAL) {
         if (c.rank == 0) {
-          for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * d + i] = c.gg[i];
-          if (tid == 0) P.lp_out[ch] = lp_new;
+          for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * P.out_stride + i] = c.gg[i];
+          if (tid == 0) P.lp_out[(long)ch * (P.out_stride == d ? 1 : P.out_stride)] = lp_new;
         }
       } else {
         // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
@@ -520,68 +599,9 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
         o[0] = lp; o[1] = dK; o[2] = dE;
       }
     } else {
-      // handle_nans (warmup.py:468-483)
-      const bool success = nf == 0.f;
-      if (!success) {
-        for (int i = tid; i < d; i += NT) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; store_param(c, i, c.thb[i]); }
-        lp = lp_old;
-        t_epsmax = eps * 0.8f;
-        dE = 0.f;
-        float v[2] = {0.f, 0.f};
-        for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-        block_sum<2, NT>(v, c.red, c.phase);
-        g2 = v[0]; ug = v[1];
-      } else {
-        bool changed = false;
-        for (int i = tid; i < d; i += NT) {
-          const float u0 = c.uu[i], g0 = c.gg[i];
-          const float u1 = nan_to_num(u0), g1 = nan_to_num(g0);
-          if (u1 != u0 || g1 != g0 || isnan(u0) || isnan(g0)) { c.uu[i] = u1; c.gg[i] = g1; changed = true; }
-        }
-        lp = nan_to_num(lp);
-        t_epsmax = nan_to_num(t_epsmax);
-        dE = nan_to_num(dE);
-        if (__syncthreads_or(changed)) {
-          float v[2] = {0.f, 0.f};
-          for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-          block_sum<2, NT>(v, c.red, c.phase);
-          g2 = v[0]; ug = v[1];
-        }
-      }
-      // step-size predictor (warmup.py:302-322)
-      const long it = P.step_base + s;
-      const float total = (float)(P.tune1 + P.tune2 + 1);
-      float target;
-      if (P.ev_start > 2.0f) {
-        const float ex = expf(-(float)it / (total / 4.f));
-        target = P.ev_start * ex + P.ev_end * (1.f - ex);
-      } else {
-        const float progress = fminf((float)it / total, 1.f);
-        target = P.ev_start - (P.ev_start - P.ev_end) * progress;
-      }
-      const float decay = (P.neff - 1.f) / (P.neff + 1.f);
-      const float xi = dE * dE / ((float)d * target) + 1e-8f;
-      const float lx = logf(xi) / (6.f * P.trust);
-      const float wgt = expf(-0.5f * lx * lx);
-      t_xavg = decay * t_xavg + wgt * (xi / powf(eps, 6.f));
-      t_time = decay * t_time + wgt;
-      float eps_new = powf(t_xavg / t_time, -1.f / 6.f);
-      eps_new = (eps_new < t_epsmax ? eps_new : 0.f) + (eps_new > t_epsmax ? t_epsmax : 0.f);
-      // streaming average of (x, x^2) in phase 2 (warmup.py:341-348); phase 1 keeps it at 0
-      if (it >= P.tune1) {
-        const float w = (success ? 1.f : 0.f) * eps_new;
-        const float denom = t_wtot + w;
-        for (int i = tid; i < d; i += NT) {
-          const float x = c.th[i];
-          c.avgx[i] = (t_wtot * c.avgx[i] + w * x) / denom;
-          c.avgx2[i] = (t_wtot * c.avgx2[i] + w * (x * x)) / denom;
-        }
-        t_wtot += w;
-      }
-      if (P.tune_info && c.rank == 0 && tid == 0) {
-        float* o = P.tune_info + ((long)s * P.C + ch) * 4;
-        o[0] = dE; o[1] = eps_new; o[2] = t_epsmax; o[3] = success ? 1.f : 0.f;
-      }
+      TuneRegs tr{t_time, t_xavg, t_epsmax, t_wtot};
+      const float eps_new = tune_epilogue<NT, true>(c, tr, eps, lp_old, nf, s, lp, dE, g2, ug);
+      t_time = tr.time; t_xavg = tr.xavg; t_epsmax = tr.epsmax; t_wtot = tr.wtot;
       eps = eps_new;
       __syncthreads();
     }

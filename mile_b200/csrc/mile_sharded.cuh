@@ -1,0 +1,91 @@
+// mile_sharded.cuh -- integrator-only kernel for the DATA-SHARDED variant (covertype):
+// the training rows are split across ranks, every rank holds all chains, and each gradient evaluation is
+//     local value_and_grad (MODE_EVAL of mile_mclmc_kernel, prior weighted 1/world)
+//  -> ncclAllReduce(sum) of the packed [C, d+1] buffer (gradient | log-density)
+//  -> this kernel: the B / A / refresh / bookkeeping stage that consumes it.
+// Every rank applies the identical update to its replica of the chain state (same inputs, same order), so the
+// replicas stay bit-identical without any further exchange.  One CTA per chain.
+#pragma once
+#include "mile_kernel.cuh"
+
+enum { SH_BEGIN = 0, SH_MID = 1, SH_END = 2 };
+
+struct ShardParams {
+  KParams K;              // model, chain state pointers, eps/L, z/seed, thinning, samples, info, tuning fields
+  const float* gl;        // [C, d+1] all-reduced (gradient | log-density) -- consumed by SH_MID / SH_END
+  float* scal;            // [C, 4]  lp_old, dK carried between the three launches of a step
+  float* thb; float* ub; float* gb;   // [C,d] state backups for handle_nans (tune mode)
+  int stage, tune;
+  long s_local;           // index of the step inside this call (noise / info / tune_info addressing)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_constant__ ShardParams S) {
+  extern __shared__ __align__(16) float smem[];
+  const KParams& P = S.K;
+  const int d = P.M.d, dS = P.dS, ch = blockIdx.x, tid = threadIdx.x;
+  Ctx c(P);
+  c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0;
+  c.th = smem; c.uu = smem + dS; c.gg = smem + 2 * dS; c.thb = smem + 3 * dS; c.ub = smem + 4 * dS; c.gb = smem + 5 * dS;
+  c.avgx = smem + 6 * dS; c.avgx2 = smem + 7 * dS; c.red = smem + 8 * dS;
+  c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
+  const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
+  float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];
+  for (int i = tid; i < d; i += NT) {
+    c.th[i] = P.theta[(long)ch * d + i];
+    c.uu[i] = P.u[(long)ch * d + i];
+    c.gg[i] = fresh ? S.gl[(long)ch * (d + 1) + i] : P.grad[(long)ch * d + i];
+  }
+  __syncthreads();
+  float v[3] = {0.f, 0.f, 0.f};
+  for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; v[2] += isfinite(c.th[i]) ? 0.f : 1.f; }
+  block_sum<3, NT>(v, c.red, c.phase);
+  float g2 = v[0], ug = v[1];
+  const float nf = v[2];
+  const bool tune = S.tune != 0;
+  float eps = tune ? P.t_eps[ch] : P.eps[ch];
+  const float Lc = tune ? P.t_L[ch] : P.L[ch];
+  const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
+  const int nslot = P.refresh_mode ? 2 : 1;
+  float lp_old = S.scal[ch * 4 + 0], dK = S.scal[ch * 4 + 1];
+  if (S.stage == SH_BEGIN) {
+    lp_old = lp; dK = 0.f;
+    if (tune) for (int i = tid; i < d; i += NT) {
+      S.thb[(long)ch * d + i] = c.th[i]; S.ub[(long)ch * d + i] = c.uu[i]; S.gb[(long)ch * d + i] = c.gg[i];
+    }
+    if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, S.s_local, 0, nslot, ug);
+  }
+  if (S.stage != SH_END) {
+    dK += esh_update<NT>(c, eps, S.stage == SH_BEGIN ? b1 : b2, g2, ug);
+    const float st = eps * 0.5f;
+    for (int i = tid; i < d; i += NT) c.th[i] += st * c.uu[i];
+  } else {
+    dK += esh_update<NT>(c, eps, b1, g2, ug);
+    refresh_momentum<NT>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, S.s_local, nslot - 1, nslot, ug);
+    float dE = dK - lp + lp_old;
+    if (!tune) {
+      if (P.info && tid == 0) { float* o = P.info + ((long)S.s_local * P.C + ch) * 3; o[0] = lp; o[1] = dK; o[2] = dE; }
+      const long idx = P.step_base + S.s_local;
+      if (idx % P.thin == 0) {
+        const long slot = idx / P.thin - P.sample_base;
+        if (P.samples && slot >= 0 && slot < P.n_slots)
+          for (int i = tid; i < d; i += NT) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
+      }
+    } else {
+      for (int i = tid; i < d; i += NT) {
+        c.thb[i] = S.thb[(long)ch * d + i]; c.ub[i] = S.ub[(long)ch * d + i]; c.gb[i] = S.gb[(long)ch * d + i];
+        c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i];
+      }
+      TuneRegs tr{P.t_time[ch], P.t_xavg[ch], P.t_epsmax[ch], P.t_wtot[ch]};
+      eps = tune_epilogue<NT, false>(c, tr, eps, lp_old, nf, S.s_local, lp, dE, g2, ug);
+      for (int i = tid; i < d; i += NT) { P.avg_x[(long)ch * d + i] = c.avgx[i]; P.avg_x2[(long)ch * d + i] = c.avgx2[i]; }
+      if (tid == 0) { P.t_time[ch] = tr.time; P.t_xavg[ch] = tr.xavg; P.t_epsmax[ch] = tr.epsmax; P.t_wtot[ch] = tr.wtot; P.t_eps[ch] = eps; }
+    }
+  }
+  for (int i = tid; i < d; i += NT) {
+    P.theta[(long)ch * d + i] = c.th[i];
+    P.u[(long)ch * d + i] = c.uu[i];
+    P.grad[(long)ch * d + i] = c.gg[i];
+  }
+  if (tid == 0) { P.lp[ch] = lp; S.scal[ch * 4 + 0] = lp_old; S.scal[ch * 4 + 1] = dK; }
+}

@@ -297,6 +297,73 @@ class Ensemble:
         return out.cpu().numpy()
 
 
+class ShardedEnsemble(Ensemble):
+    """Data-sharded variant (covertype): every rank holds all chains and 1/world of the
+    training rows; gradients are all-reduced over NCCL at every evaluation.  Call `set_data` with the LOCAL shard."""
+
+    def __init__(self, spec: FCNSpec, n_chains: int, device: int = 0, rank: int | None = None, world: int | None = None,
+                 **options):
+        super().__init__(spec, n_chains, device, **options)
+        import torch
+        import torch.distributed as dist
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank, self.world = rank, world
+        uid = np.zeros(128, np.uint8)
+        if world > 1:
+            if rank == 0:
+                capi.check(self.lib.mile_nccl_unique_id(capi.host_ptr(uid)))
+            t = torch.from_numpy(uid).to(f'cuda:{device}' if dist.get_backend() == 'nccl' else 'cpu')
+            dist.broadcast(t, 0)
+            uid = np.ascontiguousarray(t.cpu().numpy())
+        capi.check(self.lib.mile_shard_init(self.h, capi.host_ptr(uid), rank, world))
+
+    @staticmethod
+    def shard_rows(n_rows: int, rank: int, world: int) -> slice:
+        per = -(-n_rows // world)
+        return slice(rank * per, min(n_rows, (rank + 1) * per))
+
+    def _dev(self, a):
+        import torch
+        return None if a is None else torch.from_numpy(_f32(a)).to(f'cuda:{self.device}')
+
+    def init(self, theta0, z0=None, seed: int = 0):
+        import torch
+        th, z = self._dev(np.reshape(theta0, (self.n_chains, self.d))), self._dev(z0)
+        capi.check(self.lib.mile_shard_mclmc_init(self.h, _dev_ptr(th), _dev_ptr(z), seed, _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def sample(self, n_steps, step_size, L, *, step_base=0, n_thinning=1, z=None, seed=0, keep=True, info=False,
+               lppd=False):
+        import torch
+        if lppd:
+            raise NotImplementedError('fused LPPD is not part of the sharded step loop; use lppd_accumulate')
+        C_, d = self.n_chains, self.d
+        eps, Ls = self._dev(np.broadcast_to(step_size, (C_,))), self._dev(np.broadcast_to(L, (C_,)))
+        first, last = -(-step_base // n_thinning), (step_base + n_steps - 1) // n_thinning
+        n_slots = max(0, last - first + 1) if keep and n_steps > 0 else 0
+        dev = eps.device
+        smp = torch.empty((n_slots, C_, d), dtype=torch.float32, device=dev) if keep else None
+        inf = torch.empty((n_steps, C_, 3), dtype=torch.float32, device=dev) if info else None
+        zd = self._dev(z)
+        capi.check(self.lib.mile_shard_mclmc_sample(self.h, n_steps, step_base, n_thinning, first, _dev_ptr(eps),
+                                                    _dev_ptr(Ls), _dev_ptr(zd), seed, _dev_ptr(smp), n_slots,
+                                                    _dev_ptr(inf), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return (None if smp is None else smp.cpu().numpy()), (None if inf is None else inf.cpu().numpy())
+
+    def tune(self, n_steps, step_base, cfg: capi.TuneCfg, z=None, seed=0, info=False):
+        import torch
+        dev = f'cuda:{self.device}'
+        inf = torch.empty((n_steps, self.n_chains, 4), dtype=torch.float32, device=dev) if info else None
+        zd = self._dev(z)
+        capi.check(self.lib.mile_shard_mclmc_tune(self.h, n_steps, step_base, C.byref(cfg), _dev_ptr(zd), seed,
+                                                  _dev_ptr(inf), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return None if inf is None else inf.cpu().numpy()
+
+
 def lppd_from_state(m: np.ndarray, s: np.ndarray, total_samples: int) -> float:
     """Merge per-chain online (max, sum-exp) states into LPPD = mean_n logsumexp_{c,s}(lp) - log(C*S)
     (src/inference/metrics.py:296-312)."""
