@@ -116,7 +116,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   const int dS = round_up(M.d, 4);
   int S1 = 0;
   for (int l = 1; l <= M.NL; ++l) S1 += M.sA[l];
-  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 128;
+  const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 192;
   // ---- fast path: warp-specialised pipeline (mile_fast.cuh) for hidden width 16 + Gaussian head ----
   {
     bool ok = want_resident && c->opt_fast && M.task == MILE_TASK_REGRESSION &&
@@ -146,7 +146,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
         k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
         k.off_gpart = o; o += 2 * (dS + 4);
         k.off_pmap = o; o += 2 * dS;
-        k.off_red = o; o += 128;
+        k.off_red = o; o += 192;
         k.off_tile = o; o += (int)tile + TRg * M.sA[0];
         k.off_x = o; if (res) o += rows_res * M.sA[0];
         pl.G = G; pl.TR = T; pl.resident = res; pl.rows_res = rows_res; pl.fast = 1; pl.fast_fp = M.dimp[0];
@@ -187,7 +187,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
   k.off_gpart = o; o += 2 * (dS + 4);
   k.off_pmap = o; o += 2 * dS;
-  k.off_red = o; o += 128;
+  k.off_red = o; o += 192;
   k.off_tile = o; o += (int)tile + TR * M.sA[0];
   k.off_x = o; if (resident) o += rows_res * M.sA[0];
   pl.G = G; pl.TR = TR; pl.resident = resident; pl.rows_res = rows_res;
@@ -754,7 +754,7 @@ static int shard_eval(mile_ctx* c, cudaStream_t st) {
 
 static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
   S.stage = stage; S.s_local = s_local;
-  const size_t smem = ((size_t)8 * S.K.dS + 128) * 4;
+  const size_t smem = ((size_t)8 * S.K.dS + 192) * 4;
   auto kern = mile_integrator_kernel<256>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   if (smem > kSmemLimit) return fail("model too large for the integrator kernel");

@@ -70,8 +70,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Deterministic block-wide sum of NV values; every thread returns the same totals.
 // scratch: [2][NV_MAX=4][NT/32] floats, phase toggles between the two halves so
 // that a single __syncthreads per reduction suffices.
-template <int NV, int NT>
+template <int NV, int NT, int BAR = 0>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch, int& phase) {
+  // BAR == 0: the whole block (NT threads) takes part and synchronises with bar 0;
+  // BAR != 0: only the first NT threads of the block take part and use the named barrier BAR.
   constexpr int MILE_NWARPS = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* buf = scratch + phase * (4 * MILE_NWARPS);
@@ -80,7 +82,8 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch, int& p
     float s = warp_sum(v[k]);
     if (lane == 0) buf[k * MILE_NWARPS + warp] = s;
   }
-  __syncthreads();
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     float s = 0.f;

@@ -48,7 +48,8 @@ struct Ctx {
   const KParams& P;
   float *wp, *th, *uu, *gg, *thb, *ub, *gb, *gpart, *avgx, *avgx2, *red, *tile, *xbuf, *xstream;
   int* pmap;
-  int phase;   // block_sum double-buffer phase
+  int phase;   // block_sum double-buffer phase (whole block)
+  float* red2; int phase2;   // scratch / phase of the integrator thread group (named barrier 1)
   int rank, G, chain;
   __device__ Ctx(const KParams& p) : P(p) {}
 };
@@ -194,15 +195,18 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
   PROF(5);
 }
 
+#define MILE_RED(c, BAR) ((BAR) ? (c).red2 : (c).red)
+#define MILE_PH(c, BAR) ((BAR) ? (c).phase2 : (c).phase)
+
 // DSMEM all-reduce of the cluster's partial gradients + prior: afterwards gg = full gradient of
 // the log-posterior (bit-identical in every CTA), returns the log-posterior value.  Also returns
 // sum g^2, sum u.g and the number of non-finite entries of theta for the next B-step / handle_nans.
-template <int NT>
+template <int NT, int BAR>
 __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float& g2, float& ug, float& nonfinite) {
+  // (the caller has already executed the cluster / block barrier that publishes every CTA's gpart)
   const KParams& P = c.P;
   const DevModel& M = P.M;
   cg::cluster_group cluster = cg::this_cluster();
-  if (c.G > 1) cluster.sync(); else __syncthreads();
   // rank loops are unrolled to the maximum cluster size with predication so that all remote (DSMEM)
   // loads of an element are in flight together (~200 cycles each when serialised)
   const float* rp[16];
@@ -241,14 +245,14 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
     c.gg[i] = g;
     v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   }
-  block_sum<4, NT>(v, c.red, c.phase);
+  block_sum<4, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
   return v[0] + ll;
 }
 
 // ESH momentum update B(coef) (blackjax esh_dynamics_momentum_update_one_step, sqrt_diag_cov = 1).
 // delta-small-safe forms: 1-zeta = -expm1(-delta), log(1+p+(1-p)zeta^2) - ln2 = log1p(-(1-p)(1-zeta^2)/2).
-template <int NT>
+template <int NT, int BAR = 0>
 __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
   const int d = c.P.M.d;
   const float gn = sqrtf(g2);
@@ -265,7 +269,7 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
     c.uu[i] = raw;
     v[0] += raw * raw;
   }
-  block_sum<1, NT>(v, c.red, c.phase);
+  block_sum<1, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   const float rn = sqrtf(v[0]);
   const float rinv = rn > 1e-13f ? 1.f / rn : 1.f;
   for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= rinv;
@@ -273,7 +277,8 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
 }
 
-// A(coef): theta += eps*coef*u and refresh the padded weight image.
+// A(coef): theta += eps*coef*u and refresh the padded weight image (the caller synchronises the block
+// before the next gradient evaluation reads the image).
 template <int NT>
 __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
   const int d = c.P.M.d;
@@ -283,7 +288,6 @@ __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
     c.th[i] = t;
     store_param(c, i, t);
   }
-  __syncthreads();
 }
 
 __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step_local, int slot, int nslot, int i) {
@@ -292,7 +296,7 @@ __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step
 }
 
 // partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
-template <int NT>
+template <int NT, int BAR = 0>
 __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, long step_local, int slot, int nslot,
                                                  float& ug_out) {
   const KParams& P = c.P;
@@ -300,7 +304,7 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
   if (isinf(L)) {
     float v[1] = {0.f};
     for (int i = threadIdx.x; i < d; i += NT) v[0] += c.uu[i] * c.gg[i];
-    block_sum<1, NT>(v, c.red, c.phase);
+    block_sum<1, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
     ug_out = v[0];
     return;
   }
@@ -311,7 +315,7 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
     c.uu[i] = w;
     v[0] += w * w; v[1] += w * c.gg[i];
   }
-  block_sum<2, NT>(v, c.red, c.phase);
+  block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   const float inv = 1.f / sqrtf(v[0]);
   for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= inv;
   ug_out = v[1] * inv;
@@ -328,7 +332,7 @@ struct TuneRegs { float time, xavg, epsmax, wtot; };
 
 // End of a tuning iteration (warmup.py:293-350): handle_nans, energy-variance step-size predictor, streaming
 // average of (x, x^2).  Returns the new step size; lp / dE / g2 / ug are updated in place.
-template <int NT, bool HAS_WP>
+template <int NT, bool HAS_WP, int BAR = 0>
 __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, float lp_old, float nf, long s_local,
                                                float& lp, float& dE, float& g2, float& ug) {
   const KParams& P = c.P;
@@ -344,7 +348,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         dE = 0.f;
         float v[2] = {0.f, 0.f};
         for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-        block_sum<2, NT>(v, c.red, c.phase);
+        block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
         g2 = v[0]; ug = v[1];
       } else {
         bool changed = false;
@@ -356,10 +360,12 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         lp = nan_to_num(lp);
         t_epsmax = nan_to_num(t_epsmax);
         dE = nan_to_num(dE);
-        if (__syncthreads_or(changed)) {
+        float chv[1] = {changed ? 1.f : 0.f};
+        block_sum<1, NT, BAR>(chv, MILE_RED(c, BAR), MILE_PH(c, BAR));
+        if (chv[0] != 0.f) {
           float v[2] = {0.f, 0.f};
           for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-          block_sum<2, NT>(v, c.red, c.phase);
+          block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
           g2 = v[0]; ug = v[1];
         }
       }
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   c.wp = smem + P.off_wp; c.th = smem + P.off_th; c.uu = smem + P.off_u; c.gg = smem + P.off_g;
   c.thb = smem + P.off_thb; c.ub = smem + P.off_ub; c.gb = smem + P.off_gb; c.gpart = smem + P.off_gpart;
   c.avgx = smem + P.off_avgx; c.avgx2 = smem + P.off_avgx2; c.pmap = reinterpret_cast<int*>(smem + P.off_pmap);
-  c.red = smem + P.off_red; c.tile = smem + P.off_tile;
+  c.red = smem + P.off_red; c.red2 = c.red + 128; c.phase2 = 0; c.tile = smem + P.off_tile;
   c.xstream = c.tile + M.tile_floats;              // one streamed X tile [TR][sA[0]]
   c.xbuf = P.resident ? smem + P.off_x : c.xstream;  // resident slice or the streamed tile
   const int d = M.d, ch = c.chain;
@@ -510,6 +516,11 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
 
   // ---- one loop over gradient evaluations: 1 for EVAL / INIT, 2 per MCLMC step otherwise.  A single
   //      call site keeps GE::run inlined exactly once (shared address space stays visible to ptxas).
+  //      The integrator phases (B / A / refresh / reductions / tuning) touch only d ~ 500-2000 floats: they run
+  //      on the first NI = 128 threads (one warp per scheduler) with named barrier 1, so the scalar math is
+  //      issued by 4 warps instead of all of them; everybody else waits at the block barrier.
+  constexpr int NI = 128, IB = 1;
+  const bool integ = tid < NI;
   const bool stepping = P.mode == MODE_SAMPLE || P.mode == MODE_TUNE;
   const bool tune = P.mode == MODE_TUNE;
   float g2 = 0.f, ug = 0.f, nf = 0.f;
@@ -517,20 +528,20 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   float t_time = 0.f, t_xavg = 0.f, t_epsmax = INFINITY, t_wtot = 0.f;
   const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
   const int nslot = P.refresh_mode ? 2 : 1;
-  if (stepping) {
+  if (stepping && integ) {
     lp = P.lp[ch];
     eps = tune ? P.t_eps[ch] : P.eps[ch];
     Lc = tune ? P.t_L[ch] : P.L[ch];
     if (tune) {
       t_time = P.t_time[ch]; t_xavg = P.t_xavg[ch]; t_epsmax = P.t_epsmax[ch]; t_wtot = P.t_wtot[ch];
-      for (int i = tid; i < d; i += NT) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
+      for (int i = tid; i < d; i += NI) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
     }
     if (P.carry_valid) {
       g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
     } else {  // cached gradient: sum g^2 and u.g for the first B-step
       float v[2] = {0.f, 0.f};
-      for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-      block_sum<2, NT>(v, c.red, c.phase);
+      for (int i = tid; i < d; i += NI) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+      block_sum<2, NI, IB>(v, c.red2, c.phase2);
       g2 = v[0]; ug = v[1];
     }
   }
@@ -540,85 +551,90 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
 #pragma unroll 1
   for (int e = 0; e < n_evals; ++e) {
     const int h = e & 1, s = e >> 1;   // half-step h of MCLMC step s
-    if (stepping) {
+    if (stepping && integ) {
       if (h == 0) {
         lp_old = lp; dK = 0.f;
-        if (tune) for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
-        if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, s, 0, nslot, ug);
+        if (tune) for (int i = tid; i < d; i += NI) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+        if (P.refresh_mode) refresh_momentum<NI, IB>(c, 0.5f * eps, Lc, s, 0, nslot, ug);
       }
       // B(b1) A(1/2) grad | B(1-2 b1) A(1/2) grad
-      dK += esh_update<NT>(c, eps, h == 0 ? b1 : b2, g2, ug);
+      dK += esh_update<NI, IB>(c, eps, h == 0 ? b1 : b2, g2, ug);
       PROF(8);
-      position_update<NT>(c, eps, 0.5f);
+      position_update<NI>(c, eps, 0.5f);
       PROF(9);
     }
+    __syncthreads();   // weight image (and, after a handle_nans restore, theta) visible to the whole block
     float* gp = c.gpart + (e & 1) * (P.dS + 4);
     GE::run(c, r0, r1, gp);
     PROF(10);
-    const float lp_new = cluster_reduce_grad<NT>(c, gp, g2, ug, nf);
-    PROF(11);
-    if (!stepping) {
-      if (P.mode == MODE_EVAL) {
-        if (c.rank == 0) {
-          for (int i = tid; i < d; i += NT) P.grad_out[(long)ch * P.out_stride + i] = c.gg[i];
-          if (tid == 0) P.lp_out[(long)ch * (P.out_stride == d ? 1 : P.out_stride)] = lp_new;
+    if (c.G > 1) cluster.sync(); else __syncthreads();   // publishes every CTA's partial gradient
+    if (integ) {
+      const float lp_new = cluster_reduce_grad<NI, IB>(c, gp, g2, ug, nf);
+      PROF(11);
+      if (!stepping) {
+        if (P.mode == MODE_EVAL) {
+          if (c.rank == 0) {
+            for (int i = tid; i < d; i += NI) P.grad_out[(long)ch * P.out_stride + i] = c.gg[i];
+            if (tid == 0) P.lp_out[(long)ch * (P.out_stride == d ? 1 : P.out_stride)] = lp_new;
+          }
+        } else {
+          // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
+          float v[1] = {0.f};
+          for (int i = tid; i < d; i += NI) {
+            const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+            c.uu[i] = zz; v[0] += zz * zz;
+          }
+          block_sum<1, NI, IB>(v, c.red2, c.phase2);
+          const float inv = 1.f / sqrtf(v[0]);
+          if (c.rank == 0) {
+            for (int i = tid; i < d; i += NI) {
+              P.theta[(long)ch * d + i] = c.th[i];
+              P.u[(long)ch * d + i] = c.uu[i] * inv;
+              P.grad[(long)ch * d + i] = c.gg[i];
+            }
+            if (tid == 0) P.lp[ch] = lp_new;
+          }
         }
       } else {
-        // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
-        float v[1] = {0.f};
-        for (int i = tid; i < d; i += NT) {
-          const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
-          c.uu[i] = zz; v[0] += zz * zz;
-        }
-        block_sum<1, NT>(v, c.red, c.phase);
-        const float inv = 1.f / sqrtf(v[0]);
-        if (c.rank == 0) {
-          for (int i = tid; i < d; i += NT) {
-            P.theta[(long)ch * d + i] = c.th[i];
-            P.u[(long)ch * d + i] = c.uu[i] * inv;
-            P.grad[(long)ch * d + i] = c.gg[i];
+        lp = lp_new;
+        if (h == 1) {
+          // ---- end of MCLMC step s: last B, partial refresh, energy bookkeeping ----------------------
+          dK += esh_update<NI, IB>(c, eps, b1, g2, ug);
+          PROF(8);
+          refresh_momentum<NI, IB>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
+          PROF(12);
+          float dE = dK - lp + lp_old;
+          if (!tune) {
+            if (P.info && c.rank == 0 && tid == 0) {
+              float* o = P.info + ((long)s * P.C + ch) * 3;
+              o[0] = lp; o[1] = dK; o[2] = dE;
+            }
+            // thinned sample capture (sampling.py:152-164)
+            const long idx = P.step_base + s;
+            if (idx % P.thin == 0) {
+              const long slot = idx / P.thin - P.sample_base;
+              if (P.samples && c.rank == 0 && slot >= 0 && slot < P.n_slots)
+                for (int i = tid; i < d; i += NI) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
+            }
+          } else {
+            TuneRegs tr{t_time, t_xavg, t_epsmax, t_wtot};
+            const float eps_new = tune_epilogue<NI, true, IB>(c, tr, eps, lp_old, nf, s, lp, dE, g2, ug);
+            t_time = tr.time; t_xavg = tr.xavg; t_epsmax = tr.epsmax; t_wtot = tr.wtot;
+            eps = eps_new;
           }
-          if (tid == 0) P.lp[ch] = lp_new;
         }
       }
-      if (c.G > 1) cluster.sync();
-      return;
     }
-    lp = lp_new;
-    if (h == 0) continue;
-    // ---- end of MCLMC step s: last B, partial refresh, energy bookkeeping --------------------------
-    dK += esh_update<NT>(c, eps, b1, g2, ug);
-    PROF(8);
-    refresh_momentum<NT>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, s, nslot - 1, nslot, ug);
-    PROF(12);
-    float dE = dK - lp + lp_old;
-
-    if (!tune) {
-      if (P.info && c.rank == 0 && tid == 0) {
-        float* o = P.info + ((long)s * P.C + ch) * 3;
-        o[0] = lp; o[1] = dK; o[2] = dE;
-      }
-    } else {
-      TuneRegs tr{t_time, t_xavg, t_epsmax, t_wtot};
-      const float eps_new = tune_epilogue<NT, true>(c, tr, eps, lp_old, nf, s, lp, dE, g2, ug);
-      t_time = tr.time; t_xavg = tr.xavg; t_epsmax = tr.epsmax; t_wtot = tr.wtot;
-      eps = eps_new;
+    if (!stepping) break;
+    // fused posterior-predictive fold at every kept position (whole block; the weight image still holds theta)
+    if (h == 1 && !tune && P.do_lppd && (P.step_base + s) % P.thin == 0) {
       __syncthreads();
-    }
-    // thinned sample capture (sampling.py:152-164) + fused posterior-predictive fold
-    if (!tune) {
-      const long idx = P.step_base + s;
-      if (idx % P.thin == 0) {
-        const long slot = idx / P.thin - P.sample_base;
-        if (P.samples && c.rank == 0 && slot >= 0 && slot < P.n_slots)
-          for (int i = tid; i < d; i += NT) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
-        if (P.do_lppd) lppd_fold<NT>(c, ch);
-      }
+      lppd_fold<NT>(c, ch);
     }
   }
   // ---- epilogue: write state back ------------------------------------------------------------
-  if (c.rank == 0) {
-    for (int i = tid; i < d; i += NT) {
+  if (stepping && integ && c.rank == 0) {
+    for (int i = tid; i < d; i += NI) {
       P.theta[(long)ch * d + i] = c.th[i];
       P.u[(long)ch * d + i] = c.uu[i];
       P.grad[(long)ch * d + i] = c.gg[i];

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   Ctx c(P);
   c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0;
   c.th = smem; c.uu = smem + dS; c.gg = smem + 2 * dS; c.thb = smem + 3 * dS; c.ub = smem + 4 * dS; c.gb = smem + 5 * dS;
-  c.avgx = smem + 6 * dS; c.avgx2 = smem + 7 * dS; c.red = smem + 8 * dS;
+  c.avgx = smem + 6 * dS; c.avgx2 = smem + 7 * dS; c.red = smem + 8 * dS; c.red2 = c.red + 128; c.phase2 = 0;
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
   float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];

@@ -34,9 +34,10 @@ def test_world1_sharded_equals_fused(name):
     sa, ia = a.sample(n, 0.01, 20.0, z=z, n_thinning=2, info=True)
     b = ShardedEnsemble(spec, C, rank=0, world=1); b.set_data(X, y); b.init(th0, z0)
     sb, ib = b.sample(n, 0.01, 20.0, z=z, n_thinning=2, info=True)
+    # (the two paths reduce over different thread groupings: agreement to fp32 rounding, not bit-exact)
     for u, v in zip(a.get_state(), b.get_state()):
-        assert rel(v, u) <= 2e-6
-    assert rel(sb, sa) <= 2e-6 and np.max(np.abs(ib - ia)) <= 2e-5 * np.max(np.abs(ia[..., 0]))
+        assert rel(v, u) <= 1e-5
+    assert rel(sb, sa) <= 1e-5 and np.max(np.abs(ib - ia)) <= 2e-5 * np.max(np.abs(ia[..., 0]))
     # tuning loop as well
     tc = a.tune_cfg(4, 4, 0.5, 0.1, 1.5, 100)
     zt = rng.standard_normal((8, C, d)).astype(np.float32)
