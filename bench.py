@@ -36,6 +36,7 @@ WORKLOADS = {
     'protein_2x16': ('protein_2x16', 10, 200),
     'covertype_ref': ('covertype_ref', 12, 500),
     'airfoil_3x16_1024': ('airfoil_3x16', 1024, 200),
+    'wide_4x256': ('wide_4x256', 8, 10),          # HBM-resident chain-batched GEMM path (no fused LPPD fold)
 }
 N_THINNING = 10  # every reference MCLMC YAML (experiments/*/mclmc.yaml: n_thinning 10)
 
@@ -207,16 +208,19 @@ def run_ours(args):
     if args.tile_rows:
         ens.set_option('tile_rows', args.tile_rows)
     ens.set_data(X, y)
-    ens.set_test(Xt, yt)          # fused posterior-predictive LPPD fold at every kept sample
-    th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * rank)
+    fused_lppd = key != 'wide_4x256'
+    if fused_lppd:
+        ens.set_test(Xt, yt)      # fused posterior-predictive LPPD fold at every kept sample
+    th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * rank, scale=0.3 if key != 'wide_4x256' else 0.05)
     ens.init(th0, seed=17 + rank)
     # short tuning run -> frozen (eps, L); fallback eps=0.02, L=sqrt(d)
     eps = np.full(C, 0.02, np.float32)
     L = np.full(C, np.sqrt(d), np.float32)
     if not args.no_tune:
         ens.tune_reset(0.01)
-        tc = ens.tune_cfg(800, 100, 0.5, 0.1, 1.5, 100)
-        ens.tune(900, 0, tc, seed=99 + rank)
+        nt1, nt2 = (800, 100) if key != 'wide_4x256' else (40, 10)
+        tc = ens.tune_cfg(nt1, nt2, 0.5, 0.1, 1.5, 100)
+        ens.tune(nt1 + nt2, 0, tc, seed=99 + rank)
         ens.tune_finish_phase2()
         e, l, _ = ens.get_tuning()
         if np.all(np.isfinite(e)) and np.all(e > 0) and np.all(np.isfinite(l)) and np.all(l > 0):
@@ -229,7 +233,7 @@ def run_ours(args):
 
     def one_step(i):
         ens.sample_device(inner, eps_d, L_d, step_base=i * inner, n_thinning=N_THINNING,
-                          sample_base=i * n_slots, seed=1234, samples_dev=samples_d, n_slots=n_slots, lppd=True)
+                          sample_base=i * n_slots, seed=1234, samples_dev=samples_d, n_slots=n_slots, lppd=fused_lppd)
 
     def barrier():
         if world > 1:
@@ -240,7 +244,8 @@ def run_ours(args):
         flush.zero_()
         one_step(i)
     barrier()
-    ens.lppd_reset()
+    if fused_lppd:
+        ens.lppd_reset()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = ens.launches
@@ -269,8 +274,10 @@ def run_ours(args):
     # the one exchange step of the path: merge the per-chain online logsumexp states (NCCL all-gather)
     from mile_b200.distributed import merge_lppd_states
     t0 = time.perf_counter()
-    m_, s_, cnt_ = ens.lppd_state()
-    lppd_val, lppd_total = merge_lppd_states(m_, s_, cnt_, device=dev)
+    lppd_val, lppd_total = None, 0
+    if fused_lppd:
+        m_, s_, cnt_ = ens.lppd_state()
+        lppd_val, lppd_total = merge_lppd_states(m_, s_, cnt_, device=dev)
     lppd_ms = 1e3 * (time.perf_counter() - t0)
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside) --------
@@ -284,7 +291,7 @@ def run_ours(args):
     for i in range(e2e_steps):
         ens.set_data(Xp, y)
         ens.set_state(*st)
-        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=True)
+        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=fused_lppd)
         st = ens.get_state()
     barrier()
     t_e2e = time.perf_counter() - t0

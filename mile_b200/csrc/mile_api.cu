@@ -3,6 +3,7 @@
 // cluster shape, and launches the persistent kernel of mile_kernel.cuh.  Links cudart only.
 #include "mile_fast.cuh"
 #include "mile_sharded.cuh"
+#include "mile_wide.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -68,6 +69,10 @@ struct mile_ctx {
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
   void* nccl_comm = nullptr; int world = 1, rank = 0;
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
+  // wide / large-d path (mile_wide.cuh): HBM-resident activations, chain-batched GEMMs
+  int wide = 0; long w_rows = 0; int w_chains = 0, w_kslices = 1, w_nblk = 0;
+  float *w_act = nullptr, *w_delta[2] = {nullptr, nullptr}, *w_part = nullptr, *w_llpart = nullptr, *w_ones = nullptr;
+  float* w_gl = nullptr;   // packed [n, d+1] output of a stand-alone value_and_grad call
   // staging for the *_host entry points
   std::vector<std::pair<void*, size_t>> scratch;  // slot -> (ptr, bytes)
   cudaStream_t own_stream = nullptr;
@@ -289,6 +294,8 @@ static void* scratch(mile_ctx* c, int slot, size_t bytes) {
 
 extern "C" {
 
+static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st);
+
 const char* mile_last_error(void) { return g_err.c_str(); }
 int mile_version(void) { return 100; }
 
@@ -317,6 +324,13 @@ int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, m
   CK(cudaMalloc(&c->carry, 2 * Cb));
   CK(cudaMemset(c->theta, 0, Cd)); CK(cudaMemset(c->u, 0, Cd)); CK(cudaMemset(c->grad, 0, Cd)); CK(cudaMemset(c->lp, 0, Cb));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  {  // shapes the shared-memory kernels cannot hold run on the HBM-resident layer-by-layer path
+    Plan probe;
+    if (make_plan(c, n_chains, 4096, true, probe) != 0) {
+      if (desc->activation == MILE_ACT_GELU) { mile_destroy(c); return fail("gelu is not supported on the wide path"); }
+      c->wide = 1; g_err.clear();
+    }
+  }
   *out = c;
   return 0;
 }
@@ -327,7 +341,8 @@ void mile_destroy(mile_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
-                  c->gl, c->scal, c->thb, c->ub, c->gb};
+                  c->gl, c->scal, c->thb, c->ub, c->gb, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
+                  c->w_ones, c->w_gl};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -431,6 +446,14 @@ int mile_logpost_value_and_grad(mile_ctx* c, const float* theta_dev, int32_t n, 
   if (!c) return fail("null ctx");
   if (!c->X) return fail("mile_set_data has not been called");
   if (n < 1) return fail("n must be >= 1");
+  if (c->wide) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (wide_eval(c, theta_dev, n, nullptr, 1.f, st)) return -1;
+    const size_t rowb = (size_t)(c->d + 1) * 4;
+    CK(cudaMemcpy2DAsync(grad_dev, (size_t)c->d * 4, c->w_gl, rowb, (size_t)c->d * 4, n, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(lp_dev, 4, c->w_gl + c->d, rowb, 4, n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   Plan pl;
   if (make_plan(c, n, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
@@ -453,9 +476,21 @@ int mile_logpost_value_and_grad_host(mile_ctx* c, const float* theta, int32_t n,
   return 0;
 }
 
+int mile_shard_init(mile_ctx* c, const void* unique_id128, int32_t rank, int32_t world);
+int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream);
+int mile_shard_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
+                            const float* step_size_dev, const float* L_dev, const float* z_dev, uint64_t seed,
+                            float* samples_dev, int64_t n_slots, float* info_dev, void* stream);
+int mile_shard_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg, const float* z_dev,
+                          uint64_t seed, float* tune_info_dev, void* stream);
+
 int mile_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream) {
   if (!c) return fail("null ctx");
   if (!c->X) return fail("mile_set_data has not been called");
+  if (c->wide) {   // HBM-resident layer-by-layer path: same launch structure as the data-sharded variant, world = 1
+    if (!c->gl && mile_shard_init(c, nullptr, 0, 1)) return -1;
+    return mile_shard_mclmc_init(c, theta0_dev, z0_dev, seed, stream);
+  }
   Plan pl;
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
@@ -519,6 +554,12 @@ int mile_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n
   if (lppd && !c->Xt) return fail("lppd requested but mile_set_test has not been called");
   if (!step_size_dev || !L_dev) return fail("step_size / L are required");
   if (n_steps == 0) return 0;
+  if (c->wide) {
+    if (lppd) return fail("the fused LPPD fold is not available on the wide path");
+    if (!c->gl && mile_shard_init(c, nullptr, 0, 1)) return -1;
+    return mile_shard_mclmc_sample(c, n_steps, step_base, n_thinning, sample_base, step_size_dev, L_dev, z_dev, seed,
+                                   samples_dev, n_slots, info_dev, stream);
+  }
   Plan pl;
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
@@ -583,6 +624,10 @@ int mile_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const mile_
   if (!c || !cfg) return fail("null argument");
   if (!c->X) return fail("mile_set_data has not been called");
   if (n_steps <= 0) return 0;
+  if (c->wide) {
+    if (!c->gl && mile_shard_init(c, nullptr, 0, 1)) return -1;
+    return mile_shard_mclmc_tune(c, n_steps, step_base, cfg, z_dev, seed, tune_info_dev, stream);
+  }
   Plan pl;
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
@@ -739,8 +784,112 @@ int mile_shard_init(mile_ctx* c, const void* unique_id128, int32_t rank, int32_t
   return 0;
 }
 
+
+// ---- wide path orchestration ----------------------------------------------------------------------------
+static int wide_alloc(mile_ctx* c, int n_chains) {
+  if (c->w_act && c->w_rows == c->N && c->w_chains >= n_chains) return 0;
+  float** ptrs[] = {&c->w_act, &c->w_delta[0], &c->w_delta[1], &c->w_part, &c->w_llpart, &c->w_ones, &c->w_gl};
+  for (float** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+  const DevModel& M = c->M;
+  const long N = c->N;
+  long act_per_row = 0; int maxw = 0; long maxio = 0;
+  for (int l = 1; l <= M.NL; ++l) { act_per_row += M.dims[l]; if (M.dims[l] > maxw) maxw = M.dims[l]; }
+  for (int l = 0; l < M.NL; ++l) { long io = (long)M.dims[l] * M.dims[l + 1]; if (io > maxio) maxio = io; }
+  c->w_kslices = (int)((N + 1023) / 1024); if (c->w_kslices > 64) c->w_kslices = 64; if (c->w_kslices < 1) c->w_kslices = 1;
+  c->w_nblk = (int)((N + 255) / 256);
+  CK(cudaMalloc(&c->w_act, (size_t)n_chains * N * act_per_row * 4));
+  CK(cudaMalloc(&c->w_delta[0], (size_t)n_chains * N * maxw * 4));
+  CK(cudaMalloc(&c->w_delta[1], (size_t)n_chains * N * maxw * 4));
+  CK(cudaMalloc(&c->w_part, (size_t)n_chains * c->w_kslices * maxio * 4));
+  CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4));
+  CK(cudaMalloc(&c->w_ones, (size_t)N * 4));
+  CK(cudaMalloc(&c->w_gl, (size_t)n_chains * (c->d + 1) * 4));
+  fill_kernel<<<148, 256>>>(c->w_ones, N, 1.f);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  c->w_rows = N; c->w_chains = n_chains;
+  return 0;
+}
+
+static int wide_gemm(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.N + WG_BN - 1) / WG_BN, (g.M + WG_BM - 1) / WG_BM, g.nbatch * g.kslices);
+  wide_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// value_and_grad of n chains (theta [n,d]) over the local rows into the packed buffer gl [n, d+1]
+static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st) {
+  if (wide_alloc(c, n > c->C ? n : c->C)) return -1;
+  if (!gl) gl = c->w_gl;
+  const DevModel& M = c->M;
+  const long N = c->N;
+  const int d = c->d, NL = M.NL;
+  std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N][dims[l]]
+  for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N * M.dims[l];
+  auto act = [&](int l) { return c->w_act + aoff[l]; };
+  for (int l = 0; l < NL; ++l) {              // forward
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    const int IN = M.dims[l], OUT = M.dims[l + 1];
+    if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
+    else { g.A = act(l); g.a_batch = N * IN; g.sam = IN; g.sak = 1; }
+    g.B = theta + M.kern_off[l]; g.b_batch = d; g.sbk = OUT; g.sbn = 1;
+    g.C = act(l + 1); g.c_batch = N * OUT; g.ldc = OUT; g.M = (int)N; g.N = OUT; g.K = IN; g.kslices = 1;
+    g.epi = l < NL - 1 ? 1 : 2; g.bias = theta + M.bias_off[l]; g.bias_batch = d; g.act = M.act; g.nbatch = n;
+    if (wide_gemm(c, g, st)) return -1;
+  }
+  const int K = M.dims[NL];
+  float* dcur = c->w_delta[(NL - 1) & 1];
+  wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, c->w_llpart);
+  CK(cudaGetLastError());
+  c->launches++;
+  (void)K;
+  for (int l = NL - 1; l >= 0; --l) {         // dW_l, db_l, then the delta of the layer below
+    const int IN = M.dims[l], OUT = M.dims[l + 1];
+    float* D = c->w_delta[l & 1];
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = 1; g.sak = M.sA[0]; }
+    else { g.A = act(l); g.a_batch = N * IN; g.sam = 1; g.sak = IN; }
+    g.B = D; g.b_batch = N * OUT; g.sbk = OUT; g.sbn = 1;
+    g.M = IN; g.N = OUT; g.K = (int)N; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
+    g.C = c->w_part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
+    if (wide_gemm(c, g, st)) return -1;
+    wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
+                                                 d + 1, (long)IN * OUT, n);
+    GemmArgs b; memset(&b, 0, sizeof(b));     // bias gradient: 1^T D
+    b.A = c->w_ones; b.a_batch = 0; b.sam = 0; b.sak = 1;
+    b.B = D; b.b_batch = N * OUT; b.sbk = OUT; b.sbn = 1;
+    b.M = 1; b.N = OUT; b.K = (int)N; b.kslices = c->w_kslices; b.nbatch = n; b.epi = 0;
+    b.C = c->w_part; b.c_slice = OUT; b.c_batch = (long)c->w_kslices * OUT; b.ldc = OUT;
+    if (wide_gemm(c, b, st)) return -1;
+    wide_slice_reduce_kernel<<<32, 256, 0, st>>>(c->w_part, b.c_batch, b.c_slice, c->w_kslices, gl + M.bias_off[l], d + 1,
+                                                (long)OUT, n);
+    CK(cudaGetLastError());
+    c->launches += 2;
+    if (l > 0) {
+      GemmArgs w; memset(&w, 0, sizeof(w));
+      w.A = D; w.a_batch = N * OUT; w.sam = OUT; w.sak = 1;
+      w.B = theta + M.kern_off[l]; w.b_batch = d; w.sbk = 1; w.sbn = OUT;     // B(k=j, n=i) = W[i][j]
+      w.C = c->w_delta[(l - 1) & 1]; w.c_batch = N * IN; w.ldc = IN; w.M = (int)N; w.N = IN; w.K = OUT; w.kslices = 1;
+      w.epi = 3; w.aux = act(l); w.aux_batch = N * IN; w.ldaux = IN; w.act = M.act; w.nbatch = n;
+      if (wide_gemm(c, w, st)) return -1;
+    }
+  }
+  wide_finalize_kernel<<<n, 256, 0, st>>>(M, theta, gl, c->w_llpart, c->w_nblk, prior_weight);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
 // local value_and_grad of the rank's row shard into the packed buffer, then all-reduce over the ranks
 static int shard_eval(mile_ctx* c, cudaStream_t st) {
+  if (c->wide) {
+    if (wide_eval(c, c->theta, c->C, c->gl, 1.f / (float)c->world, st)) return -1;
+    if (c->world > 1)
+      NCK(g_nccl.AllReduce(c->gl, c->gl, (size_t)c->C * (c->d + 1), ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, st));
+    return 0;
+  }
   Plan pl;
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
   fill_common(c, pl.kp);
@@ -754,11 +903,7 @@ static int shard_eval(mile_ctx* c, cudaStream_t st) {
 
 static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
   S.stage = stage; S.s_local = s_local;
-  const size_t smem = ((size_t)8 * S.K.dS + 192) * 4;
-  auto kern = mile_integrator_kernel<256>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-  if (smem > kSmemLimit) return fail("model too large for the integrator kernel");
-  kern<<<c->C, 256, smem, st>>>(S);
+  mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
   CK(cudaGetLastError());
   c->launches++;
   return 0;
@@ -780,13 +925,9 @@ int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_
   const size_t Cd = (size_t)c->C * c->d * 4;
   CK(cudaMemcpyAsync(c->theta, theta0_dev, Cd, cudaMemcpyDeviceToDevice, st));
   if (shard_eval(c, st)) return -1;
-  // unit momentum: reuse MODE_INIT's generator by running the fused init on a zero-row problem is not possible;
-  // instead: INIT on the local shard (u only depends on z / seed), then overwrite (lp, grad) with the reduced ones
-  Plan pl;
-  if (make_plan(c, c->C, c->N, true, pl)) return -1;
-  fill_common(c, pl.kp);
-  pl.kp.mode = MODE_INIT; pl.kp.theta_in = theta0_dev; pl.kp.z = z0_dev; pl.kp.seed = seed;
-  if (launch(c, pl, c->C, st)) return -1;
+  mile_unit_momentum_kernel<256><<<c->C, 256, 0, st>>>(c->u, z0_dev, seed, c->d);
+  CK(cudaGetLastError());
+  c->launches++;
   CK(cudaMemcpy2DAsync(c->grad, (size_t)c->d * 4, c->gl, (size_t)(c->d + 1) * 4, (size_t)c->d * 4, c->C, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpy2DAsync(c->lp, 4, c->gl + c->d, (size_t)(c->d + 1) * 4, 4, c->C, cudaMemcpyDeviceToDevice, st));
   c->carry_valid = 0;

@@ -21,21 +21,20 @@ struct ShardParams {
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_constant__ ShardParams S) {
-  extern __shared__ __align__(16) float smem[];
+  // works IN PLACE on the global chain state (every element is owned by one thread: i = tid mod NT), so it has
+  // no shared-memory size limit and also serves the wide / large-d path (mile_wide.cuh)
+  __shared__ float red[192];
   const KParams& P = S.K;
-  const int d = P.M.d, dS = P.dS, ch = blockIdx.x, tid = threadIdx.x;
+  const int d = P.M.d, ch = blockIdx.x, tid = threadIdx.x;
   Ctx c(P);
-  c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0;
-  c.th = smem; c.uu = smem + dS; c.gg = smem + 2 * dS; c.thb = smem + 3 * dS; c.ub = smem + 4 * dS; c.gb = smem + 5 * dS;
-  c.avgx = smem + 6 * dS; c.avgx2 = smem + 7 * dS; c.red = smem + 8 * dS; c.red2 = c.red + 128; c.phase2 = 0;
+  c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0; c.phase2 = 0;
+  c.th = P.theta + (long)ch * d; c.uu = P.u + (long)ch * d; c.gg = P.grad + (long)ch * d;
+  c.thb = S.thb + (long)ch * d; c.ub = S.ub + (long)ch * d; c.gb = S.gb + (long)ch * d;
+  c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 128;
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
   float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];
-  for (int i = tid; i < d; i += NT) {
-    c.th[i] = P.theta[(long)ch * d + i];
-    c.uu[i] = P.u[(long)ch * d + i];
-    c.gg[i] = fresh ? S.gl[(long)ch * (d + 1) + i] : P.grad[(long)ch * d + i];
-  }
+  if (fresh) for (int i = tid; i < d; i += NT) c.gg[i] = S.gl[(long)ch * (d + 1) + i];
   __syncthreads();
   float v[3] = {0.f, 0.f, 0.f};
   for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; v[2] += isfinite(c.th[i]) ? 0.f : 1.f; }
@@ -50,9 +49,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   float lp_old = S.scal[ch * 4 + 0], dK = S.scal[ch * 4 + 1];
   if (S.stage == SH_BEGIN) {
     lp_old = lp; dK = 0.f;
-    if (tune) for (int i = tid; i < d; i += NT) {
-      S.thb[(long)ch * d + i] = c.th[i]; S.ub[(long)ch * d + i] = c.uu[i]; S.gb[(long)ch * d + i] = c.gg[i];
-    }
+    if (tune) for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
     if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, S.s_local, 0, nslot, ug);
   }
   if (S.stage != SH_END) {
@@ -72,20 +69,27 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
           for (int i = tid; i < d; i += NT) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
       }
     } else {
-      for (int i = tid; i < d; i += NT) {
-        c.thb[i] = S.thb[(long)ch * d + i]; c.ub[i] = S.ub[(long)ch * d + i]; c.gb[i] = S.gb[(long)ch * d + i];
-        c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i];
-      }
       TuneRegs tr{P.t_time[ch], P.t_xavg[ch], P.t_epsmax[ch], P.t_wtot[ch]};
       eps = tune_epilogue<NT, false>(c, tr, eps, lp_old, nf, S.s_local, lp, dE, g2, ug);
-      for (int i = tid; i < d; i += NT) { P.avg_x[(long)ch * d + i] = c.avgx[i]; P.avg_x2[(long)ch * d + i] = c.avgx2[i]; }
       if (tid == 0) { P.t_time[ch] = tr.time; P.t_xavg[ch] = tr.xavg; P.t_epsmax[ch] = tr.epsmax; P.t_wtot[ch] = tr.wtot; P.t_eps[ch] = eps; }
     }
   }
-  for (int i = tid; i < d; i += NT) {
-    P.theta[(long)ch * d + i] = c.th[i];
-    P.u[(long)ch * d + i] = c.uu[i];
-    P.grad[(long)ch * d + i] = c.gg[i];
-  }
   if (tid == 0) { P.lp[ch] = lp; S.scal[ch * 4 + 0] = lp_old; S.scal[ch * 4 + 1] = dK; }
+}
+
+// blackjax generate_unit_vector for all chains: u = z / |z| (z host-supplied or the same Philox draw MODE_INIT uses)
+template <int NT>
+__global__ void __launch_bounds__(NT) mile_unit_momentum_kernel(float* __restrict__ u, const float* __restrict__ z0,
+                                                                unsigned long long seed, int d) {
+  __shared__ float red[64];
+  int phase = 0;
+  const int ch = blockIdx.x;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < d; i += NT) {
+    const float zz = z0 ? z0[(long)ch * d + i] : philox_normal(seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+    u[(long)ch * d + i] = zz; v[0] += zz * zz;
+  }
+  block_sum<1, NT>(v, red, phase);
+  const float inv = 1.f / sqrtf(v[0]);
+  for (int i = threadIdx.x; i < d; i += NT) u[(long)ch * d + i] *= inv;
 }

@@ -1,0 +1,185 @@
+// mile_wide.cuh -- HBM-resident layer-by-layer path for networks that do not fit the shared-memory kernels
+// (wide / large-d configs such as the 4x256 complexity-ablation shape, d = 201 218).
+//
+// The per-chain value_and_grad becomes a sequence of chain-batched GEMMs with fused epilogues
+//   forward   A_{l+1}[c] = act(A_l[c] W_l[c] + b_l[c])                 [N x in] [in x out]
+//   backward  D_{l-1}[c] = act'(A_l[c]) .* (D_l[c] W_l[c]^T)           [N x out][out x in]
+//   dW_l[c]   = A_l[c]^T D_l[c]  (split-K over the rows, two-pass deterministic reduce),  db_l = 1^T D_l
+// followed by the same integrator-only kernel the data-sharded variant uses (mile_sharded.cuh).
+// The GEMM core here is a plain FP32 SIMT tile kernel (128x128x16 tiles, 8x8 register micro-tiles): exact fp32
+// like the reference.  The tcgen05 / TMEM version of this core (3xTF32 split) is the planned replacement
+// (DESIGN.md section 4.4); the orchestration, epilogues and parity tests stay.
+#pragma once
+#include "mile_device.cuh"
+
+struct GemmArgs {
+  const float* A; long a_batch; long sam, sak;     // A(m,k) = A[b*a_batch + m*sam + k*sak]
+  const float* B; long b_batch; long sbk, sbn;     // B(k,n) = B[b*b_batch + k*sbk + n*sbn]
+  float* C; long c_batch; long ldc;                // C(m,n) = C[b*c_batch + s*c_slice + m*ldc + n]
+  int M, N, K, kslices; long c_slice;
+  int epi;                                         // 0 none | 1 +bias, act | 2 +bias | 3 * act'(aux value)
+  const float* bias; long bias_batch;
+  const float* aux; long aux_batch; long ldaux;
+  int act, nbatch;
+};
+
+__device__ __forceinline__ float act_value(int act, float z) {
+  float a, da;
+  act_eval(act, z, a, da);
+  return a;
+}
+// act' from the activation VALUE (valid for identity / relu / sigmoid / tanh / leaky_relu)
+__device__ __forceinline__ float act_deriv_from_value(int act, float a) {
+  switch (act) {
+    case MILE_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case MILE_ACT_SIGMOID: return a * (1.f - a);
+    case MILE_ACT_TANH: return 1.f - a * a;
+    case MILE_ACT_LEAKY_RELU: return a >= 0.f ? 1.f : 0.01f;
+    default: return 1.f;
+  }
+}
+
+#define WG_BM 128
+#define WG_BN 128
+#define WG_BK 16
+
+__global__ void __launch_bounds__(256) wide_gemm_kernel(const GemmArgs g) {
+  __shared__ float As[WG_BK][WG_BM + 4];
+  __shared__ float Bs[WG_BK][WG_BN + 4];
+  const int b = blockIdx.z / g.kslices, ks = blockIdx.z % g.kslices;
+  const int m0 = blockIdx.y * WG_BM, n0 = blockIdx.x * WG_BN;
+  const int kper = ((g.K + g.kslices - 1) / g.kslices + WG_BK - 1) / WG_BK * WG_BK;
+  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
+  const float* A = g.A + (long)b * g.a_batch;
+  const float* B = g.B + (long)b * g.b_batch;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader index maps: consecutive threads follow the unit-stride dimension of each operand
+  const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
+  for (int k0 = kbeg; k0 < kend; k0 += WG_BK) {
+#pragma unroll
+    for (int e = 0; e < (WG_BM * WG_BK) / 256; ++e) {
+      const int idx = tid + e * 256;
+      const int kk = a_kfast ? (idx % WG_BK) : (idx / WG_BM), mm = a_kfast ? (idx / WG_BK) : (idx % WG_BM);
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < kend) ? __ldg(A + (long)m * g.sam + (long)k * g.sak) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < (WG_BN * WG_BK) / 256; ++e) {
+      const int idx = tid + e * 256;
+      const int kk = b_nfast ? (idx / WG_BN) : (idx % WG_BK), nn = b_nfast ? (idx % WG_BN) : (idx / WG_BK);
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < kend) ? __ldg(B + (long)k * g.sbk + (long)n * g.sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < WG_BK; ++kk) {
+      float a[8], bb[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* C = g.C + (long)b * g.c_batch + (long)ks * g.c_slice;
+  const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
+  const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.epi == 1) v = act_value(g.act, v + bias[n]);
+      else if (g.epi == 2) v = v + bias[n];
+      else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n]);
+      C[(long)m * g.ldc + n] = v;
+    }
+  }
+}
+
+// sum the split-K slices: dst[b*dst_batch + e] = sum_s src[b*src_batch + s*slice + e]   (fixed order)
+__global__ void wide_slice_reduce_kernel(const float* __restrict__ src, long src_batch, long slice, int kslices,
+                                         float* __restrict__ dst, long dst_batch, long n, int nbatch) {
+  const long total = n * nbatch;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long b = t / n, e = t % n;
+    float s = 0.f;
+    for (int k = 0; k < kslices; ++k) s += src[b * src_batch + k * slice + e];
+    dst[b * dst_batch + e] = s;
+  }
+}
+
+// per (chain, row): log-likelihood term and d/d(out) (probabilistic.py:93-109); block partial sums of ll
+__global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const float* __restrict__ out, float* __restrict__ dout,
+                                                          const void* __restrict__ y, long N, float* __restrict__ llpart) {
+  __shared__ float red[64];
+  int phase = 0;
+  const int c = blockIdx.y, K = M.dims[M.NL];
+  const long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  float ll = 0.f;
+  if (r < N) {
+    const float* o = out + ((long)c * N + r) * K;
+    float* dd = dout + ((long)c * N + r) * K;
+    if (M.task == MILE_TASK_REGRESSION) {
+      const float yv = reinterpret_cast<const float*>(y)[r], mu = o[0], s = o[1];
+      const float e = expf(s), sigma = fminf(fmaxf(e, 1e-6f), 1e6f);
+      const float inside = (e > 1e-6f && e < 1e6f) ? 1.f : 0.f;
+      const float s2 = sigma * sigma, res = yv - mu, q = res * res / s2;
+      ll = (logf(6.283185307179586f * s2) + q) / -2.f;
+      float dmu = res / s2, ds = (q - 1.f) * inside;
+      if (isnan(ll)) { ll = 0.f; dmu = 0.f; ds = 0.f; }
+      dd[0] = dmu * M.n_batches; dd[1] = ds * M.n_batches;
+      for (int k = 2; k < K; ++k) dd[k] = 0.f;
+    } else {
+      const int yi = reinterpret_cast<const int*>(y)[r];
+      float m = o[0];
+      for (int k = 1; k < K; ++k) m = fmaxf(m, o[k]);
+      float se = 0.f;
+      for (int k = 0; k < K; ++k) se += expf(o[k] - m);
+      ll = o[yi] - (m + logf(se));
+      const bool bad = isnan(ll);
+      for (int k = 0; k < K; ++k) dd[k] = bad ? 0.f : (-expf(o[k] - m) / se + (k == yi ? 1.f : 0.f)) * M.n_batches;
+      if (bad) ll = 0.f;
+    }
+  }
+  float v[1] = {ll};
+  block_sum<1, 256>(v, red, phase);
+  if (threadIdx.x == 0) llpart[(long)c * gridDim.x + blockIdx.x] = v[0];
+}
+
+// gl[c][0..d) += prior gradient * w ; gl[c][d] = n_batches * sum(ll partials) + w * log prior   (one CTA per chain)
+__global__ void __launch_bounds__(256) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
+                                                            const float* __restrict__ llpart, int nblk, float prior_weight) {
+  __shared__ float red[64];
+  int phase = 0;
+  const int c = blockIdx.x, d = M.d;
+  const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
+  const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
+  float v[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < d; i += 256) {
+    const float dlt = theta[(long)c * d + i] - loc;
+    float pv, pg;
+    if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
+    else { pv = -lognorm - fabsf(dlt) / sc; pg = -((dlt > 0.f) - (dlt < 0.f)) / sc; }
+    gl[(long)c * (d + 1) + i] += pg * prior_weight;
+    v[0] += pv;
+  }
+  for (int i = threadIdx.x; i < nblk; i += 256) v[1] += llpart[(long)c * nblk + i];
+  block_sum<2, 256>(v, red, phase);
+  if (threadIdx.x == 0) gl[(long)c * (d + 1) + d] = v[1] * M.n_batches + v[0] * prior_weight;
+}

@@ -345,8 +345,43 @@ def test_errors_are_loud():
     with pytest.raises(MileError):
         ens.set_option('no_such_option', 1)
     ens.close()
-    wide = Ensemble(FCNSpec(5, (512, 512, 2)), 2)
-    wide.set_data(np.zeros((8, 5), np.float32), np.zeros(8, np.float32))
+    gel = FCNSpec(5, (512, 512, 2), 'gelu')
     with pytest.raises(MileError):
-        wide.value_and_grad(np.zeros((2, wide.d), np.float32))   # too wide for the CUDA-core path
-    wide.close()
+        Ensemble(gel, 2)                                       # gelu has no wide-path implementation: loud failure
+
+
+@pytest.mark.parametrize('widths,act,task', [((256, 256, 256, 256, 2), 'relu', 'regr'), ((96, 80, 3), 'tanh', 'class'),
+                                             ((48, 48, 48, 2), 'relu', 'regr')])
+def test_wide_path_value_and_grad_and_step(widths, act, task):
+    """Shapes that do not fit the shared-memory kernels (complexity ablation: 4x256, d = 201218) run on the
+    HBM-resident layer-by-layer path (chain-batched GEMMs + integrator kernel): same parity bar."""
+    from mile_b200 import Ensemble, FCNSpec
+    F, N, C = 12, 700, 2
+    ospec = o.ModelSpec(F, widths, act, task)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, F)).astype(np.float32)
+    y = rng.standard_normal(N).astype(np.float32) if task == 'regr' else rng.integers(0, widths[-1], N).astype(np.int32)
+    d = ospec.n_params
+    th = (rng.standard_normal((C, d)) * (0.5 / np.sqrt(max(widths)))).astype(np.float32)
+    ens = Ensemble(FCNSpec(F, widths, act, task), C)
+    ens.set_data(X, y)
+    lp, g = ens.value_and_grad(th)
+    lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
+    for c in range(C):
+        assert abs(lp[c] - lp64[c]) <= 1e-5 * abs(lp64[c])
+        assert rel(g[c], g64[c]) <= 2e-5
+    z0 = rng.standard_normal((C, d)).astype(np.float32)
+    z = rng.standard_normal((2, C, d)).astype(np.float32)
+    ens.init(th, z0)
+    samples, info = ens.sample(2, 0.01, float(np.sqrt(d)), z=z, info=True)
+    thg, ug, lpg, gg = ens.get_state()
+    f64 = lambda t: o.logpost_value_and_grad(ospec, t, X.astype(np.float64), y)
+    for c in range(C):
+        st = o.mclmc_init(f64, th[c].astype(np.float64), z0[c].astype(np.float64))
+        for s in range(2):
+            st, inf = o.mclmc_step(f64, st, 0.01, float(np.sqrt(d)), z[s, c].astype(np.float64))
+        assert rel(thg[c], st.position) <= 1e-5
+        assert rel(ug[c], st.momentum) <= 2e-5
+        assert abs(lpg[c] - st.logdensity) <= 1e-5 * abs(st.logdensity)
+        assert abs(info[1, c, 2] - inf.energy_change) <= 2e-5 * abs(st.logdensity)
+    ens.close()
