@@ -56,7 +56,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1;
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 1;
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -359,6 +359,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "refresh_mode")) c->opt_refresh = (int)v;
   else if (!strcmp(key, "resident")) c->opt_resident = (int)v;
   else if (!strcmp(key, "fast")) c->opt_fast = (int)v;
+  else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
   else return fail(std::string("unknown option ") + key);
   return 0;
 }
@@ -376,6 +377,8 @@ int64_t mile_get_option(const mile_ctx* c, const char* key) {
     return (int64_t)pl.smem;
   }
   if (!strcmp(key, "refresh_mode")) return c->opt_refresh;
+  if (!strcmp(key, "wide")) return c->wide;
+  if (!strcmp(key, "tensor")) return c->opt_tensor;
   if (!strcmp(key, "row_stride")) return c->M.sA[0];
   return -1;
 }
@@ -812,6 +815,14 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
 }
 
 static int wide_gemm(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
+  if (c->opt_tensor && g.K >= 32 && g.N >= 64 && g.M >= 64) {   // large contraction: tcgen05 / TMEM core (3xTF32)
+    CK(cudaFuncSetAttribute(wide_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    dim3 grid((g.N + TC_BN - 1) / TC_BN, (g.M + TC_BM - 1) / TC_BM, g.nbatch * g.kslices);
+    wide_gemm_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(g);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+  }
   dim3 grid((g.N + WG_BN - 1) / WG_BN, (g.M + WG_BM - 1) / WG_BM, g.nbatch * g.kslices);
   wide_gemm_kernel<<<grid, 256, 0, st>>>(g);
   CK(cudaGetLastError());

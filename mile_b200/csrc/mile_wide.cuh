@@ -183,3 +183,158 @@ __global__ void __launch_bounds__(256) wide_finalize_kernel(DevModel M, const fl
   block_sum<2, 256>(v, red, phase);
   if (threadIdx.x == 0) gl[(long)c * (d + 1) + d] = v[1] * M.n_batches + v[0] * prior_weight;
 }
+
+// =====================================================================================================
+// tcgen05 / TMEM GEMM core for the large contractions of the wide path (K >= 32, N >= 64): 3xTF32 split
+// (a = a_hi + a_lo, b = b_hi + b_lo;  a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in TMEM) so
+// the result keeps fp32-level accuracy (the parity bar is 1e-5).  Same GemmArgs / epilogues as the SIMT kernel.
+// One CTA computes a 128 x 256 output tile: all threads stage the operand k-blocks into shared memory in the
+// canonical K-major, no-swizzle UMMA layout (core matrix = 8 rows x 16 B; LBO = 128 B between the K halves,
+// SBO = 1024 B between 8-row groups), one elected thread issues tcgen05.mma kind::tf32 (M=128, N=256, K=8),
+// completion is tracked with tcgen05.commit -> mbarrier, and warps 0-3 drain the accumulator with tcgen05.ld.
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor / InstrDescriptor).
+// =====================================================================================================
+#define TC_BM 128
+#define TC_BN 256
+#define TC_BK 32
+#define TC_SMEM_BYTES ((2 * TC_BM * TC_BK + 2 * TC_BN * TC_BK) * 4 + 64)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+  // start address >> 4 | LBO (128 B) >> 4 << 16 | SBO (1024 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+
+// canonical K-major / no-swizzle byte offset of element (row r, k) inside a [rows x TC_BK] tf32 tile
+__device__ __forceinline__ uint32_t umma_off(int r, int k) {
+  return (uint32_t)((((r & 7) + (r >> 3) * 64 + (k >> 2) * 8) << 4) + ((k & 3) << 2));
+}
+
+// bounded wait on the MMA-completion mbarrier: a wrong descriptor must end in a trap, never in a hung GPU
+__device__ __forceinline__ void tc_wait(uint64_t* mbar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    if (spin > (1L << 24)) __trap();
+  }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* __restrict__ src, long s_row, long s_k,
+                                              int row0, int rows_valid, int k0, int k_end) {
+  // consecutive threads follow the unit-stride dimension of the operand in global memory
+  const bool kfast = s_k == 1;
+  for (int idx = threadIdx.x; idx < ROWS * TC_BK; idx += 256) {
+    const int k = kfast ? (idx % TC_BK) : (idx / ROWS), r = kfast ? (idx / TC_BK) : (idx % ROWS);
+    const int gr = row0 + r, gk = k0 + k;
+    const float v = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what the tf32 datapath keeps
+    const uint32_t o = umma_off(r, k);
+    *reinterpret_cast<float*>(hi + o) = h;
+    *reinterpret_cast<float*>(lo + o) = v - h;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) wide_gemm_tc_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) char tsm[];
+  char* a_hi = tsm;
+  char* a_lo = a_hi + TC_BM * TC_BK * 4;
+  char* b_hi = a_lo + TC_BM * TC_BK * 4;
+  char* b_lo = b_hi + TC_BN * TC_BK * 4;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + TC_BN * TC_BK * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z / g.kslices, ks = blockIdx.z % g.kslices;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int kper = ((g.K + g.kslices - 1) / g.kslices + TC_BK - 1) / TC_BK * TC_BK;
+  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
+  const float* A = g.A + (long)b * g.a_batch;
+  const float* B = g.B + (long)b * g.b_batch;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  uint32_t parity = 0;
+  bool first = true;
+  for (int k0 = kbeg; k0 < kend; k0 += TC_BK) {
+    if (!first) {   // the previous k-block's MMAs must have consumed the shared tiles
+      tc_wait(mbar, parity);
+      parity ^= 1;
+    }
+    tc_stage_tile<TC_BM>(a_hi, a_lo, A, g.sam, g.sak, m0, g.M, k0, kend);
+    tc_stage_tile<TC_BN>(b_hi, b_lo, B, g.sbn, g.sbk, n0, g.N, k0, kend);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+#pragma unroll
+      for (int j = 0; j < TC_BK / 8; ++j) {   // one MMA covers K = 8 tf32 = two 16-byte K halves = 256 B further
+        const uint32_t ko = j * 256;
+        umma_tf32(tmem, umma_desc_kmajor(sa_hi + ko), umma_desc_kmajor(sb_lo + ko), idesc, (first && j == 0) ? 0u : 1u);
+        umma_tf32(tmem, umma_desc_kmajor(sa_lo + ko), umma_desc_kmajor(sb_hi + ko), idesc, 1u);
+        umma_tf32(tmem, umma_desc_kmajor(sa_hi + ko), umma_desc_kmajor(sb_hi + ko), idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+    }
+    first = false;
+  }
+  tc_wait(mbar, parity);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp < 4) {   // epilogue: warp w owns TMEM lanes [32w, 32w+32) == output rows m0 + 32w + lane
+    float* C = g.C + (long)b * g.c_batch + (long)ks * g.c_slice;
+    const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
+    const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+          "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (m < g.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < g.N) {
+            float v = __uint_as_float(r[j]);
+            if (g.epi == 1) v = act_value(g.act, v + bias[n]);
+            else if (g.epi == 2) v = v + bias[n];
+            else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n]);
+            C[(long)m * g.ldc + n] = v;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_BN));
+}
