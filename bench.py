@@ -207,6 +207,8 @@ def run_ours(args):
         ens.set_option('cluster_size', args.cluster)
     if args.tile_rows:
         ens.set_option('tile_rows', args.tile_rows)
+    if args.tensor >= 0:
+        ens.set_option('tensor', args.tensor)
     ens.set_data(X, y)
     fused_lppd = key != 'wide_4x256'
     if fused_lppd:
@@ -324,6 +326,7 @@ def run_ours(args):
                        'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10',
                        'cluster_size': ens.get_option('cluster_size'), 'tile_rows': ens.get_option('tile_rows'),
                        'x_resident_in_smem': bool(ens.get_option('resident')),
+                       'kernel_path': ('wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')) if ens.get_option('wide') else ('FastGE pipeline' if ens.get_option('fast') else 'GenericGE'),
                        'l2': 'flushed between timed iterations (256 MiB write); working set is SMEM-resident',
                        'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()), 'parallelism': f'chains x{world}'},
             'grad_evals_per_s': 2 * value,
@@ -363,6 +366,7 @@ def main():
     ap.add_argument('--inner', type=int, default=0)
     ap.add_argument('--cluster', type=int, default=0)
     ap.add_argument('--tile-rows', type=int, default=0)
+    ap.add_argument('--tensor', type=int, default=-1, help='wide path: 1 = tcgen05 3xTF32 GEMM core, 0 = FP32 SIMT core')
     ap.add_argument('--no-tune', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

@@ -868,14 +868,10 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
     if (wide_gemm(c, g, st)) return -1;
     wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
                                                  d + 1, (long)IN * OUT, n);
-    GemmArgs b; memset(&b, 0, sizeof(b));     // bias gradient: 1^T D
-    b.A = c->w_ones; b.a_batch = 0; b.sam = 0; b.sak = 1;
-    b.B = D; b.b_batch = N * OUT; b.sbk = OUT; b.sbn = 1;
-    b.M = 1; b.N = OUT; b.K = (int)N; b.kslices = c->w_kslices; b.nbatch = n; b.epi = 0;
-    b.C = c->w_part; b.c_slice = OUT; b.c_batch = (long)c->w_kslices * OUT; b.ldc = OUT;
-    if (wide_gemm(c, b, st)) return -1;
-    wide_slice_reduce_kernel<<<32, 256, 0, st>>>(c->w_part, b.c_batch, b.c_slice, c->w_kslices, gl + M.bias_off[l], d + 1,
-                                                (long)OUT, n);
+    wide_colsum_kernel<<<dim3((OUT + 255) / 256, c->w_kslices, n), 256, 0, st>>>(D, N * OUT, N, OUT, c->w_kslices, c->w_part,
+                                                                                   (long)c->w_kslices * OUT);
+    wide_slice_reduce_kernel<<<32, 256, 0, st>>>(c->w_part, (long)c->w_kslices * OUT, OUT, c->w_kslices, gl + M.bias_off[l],
+                                                d + 1, (long)OUT, n);
     CK(cudaGetLastError());
     c->launches += 2;
     if (l > 0) {
@@ -887,7 +883,7 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
       if (wide_gemm(c, w, st)) return -1;
     }
   }
-  wide_finalize_kernel<<<n, 256, 0, st>>>(M, theta, gl, c->w_llpart, c->w_nblk, prior_weight);
+  wide_finalize_kernel<<<n, 1024, 0, st>>>(M, theta, gl, c->w_llpart, c->w_nblk, prior_weight);
   CK(cudaGetLastError());
   c->launches++;
   return 0;
@@ -914,7 +910,8 @@ static int shard_eval(mile_ctx* c, cudaStream_t st) {
 
 static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
   S.stage = stage; S.s_local = s_local;
-  mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
+  if (c->d > 8192) mile_integrator_kernel<1024><<<c->C, 1024, 0, st>>>(S);
+  else mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
   CK(cudaGetLastError());
   c->launches++;
   return 0;

@@ -23,14 +23,14 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_constant__ ShardParams S) {
   // works IN PLACE on the global chain state (every element is owned by one thread: i = tid mod NT), so it has
   // no shared-memory size limit and also serves the wide / large-d path (mile_wide.cuh)
-  __shared__ float red[192];
+  __shared__ float red[2 * 4 * (NT / 32) + 64];
   const KParams& P = S.K;
   const int d = P.M.d, ch = blockIdx.x, tid = threadIdx.x;
   Ctx c(P);
   c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0; c.phase2 = 0;
   c.th = P.theta + (long)ch * d; c.uu = P.u + (long)ch * d; c.gg = P.grad + (long)ch * d;
   c.thb = S.thb + (long)ch * d; c.ub = S.ub + (long)ch * d; c.gb = S.gb + (long)ch * d;
-  c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 128;
+  c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 2 * 4 * (NT / 32);
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
   float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];

@@ -124,6 +124,21 @@ __global__ void wide_slice_reduce_kernel(const float* __restrict__ src, long src
   }
 }
 
+// bias gradient: partial column sums of D [rows x ncols] over a row slice (deterministic two-pass with
+// wide_slice_reduce_kernel); grid (ceil(ncols/256), kslices, chains), thread = column
+__global__ void __launch_bounds__(256) wide_colsum_kernel(const float* __restrict__ D, long d_batch, long N, int ncols,
+                                                          int kslices, float* __restrict__ part, long p_batch) {
+  const int j = blockIdx.x * 256 + threadIdx.x, ks = blockIdx.y, c = blockIdx.z;
+  if (j >= ncols) return;
+  const long per = (N + kslices - 1) / kslices, r0 = ks * per, r1 = min(N, r0 + per);
+  const float* p = D + (long)c * d_batch + j;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long r = r0;
+  for (; r + 3 < r1; r += 4) { s0 += p[r * ncols]; s1 += p[(r + 1) * ncols]; s2 += p[(r + 2) * ncols]; s3 += p[(r + 3) * ncols]; }
+  for (; r < r1; ++r) s0 += p[r * ncols];
+  part[(long)c * p_batch + (long)ks * ncols + j] = (s0 + s1) + (s2 + s3);
+}
+
 // per (chain, row): log-likelihood term and d/d(out) (probabilistic.py:93-109); block partial sums of ll
 __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const float* __restrict__ out, float* __restrict__ dout,
                                                           const void* __restrict__ y, long N, float* __restrict__ llpart) {
@@ -163,15 +178,15 @@ __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const floa
 }
 
 // gl[c][0..d) += prior gradient * w ; gl[c][d] = n_batches * sum(ll partials) + w * log prior   (one CTA per chain)
-__global__ void __launch_bounds__(256) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
+__global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
                                                             const float* __restrict__ llpart, int nblk, float prior_weight) {
-  __shared__ float red[64];
+  __shared__ float red[256];
   int phase = 0;
   const int c = blockIdx.x, d = M.d;
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
   const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
   float v[2] = {0.f, 0.f};
-  for (int i = threadIdx.x; i < d; i += 256) {
+  for (int i = threadIdx.x; i < d; i += 1024) {
     const float dlt = theta[(long)c * d + i] - loc;
     float pv, pg;
     if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
@@ -179,8 +194,8 @@ __global__ void __launch_bounds__(256) wide_finalize_kernel(DevModel M, const fl
     gl[(long)c * (d + 1) + i] += pg * prior_weight;
     v[0] += pv;
   }
-  for (int i = threadIdx.x; i < nblk; i += 256) v[1] += llpart[(long)c * nblk + i];
-  block_sum<2, 256>(v, red, phase);
+  for (int i = threadIdx.x; i < nblk; i += 1024) v[1] += llpart[(long)c * nblk + i];
+  block_sum<2, 1024>(v, red, phase);
   if (threadIdx.x == 0) gl[(long)c * (d + 1) + d] = v[1] * M.n_batches + v[0] * prior_weight;
 }
 
@@ -229,13 +244,42 @@ __device__ __forceinline__ void tc_wait(uint64_t* mbar, uint32_t parity) {
   }
 }
 
+// Stage a [ROWS x TC_BK] operand k-block into the canonical layout, split into tf32 hi / lo parts.  Every warp
+// store instruction fills exactly one 128-byte core matrix (8 rows x 16 B): conflict-free in shared memory, and
+// the global side reads whole 32-byte sectors whichever dimension of the operand is contiguous.
 template <int ROWS>
 __device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* __restrict__ src, long s_row, long s_k,
                                               int row0, int rows_valid, int k0, int k_end) {
-  // consecutive threads follow the unit-stride dimension of the operand in global memory
   const bool kfast = s_k == 1;
+  if (kfast && (s_row & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (k0 & 3) == 0) {
+    // k contiguous and 16-byte aligned: one float4 (4 k's of one row) per thread
+    for (int idx = threadIdx.x; idx < ROWS * (TC_BK / 4); idx += 256) {
+      const int r8 = idx & 7, kq = (idx >> 3) & 7, rg = idx >> 6;
+      const int r = rg * 8 + r8, gr = row0 + r, gk = k0 + kq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < rows_valid) {
+        if (gk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src + (long)gr * s_row + gk));
+        else {
+          if (gk < k_end) v.x = __ldg(src + (long)gr * s_row + gk);
+          if (gk + 1 < k_end) v.y = __ldg(src + (long)gr * s_row + gk + 1);
+          if (gk + 2 < k_end) v.z = __ldg(src + (long)gr * s_row + gk + 2);
+        }
+      }
+      float4 h;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+      const uint32_t o = (uint32_t)((r8 + rg * 64 + kq * 8) << 4);
+      *reinterpret_cast<float4*>(hi + o) = h;
+      *reinterpret_cast<float4*>(lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < ROWS * TC_BK; idx += 256) {
-    const int k = kfast ? (idx % TC_BK) : (idx / ROWS), r = kfast ? (idx / TC_BK) : (idx % ROWS);
+    // one core matrix (8 rows x 4 k) per warp instruction; the contiguous source dimension varies fastest
+    const int lane5 = idx & 31, cm = idx >> 5;
+    const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
+    const int kq = cm & 7, rg = cm >> 3;
+    const int r = rg * 8 + r8, k = kq * 4 + kk;
     const int gr = row0 + r, gk = k0 + k;
     const float v = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what the tf32 datapath keeps
