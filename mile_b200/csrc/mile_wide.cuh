@@ -253,7 +253,9 @@ __device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* _
   const bool kfast = s_k == 1;
   if (kfast && (s_row & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (k0 & 3) == 0) {
     // k contiguous and 16-byte aligned: one float4 (4 k's of one row) per thread
-    for (int idx = threadIdx.x; idx < ROWS * (TC_BK / 4); idx += 256) {
+#pragma unroll
+    for (int it = 0; it < ROWS * (TC_BK / 4) / 256; ++it) {
+      const int idx = threadIdx.x + it * 256;
       const int r8 = idx & 7, kq = (idx >> 3) & 7, rg = idx >> 6;
       const int r = rg * 8 + r8, gr = row0 + r, gk = k0 + kq * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -274,18 +276,29 @@ __device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* _
     }
     return;
   }
-  for (int idx = threadIdx.x; idx < ROWS * TC_BK; idx += 256) {
-    // one core matrix (8 rows x 4 k) per warp instruction; the contiguous source dimension varies fastest
-    const int lane5 = idx & 31, cm = idx >> 5;
-    const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
-    const int kq = cm & 7, rg = cm >> 3;
-    const int r = rg * 8 + r8, k = kq * 4 + kk;
-    const int gr = row0 + r, gk = k0 + k;
-    const float v = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
-    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what the tf32 datapath keeps
-    const uint32_t o = umma_off(r, k);
-    *reinterpret_cast<float*>(hi + o) = h;
-    *reinterpret_cast<float*>(lo + o) = v - h;
+  // one core matrix (8 rows x 4 k) per warp instruction; the contiguous source dimension varies fastest.
+  // Loads are issued in batches of 8 independent requests before anything is stored.
+  const int lane5 = threadIdx.x & 31;
+  const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
+#pragma unroll 1
+  for (int it0 = 0; it0 < ROWS * TC_BK / 256; it0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int cm = (threadIdx.x >> 5) + (it0 + u) * 8;      // core-matrix index of this warp at this iteration
+      const int kq = cm & 7, rg = cm >> 3;
+      const int gr = row0 + rg * 8 + r8, gk = k0 + kq * 4 + kk;
+      v[u] = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int cm = (threadIdx.x >> 5) + (it0 + u) * 8;
+      const int kq = cm & 7, rg = cm >> 3;
+      const float h = __uint_as_float(__float_as_uint(v[u]) & 0xFFFFE000u);   // what the tf32 datapath keeps
+      const uint32_t o = umma_off(rg * 8 + r8, kq * 4 + kk);
+      *reinterpret_cast<float*>(hi + o) = h;
+      *reinterpret_cast<float*>(lo + o) = v[u] - h;
+    }
   }
 }
 
@@ -364,16 +377,25 @@ __global__ void __launch_bounds__(256, 1) wide_gemm_tc_kernel(const GemmArgs g) 
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
       if (m < g.M) {
+        float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + c0 + j;
+          float v = __uint_as_float(r[j]);
           if (n < g.N) {
-            float v = __uint_as_float(r[j]);
             if (g.epi == 1) v = act_value(g.act, v + bias[n]);
             else if (g.epi == 2) v = v + bias[n];
             else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n]);
-            C[(long)m * g.ldc + n] = v;
           }
+          o[j] = v;
+        }
+        float* crow = C + (long)m * g.ldc + n0 + c0;
+        if (n0 + c0 + 32 <= g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) crow[j] = o[j];
         }
       }
     }
