@@ -244,20 +244,28 @@ __device__ __forceinline__ void tc_wait(uint64_t* mbar, uint32_t parity) {
   }
 }
 
-// Stage a [ROWS x TC_BK] operand k-block into the canonical layout, split into tf32 hi / lo parts.  Every warp
-// store instruction fills exactly one 128-byte core matrix (8 rows x 16 B): conflict-free in shared memory, and
-// the global side reads whole 32-byte sectors whichever dimension of the operand is contiguous.
+// Staging of a [ROWS x TC_BK] operand k-block in two halves so that the global loads of block i+1 overlap the
+// MMAs of block i: tc_load_tile pulls the block into registers, tc_store_tile splits it into tf32 hi / lo parts
+// and writes the canonical layout.  Every warp store instruction fills exactly one 128-byte core matrix
+// (8 rows x 16 B): conflict-free in shared memory, and the global side reads whole 32-byte sectors whichever
+// dimension of the operand is contiguous.
 template <int ROWS>
-__device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* __restrict__ src, long s_row, long s_k,
-                                              int row0, int rows_valid, int k0, int k_end) {
-  const bool kfast = s_k == 1;
-  if (kfast && (s_row & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (k0 & 3) == 0) {
-    // k contiguous and 16-byte aligned: one float4 (4 k's of one row) per thread
+struct TcRegs { float v[ROWS * TC_BK / 256]; };
+
+template <int ROWS>
+__device__ __forceinline__ bool tc_vec_ok(const float* src, long s_row, long s_k) {
+  return s_k == 1 && (s_row & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+}
+
+template <int ROWS>
+__device__ __forceinline__ void tc_load_tile(TcRegs<ROWS>& R, const float* __restrict__ src, long s_row, long s_k, int row0,
+                                             int rows_valid, int k0, int k_end, bool vec) {
+  if (vec) {   // k contiguous and 16-byte aligned: float4 = 4 k's of one row
 #pragma unroll
     for (int it = 0; it < ROWS * (TC_BK / 4) / 256; ++it) {
       const int idx = threadIdx.x + it * 256;
       const int r8 = idx & 7, kq = (idx >> 3) & 7, rg = idx >> 6;
-      const int r = rg * 8 + r8, gr = row0 + r, gk = k0 + kq * 4;
+      const int gr = row0 + rg * 8 + r8, gk = k0 + kq * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr < rows_valid) {
         if (gk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src + (long)gr * s_row + gk));
@@ -267,42 +275,53 @@ __device__ __forceinline__ void tc_stage_tile(char* hi, char* lo, const float* _
           if (gk + 2 < k_end) v.z = __ldg(src + (long)gr * s_row + gk + 2);
         }
       }
-      float4 h;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-      const uint32_t o = (uint32_t)((r8 + rg * 64 + kq * 8) << 4);
-      *reinterpret_cast<float4*>(hi + o) = h;
-      *reinterpret_cast<float4*>(lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      R.v[it * 4] = v.x; R.v[it * 4 + 1] = v.y; R.v[it * 4 + 2] = v.z; R.v[it * 4 + 3] = v.w;
     }
-    return;
-  }
-  // one core matrix (8 rows x 4 k) per warp instruction; the contiguous source dimension varies fastest.
-  // Loads are issued in batches of 8 independent requests before anything is stored.
-  const int lane5 = threadIdx.x & 31;
-  const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
-#pragma unroll 1
-  for (int it0 = 0; it0 < ROWS * TC_BK / 256; it0 += 8) {
-    float v[8];
+  } else {     // one core matrix (8 rows x 4 k) per warp instruction; the contiguous source dimension varies fastest
+    const bool kfast = s_k == 1;
+    const int lane5 = threadIdx.x & 31;
+    const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int cm = (threadIdx.x >> 5) + (it0 + u) * 8;      // core-matrix index of this warp at this iteration
+    for (int u = 0; u < ROWS * TC_BK / 256; ++u) {
+      const int cm = (threadIdx.x >> 5) + u * 8;
       const int kq = cm & 7, rg = cm >> 3;
       const int gr = row0 + rg * 8 + r8, gk = k0 + kq * 4 + kk;
-      v[u] = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int cm = (threadIdx.x >> 5) + (it0 + u) * 8;
-      const int kq = cm & 7, rg = cm >> 3;
-      const float h = __uint_as_float(__float_as_uint(v[u]) & 0xFFFFE000u);   // what the tf32 datapath keeps
-      const uint32_t o = umma_off(rg * 8 + r8, kq * 4 + kk);
-      *reinterpret_cast<float*>(hi + o) = h;
-      *reinterpret_cast<float*>(lo + o) = v[u] - h;
+      R.v[u] = (gr < rows_valid && gk < k_end) ? __ldg(src + (long)gr * s_row + (long)gk * s_k) : 0.f;
     }
   }
 }
 
-__global__ void __launch_bounds__(256, 1) wide_gemm_tc_kernel(const GemmArgs g) {
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }  // what the tf32 datapath keeps
+
+template <int ROWS>
+__device__ __forceinline__ void tc_store_tile(const TcRegs<ROWS>& R, char* hi, char* lo, bool kfast, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < ROWS * (TC_BK / 4) / 256; ++it) {
+      const int idx = threadIdx.x + it * 256;
+      const int r8 = idx & 7, kq = (idx >> 3) & 7, rg = idx >> 6;
+      const float4 v = make_float4(R.v[it * 4], R.v[it * 4 + 1], R.v[it * 4 + 2], R.v[it * 4 + 3]);
+      const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      const uint32_t o = (uint32_t)((r8 + rg * 64 + kq * 8) << 4);
+      *reinterpret_cast<float4*>(hi + o) = h;
+      *reinterpret_cast<float4*>(lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    }
+  } else {
+    const int lane5 = threadIdx.x & 31;
+    const int r8 = kfast ? (lane5 >> 2) : (lane5 & 7), kk = kfast ? (lane5 & 3) : (lane5 >> 3);
+#pragma unroll
+    for (int u = 0; u < ROWS * TC_BK / 256; ++u) {
+      const int cm = (threadIdx.x >> 5) + u * 8;
+      const int kq = cm & 7, rg = cm >> 3;
+      const float h = tf32_hi(R.v[u]);
+      const uint32_t o = umma_off(rg * 8 + r8, kq * 4 + kk);
+      *reinterpret_cast<float*>(hi + o) = h;
+      *reinterpret_cast<float*>(lo + o) = R.v[u] - h;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) char tsm[];
   char* a_hi = tsm;
   char* a_lo = a_hi + TC_BM * TC_BK * 4;
@@ -333,13 +352,19 @@ __global__ void __launch_bounds__(256, 1) wide_gemm_tc_kernel(const GemmArgs g) 
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   uint32_t parity = 0;
   bool first = true;
+  const bool a_vec = tc_vec_ok<TC_BM>(A, g.sam, g.sak), b_vec = tc_vec_ok<TC_BN>(B, g.sbn, g.sbk);
+  const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
+  TcRegs<TC_BM> ra;
+  TcRegs<TC_BN> rb;
+  tc_load_tile<TC_BM>(ra, A, g.sam, g.sak, m0, g.M, kbeg, kend, a_vec);
+  tc_load_tile<TC_BN>(rb, B, g.sbn, g.sbk, n0, g.N, kbeg, kend, b_vec);
   for (int k0 = kbeg; k0 < kend; k0 += TC_BK) {
     if (!first) {   // the previous k-block's MMAs must have consumed the shared tiles
       tc_wait(mbar, parity);
       parity ^= 1;
     }
-    tc_stage_tile<TC_BM>(a_hi, a_lo, A, g.sam, g.sak, m0, g.M, k0, kend);
-    tc_stage_tile<TC_BN>(b_hi, b_lo, B, g.sbn, g.sbk, n0, g.N, k0, kend);
+    tc_store_tile<TC_BM>(ra, a_hi, a_lo, a_kfast, a_vec);
+    tc_store_tile<TC_BN>(rb, b_hi, b_lo, b_kfast, b_vec);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -355,6 +380,10 @@ __global__ void __launch_bounds__(256, 1) wide_gemm_tc_kernel(const GemmArgs g) 
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
     }
     first = false;
+    if (k0 + TC_BK < kend) {   // global loads of the next k-block fly while the tensor core works on this one
+      tc_load_tile<TC_BM>(ra, A, g.sam, g.sak, m0, g.M, k0 + TC_BK, kend, a_vec);
+      tc_load_tile<TC_BN>(rb, B, g.sbn, g.sbk, n0, g.N, k0 + TC_BK, kend, b_vec);
+    }
   }
   tc_wait(mbar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
