@@ -66,6 +66,7 @@ struct mile_ctx {
         *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
   float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
   float* carry = nullptr; int carry_valid = 0;
+  float* xchg = nullptr; unsigned int* xcount = nullptr; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
   void* nccl_comm = nullptr; int world = 1, rank = 0;
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
@@ -104,19 +105,26 @@ static void build_model(mile_ctx* c) {
 }
 
 struct Plan {
-  int G, TR, resident, rows_res, fast = 0, fast_fp = 0;
+  int G, TR, resident, rows_res, fast = 0, fast_fp = 0, sync_mode = 0;
   size_t smem;
   KParams kp;  // offsets + model filled in
 };
 
 static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl) {
   DevModel M = c->M;
-  int G = c->opt_cluster;
+  int G = c->opt_cluster, sync_mode = 0;
   if (G <= 0) {
     if (n_chains * 8 <= 128) G = 8; else if (n_chains * 4 <= 148) G = 4; else if (n_chains * 2 <= 148) G = 2; else G = 1;
     while (G > 1 && nrows_for_split / G < 64) G >>= 1;
+    // few chains: more than 8 CTAs per chain only fit with the global-memory exchange (cooperative launch)
+    const int gmax = c->n_sms / n_chains;
+    if (c->opt_sync != 0 && G == 8 && gmax > 9 && nrows_for_split / gmax >= 256) { G = gmax > 16 ? 16 : gmax; sync_mode = 1; }
+  } else if (c->opt_sync == 1 || (G > 8) || (G & (G - 1))) {
+    sync_mode = 1;
   }
-  if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16) return fail("cluster_size must be 1,2,4,8 or 16");
+  if (G < 1 || G > 16) return fail("cluster_size must be in [1, 16]");
+  if (sync_mode && (long)G * n_chains > c->n_sms) return fail("cluster_size x chains exceeds the SM count (cooperative launch)");
+  if (G == 1) sync_mode = 0;
   const long rows_cta = (nrows_for_split + G - 1) / G;
   const int dS = round_up(M.d, 4);
   int S1 = 0;
@@ -154,7 +162,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
         k.off_red = o; o += 192;
         k.off_tile = o; o += (int)tile + TRg * M.sA[0];
         k.off_x = o; if (res) o += rows_res * M.sA[0];
-        pl.G = G; pl.TR = T; pl.resident = res; pl.rows_res = rows_res; pl.fast = 1; pl.fast_fp = M.dimp[0];
+        pl.G = G; pl.TR = T; pl.resident = res; pl.rows_res = rows_res; pl.fast = 1; pl.fast_fp = M.dimp[0]; pl.sync_mode = sync_mode;
         pl.smem = (size_t)o * 4;
         k.G = G; k.resident = res; k.rows_res = rows_res; k.C = n_chains;
         return 0;
@@ -195,7 +203,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   k.off_red = o; o += 192;
   k.off_tile = o; o += (int)tile + TR * M.sA[0];
   k.off_x = o; if (resident) o += rows_res * M.sA[0];
-  pl.G = G; pl.TR = TR; pl.resident = resident; pl.rows_res = rows_res;
+  pl.G = G; pl.TR = TR; pl.resident = resident; pl.rows_res = rows_res; pl.sync_mode = sync_mode;
   pl.smem = (size_t)o * 4;
   if (pl.smem > kSmemLimit) return fail("internal: shared-memory plan exceeds the limit");
   k.G = G; k.resident = resident; k.rows_res = rows_res; k.C = n_chains;
@@ -217,15 +225,33 @@ static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pl.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  if (pl.sync_mode) {   // global-memory exchange: every CTA must be co-resident -> cooperative launch, no cluster
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+  } else {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  }
   cfg.attrs = attr; cfg.numAttrs = 1;
   CK(cudaLaunchKernelEx(&cfg, kern, pl.kp));
   return 0;
 }
 
-static int launch(mile_ctx* c, const Plan& pl, int n_chains, cudaStream_t st) {
+static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   CK(cudaSetDevice(c->device));
+  pl.kp.sync_mode = pl.sync_mode;
+  if (pl.sync_mode) {
+    const size_t need = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4) * 4;
+    if (need > c->xchg_bytes || !c->xcount) {
+      if (c->xchg) cudaFree(c->xchg);
+      if (c->xcount) cudaFree(c->xcount);
+      CK(cudaMalloc(&c->xchg, need));
+      CK(cudaMalloc(&c->xcount, (size_t)(n_chains > c->C ? n_chains : c->C) * 4 + 1024));
+      c->xchg_bytes = need;
+    }
+    CK(cudaMemsetAsync(c->xcount, 0, (size_t)n_chains * 4, st));
+    pl.kp.xchg = c->xchg; pl.kp.xcount = c->xcount;
+  }
   const int NL = c->M.NL;
   int rc;
   if (pl.fast) {
@@ -313,6 +339,7 @@ int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, m
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 9) return fail("mile_b200 needs thread-block clusters (built for sm_100a)");
   mile_ctx* c = new mile_ctx();
+  c->n_sms = prop.multiProcessorCount;
   c->desc = *desc; c->C = n_chains; c->device = device;
   build_model(c);
   if (c->d < 2) { delete c; return fail("The target distribution must have more than 1 dimension for MCLMC."); }
@@ -341,7 +368,7 @@ void mile_destroy(mile_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
-                  c->gl, c->scal, c->thb, c->ub, c->gb, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
+                  c->gl, c->scal, c->thb, c->ub, c->gb, c->xchg, (float*)c->xcount, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
                   c->w_ones, c->w_gl};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
@@ -360,6 +387,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "resident")) c->opt_resident = (int)v;
   else if (!strcmp(key, "fast")) c->opt_fast = (int)v;
   else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
+  else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else return fail(std::string("unknown option ") + key);
   return 0;
 }
@@ -367,13 +395,14 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
 int64_t mile_get_option(const mile_ctx* c, const char* key) {
   if (!c || !key) return -1;
   if (!strcmp(key, "cluster_size") || !strcmp(key, "tile_rows") || !strcmp(key, "resident") || !strcmp(key, "smem_bytes") ||
-      !strcmp(key, "fast")) {
+      !strcmp(key, "fast") || !strcmp(key, "sync_mode")) {
     Plan pl;
     if (make_plan(c, c->C, c->N > 0 ? c->N : 1, true, pl)) return -1;
     if (!strcmp(key, "cluster_size")) return pl.G;
     if (!strcmp(key, "tile_rows")) return pl.TR;
     if (!strcmp(key, "resident")) return pl.resident;
     if (!strcmp(key, "fast")) return pl.fast;
+    if (!strcmp(key, "sync_mode")) return pl.sync_mode;
     return (int64_t)pl.smem;
   }
   if (!strcmp(key, "refresh_mode")) return c->opt_refresh;

@@ -37,6 +37,9 @@ struct KParams {
   int tune1, tune2; float ev_start, ev_end, trust, neff;
   // eval / init / lppd / predict io
   const float* theta_in; float* lp_out; float* grad_out; float* pred_out; int n_eval, which;
+  // global-memory exchange (sync_mode 1): any number of CTAs per chain, cooperative launch, partial gradients and an
+  // arrival counter in HBM/L2 instead of DSMEM + cluster barrier (lets <= 12 chains use all 148 SMs)
+  int sync_mode; float* xchg; unsigned int* xcount;   // xchg [C][2][G][dS+4], xcount [C]
   int out_stride;        // row stride of grad_out / lp_out (d, or d+1 for the packed [C,d+1] all-reduce buffer)
   float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)
@@ -210,13 +213,17 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   // rank loops are unrolled to the maximum cluster size with predication so that all remote (DSMEM)
   // loads of an element are in flight together (~200 cycles each when serialised)
   const float* rp[16];
+  const int stride_g = P.dS + 4;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) rp[r] = (c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
+  for (int r = 0; r < 16; ++r) {
+    if (P.sync_mode) rp[r] = gpart + (r < c.G ? r : 0) * stride_g;          // gpart = this chain's parity slab in global memory
+    else rp[r] = (c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
+  }
   float ll = 0.f;
   {
     float t[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? (P.sync_mode ? __ldcg(rp[r] + P.dS) : rp[r][P.dS]) : 0.f;
 #pragma unroll
     for (int r = 0; r < 16; ++r) ll += t[r];
   }
@@ -226,7 +233,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   for (int i = threadIdx.x; i < M.d; i += NT) {
     float t[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? (P.sync_mode ? __ldcg(rp[r] + i) : rp[r][i]) : 0.f;
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < 16; ++r) s += t[r];
@@ -450,7 +457,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   cg::cluster_group cluster = cg::this_cluster();
   Ctx c(P);
   c.G = P.G;
-  c.rank = c.G > 1 ? (int)cluster.block_rank() : 0;
+  c.rank = c.G > 1 ? (P.sync_mode ? (int)(blockIdx.x % c.G) : (int)cluster.block_rank()) : 0;
   c.chain = blockIdx.x / c.G;
   c.phase = 0;
   c.wp = smem + P.off_wp; c.th = smem + P.off_th; c.uu = smem + P.off_u; c.gg = smem + P.off_g;
@@ -505,12 +512,12 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
         P.pred_out[((long)ch * Nr + row0 + e / K) * K + e % K] = out[(e / K) * M.sA[M.NL] + e % K];
       __syncthreads();
     }
-    if (c.G > 1) cluster.sync();
+    if (c.G > 1 && !P.sync_mode) cluster.sync();
     return;
   }
   if (P.mode == MODE_LPPD) {
     lppd_fold<NT>(c, ch);
-    if (c.G > 1) cluster.sync();
+    if (c.G > 1 && !P.sync_mode) cluster.sync();
     return;
   }
 
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   //      The integrator phases (B / A / refresh / reductions / tuning) touch only d ~ 500-2000 floats: they run
   //      on the first NI = 128 threads (one warp per scheduler) with named barrier 1, so the scalar math is
   //      issued by 4 warps instead of all of them; everybody else waits at the block barrier.
-  constexpr int NI = 128, IB = 1;
+  constexpr int NI = NT, IB = 0;   // measured: the phases are latency-bound, so all threads (shorter per-thread chains) beat a 128-thread group
   const bool integ = tid < NI;
   const bool stepping = P.mode == MODE_SAMPLE || P.mode == MODE_TUNE;
   const bool tune = P.mode == MODE_TUNE;
@@ -567,9 +574,34 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     float* gp = c.gpart + (e & 1) * (P.dS + 4);
     GE::run(c, r0, r1, gp);
     PROF(10);
-    if (c.G > 1) cluster.sync(); else __syncthreads();   // publishes every CTA's partial gradient
+    float* gsrc = gp;
+    if (c.G > 1 && P.sync_mode) {
+      // global exchange: publish this CTA's partial, arrive on the chain's counter, wait for all G CTAs
+      float* slab = P.xchg + ((long)ch * 2 + (e & 1)) * c.G * (P.dS + 4);
+      float* mine = slab + c.rank * (P.dS + 4);
+      __syncthreads();
+      for (int i = tid; i <= P.dS; i += NT) __stcg(mine + i, gp[i]);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned int target = (unsigned int)c.G * (unsigned int)(e + 1);
+        atomicAdd(P.xcount + ch, 1u);
+        unsigned int seen;
+        long spin = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.xcount + ch) : "memory");
+          if (seen < target) { __nanosleep(40); if (++spin > (1L << 26)) __trap(); }
+        } while (seen < target);
+      }
+      __syncthreads();
+      gsrc = slab;
+    } else if (c.G > 1) {
+      cluster.sync();      // publishes every CTA's partial gradient (DSMEM)
+    } else {
+      __syncthreads();
+    }
     if (integ) {
-      const float lp_new = cluster_reduce_grad<NI, IB>(c, gp, g2, ug, nf);
+      const float lp_new = cluster_reduce_grad<NI, IB>(c, gsrc, g2, ug, nf);
       PROF(11);
       if (!stepping) {
         if (P.mode == MODE_EVAL) {
@@ -646,5 +678,5 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
       if (tune) { P.t_time[ch] = t_time; P.t_xavg[ch] = t_xavg; P.t_epsmax[ch] = t_epsmax; P.t_eps[ch] = eps; P.t_wtot[ch] = t_wtot; }
     }
   }
-  if (c.G > 1) cluster.sync();
+  if (c.G > 1 && !P.sync_mode) cluster.sync();
 }

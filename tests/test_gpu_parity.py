@@ -25,7 +25,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize('name', CONFIGS)
-@pytest.mark.parametrize('G', [1, 2, 8])
+@pytest.mark.parametrize('G', [1, 2, 8, 14])   # 14: global-memory exchange + cooperative launch (no cluster)
 @pytest.mark.parametrize('fast', [1, 0])
 def test_value_and_grad_matches_oracle(name, G, fast):
     """fast=1: warp-specialised pipeline kernel where the shape is eligible (hidden width 16, Gaussian head),
@@ -103,7 +103,8 @@ def test_deep_narrow_network():
 
 @pytest.mark.parametrize('name,G,fast', [('airfoil_3x16', 1, 1), ('airfoil_3x16', 8, 1), ('airfoil_3x16', 8, 0),
                                          ('bikesharing_2x16', 8, 1), ('bikesharing_2x16', 8, 0),
-                                         ('covertype_ref', 4, 0), ('protein_2x16', 8, 1), ('airfoil_2x16', 2, 1)])
+                                         ('covertype_ref', 4, 0), ('protein_2x16', 8, 1), ('airfoil_2x16', 2, 1),
+                                         ('bikesharing_2x16', 14, 1), ('covertype_ref', 11, 0), ('bikesharing_2x16', 0, 1)])
 def test_single_step_parity(name, G, fast):
     """The north-star criterion: identical (theta,u,l,g,eps,L,z) in -> (theta',u',l',dK,dE) within 1e-5."""
     C = 3
@@ -176,7 +177,7 @@ def test_cluster_sizes_agree_bitwise_on_state_layout():
     """Different cluster sizes change the summation order only: results agree to fp32 rounding."""
     name, C = 'bikesharing_2x16', 2
     outs = []
-    for G in (1, 2, 4, 8):
+    for G in (1, 2, 4, 8, 13):
         ospec, ens, X, y, _, _ = make(name, C, cluster_size=G)
         th0 = o.synthetic_theta0(ospec, C)
         rng = np.random.default_rng(1)
@@ -186,7 +187,7 @@ def test_cluster_sizes_agree_bitwise_on_state_layout():
         ens.sample(3, 0.01, 22.0, z=z, keep=False)
         outs.append(ens.get_state())
         ens.close()
-    for k in range(1, 4):
+    for k in range(1, 5):
         assert rel(outs[k][0], outs[0][0]) <= 1e-6
         assert rel(outs[k][1], outs[0][1]) <= 1e-5
 
