@@ -270,16 +270,12 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const float zeta = 1.f - omz;
   const float ce = omz * (1.f + zeta + p * omz);
   const float cu = 2.f * zeta;
-  float v[1] = {0.f};
-  for (int i = threadIdx.x; i < d; i += NT) {
-    const float raw = (c.gg[i] * ginv) * ce + cu * c.uu[i];
-    c.uu[i] = raw;
-    v[0] += raw * raw;
-  }
-  block_sum<1, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
-  const float rn = sqrtf(v[0]);
-  const float rinv = rn > 1e-13f ? 1.f / rn : 1.f;
-  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= rinv;
+  // |raw|^2 in closed form: raw = ce * e + cu * u with |e| = |u| = 1 and u.e = p  (saves one block reduction per
+  // B-step; |u| is re-normalised numerically by the partial refresh once per step, so rounding cannot accumulate)
+  const float rn2 = ce * ce + cu * cu + 2.f * ce * cu * p;
+  const float rinv = rn2 > 1e-26f ? rsqrtf(rn2) : 1.f;
+  const float ae = ce * ginv * rinv, au = cu * rinv;
+  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
   const float omz2 = omz * (1.f + zeta);   // 1 - zeta^2
   return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
 }
@@ -308,11 +304,13 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
                                                  float& ug_out) {
   const KParams& P = c.P;
   const int d = P.M.d;
-  if (isinf(L)) {
-    float v[1] = {0.f};
-    for (int i = threadIdx.x; i < d; i += NT) v[0] += c.uu[i] * c.gg[i];
-    block_sum<1, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
-    ug_out = v[0];
+  if (isinf(L)) {   // no refresh: still re-normalise numerically (the B-steps use the closed-form norm)
+    float v[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < d; i += NT) { v[0] += c.uu[i] * c.uu[i]; v[1] += c.uu[i] * c.gg[i]; }
+    block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+    const float inv = 1.f / sqrtf(v[0]);
+    for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= inv;
+    ug_out = v[1] * inv;
     return;
   }
   const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
@@ -581,17 +579,18 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
       float* mine = slab + c.rank * (P.dS + 4);
       __syncthreads();
       for (int i = tid; i <= P.dS; i += NT) __stcg(mine + i, gp[i]);
-      __threadfence();
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0) {   // same release / acquire pattern as cooperative_groups::grid_group::sync
         const unsigned int target = (unsigned int)c.G * (unsigned int)(e + 1);
+        __threadfence();
         atomicAdd(P.xcount + ch, 1u);
         unsigned int seen;
         long spin = 0;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.xcount + ch) : "memory");
-          if (seen < target) { __nanosleep(40); if (++spin > (1L << 26)) __trap(); }
+          if (seen < target && ++spin > (1L << 28)) __trap();
         } while (seen < target);
+        __threadfence();
       }
       __syncthreads();
       gsrc = slab;
