@@ -9,9 +9,12 @@
 #include <nccl.h>
 
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 static thread_local std::string g_err;
@@ -56,7 +59,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 1;
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 1;   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -74,6 +77,11 @@ struct mile_ctx {
   int wide = 0; long w_rows = 0; int w_chains = 0, w_kslices = 1, w_nblk = 0;
   float *w_act = nullptr, *w_delta[2] = {nullptr, nullptr}, *w_part = nullptr, *w_llpart = nullptr, *w_ones = nullptr;
   float* w_gl = nullptr;   // packed [n, d+1] output of a stand-alone value_and_grad call
+  // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
+  float *w_act_lo = nullptr, *w_delta_lo[2] = {nullptr, nullptr}, *w_wpk = nullptr, *w_wpk_lo = nullptr, *w_wpkT = nullptr,
+        *w_wpkT_lo = nullptr;
+  long w_n8 = 0, w_wstride = 0; long w_woff[MILE_MAX_LAYERS] = {0};
+  std::map<std::tuple<const void*, long, long, long, long, int, int, int>, CUtensorMap> tmaps;
   // staging for the *_host entry points
   std::vector<std::pair<void*, size_t>> scratch;  // slot -> (ptr, bytes)
   cudaStream_t own_stream = nullptr;
@@ -369,7 +377,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->xchg, (float*)c->xcount, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl};
+                  c->w_ones, c->w_gl, c->w_act_lo, c->w_delta_lo[0], c->w_delta_lo[1], c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -820,18 +828,32 @@ int mile_shard_init(mile_ctx* c, const void* unique_id128, int32_t rank, int32_t
 // ---- wide path orchestration ----------------------------------------------------------------------------
 static int wide_alloc(mile_ctx* c, int n_chains) {
   if (c->w_act && c->w_rows == c->N && c->w_chains >= n_chains) return 0;
-  float** ptrs[] = {&c->w_act, &c->w_delta[0], &c->w_delta[1], &c->w_part, &c->w_llpart, &c->w_ones, &c->w_gl};
+  float** ptrs[] = {&c->w_act, &c->w_delta[0], &c->w_delta[1], &c->w_part, &c->w_llpart, &c->w_ones, &c->w_gl,
+                    &c->w_act_lo, &c->w_delta_lo[0], &c->w_delta_lo[1], &c->w_wpk, &c->w_wpk_lo, &c->w_wpkT, &c->w_wpkT_lo};
   for (float** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+  c->tmaps.clear();
   const DevModel& M = c->M;
-  const long N = c->N;
-  long act_per_row = 0; int maxw = 0; long maxio = 0;
+  const long N = c->N, N8 = (N + 7) / 8 * 8;   // rows padded to the 8-row core matrices of the TMA views; pad rows stay 0
+  long act_per_row = 0; int maxw = 0; long maxio = 0, wsum = 0;
   for (int l = 1; l <= M.NL; ++l) { act_per_row += M.dims[l]; if (M.dims[l] > maxw) maxw = M.dims[l]; }
-  for (int l = 0; l < M.NL; ++l) { long io = (long)M.dims[l] * M.dims[l + 1]; if (io > maxio) maxio = io; }
+  for (int l = 0; l < M.NL; ++l) {
+    long io = (long)M.dims[l] * M.dims[l + 1]; if (io > maxio) maxio = io;
+    c->w_woff[l] = wsum; wsum += (long)((M.dims[l] + 7) / 8 * 8) * ((M.dims[l + 1] + 7) / 8 * 8);
+  }
+  c->w_wstride = wsum; c->w_n8 = N8;
   c->w_kslices = (int)((N + 1023) / 1024); if (c->w_kslices > 64) c->w_kslices = 64; if (c->w_kslices < 1) c->w_kslices = 1;
   c->w_nblk = (int)((N + 255) / 256);
-  CK(cudaMalloc(&c->w_act, (size_t)n_chains * N * act_per_row * 4));
-  CK(cudaMalloc(&c->w_delta[0], (size_t)n_chains * N * maxw * 4));
-  CK(cudaMalloc(&c->w_delta[1], (size_t)n_chains * N * maxw * 4));
+  const size_t actb = (size_t)n_chains * N8 * act_per_row * 4, delb = (size_t)n_chains * N8 * maxw * 4;
+  CK(cudaMalloc(&c->w_act, actb)); CK(cudaMalloc(&c->w_act_lo, actb));
+  CK(cudaMalloc(&c->w_delta[0], delb)); CK(cudaMalloc(&c->w_delta[1], delb));
+  CK(cudaMalloc(&c->w_delta_lo[0], delb)); CK(cudaMalloc(&c->w_delta_lo[1], delb));
+  CK(cudaMalloc(&c->w_wpk, (size_t)n_chains * wsum * 4)); CK(cudaMalloc(&c->w_wpk_lo, (size_t)n_chains * wsum * 4));
+  CK(cudaMalloc(&c->w_wpkT, (size_t)n_chains * wsum * 4)); CK(cudaMalloc(&c->w_wpkT_lo, (size_t)n_chains * wsum * 4));
+  CK(cudaMemset(c->w_wpkT, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpkT_lo, 0, (size_t)n_chains * wsum * 4));
+  CK(cudaMemset(c->w_act, 0, actb)); CK(cudaMemset(c->w_act_lo, 0, actb));
+  CK(cudaMemset(c->w_delta[0], 0, delb)); CK(cudaMemset(c->w_delta[1], 0, delb));
+  CK(cudaMemset(c->w_delta_lo[0], 0, delb)); CK(cudaMemset(c->w_delta_lo[1], 0, delb));
+  CK(cudaMemset(c->w_wpk, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpk_lo, 0, (size_t)n_chains * wsum * 4));
   CK(cudaMalloc(&c->w_part, (size_t)n_chains * c->w_kslices * maxio * 4));
   CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4));
   CK(cudaMalloc(&c->w_ones, (size_t)N * 4));
@@ -843,7 +865,72 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
   return 0;
 }
 
+// ---- TMA tensor maps for the tcgen05 v2 core: 5-D core-matrix view of a row-major [R x Ccols] fp32 matrix ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int tmap_get(mile_ctx* c, const float* ptr, long R, long Ccols, long ld, long bstride, int nbatch, int box_cols, int box_rows,
+                    CUtensorMap* out) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+      return fail("cuTensorMapEncodeTiled is not available");
+    g_encode = (EncodeTiledFn)fn;
+  }
+  auto key = std::make_tuple((const void*)ptr, R, Ccols, ld, bstride, nbatch, box_cols, box_rows);
+  auto it = c->tmaps.find(key);
+  if (it != c->tmaps.end()) { *out = it->second; return 0; }
+  alignas(64) CUtensorMap tm;
+  // row-major [nbatch][R][Ccols] fp32, K (= columns) contiguous; box = box_rows x 32 floats (one 128-byte swizzle atom per row)
+  cuuint64_t dims[3] = {(cuuint64_t)Ccols, (cuuint64_t)R, (cuuint64_t)(nbatch > 0 ? nbatch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(bstride > 0 ? bstride : R * ld) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  c->tmaps[key] = tm;
+  *out = tm;
+  return 0;
+}
+
+static bool tc2_operand_ok(const float* p, const float* plo, long ld, long bstride) {
+  return p && plo && (ld & 3) == 0 && (bstride & 3) == 0 && ((uintptr_t)p & 15) == 0 && ((uintptr_t)plo & 15) == 0;
+}
+
+// returns 1 if launched on the v2 core, 0 if not eligible, -1 on error
+static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
+  const bool a_mn = g.sam == 1 && g.sak != 1, b_mn = g.sbn == 1 && g.sbk != 1;
+  const bool a_k = g.sak == 1, b_k = g.sbk == 1;
+  if (!a_k || !b_k) return 0;   // MN-major tf32 operands: handled by the v1 core (transposes while staging)
+  (void)a_mn; (void)b_mn;
+  const long a_ld = a_mn ? g.sak : g.sam, b_ld = b_mn ? g.sbk : g.sbn;
+  if (!tc2_operand_ok(g.A, g.A_lo, a_ld, g.a_batch) || !tc2_operand_ok(g.B, g.B_lo, b_ld, g.b_batch)) return 0;
+  if ((g.K & 3) || (a_mn && (g.M & 3)) || (b_mn && (g.N & 3))) return 0;
+  Tc2Args t;
+  memset(&t, 0, sizeof(t));
+  if (tmap_get(c, g.A, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_hi)) return -1;
+  if (tmap_get(c, g.A_lo, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_lo)) return -1;
+  if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_hi)) return -1;
+  if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_lo)) return -1;
+  t.M = g.M; t.N = g.N; t.K = g.K; t.kslices = g.kslices; t.nbatch = g.nbatch;
+  t.C = g.C; t.C_lo = g.C_lo; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
+  t.bias = g.bias; t.bias_batch = g.bias_batch; t.aux = g.aux; t.aux_batch = g.aux_batch; t.ldaux = g.ldaux;
+  CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+  dim3 grid((g.N + T2_BN - 1) / T2_BN, (g.M + T2_BM - 1) / T2_BM, g.nbatch * g.kslices);
+  wide_gemm_tc2_kernel<<<grid, 192, T2_SMEM_BYTES, st>>>(t);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
 static int wide_gemm(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
+  if (c->opt_tensor >= 2 && g.K >= 32 && g.N >= 64 && g.M >= 64) {   // TMA-fed warp-specialised tcgen05 core
+    const int r = wide_gemm_tc2(c, g, st);
+    if (r != 0) return r < 0 ? -1 : 0;
+  }
   if (c->opt_tensor && g.K >= 32 && g.N >= 64 && g.M >= 64) {   // large contraction: tcgen05 / TMEM core (3xTF32)
     CK(cudaFuncSetAttribute(wide_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     dim3 grid((g.N + TC_BN - 1) / TC_BN, (g.M + TC_BM - 1) / TC_BM, g.nbatch * g.kslices);
@@ -864,51 +951,67 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   if (wide_alloc(c, n > c->C ? n : c->C)) return -1;
   if (!gl) gl = c->w_gl;
   const DevModel& M = c->M;
-  const long N = c->N;
+  const long N = c->N, N8 = c->w_n8;          // buffers hold N8 rows per chain (pad rows stay zero)
   const int d = c->d, NL = M.NL;
-  std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N][dims[l]]
-  for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N * M.dims[l];
+  std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N8][dims[l]]
+  for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
   auto act = [&](int l) { return c->w_act + aoff[l]; };
+  auto act_lo = [&](int l) { return c->w_act_lo + aoff[l]; };
+  const bool tc2 = c->opt_tensor >= 2;
+  if (tc2) {                                  // aligned packed copies of the weights + their tf32 remainders
+    for (int l = 0; l < NL; ++l) {
+      wide_pack_weights_kernel<<<148, 256, 0, st>>>(theta, d, M.kern_off[l], M.dims[l], M.dims[l + 1], c->w_wpk, c->w_wpk_lo, c->w_wpkT,
+                                                    c->w_wpkT_lo, c->w_woff[l], c->w_wstride, n);
+      c->launches++;
+    }
+    CK(cudaGetLastError());
+  }
   for (int l = 0; l < NL; ++l) {              // forward
     GemmArgs g; memset(&g, 0, sizeof(g));
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
-    else { g.A = act(l); g.a_batch = N * IN; g.sam = IN; g.sak = 1; }
-    g.B = theta + M.kern_off[l]; g.b_batch = d; g.sbk = OUT; g.sbn = 1;
-    g.C = act(l + 1); g.c_batch = N * OUT; g.ldc = OUT; g.M = (int)N; g.N = OUT; g.K = IN; g.kslices = 1;
+    else { g.A = act(l); g.A_lo = act_lo(l); g.a_batch = N8 * IN; g.sam = IN; g.sak = 1; }
+    if (tc2) {   // W^T [OUT x IN]: K-major B for the TMA-fed core (MN-major tf32 operands are not used)
+      g.B = c->w_wpkT + c->w_woff[l]; g.B_lo = c->w_wpkT_lo + c->w_woff[l]; g.b_batch = c->w_wstride; g.sbk = 1; g.sbn = IN;
+    } else { g.B = theta + M.kern_off[l]; g.b_batch = d; g.sbk = OUT; g.sbn = 1; }
+    g.C = act(l + 1); g.C_lo = (tc2 && l < NL - 1) ? act_lo(l + 1) : nullptr;
+    g.c_batch = N8 * OUT; g.ldc = OUT; g.M = (int)N; g.N = OUT; g.K = IN; g.kslices = 1;
     g.epi = l < NL - 1 ? 1 : 2; g.bias = theta + M.bias_off[l]; g.bias_batch = d; g.act = M.act; g.nbatch = n;
     if (wide_gemm(c, g, st)) return -1;
   }
-  const int K = M.dims[NL];
   float* dcur = c->w_delta[(NL - 1) & 1];
-  wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, c->w_llpart);
+  wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, N8, c->w_llpart);
   CK(cudaGetLastError());
   c->launches++;
-  (void)K;
   for (int l = NL - 1; l >= 0; --l) {         // dW_l, db_l, then the delta of the layer below
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     float* D = c->w_delta[l & 1];
+    float* Dlo = c->w_delta_lo[l & 1];
+    const bool d_has_lo = tc2 && l < NL - 1;   // the output-layer delta (from loglik) carries no remainder tensor
     GemmArgs g; memset(&g, 0, sizeof(g));
     if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = 1; g.sak = M.sA[0]; }
-    else { g.A = act(l); g.a_batch = N * IN; g.sam = 1; g.sak = IN; }
-    g.B = D; g.b_batch = N * OUT; g.sbk = OUT; g.sbn = 1;
-    g.M = IN; g.N = OUT; g.K = (int)N; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
+    else { g.A = act(l); g.A_lo = tc2 ? act_lo(l) : nullptr; g.a_batch = N8 * IN; g.sam = 1; g.sak = IN; }
+    g.B = D; g.B_lo = d_has_lo ? Dlo : nullptr; g.b_batch = N8 * OUT; g.sbk = OUT; g.sbn = 1;
+    g.M = IN; g.N = OUT; g.K = (int)N8; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
     g.C = c->w_part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
     if (wide_gemm(c, g, st)) return -1;
     wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
                                                  d + 1, (long)IN * OUT, n);
-    wide_colsum_kernel<<<dim3((OUT + 255) / 256, c->w_kslices, n), 256, 0, st>>>(D, N * OUT, N, OUT, c->w_kslices, c->w_part,
+    wide_colsum_kernel<<<dim3((OUT + 255) / 256, c->w_kslices, n), 256, 0, st>>>(D, N8 * OUT, N, OUT, c->w_kslices, c->w_part,
                                                                                    (long)c->w_kslices * OUT);
     wide_slice_reduce_kernel<<<32, 256, 0, st>>>(c->w_part, (long)c->w_kslices * OUT, OUT, c->w_kslices, gl + M.bias_off[l],
                                                 d + 1, (long)OUT, n);
     CK(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 3;
     if (l > 0) {
       GemmArgs w; memset(&w, 0, sizeof(w));
-      w.A = D; w.a_batch = N * OUT; w.sam = OUT; w.sak = 1;
-      w.B = theta + M.kern_off[l]; w.b_batch = d; w.sbk = 1; w.sbn = OUT;     // B(k=j, n=i) = W[i][j]
-      w.C = c->w_delta[(l - 1) & 1]; w.c_batch = N * IN; w.ldc = IN; w.M = (int)N; w.N = IN; w.K = OUT; w.kslices = 1;
-      w.epi = 3; w.aux = act(l); w.aux_batch = N * IN; w.ldaux = IN; w.act = M.act; w.nbatch = n;
+      w.A = D; w.A_lo = d_has_lo ? Dlo : nullptr; w.a_batch = N8 * OUT; w.sam = OUT; w.sak = 1;
+      if (tc2) { w.B = c->w_wpk + c->w_woff[l]; w.B_lo = c->w_wpk_lo + c->w_woff[l]; w.b_batch = c->w_wstride; }
+      else { w.B = theta + M.kern_off[l]; w.b_batch = d; }
+      w.sbk = 1; w.sbn = OUT;                                                   // B(k=j, n=i) = W[i][j]
+      w.C = c->w_delta[(l - 1) & 1]; w.C_lo = tc2 ? c->w_delta_lo[(l - 1) & 1] : nullptr;
+      w.c_batch = N8 * IN; w.ldc = IN; w.M = (int)N; w.N = IN; w.K = OUT; w.kslices = 1;
+      w.epi = 3; w.aux = act(l); w.aux_batch = N8 * IN; w.ldaux = IN; w.act = M.act; w.nbatch = n;
       if (wide_gemm(c, w, st)) return -1;
     }
   }
@@ -1010,6 +1113,39 @@ int mile_shard_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const
   k.ev_end = cfg->desired_energy_var_end; k.trust = cfg->trust_in_estimate; k.neff = cfg->num_effective_samples;
   S.tune = 1;
   return shard_run(c, S, n_steps, (cudaStream_t)stream);
+}
+
+
+// Developer / test hook: C[M,N] = A(M,K) * B(K,N) with chosen operand orientations through the wide-path GEMM cores
+// (core: 0 SIMT, 1 tcgen05 v1, 2 tcgen05 v2 TMA).  a_mn: A stored [K x M] (m contiguous) instead of [M x K];
+// b_mn: B stored [K x N] (n contiguous) instead of [N x K].  Host pointers.
+int mile_debug_wide_gemm(int32_t device, int32_t core, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                         const float* A_host, const float* B_host, float* C_host) {
+  CK(cudaSetDevice(device));
+  mile_ctx ctx;   // only the tensor-map cache / launch counter are used
+  ctx.opt_tensor = core;
+  float *A, *Alo, *B, *Blo, *Cd;
+  const long K8 = (K + 7) / 8 * 8;
+  const size_t ab = (size_t)(a_mn ? K8 * M : (long)((M + 7) / 8 * 8) * K) * 4, bb = (size_t)(b_mn ? K8 * N : (long)((N + 7) / 8 * 8) * K) * 4;
+  CK(cudaMalloc(&A, ab)); CK(cudaMalloc(&Alo, ab)); CK(cudaMalloc(&B, bb)); CK(cudaMalloc(&Blo, bb)); CK(cudaMalloc(&Cd, (size_t)M * N * 4));
+  CK(cudaMemset(A, 0, ab)); CK(cudaMemset(Alo, 0, ab)); CK(cudaMemset(B, 0, bb)); CK(cudaMemset(Blo, 0, bb));
+  std::vector<float> lo;
+  auto up = [&](float* hi_d, float* lo_d, const float* h, size_t n) -> int {
+    lo.resize(n);
+    for (size_t i = 0; i < n; ++i) { uint32_t u; memcpy(&u, &h[i], 4); u &= 0xFFFFE000u; float t; memcpy(&t, &u, 4); lo[i] = h[i] - t; }
+    CK(cudaMemcpy(hi_d, h, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(lo_d, lo.data(), n * 4, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (up(A, Alo, A_host, (size_t)M * K) || up(B, Blo, B_host, (size_t)N * K)) return -1;
+  GemmArgs g; memset(&g, 0, sizeof(g));
+  g.A = A; g.A_lo = Alo; g.B = B; g.B_lo = Blo; g.C = Cd; g.ldc = N; g.M = M; g.N = N; g.K = K; g.kslices = 1; g.nbatch = 1;
+  if (a_mn) { g.sam = 1; g.sak = M; } else { g.sam = K; g.sak = 1; }
+  if (b_mn) { g.sbk = N; g.sbn = 1; } else { g.sbk = 1; g.sbn = K; }
+  if (wide_gemm(&ctx, g, 0)) return -1;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(C_host, Cd, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  cudaFree(A); cudaFree(Alo); cudaFree(B); cudaFree(Blo); cudaFree(Cd);
+  return 0;
 }
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }

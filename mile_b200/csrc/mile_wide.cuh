@@ -16,6 +16,7 @@ struct GemmArgs {
   const float* A; long a_batch; long sam, sak;     // A(m,k) = A[b*a_batch + m*sam + k*sak]
   const float* B; long b_batch; long sbk, sbn;     // B(k,n) = B[b*b_batch + k*sbk + n*sbn]
   float* C; long c_batch; long ldc;                // C(m,n) = C[b*c_batch + s*c_slice + m*ldc + n]
+  const float* A_lo; const float* B_lo; float* C_lo;   // tf32 remainders (v - tf32(v)) for the tcgen05 v2 core; C_lo optional output
   int M, N, K, kslices; long c_slice;
   int epi;                                         // 0 none | 1 +bias, act | 2 +bias | 3 * act'(aux value)
   const float* bias; long bias_batch;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(const GemmArgs g) {
       else if (g.epi == 2) v = v + bias[n];
       else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n]);
       C[(long)m * g.ldc + n] = v;
+      if (g.C_lo) g.C_lo[(long)b * g.c_batch + (long)ks * g.c_slice + (long)m * g.ldc + n] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
   }
 }
@@ -141,15 +143,15 @@ __global__ void __launch_bounds__(256) wide_colsum_kernel(const float* __restric
 
 // per (chain, row): log-likelihood term and d/d(out) (probabilistic.py:93-109); block partial sums of ll
 __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const float* __restrict__ out, float* __restrict__ dout,
-                                                          const void* __restrict__ y, long N, float* __restrict__ llpart) {
+                                                          const void* __restrict__ y, long N, long N8, float* __restrict__ llpart) {
   __shared__ float red[64];
   int phase = 0;
   const int c = blockIdx.y, K = M.dims[M.NL];
   const long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
   float ll = 0.f;
   if (r < N) {
-    const float* o = out + ((long)c * N + r) * K;
-    float* dd = dout + ((long)c * N + r) * K;
+    const float* o = out + ((long)c * N8 + r) * K;
+    float* dd = dout + ((long)c * N8 + r) * K;
     if (M.task == MILE_TASK_REGRESSION) {
       const float yv = reinterpret_cast<const float*>(y)[r], mu = o[0], s = o[1];
       const float e = expf(s), sigma = fminf(fmaxf(e, 1e-6f), 1e6f);
@@ -387,15 +389,201 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
   }
   tc_wait(mbar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  if (warp < 4) {   // epilogue: warp w owns TMEM lanes [32w, 32w+32) == output rows m0 + 32w + lane
+  // Epilogue through shared memory (the operand stages are free now): warps 0-3 drain 32 accumulator columns at a
+  // time from TMEM into a [128][36] tile (conflict-free float4 rows), then ALL warps apply bias / activation / act'
+  // and write float4s with 8 lanes covering one 128-byte row segment -> fully coalesced global stores and aux loads.
+  {
     float* C = g.C + (long)b * g.c_batch + (long)ks * g.c_slice;
+    float* Clo = g.C_lo ? g.C_lo + (long)b * g.c_batch + (long)ks * g.c_slice : nullptr;
     const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
     const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
-    const int m = m0 + warp * 32 + lane;
+    float* tile = reinterpret_cast<float*>(tsm);          // 2 x [128][36] floats (double buffered)
+    constexpr int TS = 36;
 #pragma unroll 1
     for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      float* tb = tile + ((c0 >> 5) & 1) * (TC_BM * TS);
+      if (warp < 4) {   // warp w owns TMEM lanes [32w, 32w+32) == tile rows 32w + lane
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        float* trow = tb + (warp * 32 + lane) * TS;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(trow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                             __uint_as_float(r[j + 3]));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < (TC_BM * 8) / 256; ++it) {
+        const int idx = tid + it * 256, row = idx >> 3, cq = idx & 7;
+        const int m = m0 + row, n = n0 + c0 + cq * 4;
+        if (m >= g.M || n >= g.N) continue;
+        const float4 t4 = *reinterpret_cast<const float4*>(tb + row * TS + cq * 4);
+        float o[4] = {t4.x, t4.y, t4.z, t4.w};
+        float* crow = C + (long)m * g.ldc + n;
+        const bool full4 = n + 3 < g.N, al = full4 && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (n + e < g.N) {
+            if (g.epi == 1) o[e] = act_value(g.act, o[e] + bias[n + e]);
+            else if (g.epi == 2) o[e] = o[e] + bias[n + e];
+            else if (g.epi == 3) o[e] = o[e] * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n + e]);
+          }
+        }
+        if (al) {
+          *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+          if (Clo) *reinterpret_cast<float4*>(Clo + (long)m * g.ldc + n) =
+              make_float4(o[0] - tf32_hi(o[0]), o[1] - tf32_hi(o[1]), o[2] - tf32_hi(o[2]), o[3] - tf32_hi(o[3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (n + e < g.N) { crow[e] = o[e]; if (Clo) Clo[(long)m * g.ldc + n + e] = o[e] - tf32_hi(o[e]); }
+        }
+      }
+      // (double buffered: the tile written two chunks ago is only overwritten after the next __syncthreads)
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_BN));
+}
+
+// =====================================================================================================
+// tcgen05 GEMM, version 2: TMA-fed, warp-specialised, 4-stage pipeline.
+// Operands are pre-split once by their producers (every epilogue writes v and lo = v - tf32(v); the tf32 datapath
+// truncates v itself, so v serves as the "hi" operand), which leaves NO thread work in the main loop:
+//   warp 0 (one lane)  TMA producer: 4 cp.async.bulk.tensor.5d per stage (A, A_lo, B, B_lo) -> full barrier
+//   warp 1 (one lane)  MMA issuer: 6 tcgen05.mma kind::tf32 (M128 N256 K8, 3xTF32) per stage, tcgen05.commit -> empty barrier
+//   warps 2-5          epilogue: tcgen05.ld -> bias / activation / act' -> v and lo to global
+// Operands are K-major (rows = M / N index, K contiguous) [rows x 32 fp32] tiles = one 128-byte swizzle atom per row:
+// 3-D tensor maps {K, rows, batch}, box {32, rows, 1}, CU_TENSOR_MAP_SWIZZLE_128B; UMMA descriptors with
+// SWIZZLE_128B, SBO = 1024 B (8 rows x 128 B), k-step = +32 B inside the atom.  (A 5-D "core matrix" view that
+// lands boxes in the no-swizzle canonical layout also works -- tools/tma_probe.cu -- but its 16-byte inner
+// extent makes TMA the bottleneck; MN-major tf32 operands did not give correct results with the no-swizzle
+// descriptors, so the dW GEMMs (K = data rows) stay on the v1 core, which transposes while staging.)
+// =====================================================================================================
+#include <cuda.h>
+
+#define T2_BM 128
+#define T2_BN 256
+#define T2_BK 32
+#define T2_STAGES 2
+#define T2_A_BYTES (T2_BM * T2_BK * 4)
+#define T2_B_BYTES (T2_BN * T2_BK * 4)
+#define T2_STAGE_BYTES (2 * T2_A_BYTES + 2 * T2_B_BYTES)
+#define T2_SMEM_BYTES (T2_STAGES * T2_STAGE_BYTES + 256)
+
+struct Tc2Args {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int M, N, K, kslices, nbatch;
+  float* C; float* C_lo; long c_batch, c_slice, ldc;
+  int epi, act;
+  const float* bias; long bias_batch;
+  const float* aux; long aux_batch, ldaux;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1L << 24)) __trap();   // a wrong descriptor must end in a trap, never in a hung GPU
+  }
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B descriptor: LBO unused (1), SBO = 1024 B between 8-row groups, layout type 2
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(192, 1) wide_gemm_tc2_kernel(const __grid_constant__ Tc2Args g) {
+  extern __shared__ __align__(1024) char sm2[];
+  const uint32_t sbase = smem_u32(sm2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm2 + T2_STAGES * T2_STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);                       // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (S + s), tmem_full = bar0 + 16 S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z / g.kslices, ks = blockIdx.z % g.kslices;
+  const int m0 = blockIdx.y * T2_BM, n0 = blockIdx.x * T2_BN;
+  const int kper = ((g.K + g.kslices - 1) / g.kslices + T2_BK - 1) / T2_BK * T2_BK;
+  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
+  const int nkb = kend > kbeg ? (kend - kbeg + T2_BK - 1) / T2_BK : 0;
+  if (tid == 0) {
+    for (int s = 0; s < 2 * T2_STAGES + 1; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(T2_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer ----
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
+        mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
+        const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)T2_STAGE_BYTES) : "memory");
+        const int k0 = kbeg + kb * T2_BK;
+        tma_load_3d(st, &g.a_hi, k0, m0, b, full);
+        tma_load_3d(st + T2_A_BYTES, &g.a_lo, k0, m0, b, full);
+        tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0, b, full);
+        tma_load_3d(st + 2 * T2_A_BYTES + T2_B_BYTES, &g.b_lo, k0, n0, b, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer ----
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
+        mbar_wait(bar0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sbase + s * T2_STAGE_BYTES;
+        const uint32_t ahi = st, alo = st + T2_A_BYTES, bhi = st + 2 * T2_A_BYTES, blo = bhi + T2_B_BYTES;
+#pragma unroll
+        for (int j = 0; j < T2_BK / 8; ++j) {   // K = 8 tf32 = 32 B further inside the 128-byte swizzle atom
+          const uint32_t o = j * 32;
+          umma_tf32(tmem, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, (kb == 0 && j == 0) ? 0u : 1u);
+          umma_tf32(tmem, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
+          umma_tf32(tmem, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (T2_STAGES + s)) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 * T2_STAGES) : "memory");
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----
+    mbar_wait(bar0 + 16 * T2_STAGES, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    float* C = g.C + (long)b * g.c_batch + (long)ks * g.c_slice;
+    float* Clo = g.C_lo ? g.C_lo + (long)b * g.c_batch + (long)ks * g.c_slice : nullptr;
+    const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
+    const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < T2_BN; c0 += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
           "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -404,8 +592,8 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
             "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      if (m < g.M) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < g.M && nkb > 0) {
         float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -419,17 +607,50 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
           o[j] = v;
         }
         float* crow = C + (long)m * g.ldc + n0 + c0;
-        if (n0 + c0 + 32 <= g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+        const bool vec = n0 + c0 + 32 <= g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+        if (vec) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) crow[j] = o[j];
         }
+        if (Clo) {
+          float* lrow = Clo + (long)m * g.ldc + n0 + c0;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(lrow + j) = make_float4(o[j] - tf32_hi(o[j]), o[j + 1] - tf32_hi(o[j + 1]),
+                                                                 o[j + 2] - tf32_hi(o[j + 2]), o[j + 3] - tf32_hi(o[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) lrow[j] = o[j] - tf32_hi(o[j]);
+          }
+        }
+      } else if (m < g.M && nkb == 0) {   // empty k-slice: contributes zeros
+        for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) C[(long)m * g.ldc + n0 + c0 + j] = 0.f;
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_BN));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(T2_BN));
+}
+
+// lo = v - tf32(v) of the layer weights into 16-byte aligned packed buffers (theta's own offsets / chain stride are not
+// TMA-aligned): wpk_hi[c][off_l + e] = W_l[e], wpk_lo = W_l[e] - tf32(W_l[e])
+__global__ void wide_pack_weights_kernel(const float* __restrict__ theta, int d, int kern_off, int IN, int OUT, float* __restrict__ hi,
+                                         float* __restrict__ lo, float* __restrict__ hiT, float* __restrict__ loT, long pack_off,
+                                         long pack_stride, int nbatch) {
+  // W [IN x OUT] row-major (K-major B of the backward GEMM) and W^T [OUT x IN] (K-major B of the forward GEMM)
+  const long n_elem = (long)IN * OUT, total = n_elem * nbatch;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long b = t / n_elem, e = t % n_elem;
+    const int i = (int)(e / OUT), j = (int)(e % OUT);
+    const float v = theta[b * d + kern_off + e], l = v - tf32_hi(v);
+    hi[b * pack_stride + pack_off + e] = v;
+    lo[b * pack_stride + pack_off + e] = l;
+    hiT[b * pack_stride + pack_off + (long)j * IN + i] = v;
+    loT[b * pack_stride + pack_off + (long)j * IN + i] = l;
+  }
 }
