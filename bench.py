@@ -288,6 +288,10 @@ def run_ours(args):
     h2d = X.nbytes + y.nbytes + 3 * C * d * 4 + C * 4 + 2 * C * 4
     d2h = n_slots * C * d * 4 + 3 * C * d * 4 + C * 4
     e2e_steps = max(1, min(args.steps, 5))
+    # one untimed pass first: the host-buffer entry points allocate their pinned staging buffers on first use
+    ens.set_data(Xp, y); ens.set_state(*st)
+    ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4320, lppd=False)
+    ens.set_state(*st)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):

@@ -69,7 +69,7 @@ struct mile_ctx {
         *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
   float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
   float* carry = nullptr; int carry_valid = 0;
-  float* xchg = nullptr; unsigned int* xcount = nullptr; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
+  float2* xchg = nullptr; unsigned int xepoch = 0; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
   void* nccl_comm = nullptr; int world = 1, rank = 0;
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
@@ -249,16 +249,19 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   CK(cudaSetDevice(c->device));
   pl.kp.sync_mode = pl.sync_mode;
   if (pl.sync_mode) {
-    const size_t need = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4) * 4;
-    if (need > c->xchg_bytes || !c->xcount) {
-      if (c->xchg) cudaFree(c->xchg);
-      if (c->xcount) cudaFree(c->xcount);
-      CK(cudaMalloc(&c->xchg, need));
-      CK(cudaMalloc(&c->xcount, (size_t)(n_chains > c->C ? n_chains : c->C) * 4 + 1024));
-      c->xchg_bytes = need;
+    const size_t need = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4) * sizeof(float2);
+    const unsigned int adv = 2u * (unsigned int)(pl.kp.n_steps > 0 ? pl.kp.n_steps : 0) + 2u;
+    if (need > c->xchg_bytes || c->xepoch > 0xF0000000u - adv) {   // (re)allocate, or restart the flag epoch before it wraps
+      if (need > c->xchg_bytes) {
+        if (c->xchg) cudaFree(c->xchg);
+        CK(cudaMalloc(&c->xchg, need));
+        c->xchg_bytes = need;
+      }
+      CK(cudaMemsetAsync(c->xchg, 0, c->xchg_bytes, st));
+      c->xepoch = 0;
     }
-    CK(cudaMemsetAsync(c->xcount, 0, (size_t)n_chains * 4, st));
-    pl.kp.xchg = c->xchg; pl.kp.xcount = c->xcount;
+    pl.kp.xchg = c->xchg; pl.kp.xbase = c->xepoch;   // flags of this launch: xbase+1 .. xbase+n_evals (never 0, never reused)
+    c->xepoch += adv;
   }
   const int NL = c->M.NL;
   int rc;
@@ -376,7 +379,7 @@ void mile_destroy(mile_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
-                  c->gl, c->scal, c->thb, c->ub, c->gb, c->xchg, (float*)c->xcount, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
+                  c->gl, c->scal, c->thb, c->ub, c->gb, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
                   c->w_ones, c->w_gl, c->w_act_lo, c->w_delta_lo[0], c->w_delta_lo[1], c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);

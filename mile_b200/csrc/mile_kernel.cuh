@@ -39,7 +39,9 @@ struct KParams {
   const float* theta_in; float* lp_out; float* grad_out; float* pred_out; int n_eval, which;
   // global-memory exchange (sync_mode 1): any number of CTAs per chain, cooperative launch, partial gradients and an
   // arrival counter in HBM/L2 instead of DSMEM + cluster barrier (lets <= 12 chains use all 148 SMs)
-  int sync_mode; float* xchg; unsigned int* xcount;   // xchg [C][2][G][dS+4], xcount [C]
+  // Exchange words are {value, epoch flag} pairs written with one 8-byte store each (the NCCL "LL" idea): a reader
+  // spins on the data word itself, so there is no fence, no atomic counter and no separate barrier on the critical path.
+  int sync_mode; float2* xchg; unsigned int xbase;   // xchg [C][2][G][dS+4] (value, flag); flag = xbase + eval + 1
   int out_stride;        // row stride of grad_out / lp_out (d, or d+1 for the packed [C,d+1] all-reduce buffer)
   float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)
@@ -204,9 +206,37 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
 // DSMEM all-reduce of the cluster's partial gradients + prior: afterwards gg = full gradient of
 // the log-posterior (bit-identical in every CTA), returns the log-posterior value.  Also returns
 // sum g^2, sum u.g and the number of non-finite entries of theta for the next B-step / handle_nans.
+// 8-byte flagged word of the global exchange (sync_mode 1)
+__device__ __forceinline__ void ll_store(float2* p, float v, unsigned int flag) {
+  asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(flag) : "memory");
+}
+// sum over the G ranks' flagged words at the same offset; spins (bounded) until every word carries `flag`
+__device__ __forceinline__ float ll_sum(const float2* base, int stride, int G, unsigned int flag) {
+  uint32_t v[16], f[16];
+  long spin = 0;
+  bool ok;
+  do {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < G) asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v[r]), "=r"(f[r]) : "l"(base + (long)r * stride) : "memory");
+      else { v[r] = 0u; f[r] = flag; }
+    }
+    ok = true;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ok = ok && (f[r] == flag);
+    if (!ok && ++spin > (1L << 24)) __trap();
+  } while (!ok);
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) s += __uint_as_float(v[r]);
+  return s;
+}
+
 template <int NT, int BAR>
-__device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float& g2, float& ug, float& nonfinite) {
-  // (the caller has already executed the cluster / block barrier that publishes every CTA's gpart)
+__device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const float2* gslab, unsigned int flag, float& g2, float& ug,
+                                                     float& nonfinite) {
+  // (DSMEM mode: the caller has already executed the cluster / block barrier that publishes every CTA's gpart;
+  //  global mode: gslab = this chain's parity slab of flagged words, waited on element by element)
   const KParams& P = c.P;
   const DevModel& M = P.M;
   cg::cluster_group cluster = cg::this_cluster();
@@ -215,15 +245,13 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   const float* rp[16];
   const int stride_g = P.dS + 4;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    if (P.sync_mode) rp[r] = gpart + (r < c.G ? r : 0) * stride_g;          // gpart = this chain's parity slab in global memory
-    else rp[r] = (c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
-  }
+  for (int r = 0; r < 16; ++r) rp[r] = (!P.sync_mode && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
   float ll = 0.f;
-  {
+  if (P.sync_mode) ll = ll_sum(gslab + P.dS, stride_g, c.G, flag);
+  else {
     float t[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? (P.sync_mode ? __ldcg(rp[r] + P.dS) : rp[r][P.dS]) : 0.f;
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
 #pragma unroll
     for (int r = 0; r < 16; ++r) ll += t[r];
   }
@@ -231,12 +259,15 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, float
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
   const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
   for (int i = threadIdx.x; i < M.d; i += NT) {
-    float t[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? (P.sync_mode ? __ldcg(rp[r] + i) : rp[r][i]) : 0.f;
     float s = 0.f;
+    if (P.sync_mode) s = ll_sum(gslab + i, stride_g, c.G, flag);
+    else {
+      float t[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s += t[r];
+      for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += t[r];
+    }
     const float th = c.th[i];
     float pg, pv;
     if (M.prior == MILE_PRIOR_NORMAL) {
@@ -572,35 +603,24 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     float* gp = c.gpart + (e & 1) * (P.dS + 4);
     GE::run(c, r0, r1, gp);
     PROF(10);
-    float* gsrc = gp;
+    const float2* gslab = nullptr;
+    const unsigned int xflag = P.xbase + (unsigned int)e + 1u;
     if (c.G > 1 && P.sync_mode) {
-      // global exchange: publish this CTA's partial, arrive on the chain's counter, wait for all G CTAs
-      float* slab = P.xchg + ((long)ch * 2 + (e & 1)) * c.G * (P.dS + 4);
-      float* mine = slab + c.rank * (P.dS + 4);
+      // global exchange: publish this CTA's partial as flagged 8-byte words; readers wait on the words themselves.
+      // Two parity slabs suffice: a CTA can only publish eval e+2 after it has read every rank's eval e+1, which
+      // each rank publishes after it finished reading eval e.
+      float2* slab = P.xchg + ((long)ch * 2 + (e & 1)) * c.G * (P.dS + 4);
+      float2* mine = slab + c.rank * (P.dS + 4);
       __syncthreads();
-      for (int i = tid; i <= P.dS; i += NT) __stcg(mine + i, gp[i]);
-      __syncthreads();
-      if (tid == 0) {   // same release / acquire pattern as cooperative_groups::grid_group::sync
-        const unsigned int target = (unsigned int)c.G * (unsigned int)(e + 1);
-        __threadfence();
-        atomicAdd(P.xcount + ch, 1u);
-        unsigned int seen;
-        long spin = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.xcount + ch) : "memory");
-          if (seen < target && ++spin > (1L << 28)) __trap();
-        } while (seen < target);
-        __threadfence();
-      }
-      __syncthreads();
-      gsrc = slab;
+      for (int i = tid; i <= P.dS; i += NT) ll_store(mine + i, gp[i], xflag);
+      gslab = slab;
     } else if (c.G > 1) {
       cluster.sync();      // publishes every CTA's partial gradient (DSMEM)
     } else {
       __syncthreads();
     }
     if (integ) {
-      const float lp_new = cluster_reduce_grad<NI, IB>(c, gsrc, g2, ug, nf);
+      const float lp_new = cluster_reduce_grad<NI, IB>(c, gp, gslab, xflag, g2, ug, nf);
       PROF(11);
       if (!stepping) {
         if (P.mode == MODE_EVAL) {
