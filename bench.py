@@ -37,8 +37,23 @@ WORKLOADS = {
     'covertype_ref': ('covertype_ref', 12, 500),
     'airfoil_3x16_1024': ('airfoil_3x16', 1024, 200),
     'wide_4x256': ('wide_4x256', 8, 10),          # HBM-resident chain-batched GEMM path (no fused LPPD fold)
+    # BASELINE.json configs[2]: every rank holds all 12 chains and 1/N of the 232 404 rows; one NCCL all-reduce of the
+    # packed [C, d+1] (gradient, log-lik) per evaluation.  Strong scaling: total work is fixed as N grows.
+    'covertype_full': ('covertype_full', 12, 20),
 }
 N_THINNING = 10  # every reference MCLMC YAML (experiments/*/mclmc.yaml: n_thinning 10)
+
+
+def load_tensor_peak():
+    """Measured dense bf16 tensor throughput (MEASURED_PEAKS.json), else the profiling recipe's fallback."""
+    try:
+        pk = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())
+        for k in ('bf16_tflops', 'bf16_tflops_sustained', 'tensor_bf16_tflops'):
+            if k in pk:
+                return float(pk[k]), f'MEASURED_PEAKS.json {k}'
+    except Exception:
+        pass
+    return 1626.1, 'fallback: measured cuBLAS bf16 figure quoted in SURVEY.md 8(d)'
 
 
 def flops_per_chain_step(n_rows, dims):
@@ -202,7 +217,15 @@ def run_ours(args):
     X, y, Xt, yt = o.synthetic_data(key, seed=1234)   # same split on every rank; the CHAINS are what shards
     d = ospec.n_params
     spec = FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task)
-    ens = Ensemble(spec, C, device=local)
+    sharded = key == 'covertype_full'
+    if sharded:
+        from mile_b200 import ShardedEnsemble
+        ens = ShardedEnsemble(spec, C, device=local, rank=rank, world=world)
+        rows = ShardedEnsemble.shard_rows(X.shape[0], rank, world)
+        Xfull, yfull = X, y
+        X, y = np.ascontiguousarray(X[rows]), np.ascontiguousarray(y[rows])
+    else:
+        ens = Ensemble(spec, C, device=local)
     if args.cluster:
         ens.set_option('cluster_size', args.cluster)
     if args.tile_rows:
@@ -210,19 +233,20 @@ def run_ours(args):
     if args.tensor >= 0:
         ens.set_option('tensor', args.tensor)
     ens.set_data(X, y)
-    fused_lppd = key != 'wide_4x256'
+    fused_lppd = key != 'wide_4x256' and not sharded
     if fused_lppd:
         ens.set_test(Xt, yt)      # fused posterior-predictive LPPD fold at every kept sample
-    th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * rank, scale=0.3 if key != 'wide_4x256' else 0.05)
-    ens.init(th0, seed=17 + rank)
+    crank = 0 if sharded else rank        # sharded: every rank carries the SAME chains (same seeds, same noise)
+    th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * crank, scale=0.3 if key != 'wide_4x256' else 0.05)
+    ens.init(th0, seed=17 + crank)
     # short tuning run -> frozen (eps, L); fallback eps=0.02, L=sqrt(d)
     eps = np.full(C, 0.02, np.float32)
     L = np.full(C, np.sqrt(d), np.float32)
     if not args.no_tune:
         ens.tune_reset(0.01)
-        nt1, nt2 = (800, 100) if key != 'wide_4x256' else (40, 10)
+        nt1, nt2 = (40, 10) if key in ('wide_4x256', 'covertype_full') else (800, 100)
         tc = ens.tune_cfg(nt1, nt2, 0.5, 0.1, 1.5, 100)
-        ens.tune(nt1 + nt2, 0, tc, seed=99 + rank)
+        ens.tune(nt1 + nt2, 0, tc, seed=99 + crank)
         ens.tune_finish_phase2()
         e, l, _ = ens.get_tuning()
         if np.all(np.isfinite(e)) and np.all(e > 0) and np.all(np.isfinite(l)) and np.all(l > 0):
@@ -271,7 +295,8 @@ def run_ours(args):
         t = torch.tensor([t_dev], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev = float(t.item())
-    chain_steps = world * C * inner * args.steps
+    nrep = 1 if sharded else world        # sharded: the ranks share one set of chains
+    chain_steps = nrep * C * inner * args.steps
     value = chain_steps / t_dev
     # the one exchange step of the path: merge the per-chain online logsumexp states (NCCL all-gather)
     from mile_b200.distributed import merge_lppd_states
@@ -305,7 +330,7 @@ def run_ours(args):
         t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    e2e_value = world * C * inner * e2e_steps / t_e2e
+    e2e_value = nrep * C * inner * e2e_steps / t_e2e
     finite = bool(np.all(np.isfinite(smp)))
 
     if rank == 0:
@@ -316,23 +341,24 @@ def run_ours(args):
             capi.check(ens.lib.mile_measure_fp32_peak(local, v, ctypes.byref(pk[v])))
         fp32_peak = max(pk[0].value, pk[1].value)
         hbm_peak, peak_src = load_peaks()
-        Ntr = X.shape[0]
+        Ntr = Xfull.shape[0] if sharded else X.shape[0]
         fl = flops_per_chain_step(Ntr, ospec.dims)
-        per_gpu_steps_per_s = value / world
+        per_gpu_steps_per_s = value / world     # (sharded: each GPU does 1/world of every chain-step's rows)
         achieved_tf = per_gpu_steps_per_s * fl / 1e12
         hbm_bytes_per_launch = C * (4 * d * 4 + n_slots * d * 4) + X.nbytes * 0  # state r/w + samples
         line = {
             'metric': 'chain-steps/sec', 'value': value, 'unit': 'chain-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
             'config': {'workload': W, 'chains_per_gpu': C, 'inner_steps_per_launch': inner, 'n_train': int(Ntr),
                        'n_features': ospec.n_features, 'hidden_structure': list(ospec.widths), 'n_params': d,
                        'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10',
                        'cluster_size': ens.get_option('cluster_size'), 'tile_rows': ens.get_option('tile_rows'),
                        'x_resident_in_smem': bool(ens.get_option('resident')),
-                       'kernel_path': ('wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')) if ens.get_option('wide') else ('FastGE pipeline' if ens.get_option('fast') else 'GenericGE'),
+                       'kernel_path': 'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step' if sharded else (('wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')) if ens.get_option('wide') else ('FastGE pipeline' if ens.get_option('fast') else 'GenericGE')),
                        'l2': 'flushed between timed iterations (256 MiB write); working set is SMEM-resident',
-                       'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()), 'parallelism': f'chains x{world}'},
+                       'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()), 'parallelism': (f'rows x{world} + NCCL all-reduce of [C, d+1] per gradient evaluation' if sharded else f'chains x{world}')},
             'grad_evals_per_s': 2 * value,
             'samples_finite': finite,
             'lppd': {'value': lppd_val, 'samples': int(lppd_total), 'merge_ms': lppd_ms,
@@ -343,15 +369,24 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
                     'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers) + get_state'},
-            'roofline': {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': None,
-                         'kernel': 'mile_mclmc_kernel', 'flops_per_chain_step': fl,
-                         'peak_source': f'live FMA micro-benchmark (FFMA {pk[0].value:.1f}, FFMA2 {pk[1].value:.1f} TFLOP/s)',
-                         'avg_launch_ms': float(np.mean(kernel_ms)),
-                         'hbm': {'achieved_gbs': hbm_bytes_per_launch / (np.mean(kernel_ms) * 1e-3) / 1e9,
-                                 'peak_gbs': hbm_peak, 'peak_source': peak_src,
-                                 'note': 'tiny by design: theta/u/g and the X slice stay in shared memory for the whole launch'}},
         }
+        roof = {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': None,
+                'kernel': 'mile_mclmc_kernel', 'flops_per_chain_step': fl,
+                'peak_source': f'live FMA micro-benchmark (FFMA {pk[0].value:.1f}, FFMA2 {pk[1].value:.1f} TFLOP/s)',
+                'note': 'SURVEY.md 8(d): these shapes are bound by the FP32 FMA pipe (working set in SMEM/L2), '
+                        'neither by HBM nor by the tensor pipe; the HBM view is given below for completeness',
+                'avg_launch_ms': float(np.mean(kernel_ms)),
+                'hbm': {'achieved_gbs': hbm_bytes_per_launch / (np.mean(kernel_ms) * 1e-3) / 1e9,
+                        'peak_gbs': hbm_peak, 'peak_source': peak_src,
+                        'note': 'tiny by design: theta/u/g and the X slice stay in shared memory for the whole launch'}}
+        if ens.get_option('wide') and ens.get_option('tensor'):
+            tpk, tsrc = load_tensor_peak()
+            roof.update({'bound': 'tensor', 'peak': tpk, 'frac': achieved_tf / tpk, 'peak_source': tsrc,
+                         'kernel': 'wide_gemm_tc_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32-level accuracy)',
+                         'note': 'achieved = ALGORITHMIC fp32 FLOPs (12 N W per chain-step); the 3xTF32 split issues 3x that '
+                                 'on the tensor pipe, and TF32 dense peak is half the bf16 figure used as denominator'})
+        line['roofline'] = roof
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_chain_steps_per_s(W)
         print(json.dumps(line))

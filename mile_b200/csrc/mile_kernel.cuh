@@ -247,8 +247,10 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
 #pragma unroll
   for (int r = 0; r < 16; ++r) rp[r] = (!P.sync_mode && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
   float ll = 0.f;
-  if (P.sync_mode) ll = ll_sum(gslab + P.dS, stride_g, c.G, flag);
-  else {
+  if (P.sync_mode) {
+    // only one thread fetches the log-likelihood partials (it folds them into its v[0] below): a second serial L2
+    // round trip for every thread would sit on the critical path
+  } else {
     float t[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
@@ -283,6 +285,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     c.gg[i] = g;
     v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   }
+  if (P.sync_mode && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, c.G, flag);
   block_sum<4, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
   return v[0] + ll;

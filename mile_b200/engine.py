@@ -353,6 +353,15 @@ class ShardedEnsemble(Ensemble):
         torch.cuda.current_stream().synchronize()
         return (None if smp is None else smp.cpu().numpy()), (None if inf is None else inf.cpu().numpy())
 
+    def sample_device(self, n_steps, step_size_dev, L_dev, *, step_base=0, n_thinning=1, sample_base=0, z_dev=None,
+                      seed=0, samples_dev=None, n_slots=0, info_dev=None, lppd=False):
+        """Device-buffer form of `sample` on torch's current stream (no host transfer, asynchronous)."""
+        if lppd:
+            raise NotImplementedError('fused LPPD is not part of the sharded step loop; use lppd_accumulate')
+        capi.check(self.lib.mile_shard_mclmc_sample(self.h, n_steps, step_base, n_thinning, sample_base,
+                                                    _dev_ptr(step_size_dev), _dev_ptr(L_dev), _dev_ptr(z_dev), seed,
+                                                    _dev_ptr(samples_dev), n_slots, _dev_ptr(info_dev), _stream_ptr()))
+
     def tune(self, n_steps, step_base, cfg: capi.TuneCfg, z=None, seed=0, info=False):
         import torch
         dev = f'cuda:{self.device}'
