@@ -59,7 +59,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 1;   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 2;   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -78,7 +78,8 @@ struct mile_ctx {
   float *w_act = nullptr, *w_delta[2] = {nullptr, nullptr}, *w_part = nullptr, *w_llpart = nullptr, *w_ones = nullptr;
   float* w_gl = nullptr;   // packed [n, d+1] output of a stand-alone value_and_grad call
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
-  float *w_act_lo = nullptr, *w_delta_lo[2] = {nullptr, nullptr}, *w_wpk = nullptr, *w_wpk_lo = nullptr, *w_wpkT = nullptr,
+  long w_part_per_chain = 0;
+  float *w_wpk = nullptr, *w_wpk_lo = nullptr, *w_wpkT = nullptr,
         *w_wpkT_lo = nullptr;
   long w_n8 = 0, w_wstride = 0; long w_woff[MILE_MAX_LAYERS] = {0};
   std::map<std::tuple<const void*, long, long, long, long, int, int, int>, CUtensorMap> tmaps;
@@ -380,7 +381,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->w_act_lo, c->w_delta_lo[0], c->w_delta_lo[1], c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
+                  c->w_ones, c->w_gl, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -832,7 +833,7 @@ int mile_shard_init(mile_ctx* c, const void* unique_id128, int32_t rank, int32_t
 static int wide_alloc(mile_ctx* c, int n_chains) {
   if (c->w_act && c->w_rows == c->N && c->w_chains >= n_chains) return 0;
   float** ptrs[] = {&c->w_act, &c->w_delta[0], &c->w_delta[1], &c->w_part, &c->w_llpart, &c->w_ones, &c->w_gl,
-                    &c->w_act_lo, &c->w_delta_lo[0], &c->w_delta_lo[1], &c->w_wpk, &c->w_wpk_lo, &c->w_wpkT, &c->w_wpkT_lo};
+                    &c->w_wpk, &c->w_wpk_lo, &c->w_wpkT, &c->w_wpkT_lo};
   for (float** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   c->tmaps.clear();
   const DevModel& M = c->M;
@@ -847,16 +848,15 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
   c->w_kslices = (int)((N + 1023) / 1024); if (c->w_kslices > 64) c->w_kslices = 64; if (c->w_kslices < 1) c->w_kslices = 1;
   c->w_nblk = (int)((N + 255) / 256);
   const size_t actb = (size_t)n_chains * N8 * act_per_row * 4, delb = (size_t)n_chains * N8 * maxw * 4;
-  CK(cudaMalloc(&c->w_act, actb)); CK(cudaMalloc(&c->w_act_lo, actb));
+  CK(cudaMalloc(&c->w_act, actb));
   CK(cudaMalloc(&c->w_delta[0], delb)); CK(cudaMalloc(&c->w_delta[1], delb));
-  CK(cudaMalloc(&c->w_delta_lo[0], delb)); CK(cudaMalloc(&c->w_delta_lo[1], delb));
   CK(cudaMalloc(&c->w_wpk, (size_t)n_chains * wsum * 4)); CK(cudaMalloc(&c->w_wpk_lo, (size_t)n_chains * wsum * 4));
   CK(cudaMalloc(&c->w_wpkT, (size_t)n_chains * wsum * 4)); CK(cudaMalloc(&c->w_wpkT_lo, (size_t)n_chains * wsum * 4));
   CK(cudaMemset(c->w_wpkT, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpkT_lo, 0, (size_t)n_chains * wsum * 4));
-  CK(cudaMemset(c->w_act, 0, actb)); CK(cudaMemset(c->w_act_lo, 0, actb));
+  CK(cudaMemset(c->w_act, 0, actb));
   CK(cudaMemset(c->w_delta[0], 0, delb)); CK(cudaMemset(c->w_delta[1], 0, delb));
-  CK(cudaMemset(c->w_delta_lo[0], 0, delb)); CK(cudaMemset(c->w_delta_lo[1], 0, delb));
   CK(cudaMemset(c->w_wpk, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpk_lo, 0, (size_t)n_chains * wsum * 4));
+  c->w_part_per_chain = (long)c->w_kslices * maxio;
   CK(cudaMalloc(&c->w_part, (size_t)n_chains * c->w_kslices * maxio * 4));
   CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4));
   CK(cudaMalloc(&c->w_ones, (size_t)N * 4));
@@ -899,8 +899,8 @@ static int tmap_get(mile_ctx* c, const float* ptr, long R, long Ccols, long ld, 
   return 0;
 }
 
-static bool tc2_operand_ok(const float* p, const float* plo, long ld, long bstride) {
-  return p && plo && (ld & 3) == 0 && (bstride & 3) == 0 && ((uintptr_t)p & 15) == 0 && ((uintptr_t)plo & 15) == 0;
+static bool tc2_operand_ok(const float* p, long ld, long bstride) {
+  return p && (ld & 3) == 0 && (bstride & 3) == 0 && ((uintptr_t)p & 15) == 0;
 }
 
 // returns 1 if launched on the v2 core, 0 if not eligible, -1 on error
@@ -910,20 +910,29 @@ static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   if (!a_k || !b_k) return 0;   // MN-major tf32 operands: handled by the v1 core (transposes while staging)
   (void)a_mn; (void)b_mn;
   const long a_ld = a_mn ? g.sak : g.sam, b_ld = b_mn ? g.sbk : g.sbn;
-  if (!tc2_operand_ok(g.A, g.A_lo, a_ld, g.a_batch) || !tc2_operand_ok(g.B, g.B_lo, b_ld, g.b_batch)) return 0;
+  if (!tc2_operand_ok(g.A, a_ld, g.a_batch) || !tc2_operand_ok(g.B, b_ld, g.b_batch) || !tc2_operand_ok(g.B_lo, b_ld, g.b_batch)) return 0;
   if ((g.K & 3) || (a_mn && (g.M & 3)) || (b_mn && (g.N & 3))) return 0;
   Tc2Args t;
   memset(&t, 0, sizeof(t));
   if (tmap_get(c, g.A, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_hi)) return -1;
-  if (tmap_get(c, g.A_lo, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_lo)) return -1;
   if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_hi)) return -1;
   if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_lo)) return -1;
   t.M = g.M; t.N = g.N; t.K = g.K; t.kslices = g.kslices; t.nbatch = g.nbatch;
-  t.C = g.C; t.C_lo = g.C_lo; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
+  t.C = g.C; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
   t.bias = g.bias; t.bias_batch = g.bias_batch; t.aux = g.aux; t.aux_batch = g.aux_batch; t.ldaux = g.ldaux;
-  CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-  dim3 grid((g.N + T2_BN - 1) / T2_BN, (g.M + T2_BM - 1) / T2_BM, g.nbatch * g.kslices);
-  wide_gemm_tc2_kernel<<<grid, 192, T2_SMEM_BYTES, st>>>(t);
+  const int ntiles = ((g.M + T2_BM - 1) / T2_BM) * ((g.N + T2_BN - 1) / T2_BN) * g.nbatch * g.kslices;
+  const int grid = ntiles < c->n_sms ? ntiles : c->n_sms;      // persistent: one CTA per SM, tiles strided over the grid
+  const bool relu = g.act == MILE_ACT_RELU;
+#define T2_LAUNCH(E, R)                                                                                                   \
+  do {                                                                                                                    \
+    CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));       \
+    wide_gemm_tc2_kernel<E, R><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(t);                                               \
+  } while (0)
+  if (g.epi == 0) T2_LAUNCH(0, false);
+  else if (g.epi == 2) T2_LAUNCH(2, false);
+  else if (g.epi == 1) { if (relu) T2_LAUNCH(1, true); else T2_LAUNCH(1, false); }
+  else { if (relu) T2_LAUNCH(3, true); else T2_LAUNCH(3, false); }
+#undef T2_LAUNCH
   CK(cudaGetLastError());
   c->launches++;
   return 1;
@@ -949,6 +958,33 @@ static int wide_gemm(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   return 0;
 }
 
+// skinny GEMM (K <= 16 or N <= 8): streaming kernels, no tile padding
+static int wide_skinny(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
+  if (g.K <= WS_KMAX) wide_smallk_kernel<<<dim3((g.M + 63) / 64, (g.N + 255) / 256, g.nbatch), 256, 0, st>>>(g);
+  else wide_smalln_kernel<<<dim3((g.M + 63) / 64, 1, g.nbatch), 256, 0, st>>>(g);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// dst[b][...] = sum_r Wd(r, t) S(r, q) (S == nullptr: column sums) through row slices + the fixed-order slice reduction
+static int wide_rowreduce(mile_ctx* c, const float* Wd, long wd_batch, long wd_ld, int WD, const float* S, long s_batch, long s_ld,
+                          int s, int small_is_row, long rows, int n, float* dst, long dst_batch, long n_out, cudaStream_t st) {
+  RowReduceArgs a;
+  a.Wd = Wd; a.wd_batch = wd_batch; a.wd_ld = wd_ld; a.WD = WD; a.S = S; a.s_batch = s_batch; a.s_ld = s_ld; a.s = s;
+  a.small_is_row = small_is_row; a.rows = rows;
+  long nsl = 64;
+  if (nsl * n_out > c->w_part_per_chain) nsl = c->w_part_per_chain / n_out;
+  if (nsl < 1) return fail("wide path: partial buffer too small");
+  if (nsl > rows) nsl = rows;
+  a.nslices = (int)nsl; a.part = c->w_part; a.p_slice = n_out; a.p_batch = nsl * n_out;
+  wide_rowreduce_kernel<<<dim3((unsigned)nsl, (WD + 255) / 256, n), 256, 0, st>>>(a);
+  wide_slice_reduce_kernel<<<n_out * n >= 148 * 256 ? 148 : 32, 256, 0, st>>>(c->w_part, a.p_batch, a.p_slice, (int)nsl, dst, dst_batch, n_out, n);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
 // value_and_grad of n chains (theta [n,d]) over the local rows into the packed buffer gl [n, d+1]
 static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st) {
   if (wide_alloc(c, n > c->C ? n : c->C)) return -1;
@@ -959,7 +995,6 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N8][dims[l]]
   for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
   auto act = [&](int l) { return c->w_act + aoff[l]; };
-  auto act_lo = [&](int l) { return c->w_act_lo + aoff[l]; };
   const bool tc2 = c->opt_tensor >= 2;
   if (tc2) {                                  // aligned packed copies of the weights + their tf32 remainders
     for (int l = 0; l < NL; ++l) {
@@ -973,14 +1008,17 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
     GemmArgs g; memset(&g, 0, sizeof(g));
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
-    else { g.A = act(l); g.A_lo = act_lo(l); g.a_batch = N8 * IN; g.sam = IN; g.sak = 1; }
+    else { g.A = act(l); g.a_batch = N8 * IN; g.sam = IN; g.sak = 1; }
     if (tc2) {   // W^T [OUT x IN]: K-major B for the TMA-fed core (MN-major tf32 operands are not used)
       g.B = c->w_wpkT + c->w_woff[l]; g.B_lo = c->w_wpkT_lo + c->w_woff[l]; g.b_batch = c->w_wstride; g.sbk = 1; g.sbn = IN;
     } else { g.B = theta + M.kern_off[l]; g.b_batch = d; g.sbk = OUT; g.sbn = 1; }
-    g.C = act(l + 1); g.C_lo = (tc2 && l < NL - 1) ? act_lo(l + 1) : nullptr;
+    g.C = act(l + 1);
     g.c_batch = N8 * OUT; g.ldc = OUT; g.M = (int)N; g.N = OUT; g.K = IN; g.kslices = 1;
     g.epi = l < NL - 1 ? 1 : 2; g.bias = theta + M.bias_off[l]; g.bias_batch = d; g.act = M.act; g.nbatch = n;
-    if (wide_gemm(c, g, st)) return -1;
+    if (IN <= WS_KMAX || (OUT <= WS_NMAX && IN <= 1024)) {   // skinny layer: stream it from theta directly
+      g.B = theta + M.kern_off[l]; g.B_lo = nullptr; g.b_batch = d; g.sbk = OUT; g.sbn = 1;
+      if (wide_skinny(c, g, st)) return -1;
+    } else if (wide_gemm(c, g, st)) return -1;
   }
   float* dcur = c->w_delta[(NL - 1) & 1];
   wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, N8, c->w_llpart);
@@ -989,33 +1027,39 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   for (int l = NL - 1; l >= 0; --l) {         // dW_l, db_l, then the delta of the layer below
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     float* D = c->w_delta[l & 1];
-    float* Dlo = c->w_delta_lo[l & 1];
-    const bool d_has_lo = tc2 && l < NL - 1;   // the output-layer delta (from loglik) carries no remainder tensor
-    GemmArgs g; memset(&g, 0, sizeof(g));
-    if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = 1; g.sak = M.sA[0]; }
-    else { g.A = act(l); g.A_lo = tc2 ? act_lo(l) : nullptr; g.a_batch = N8 * IN; g.sam = 1; g.sak = IN; }
-    g.B = D; g.B_lo = d_has_lo ? Dlo : nullptr; g.b_batch = N8 * OUT; g.sbk = OUT; g.sbn = 1;
-    g.M = IN; g.N = OUT; g.K = (int)N8; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
-    g.C = c->w_part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
-    if (wide_gemm(c, g, st)) return -1;
-    wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
-                                                 d + 1, (long)IN * OUT, n);
-    wide_colsum_kernel<<<dim3((OUT + 255) / 256, c->w_kslices, n), 256, 0, st>>>(D, N8 * OUT, N, OUT, c->w_kslices, c->w_part,
-                                                                                   (long)c->w_kslices * OUT);
-    wide_slice_reduce_kernel<<<32, 256, 0, st>>>(c->w_part, (long)c->w_kslices * OUT, OUT, c->w_kslices, gl + M.bias_off[l],
-                                                d + 1, (long)OUT, n);
-    CK(cudaGetLastError());
-    c->launches += 3;
+    const float* Aop = l == 0 ? c->X : act(l);
+    const long a_bs = l == 0 ? 0 : N8 * IN, a_ld = l == 0 ? M.sA[0] : IN;
+    if (IN <= WS_KMAX) {          // dW[i][j] = sum_r A(r,i) D(r,j), few rows i: thread = column j of D
+      if (wide_rowreduce(c, D, N8 * OUT, OUT, OUT, Aop, a_bs, a_ld, IN, 1, N, n, gl + M.kern_off[l], d + 1, (long)IN * OUT, st)) return -1;
+    } else if (OUT <= WS_KMAX) {  // few columns j: thread = column i of A
+      if (wide_rowreduce(c, Aop, a_bs, a_ld, IN, D, N8 * OUT, OUT, OUT, 0, N, n, gl + M.kern_off[l], d + 1, (long)IN * OUT, st)) return -1;
+    } else {
+      GemmArgs g; memset(&g, 0, sizeof(g));
+      g.A = Aop; g.a_batch = a_bs; g.sam = 1; g.sak = a_ld;
+      g.B = D; g.b_batch = N8 * OUT; g.sbk = OUT; g.sbn = 1;
+      g.M = IN; g.N = OUT; g.K = (int)N8; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
+      g.C = c->w_part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
+      if (wide_gemm(c, g, st)) return -1;
+      wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
+                                                   d + 1, (long)IN * OUT, n);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+    // bias gradient = column sums of D
+    if (wide_rowreduce(c, D, N8 * OUT, OUT, OUT, nullptr, 0, 0, 1, 1, N, n, gl + M.bias_off[l], d + 1, (long)OUT, st)) return -1;
     if (l > 0) {
       GemmArgs w; memset(&w, 0, sizeof(w));
-      w.A = D; w.A_lo = d_has_lo ? Dlo : nullptr; w.a_batch = N8 * OUT; w.sam = OUT; w.sak = 1;
+      w.A = D; w.a_batch = N8 * OUT; w.sam = OUT; w.sak = 1;
       if (tc2) { w.B = c->w_wpk + c->w_woff[l]; w.B_lo = c->w_wpk_lo + c->w_woff[l]; w.b_batch = c->w_wstride; }
       else { w.B = theta + M.kern_off[l]; w.b_batch = d; }
       w.sbk = 1; w.sbn = OUT;                                                   // B(k=j, n=i) = W[i][j]
-      w.C = c->w_delta[(l - 1) & 1]; w.C_lo = tc2 ? c->w_delta_lo[(l - 1) & 1] : nullptr;
+      w.C = c->w_delta[(l - 1) & 1];
       w.c_batch = N8 * IN; w.ldc = IN; w.M = (int)N; w.N = IN; w.K = OUT; w.kslices = 1;
       w.epi = 3; w.aux = act(l); w.aux_batch = N8 * IN; w.ldaux = IN; w.act = M.act; w.nbatch = n;
-      if (wide_gemm(c, w, st)) return -1;
+      if (OUT <= WS_KMAX) {
+        w.B = theta + M.kern_off[l]; w.B_lo = nullptr; w.b_batch = d;
+        if (wide_skinny(c, w, st)) return -1;
+      } else if (wide_gemm(c, w, st)) return -1;
     }
   }
   wide_finalize_kernel<<<n, 1024, 0, st>>>(M, theta, gl, c->w_llpart, c->w_nblk, prior_weight);
@@ -1146,6 +1190,17 @@ int mile_debug_wide_gemm(int32_t device, int32_t core, int32_t M, int32_t N, int
   if (b_mn) { g.sbk = N; g.sbn = 1; } else { g.sbk = 1; g.sbn = K; }
   if (wide_gemm(&ctx, g, 0)) return -1;
   CK(cudaDeviceSynchronize());
+  if (getenv("MILE_DEBUG_TIMING")) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (int r = 0; r < 10; ++r) if (wide_gemm(&ctx, g, 0)) return -1;
+    cudaEventRecord(e1, 0);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[mile debug] gemm core %d M %d N %d K %d: %.1f us per launch\n", core, M, N, K, ms * 100.f);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   CK(cudaMemcpy(C_host, Cd, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
   cudaFree(A); cudaFree(Alo); cudaFree(B); cudaFree(Blo); cudaFree(Cd);
   return 0;

@@ -19,11 +19,12 @@ namespace cg = cooperative_groups;
 // accumulates clock64() deltas per phase into g_prof[].
 #ifdef MILE_PROFILE
 __device__ unsigned long long g_prof[32];
-#define PROF_DECL long long prof_t_ = clock64()
+__device__ long long g_prof_t;
+#define PROF_DECL do { if (threadIdx.x == 0 && blockIdx.x == 0) g_prof_t = clock64(); } while (0)
 #define PROF(i)                                                                            \
   do {                                                                                     \
     if (threadIdx.x == 0 && blockIdx.x == 0) {                                             \
-      long long n_ = clock64(); g_prof[i] += (unsigned long long)(n_ - prof_t_); prof_t_ = n_; \
+      long long n_ = clock64(); g_prof[i] += (unsigned long long)(n_ - g_prof_t); g_prof_t = n_; \
     }                                                                                      \
   } while (0)
 #else

@@ -285,6 +285,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     c.gg[i] = g;
     v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   }
+  PROF(14);
   if (P.sync_mode && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, c.G, flag);
   block_sum<4, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
@@ -616,6 +617,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
       float2* mine = slab + c.rank * (P.dS + 4);
       __syncthreads();
       for (int i = tid; i <= P.dS; i += NT) ll_store(mine + i, gp[i], xflag);
+      PROF(13);
       gslab = slab;
     } else if (c.G > 1) {
       cluster.sync();      // publishes every CTA's partial gradient (DSMEM)

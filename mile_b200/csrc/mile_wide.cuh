@@ -114,6 +114,171 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(const GemmArgs g) {
   }
 }
 
+// =====================================================================================================
+// Skinny shapes (first layer K = n_features, output layer N = n_outputs): pure HBM streaming, one pass over the large
+// operand, no tile padding.  A 128x128 GEMM tile would be >90% empty for them.
+// =====================================================================================================
+#define WS_KMAX 16
+#define WS_NMAX 8
+
+// C[M x N] = epi(A[M x K] B[K x N]) with K <= 16: thread = (row, 4 consecutive columns); B and bias live in shared memory.
+// grid (ceil(M/64), ceil(N/256), batch), 256 threads.
+__global__ void __launch_bounds__(256) wide_smallk_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float Bs[WS_KMAX][256];
+  __shared__ __align__(16) float bs[256];
+  const int b = blockIdx.z, n0 = blockIdx.y * 256, tid = threadIdx.x;
+  const float* A = g.A + (long)b * g.a_batch;
+  const float* B = g.B + (long)b * g.b_batch;
+  const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
+  const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
+  float* C = g.C + (long)b * g.c_batch;
+  for (int e = tid; e < WS_KMAX * 256; e += 256) {
+    const int k = e >> 8, nn = e & 255;
+    Bs[k][nn] = (k < g.K && n0 + nn < g.N) ? __ldg(B + (long)k * g.sbk + (long)(n0 + nn) * g.sbn) : 0.f;
+  }
+  bs[tid] = (bias && n0 + tid < g.N) ? __ldg(bias + n0 + tid) : 0.f;
+  __syncthreads();
+  const int tx = tid & 63, ty = tid >> 6, n = n0 + tx * 4;
+  if (n >= g.N) return;
+  const bool vec = n + 3 < g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                   (g.epi != 3 || ((g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0));
+  const int mend = min(g.M, (int)(blockIdx.x + 1) * 64);
+  for (int m = blockIdx.x * 64 + ty; m < mend; m += 4) {
+    float a[WS_KMAX];
+#pragma unroll
+    for (int k = 0; k < WS_KMAX; ++k) a[k] = k < g.K ? __ldg(A + (long)m * g.sam + (long)k * g.sak) : 0.f;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < WS_KMAX; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      o[0] = fmaf(a[k], w.x, o[0]); o[1] = fmaf(a[k], w.y, o[1]); o[2] = fmaf(a[k], w.z, o[2]); o[3] = fmaf(a[k], w.w, o[3]);
+    }
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.epi == 3) {
+      if (vec) { const float4 t = *reinterpret_cast<const float4*>(aux + (long)m * g.ldaux + n); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+      else for (int e = 0; e < 4; ++e) if (n + e < g.N) x[e] = aux[(long)m * g.ldaux + n + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (g.epi == 1) o[e] = act_value(g.act, o[e] + bs[tx * 4 + e]);
+      else if (g.epi == 2) o[e] = o[e] + bs[tx * 4 + e];
+      else if (g.epi == 3) o[e] = o[e] * act_deriv_from_value(g.act, x[e]);
+    }
+    if (vec) *reinterpret_cast<float4*>(C + (long)m * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+    else for (int e = 0; e < 4; ++e) if (n + e < g.N) C[(long)m * g.ldc + n + e] = o[e];
+  }
+}
+
+// C[M x N] = epi(A[M x K] B[K x N]) with N <= 8: one warp per row, lanes stride K (float4 when A rows are contiguous and
+// aligned), warp-shuffle reduction.  B [K x N] in shared memory (K <= 1024).  grid (ceil(M/64), 1, batch), 256 threads.
+__global__ void __launch_bounds__(256) wide_smalln_kernel(const GemmArgs g) {
+  __shared__ float Bs[1024 * WS_NMAX];
+  const int b = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* A = g.A + (long)b * g.a_batch;
+  const float* B = g.B + (long)b * g.b_batch;
+  const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
+  const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
+  float* C = g.C + (long)b * g.c_batch;
+  for (int e = tid; e < g.K * WS_NMAX; e += 256) {
+    const int k = e / WS_NMAX, j = e % WS_NMAX;
+    Bs[e] = j < g.N ? __ldg(B + (long)k * g.sbk + (long)j * g.sbn) : 0.f;
+  }
+  __syncthreads();
+  const bool vec = g.sak == 1 && (g.sam & 3) == 0 && (g.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const int mend = min(g.M, (int)(blockIdx.x + 1) * 64);
+  for (int m = blockIdx.x * 64 + warp; m < mend; m += 8) {
+    float acc[WS_NMAX];
+#pragma unroll
+    for (int j = 0; j < WS_NMAX; ++j) acc[j] = 0.f;
+    if (vec) {
+      const float4* row = reinterpret_cast<const float4*>(A + (long)m * g.sam);
+      for (int k4 = lane; k4 < (g.K >> 2); k4 += 32) {
+        const float4 a = __ldg(row + k4);
+        const float* w = Bs + k4 * 4 * WS_NMAX;
+#pragma unroll
+        for (int j = 0; j < WS_NMAX; ++j)
+          acc[j] += a.x * w[j] + a.y * w[WS_NMAX + j] + a.z * w[2 * WS_NMAX + j] + a.w * w[3 * WS_NMAX + j];
+      }
+    } else {
+      for (int k = lane; k < g.K; k += 32) {
+        const float a = __ldg(A + (long)m * g.sam + (long)k * g.sak);
+#pragma unroll
+        for (int j = 0; j < WS_NMAX; ++j) acc[j] = fmaf(a, Bs[k * WS_NMAX + j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < WS_NMAX; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (lane < g.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < WS_NMAX; ++j) if (j == lane) v = acc[j];
+      if (g.epi == 1) v = act_value(g.act, v + bias[lane]);
+      else if (g.epi == 2) v = v + bias[lane];
+      else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + lane]);
+      C[(long)m * g.ldc + lane] = v;
+    }
+  }
+}
+
+// Row-reduction products for the parameter gradients of skinny layers and for every bias gradient:
+//   part[b][slice][...] = sum_{r in slice} Wd(r, t) * S(r, q),   t < WD (thread = column of the wide operand), q < s <= 16
+// `S == nullptr` means S == 1 (column sums of Wd: the bias gradient).  small_is_row: output index q * WD + t (S indexes the
+// rows of dW) else t * s + q.  grid (nslices, ceil(WD/256), batch), 256 threads; deterministic two-pass with
+// wide_slice_reduce_kernel.
+struct RowReduceArgs {
+  const float* Wd; long wd_batch, wd_ld; int WD;
+  const float* S; long s_batch, s_ld; int s; int small_is_row;
+  long rows; int nslices;
+  float* part; long p_batch, p_slice;
+};
+
+__global__ void __launch_bounds__(256) wide_rowreduce_kernel(const RowReduceArgs g) {
+  const int t = blockIdx.y * 256 + threadIdx.x, b = blockIdx.z, sl = blockIdx.x;
+  if (t >= g.WD) return;
+  const long per = (g.rows + g.nslices - 1) / g.nslices, r0 = sl * per, r1 = min(g.rows, r0 + per);
+  const float* W = g.Wd + (long)b * g.wd_batch + t;
+  const float* S = g.S ? g.S + (long)b * g.s_batch : nullptr;
+  float acc[WS_KMAX];
+#pragma unroll
+  for (int q = 0; q < WS_KMAX; ++q) acc[q] = 0.f;
+  long r = r0;
+  if (!S) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (; r + 7 < r1; r += 8) {
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
+      s0 += w[0] + w[4]; s1 += w[1] + w[5]; s2 += w[2] + w[6]; s3 += w[3] + w[7];
+    }
+    for (; r < r1; ++r) s0 += __ldg(W + r * g.wd_ld);
+    acc[0] = (s0 + s1) + (s2 + s3);
+  } else {
+    for (; r + 3 < r1; r += 4) {
+      float w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < WS_KMAX; ++q)
+          if (q < g.s) acc[q] = fmaf(w[i], __ldg(S + (r + i) * g.s_ld + q), acc[q]);
+    }
+    for (; r < r1; ++r) {
+      const float w = __ldg(W + r * g.wd_ld);
+#pragma unroll
+      for (int q = 0; q < WS_KMAX; ++q)
+        if (q < g.s) acc[q] = fmaf(w, __ldg(S + r * g.s_ld + q), acc[q]);
+    }
+  }
+  float* out = g.part + (long)b * g.p_batch + (long)sl * g.p_slice;
+  const int s = S ? g.s : 1;
+#pragma unroll
+  for (int q = 0; q < WS_KMAX; ++q)
+    if (q < s) out[g.small_is_row ? (long)q * g.WD + t : (long)t * s + q] = acc[q];
+}
+
 // sum the split-K slices: dst[b*dst_batch + e] = sum_s src[b*src_batch + s*slice + e]   (fixed order)
 __global__ void wide_slice_reduce_kernel(const float* __restrict__ src, long src_batch, long slice, int kslices,
                                          float* __restrict__ dst, long dst_batch, long n, int nbatch) {
@@ -421,7 +586,7 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
                                                              __uint_as_float(r[j + 3]));
       }
       __syncthreads();
-#pragma unroll
+#pragma unroll 1   // keep the epilogue compact: the activation switch unrolled 8x thrashes the instruction cache
       for (int it = 0; it < (TC_BM * 8) / 256; ++it) {
         const int idx = tid + it * 256, row = idx >> 3, cq = idx & 7;
         const int m = m0 + row, n = n0 + c0 + cq * 4;
@@ -456,18 +621,19 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
 }
 
 // =====================================================================================================
-// tcgen05 GEMM, version 2: TMA-fed, warp-specialised, 4-stage pipeline.
-// Operands are pre-split once by their producers (every epilogue writes v and lo = v - tf32(v); the tf32 datapath
-// truncates v itself, so v serves as the "hi" operand), which leaves NO thread work in the main loop:
-//   warp 0 (one lane)  TMA producer: 4 cp.async.bulk.tensor.5d per stage (A, A_lo, B, B_lo) -> full barrier
-//   warp 1 (one lane)  MMA issuer: 6 tcgen05.mma kind::tf32 (M128 N256 K8, 3xTF32) per stage, tcgen05.commit -> empty barrier
-//   warps 2-5          epilogue: tcgen05.ld -> bias / activation / act' -> v and lo to global
-// Operands are K-major (rows = M / N index, K contiguous) [rows x 32 fp32] tiles = one 128-byte swizzle atom per row:
-// 3-D tensor maps {K, rows, batch}, box {32, rows, 1}, CU_TENSOR_MAP_SWIZZLE_128B; UMMA descriptors with
-// SWIZZLE_128B, SBO = 1024 B (8 rows x 128 B), k-step = +32 B inside the atom.  (A 5-D "core matrix" view that
-// lands boxes in the no-swizzle canonical layout also works -- tools/tma_probe.cu -- but its 16-byte inner
-// extent makes TMA the bottleneck; MN-major tf32 operands did not give correct results with the no-swizzle
-// descriptors, so the dW GEMMs (K = data rows) stay on the v1 core, which transposes while staging.)
+// tcgen05 GEMM, version 2: TMA-fed, warp-specialised, mbarrier pipeline (K-major operands only).
+//   warp 0 (one lane)  TMA producer: A, B, B_lo boxes of one k-block per stage -> full barrier (expect_tx)
+//   warps 2-5          converters: A_lo = A - tf32(A) computed in shared memory (element-wise, so the 128-byte swizzle
+//                      is irrelevant), fence.proxy.async, arrive on the stage's "converted" barrier; after the main
+//                      loop the same warps run the epilogue (tcgen05.ld -> per-warp smem tile -> coalesced stores)
+//   warp 1 (one lane)  MMA issuer: per 8-wide k-step three tcgen05.mma kind::tf32 M128 N256 K8 (a_hi*b_lo, a_lo*b_hi,
+//                      a_hi*b_hi; the tf32 datapath truncates, so v itself serves as "hi"); tcgen05.commit -> empty
+// Activations / deltas therefore live in HBM ONCE (no remainder tensors): the minimum traffic of a launch is
+// A + C.  Only the (small, L2-resident) weights carry a pre-packed remainder copy.
+// Operands are K-major [rows x 32 fp32] tiles = one 128-byte swizzle atom per row: 3-D tensor maps {K, rows, batch},
+// box {32, rows, 1}, CU_TENSOR_MAP_SWIZZLE_128B; UMMA descriptors SWIZZLE_128B, SBO = 1024 B, k-step = +32 B in the atom.
+// (MN-major tf32 operands did not give correct results with the no-swizzle descriptors, so the dW GEMMs
+// (K = data rows) stay on the v1 core, which transposes while staging.)
 // =====================================================================================================
 #include <cuda.h>
 
@@ -478,12 +644,13 @@ __global__ void __launch_bounds__(256, 2) wide_gemm_tc_kernel(const GemmArgs g) 
 #define T2_A_BYTES (T2_BM * T2_BK * 4)
 #define T2_B_BYTES (T2_BN * T2_BK * 4)
 #define T2_STAGE_BYTES (2 * T2_A_BYTES + 2 * T2_B_BYTES)
-#define T2_SMEM_BYTES (T2_STAGES * T2_STAGE_BYTES + 256)
+#define T2_TS 20   // epilogue tile row stride (floats): 16 columns + 4 pad, float4-aligned, conflict-free row writes
+#define T2_SMEM_BYTES (T2_STAGES * T2_STAGE_BYTES + 8 * 32 * T2_TS * 4 + 256)
 
 struct Tc2Args {
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap a_hi, b_hi, b_lo;
   int M, N, K, kslices, nbatch;
-  float* C; float* C_lo; long c_batch, c_slice, ldc;
+  float* C; long c_batch, c_slice, ldc;
   int epi, act;
   const float* bias; long bias_batch;
   const float* aux; long aux_batch, ldaux;
@@ -512,129 +679,217 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-__global__ void __launch_bounds__(192, 1) wide_gemm_tc2_kernel(const __grid_constant__ Tc2Args g) {
+#define T2_EPI_WARPS 8
+#define T2_CVT_WARPS 4
+#define T2_THREADS (64 + 32 * T2_CVT_WARPS + 32 * T2_EPI_WARPS)
+
+// One output element of the epilogue.  EPI: 0 plain, 1 act(v + bias), 2 v + bias, 3 v * act'(aux).  RELU = compile-time
+// fast path; otherwise the runtime activation switch.
+template <int EPI, bool RELU>
+__device__ __forceinline__ float t2_epi(float v, float bias, float aux, int act) {
+  if (EPI == 1) { v += bias; return RELU ? fmaxf(v, 0.f) : act_value(act, v); }
+  if (EPI == 2) return v + bias;
+  if (EPI == 3) return RELU ? (aux > 0.f ? v : 0.f) : v * act_deriv_from_value(act, aux);
+  return v;
+}
+
+// Persistent: CTA i works on tiles i, i + gridDim.x, ... (tile = (batch*kslice, m-block); N <= 256 is one n-block per
+// tile row, larger N adds n-blocks).  Two TMEM accumulators (2 x 256 columns) let the epilogue of tile t overlap the
+// main loop of tile t+1:
+//   tmem_full[a]  MMA -> epilogue  (accumulator a complete)
+//   tmem_empty[a] epilogue -> MMA  (accumulator a drained; count = T2_EPI_WARPS)
+template <int EPI, bool RELU>
+__global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __grid_constant__ Tc2Args g) {
   extern __shared__ __align__(1024) char sm2[];
   const uint32_t sbase = smem_u32(sm2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm2 + T2_STAGES * T2_STAGE_BYTES);
-  const uint32_t bar0 = smem_u32(bars);                       // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (S + s), tmem_full = bar0 + 16 S
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 1);
+  // stage memory, then the epilogue tiles (T2_EPI_WARPS x [32][36] floats), then the barriers
+  constexpr int TS = T2_TS;
+  float* tiles = reinterpret_cast<float*>(sm2 + T2_STAGES * T2_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm2 + T2_STAGES * T2_STAGE_BYTES + T2_EPI_WARPS * 32 * TS * 4);
+  // full[s] = bar0 + 8 s, empty[s] = +8 (S + s), converted[s] = +8 (2S + s), tmem_full[a] = +8 (3S + a), tmem_empty[a] = +8 (3S + 2 + a)
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * T2_STAGES + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z / g.kslices, ks = blockIdx.z % g.kslices;
-  const int m0 = blockIdx.y * T2_BM, n0 = blockIdx.x * T2_BN;
+  const int nmb = (g.M + T2_BM - 1) / T2_BM, nnb = (g.N + T2_BN - 1) / T2_BN;
+  const int ntiles = nmb * nnb * g.nbatch * g.kslices;
   const int kper = ((g.K + g.kslices - 1) / g.kslices + T2_BK - 1) / T2_BK * T2_BK;
-  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
-  const int nkb = kend > kbeg ? (kend - kbeg + T2_BK - 1) / T2_BK : 0;
   if (tid == 0) {
-    for (int s = 0; s < 2 * T2_STAGES + 1; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
+    for (int s = 0; s < 3 * T2_STAGES + 4; ++s) {
+      const int cnt = (s >= 2 * T2_STAGES && s < 3 * T2_STAGES) ? T2_CVT_WARPS : (s >= 3 * T2_STAGES + 2 ? T2_EPI_WARPS : 1);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(cnt));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(T2_BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * T2_BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  // tile index -> (batch b, k-slice ks, m0, n0, k range)
+  auto tile_coords = [&](int t, int& b, int& ks, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int nb = t % nnb; t /= nnb;
+    const int mb = t % nmb; t /= nmb;
+    ks = t % g.kslices; b = t / g.kslices;
+    m0 = mb * T2_BM; n0 = nb * T2_BN;
+    kbeg = ks * kper;
+    const int kend = min(g.K, kbeg + kper);
+    nkb = kend > kbeg ? (kend - kbeg + T2_BK - 1) / T2_BK : 0;
+  };
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer ----
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
-        mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
-        const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)T2_STAGE_BYTES) : "memory");
-        const int k0 = kbeg + kb * T2_BK;
-        tma_load_3d(st, &g.a_hi, k0, m0, b, full);
-        tma_load_3d(st + T2_A_BYTES, &g.a_lo, k0, m0, b, full);
-        tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0, b, full);
-        tma_load_3d(st + 2 * T2_A_BYTES + T2_B_BYTES, &g.b_lo, k0, n0, b, full);
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int b, ks, m0, n0, kbeg, nkb;
+        tile_coords(t, b, ks, m0, n0, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
+          mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
+          const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(T2_A_BYTES + 2 * T2_B_BYTES)) : "memory");
+          const int k0 = kbeg + kb * T2_BK;
+          tma_load_3d(st, &g.a_hi, k0, m0, b, full);
+          tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0, b, full);
+          tma_load_3d(st + 2 * T2_A_BYTES + T2_B_BYTES, &g.b_lo, k0, n0, b, full);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer ----
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
-        mbar_wait(bar0 + 8 * s, ph);
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+        int b, ks, m0, n0, kbeg, nkb;
+        tile_coords(t, b, ks, m0, n0, kbeg, nkb);
+        const int acc = tl & 1, aph = (tl >> 1) & 1;
+        mbar_wait(bar0 + 8 * (3 * T2_STAGES + 2 + acc), aph ^ 1);      // accumulator drained by the epilogue of tile tl-2
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sbase + s * T2_STAGE_BYTES;
-        const uint32_t ahi = st, alo = st + T2_A_BYTES, bhi = st + 2 * T2_A_BYTES, blo = bhi + T2_B_BYTES;
+        const uint32_t tacc = tmem + (uint32_t)(acc * T2_BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
+          mbar_wait(bar0 + 8 * (2 * T2_STAGES + s), ph);     // converted => the TMA boxes have landed too
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = sbase + s * T2_STAGE_BYTES;
+          const uint32_t ahi = st, alo = st + T2_A_BYTES, bhi = st + 2 * T2_A_BYTES, blo = bhi + T2_B_BYTES;
 #pragma unroll
-        for (int j = 0; j < T2_BK / 8; ++j) {   // K = 8 tf32 = 32 B further inside the 128-byte swizzle atom
-          const uint32_t o = j * 32;
-          umma_tf32(tmem, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, (kb == 0 && j == 0) ? 0u : 1u);
-          umma_tf32(tmem, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
-          umma_tf32(tmem, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+          for (int j = 0; j < T2_BK / 8; ++j) {   // K = 8 tf32 = 32 B further inside the 128-byte swizzle atom
+            const uint32_t o = j * 32;
+            umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, (kb == 0 && j == 0) ? 0u : 1u);
+            umma_tf32(tacc, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
+            umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (T2_STAGES + s)) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (T2_STAGES + s)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (3 * T2_STAGES + acc)) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 * T2_STAGES) : "memory");
+    }
+  } else if (warp < 2 + T2_CVT_WARPS) {
+    // ---- converter warps: remainder tile of A for every stage ----
+    const int ct = tid - 64;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int b, ks, m0, n0, kbeg, nkb;
+      tile_coords(t, b, ks, m0, n0, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
+        mbar_wait(bar0 + 8 * s, ph);
+        const uint32_t ahi = sbase + s * T2_STAGE_BYTES, alo = ahi + T2_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < T2_A_BYTES / 16 / (32 * T2_CVT_WARPS); ++i) {
+          const uint32_t off = (uint32_t)(ct + i * 32 * T2_CVT_WARPS) * 16u;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ahi + off));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(alo + off), "f"(v.x - tf32_hi(v.x)), "f"(v.y - tf32_hi(v.y)),
+                       "f"(v.z - tf32_hi(v.z)), "f"(v.w - tf32_hi(v.w)) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (2 * T2_STAGES + s)) : "memory");
+      }
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----
-    mbar_wait(bar0 + 16 * T2_STAGES, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;
-    float* C = g.C + (long)b * g.c_batch + (long)ks * g.c_slice;
-    float* Clo = g.C_lo ? g.C_lo + (long)b * g.c_batch + (long)ks * g.c_slice : nullptr;
-    const float* bias = g.bias ? g.bias + (long)b * g.bias_batch : nullptr;
-    const float* aux = g.aux ? g.aux + (long)b * g.aux_batch : nullptr;
-    const int m = m0 + q * 32 + lane;
+    // ---- epilogue warps: drain accumulator (tile & 1) while the main loop of the next tile runs ----
+    const int ew = warp - 2 - T2_CVT_WARPS;
+    const int q = warp & 3, half = ew >> 2;          // TMEM lane quarter (fixed by warp id) and column half of this warp
+    float* tile = tiles + ew * (32 * TS);
+    int tl = 1;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+      int pb, pks, pm0, pn0, pkbeg, pnkb;
+      tile_coords(t, pb, pks, pm0, pn0, pkbeg, pnkb);
+      {
+        const int el = tl - 1, acc = el & 1, aph = (el >> 1) & 1;
+        mbar_wait(bar0 + 8 * (3 * T2_STAGES + acc), aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* C = g.C + (long)pb * g.c_batch + (long)pks * g.c_slice;
+        const float* bias = g.bias ? g.bias + (long)pb * g.bias_batch : nullptr;
+        const float* aux = g.aux ? g.aux + (long)pb * g.aux_batch : nullptr;
+        const bool fast = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && pn0 + T2_BN <= g.N &&
+                          (EPI != 3 || ((g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0));
 #pragma unroll 1
-    for (int c0 = 0; c0 < T2_BN; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-          "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < g.M && nkb > 0) {
-        float o[32];
+        for (int cc = 0; cc < T2_BN / 32; ++cc) {     // 16 accumulator columns per pass
+          const int c0 = half * (T2_BN / 2) + cc * 16;
+          uint32_t r[16];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();   // the previous pass has been read out of the tile
+          float* trow = tile + lane * TS;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          float v = __uint_as_float(r[j]);
-          if (n < g.N) {
-            if (g.epi == 1) v = act_value(g.act, v + bias[n]);
-            else if (g.epi == 2) v = v + bias[n];
-            else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + n]);
-          }
-          o[j] = v;
-        }
-        float* crow = C + (long)m * g.ldc + n0 + c0;
-        const bool vec = n0 + c0 + 32 <= g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-        if (vec) {
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(trow + j) = pnkb > 0 ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+          const int cq = lane & 3, n = pn0 + c0 + cq * 4;
+          if (fast) {   // 4 lanes cover one 64-byte row segment: sector-aligned stores and aux loads, no per-element branches
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == 1 || EPI == 2) b4 = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));   // (theta offsets are not 16-byte aligned)
+            float4 x4[4];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else {
+            for (int i = 0; i < 4; ++i) {
+              const int m = pm0 + q * 32 + i * 8 + (lane >> 2);
+              x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (EPI == 3 && m < g.M) x4[i] = *reinterpret_cast<const float4*>(aux + (long)m * g.ldaux + n);
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) crow[j] = o[j];
-        }
-        if (Clo) {
-          float* lrow = Clo + (long)m * g.ldc + n0 + c0;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(lrow + j) = make_float4(o[j] - tf32_hi(o[j]), o[j + 1] - tf32_hi(o[j + 1]),
-                                                                 o[j + 2] - tf32_hi(o[j + 2]), o[j + 3] - tf32_hi(o[j + 3]));
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + (lane >> 2), m = pm0 + q * 32 + row;
+              const float4 t4 = *reinterpret_cast<const float4*>(tile + row * TS + cq * 4);
+              float4 o4;
+              o4.x = t2_epi<EPI, RELU>(t4.x, b4.x, x4[i].x, g.act); o4.y = t2_epi<EPI, RELU>(t4.y, b4.y, x4[i].y, g.act);
+              o4.z = t2_epi<EPI, RELU>(t4.z, b4.z, x4[i].z, g.act); o4.w = t2_epi<EPI, RELU>(t4.w, b4.w, x4[i].w, g.act);
+              if (m < g.M) *reinterpret_cast<float4*>(C + (long)m * g.ldc + n) = o4;
+            }
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) lrow[j] = o[j] - tf32_hi(o[j]);
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + (lane >> 2), m = pm0 + q * 32 + row;
+              if (m >= g.M) continue;
+#pragma unroll 1
+              for (int e = 0; e < 4; ++e) {
+                if (n + e >= g.N) break;
+                const float v = tile[row * TS + cq * 4 + e];
+                C[(long)m * g.ldc + n + e] = t2_epi<EPI, RELU>(v, (EPI == 1 || EPI == 2) ? bias[n + e] : 0.f,
+                                                               EPI == 3 ? aux[(long)m * g.ldaux + n + e] : 0.f, g.act);
+              }
+            }
           }
         }
-      } else if (m < g.M && nkb == 0) {   // empty k-slice: contributes zeros
-        for (int j = 0; j < 32; ++j) if (n0 + c0 + j < g.N) C[(long)m * g.ldc + n0 + c0 + j] = 0.f;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (3 * T2_STAGES + 2 + acc)) : "memory");
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(T2_BN));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * T2_BN));
 }
 
 // lo = v - tf32(v) of the layer weights into 16-byte aligned packed buffers (theta's own offsets / chain stride are not
