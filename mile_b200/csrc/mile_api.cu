@@ -973,7 +973,7 @@ static int wide_rowreduce(mile_ctx* c, const float* Wd, long wd_batch, long wd_l
   RowReduceArgs a;
   a.Wd = Wd; a.wd_batch = wd_batch; a.wd_ld = wd_ld; a.WD = WD; a.S = S; a.s_batch = s_batch; a.s_ld = s_ld; a.s = s;
   a.small_is_row = small_is_row; a.rows = rows;
-  long nsl = 64;
+  long nsl = 148;   // with 8 chains: 1184 CTAs = 8 per SM
   if (nsl * n_out > c->w_part_per_chain) nsl = c->w_part_per_chain / n_out;
   if (nsl < 1) return fail("wide path: partial buffer too small");
   if (nsl > rows) nsl = rows;

@@ -186,38 +186,66 @@ __global__ void __launch_bounds__(256) wide_smalln_kernel(const GemmArgs g) {
   __syncthreads();
   const bool vec = g.sak == 1 && (g.sam & 3) == 0 && (g.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   const int mend = min(g.M, (int)(blockIdx.x + 1) * 64);
-  for (int m = blockIdx.x * 64 + warp; m < mend; m += 8) {
-    float acc[WS_NMAX];
+  // 4 rows per warp pass: all loads of the pass are issued before the first use (this kernel is a pure HBM stream)
+  for (int mb = blockIdx.x * 64 + warp * 4; mb < mend; mb += 32) {
+    float acc[4][WS_NMAX];
 #pragma unroll
-    for (int j = 0; j < WS_NMAX; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < WS_NMAX; ++j) acc[r][j] = 0.f;
     if (vec) {
-      const float4* row = reinterpret_cast<const float4*>(A + (long)m * g.sam);
-      for (int k4 = lane; k4 < (g.K >> 2); k4 += 32) {
-        const float4 a = __ldg(row + k4);
-        const float* w = Bs + k4 * 4 * WS_NMAX;
+      for (int k4 = lane; k4 < (g.K >> 2); k4 += 64) {
+        float4 a[4][2];
 #pragma unroll
-        for (int j = 0; j < WS_NMAX; ++j)
-          acc[j] += a.x * w[j] + a.y * w[WS_NMAX + j] + a.z * w[2 * WS_NMAX + j] + a.w * w[3 * WS_NMAX + j];
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            a[r][h] = (mb + r < mend && k4 + 32 * h < (g.K >> 2))
+                          ? __ldg(reinterpret_cast<const float4*>(A + (long)(mb + r) * g.sam) + k4 + 32 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (k4 + 32 * h >= (g.K >> 2)) continue;
+          const float* w = Bs + (k4 + 32 * h) * 4 * WS_NMAX;
+#pragma unroll
+          for (int j = 0; j < WS_NMAX; ++j) {
+            if (j >= g.N) continue;
+            const float w0 = w[j], w1 = w[WS_NMAX + j], w2 = w[2 * WS_NMAX + j], w3 = w[3 * WS_NMAX + j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r][j] += a[r][h].x * w0 + a[r][h].y * w1 + a[r][h].z * w2 + a[r][h].w * w3;
+          }
+        }
       }
     } else {
       for (int k = lane; k < g.K; k += 32) {
-        const float a = __ldg(A + (long)m * g.sam + (long)k * g.sak);
 #pragma unroll
-        for (int j = 0; j < WS_NMAX; ++j) acc[j] = fmaf(a, Bs[k * WS_NMAX + j], acc[j]);
+        for (int r = 0; r < 4; ++r) {
+          if (mb + r >= mend) continue;
+          const float a = __ldg(A + (long)(mb + r) * g.sam + (long)k * g.sak);
+#pragma unroll
+          for (int j = 0; j < WS_NMAX; ++j) acc[r][j] = fmaf(a, Bs[k * WS_NMAX + j], acc[r][j]);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < WS_NMAX; ++j)
+    for (int j = 0; j < WS_NMAX; ++j) {
+      if (j >= g.N) continue;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    if (lane < g.N) {
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r][j] += __shfl_xor_sync(0xffffffffu, acc[r][j], o);
+    }
+    // lane (r * 8 + j) writes output (row mb + r, column j)
+    const int r = lane >> 3, j = lane & 7, m = mb + r;
+    if (j < g.N && m < mend) {
       float v = 0.f;
 #pragma unroll
-      for (int j = 0; j < WS_NMAX; ++j) if (j == lane) v = acc[j];
-      if (g.epi == 1) v = act_value(g.act, v + bias[lane]);
-      else if (g.epi == 2) v = v + bias[lane];
-      else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + lane]);
-      C[(long)m * g.ldc + lane] = v;
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int jj = 0; jj < WS_NMAX; ++jj) if (rr == r && jj == j) v = acc[rr][jj];
+      if (g.epi == 1) v = act_value(g.act, v + bias[j]);
+      else if (g.epi == 2) v = v + bias[j];
+      else if (g.epi == 3) v = v * act_deriv_from_value(g.act, aux[(long)m * g.ldaux + j]);
+      C[(long)m * g.ldc + j] = v;
     }
   }
 }
@@ -246,21 +274,22 @@ __global__ void __launch_bounds__(256) wide_rowreduce_kernel(const RowReduceArgs
   long r = r0;
   if (!S) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (; r + 7 < r1; r += 8) {
-      float w[8];
+    for (; r + 15 < r1; r += 16) {
+      float w[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
-      s0 += w[0] + w[4]; s1 += w[1] + w[5]; s2 += w[2] + w[6]; s3 += w[3] + w[7];
+      for (int i = 0; i < 16; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
+      s0 += (w[0] + w[4]) + (w[8] + w[12]); s1 += (w[1] + w[5]) + (w[9] + w[13]);
+      s2 += (w[2] + w[6]) + (w[10] + w[14]); s3 += (w[3] + w[7]) + (w[11] + w[15]);
     }
     for (; r < r1; ++r) s0 += __ldg(W + r * g.wd_ld);
     acc[0] = (s0 + s1) + (s2 + s3);
   } else {
-    for (; r + 3 < r1; r += 4) {
-      float w[4];
+    for (; r + 7 < r1; r += 8) {
+      float w[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(W + (r + i) * g.wd_ld);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int q = 0; q < WS_KMAX; ++q)
           if (q < g.s) acc[q] = fmaf(w[i], __ldg(S + (r + i) * g.s_ld + q), acc[q]);
