@@ -1062,7 +1062,17 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
       } else if (wide_gemm(c, w, st)) return -1;
     }
   }
-  wide_finalize_kernel<<<n, 1024, 0, st>>>(M, theta, gl, c->w_llpart, c->w_nblk, prior_weight);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)n * WF_CLUSTER, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = WF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const float* th_c = theta; const float* ll_c = c->w_llpart; int nblk = c->w_nblk;
+    CK(cudaLaunchKernelEx(&cfg, wide_finalize_kernel, M, th_c, gl, ll_c, nblk, prior_weight));
+  }
   CK(cudaGetLastError());
   c->launches++;
   return 0;
@@ -1089,8 +1099,16 @@ static int shard_eval(mile_ctx* c, cudaStream_t st) {
 
 static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
   S.stage = stage; S.s_local = s_local;
-  if (c->d > 8192) mile_integrator_kernel<1024><<<c->C, 1024, 0, st>>>(S);
-  else mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
+  if (c->d > 8192) {   // large d: a cluster of 8 CTAs per chain, elements strided over its 8192 threads (DSMEM reductions)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)c->C * 8, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, mile_integrator_kernel<1024, true>, S));
+  } else mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
   CK(cudaGetLastError());
   c->launches++;
   return 0;

@@ -56,6 +56,8 @@ struct Ctx {
   int phase;   // block_sum double-buffer phase (whole block)
   float* red2; int phase2;   // scratch / phase of the integrator thread group (named barrier 1)
   int rank, G, chain;
+  // element-split mode (ES, wide / large-d integrator): the d elements are strided over the CTAs of a cluster
+  int e0, estride; float* csum; int csum_phase;
   __device__ Ctx(const KParams& p) : P(p) {}
 };
 
@@ -292,9 +294,41 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
   return v[0] + ll;
 }
 
+
+// ES (element split): element loops start at c.e0 with stride c.estride, and every block_sum is followed by a
+// DSMEM sum over the cluster's CTAs in rank order (double-buffered slots: one cluster barrier per reduction).
+#define MILE_I0(c, ES) ((ES) ? (c).e0 : (int)threadIdx.x)
+#define MILE_IS(c, ES, NT) ((ES) ? (c).estride : (NT))
+template <int NV>
+__device__ __forceinline__ void cluster_sum(Ctx& c, float (&v)[NV]) {
+  cg::cluster_group cl = cg::this_cluster();
+  float* slot = c.csum + (c.csum_phase & 1) * 8;
+  c.csum_phase++;
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) slot[k] = v[k];
+  cl.sync();
+  float t[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) t[k] = 0.f;
+  const int G = (int)cl.num_blocks();
+  for (int r = 0; r < G; ++r) {
+    const float* rs = cl.map_shared_rank(slot, r);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) t[k] += rs[k];
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = t[k];
+}
+template <int NV, int NT, int BAR, bool ES>
+__device__ __forceinline__ void all_sum(Ctx& c, float (&v)[NV]) {
+  block_sum<NV, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+  if (ES) cluster_sum<NV>(c, v);
+}
+
 // ESH momentum update B(coef) (blackjax esh_dynamics_momentum_update_one_step, sqrt_diag_cov = 1).
 // delta-small-safe forms: 1-zeta = -expm1(-delta), log(1+p+(1-p)zeta^2) - ln2 = log1p(-(1-p)(1-zeta^2)/2).
-template <int NT, int BAR = 0>
+template <int NT, int BAR = 0, bool ES = false>
 __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
   const int d = c.P.M.d;
   const float gn = sqrtf(g2);
@@ -310,7 +344,7 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const float rn2 = ce * ce + cu * cu + 2.f * ce * cu * p;
   const float rinv = rn2 > 1e-26f ? rsqrtf(rn2) : 1.f;
   const float ae = ce * ginv * rinv, au = cu * rinv;
-  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
   const float omz2 = omz * (1.f + zeta);   // 1 - zeta^2
   return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
 }
@@ -334,30 +368,30 @@ __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step
 }
 
 // partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
-template <int NT, int BAR = 0>
+template <int NT, int BAR = 0, bool ES = false>
 __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, long step_local, int slot, int nslot,
                                                  float& ug_out) {
   const KParams& P = c.P;
   const int d = P.M.d;
   if (isinf(L)) {   // no refresh: still re-normalise numerically (the B-steps use the closed-form norm)
     float v[2] = {0.f, 0.f};
-    for (int i = threadIdx.x; i < d; i += NT) { v[0] += c.uu[i] * c.uu[i]; v[1] += c.uu[i] * c.gg[i]; }
-    block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.uu[i] * c.uu[i]; v[1] += c.uu[i] * c.gg[i]; }
+    all_sum<2, NT, BAR, ES>(c, v);
     const float inv = 1.f / sqrtf(v[0]);
-    for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= inv;
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] *= inv;
     ug_out = v[1] * inv;
     return;
   }
   const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
   float v[2] = {0.f, 0.f};
-  for (int i = threadIdx.x; i < d; i += NT) {
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
     const float w = c.uu[i] + nu * noise_at(P, c.chain, step_local, slot, nslot, i);
     c.uu[i] = w;
     v[0] += w * w; v[1] += w * c.gg[i];
   }
-  block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+  all_sum<2, NT, BAR, ES>(c, v);
   const float inv = 1.f / sqrtf(v[0]);
-  for (int i = threadIdx.x; i < d; i += NT) c.uu[i] *= inv;
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] *= inv;
   ug_out = v[1] * inv;
 }
 
@@ -372,7 +406,7 @@ struct TuneRegs { float time, xavg, epsmax, wtot; };
 
 // End of a tuning iteration (warmup.py:293-350): handle_nans, energy-variance step-size predictor, streaming
 // average of (x, x^2).  Returns the new step size; lp / dE / g2 / ug are updated in place.
-template <int NT, bool HAS_WP, int BAR = 0>
+template <int NT, bool HAS_WP, int BAR = 0, bool ES = false>
 __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, float lp_old, float nf, long s_local,
                                                float& lp, float& dE, float& g2, float& ug) {
   const KParams& P = c.P;
@@ -382,17 +416,17 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
       // handle_nans (warmup.py:468-483)
       const bool success = nf == 0.f;
       if (!success) {
-        for (int i = tid; i < d; i += NT) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; if (HAS_WP) store_param(c, i, c.thb[i]); }
+        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { c.th[i] = c.thb[i]; c.uu[i] = c.ub[i]; c.gg[i] = c.gb[i]; if (HAS_WP) store_param(c, i, c.thb[i]); }
         lp = lp_old;
         t_epsmax = eps * 0.8f;
         dE = 0.f;
         float v[2] = {0.f, 0.f};
-        for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-        block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+        all_sum<2, NT, BAR, ES>(c, v);
         g2 = v[0]; ug = v[1];
       } else {
         bool changed = false;
-        for (int i = tid; i < d; i += NT) {
+        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
           const float u0 = c.uu[i], g0 = c.gg[i];
           const float u1 = nan_to_num(u0), g1 = nan_to_num(g0);
           if (u1 != u0 || g1 != g0 || isnan(u0) || isnan(g0)) { c.uu[i] = u1; c.gg[i] = g1; changed = true; }
@@ -401,11 +435,11 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         t_epsmax = nan_to_num(t_epsmax);
         dE = nan_to_num(dE);
         float chv[1] = {changed ? 1.f : 0.f};
-        block_sum<1, NT, BAR>(chv, MILE_RED(c, BAR), MILE_PH(c, BAR));
+        all_sum<1, NT, BAR, ES>(c, chv);
         if (chv[0] != 0.f) {
           float v[2] = {0.f, 0.f};
-          for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
-          block_sum<2, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+          for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+          all_sum<2, NT, BAR, ES>(c, v);
           g2 = v[0]; ug = v[1];
         }
       }
@@ -432,7 +466,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
       if (it >= P.tune1) {
         const float w = (success ? 1.f : 0.f) * eps_new;
         const float denom = t_wtot + w;
-        for (int i = tid; i < d; i += NT) {
+        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
           const float x = c.th[i];
           c.avgx[i] = (t_wtot * c.avgx[i] + w * x) / denom;
           c.avgx2[i] = (t_wtot * c.avgx2[i] + w * (x * x)) / denom;

@@ -19,26 +19,39 @@ struct ShardParams {
   long s_local;           // index of the step inside this call (noise / info / tune_info addressing)
 };
 
-template <int NT>
+// ES = element split: a cluster of CTAs per chain, the d elements strided over all of its threads and every reduction
+// completed over DSMEM -- the large-d (wide) path, where one CTA per chain would be a latency-bound 200k-element loop.
+template <int NT, bool ES = false>
 __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_constant__ ShardParams S) {
-  // works IN PLACE on the global chain state (every element is owned by one thread: i = tid mod NT), so it has
+  // works IN PLACE on the global chain state (every element is owned by one thread), so it has
   // no shared-memory size limit and also serves the wide / large-d path (mile_wide.cuh)
   __shared__ float red[2 * 4 * (NT / 32) + 64];
+  __shared__ float csum[16];
   const KParams& P = S.K;
-  const int d = P.M.d, ch = blockIdx.x, tid = threadIdx.x;
+  const int d = P.M.d, tid = threadIdx.x;
+  int ch = blockIdx.x, crank = 0, csize = 1;
+  if (ES) {
+    cg::cluster_group cl = cg::this_cluster();
+    csize = (int)cl.num_blocks(); crank = (int)cl.block_rank(); ch = blockIdx.x / csize;
+  }
   Ctx c(P);
-  c.G = 1; c.rank = 0; c.chain = ch; c.phase = 0; c.phase2 = 0;
+  c.G = 1; c.rank = crank; c.chain = ch; c.phase = 0; c.phase2 = 0;
+  c.e0 = crank * NT + tid; c.estride = csize * NT; c.csum = csum; c.csum_phase = 0;
+  const bool writer = tid == 0 && crank == 0;
   c.th = P.theta + (long)ch * d; c.uu = P.u + (long)ch * d; c.gg = P.grad + (long)ch * d;
   c.thb = S.thb + (long)ch * d; c.ub = S.ub + (long)ch * d; c.gb = S.gb + (long)ch * d;
   c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 2 * 4 * (NT / 32);
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
   float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];
-  if (fresh) for (int i = tid; i < d; i += NT) c.gg[i] = S.gl[(long)ch * (d + 1) + i];
-  __syncthreads();
+  // (the copy and the sums touch the same elements in the same thread: no barrier needed in between)
   float v[3] = {0.f, 0.f, 0.f};
-  for (int i = tid; i < d; i += NT) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; v[2] += isfinite(c.th[i]) ? 0.f : 1.f; }
-  block_sum<3, NT>(v, c.red, c.phase);
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
+    const float gi = fresh ? S.gl[(long)ch * (d + 1) + i] : c.gg[i];
+    if (fresh) c.gg[i] = gi;
+    v[0] += gi * gi; v[1] += c.uu[i] * gi; v[2] += isfinite(c.th[i]) ? 0.f : 1.f;
+  }
+  all_sum<3, NT, 0, ES>(c, v);
   float g2 = v[0], ug = v[1];
   const float nf = v[2];
   const bool tune = S.tune != 0;
@@ -49,32 +62,33 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   float lp_old = S.scal[ch * 4 + 0], dK = S.scal[ch * 4 + 1];
   if (S.stage == SH_BEGIN) {
     lp_old = lp; dK = 0.f;
-    if (tune) for (int i = tid; i < d; i += NT) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
-    if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, S.s_local, 0, nslot, ug);
+    if (tune) for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { c.thb[i] = c.th[i]; c.ub[i] = c.uu[i]; c.gb[i] = c.gg[i]; }
+    if (P.refresh_mode) refresh_momentum<NT, 0, ES>(c, 0.5f * eps, Lc, S.s_local, 0, nslot, ug);
   }
   if (S.stage != SH_END) {
-    dK += esh_update<NT>(c, eps, S.stage == SH_BEGIN ? b1 : b2, g2, ug);
+    dK += esh_update<NT, 0, ES>(c, eps, S.stage == SH_BEGIN ? b1 : b2, g2, ug);
     const float st = eps * 0.5f;
-    for (int i = tid; i < d; i += NT) c.th[i] += st * c.uu[i];
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.th[i] += st * c.uu[i];
   } else {
-    dK += esh_update<NT>(c, eps, b1, g2, ug);
-    refresh_momentum<NT>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, S.s_local, nslot - 1, nslot, ug);
+    dK += esh_update<NT, 0, ES>(c, eps, b1, g2, ug);
+    refresh_momentum<NT, 0, ES>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, S.s_local, nslot - 1, nslot, ug);
     float dE = dK - lp + lp_old;
     if (!tune) {
-      if (P.info && tid == 0) { float* o = P.info + ((long)S.s_local * P.C + ch) * 3; o[0] = lp; o[1] = dK; o[2] = dE; }
+      if (P.info && writer) { float* o = P.info + ((long)S.s_local * P.C + ch) * 3; o[0] = lp; o[1] = dK; o[2] = dE; }
       const long idx = P.step_base + S.s_local;
       if (idx % P.thin == 0) {
         const long slot = idx / P.thin - P.sample_base;
         if (P.samples && slot >= 0 && slot < P.n_slots)
-          for (int i = tid; i < d; i += NT) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
+          for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) P.samples[(slot * P.C + ch) * d + i] = c.th[i];
       }
     } else {
       TuneRegs tr{P.t_time[ch], P.t_xavg[ch], P.t_epsmax[ch], P.t_wtot[ch]};
-      eps = tune_epilogue<NT, false>(c, tr, eps, lp_old, nf, S.s_local, lp, dE, g2, ug);
-      if (tid == 0) { P.t_time[ch] = tr.time; P.t_xavg[ch] = tr.xavg; P.t_epsmax[ch] = tr.epsmax; P.t_wtot[ch] = tr.wtot; P.t_eps[ch] = eps; }
+      eps = tune_epilogue<NT, false, 0, ES>(c, tr, eps, lp_old, nf, S.s_local, lp, dE, g2, ug);
+      if (writer) { P.t_time[ch] = tr.time; P.t_xavg[ch] = tr.xavg; P.t_epsmax[ch] = tr.epsmax; P.t_wtot[ch] = tr.wtot; P.t_eps[ch] = eps; }
     }
   }
-  if (tid == 0) { P.lp[ch] = lp; S.scal[ch * 4 + 0] = lp_old; S.scal[ch * 4 + 1] = dK; }
+  if (writer) { P.lp[ch] = lp; S.scal[ch * 4 + 0] = lp_old; S.scal[ch * 4 + 1] = dK; }
+  if (ES) cg::this_cluster().sync();   // no CTA may exit while a peer still reads its reduction slots
 }
 
 // blackjax generate_unit_vector for all chains: u = z / |z| (z host-supplied or the same Philox draw MODE_INIT uses)

@@ -374,15 +374,21 @@ __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const floa
 }
 
 // gl[c][0..d) += prior gradient * w ; gl[c][d] = n_batches * sum(ll partials) + w * log prior   (one CTA per chain)
+// launched as clusters of WF_CLUSTER CTAs per chain: the d elements are strided over the cluster's threads and the two
+// partial sums are combined over DSMEM in rank order (one CTA per chain would be a latency-bound 200k-element loop)
+#define WF_CLUSTER 8
 __global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
                                                             const float* __restrict__ llpart, int nblk, float prior_weight) {
   __shared__ float red[256];
+  __shared__ float slot[2];
+  cg::cluster_group cl = cg::this_cluster();
+  const int G = (int)cl.num_blocks(), rank = (int)cl.block_rank();
   int phase = 0;
-  const int c = blockIdx.x, d = M.d;
+  const int c = blockIdx.x / G, d = M.d;
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
   const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
   float v[2] = {0.f, 0.f};
-  for (int i = threadIdx.x; i < d; i += 1024) {
+  for (int i = rank * 1024 + threadIdx.x; i < d; i += G * 1024) {
     const float dlt = theta[(long)c * d + i] - loc;
     float pv, pg;
     if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
@@ -390,9 +396,16 @@ __global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const f
     gl[(long)c * (d + 1) + i] += pg * prior_weight;
     v[0] += pv;
   }
-  for (int i = threadIdx.x; i < nblk; i += 1024) v[1] += llpart[(long)c * nblk + i];
+  for (int i = rank * 1024 + threadIdx.x; i < nblk; i += G * 1024) v[1] += llpart[(long)c * nblk + i];
   block_sum<2, 1024>(v, red, phase);
-  if (threadIdx.x == 0) gl[(long)c * (d + 1) + d] = v[1] * M.n_batches + v[0] * prior_weight;
+  if (threadIdx.x == 0) { slot[0] = v[0]; slot[1] = v[1]; }
+  cl.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    float p = 0.f, l = 0.f;
+    for (int r = 0; r < G; ++r) { const float* rs = cl.map_shared_rank(slot, r); p += rs[0]; l += rs[1]; }
+    gl[(long)c * (d + 1) + d] = l * M.n_batches + p * prior_weight;
+  }
+  cl.sync();
 }
 
 // =====================================================================================================
