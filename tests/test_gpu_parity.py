@@ -352,7 +352,9 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize('widths,act,task', [((256, 256, 256, 256, 2), 'relu', 'regr'), ((96, 80, 3), 'tanh', 'class'),
-                                             ((48, 48, 48, 2), 'relu', 'regr')])
+                                             ((48, 48, 48, 2), 'relu', 'regr'),
+                                             # more than one 256-column block, K not a multiple of the 32-wide k-block
+                                             ((272, 264, 2), 'sigmoid', 'regr')])
 def test_wide_path_value_and_grad_and_step(widths, act, task):
     """Shapes that do not fit the shared-memory kernels (complexity ablation: 4x256, d = 201218) run on the
     HBM-resident layer-by-layer path (chain-batched GEMMs + integrator kernel): same parity bar."""
