@@ -25,7 +25,7 @@ template <int NT, bool ES = false>
 __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_constant__ ShardParams S) {
   // works IN PLACE on the global chain state (every element is owned by one thread), so it has
   // no shared-memory size limit and also serves the wide / large-d path (mile_wide.cuh)
-  __shared__ float red[2 * 4 * (NT / 32) + 64];
+  __shared__ __align__(16) float red[2 * 4 * (NT / 32) + 64];
   __shared__ float csum[16];
   const KParams& P = S.K;
   const int d = P.M.d, tid = threadIdx.x;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
 template <int NT>
 __global__ void __launch_bounds__(NT) mile_unit_momentum_kernel(float* __restrict__ u, const float* __restrict__ z0,
                                                                 unsigned long long seed, int d) {
-  __shared__ float red[64];
+  __shared__ __align__(16) float red[64];
   int phase = 0;
   const int ch = blockIdx.x;
   float v[1] = {0.f};

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) wide_colsum_kernel(const float* __restric
 // per (chain, row): log-likelihood term and d/d(out) (probabilistic.py:93-109); block partial sums of ll
 __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const float* __restrict__ out, float* __restrict__ dout,
                                                           const void* __restrict__ y, long N, long N8, float* __restrict__ llpart) {
-  __shared__ float red[64];
+  __shared__ __align__(16) float red[64];
   int phase = 0;
   const int c = blockIdx.y, K = M.dims[M.NL];
   const long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const floa
 #define WF_CLUSTER 8
 __global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
                                                             const float* __restrict__ llpart, int nblk, float prior_weight) {
-  __shared__ float red[256];
+  __shared__ __align__(16) float red[256];
   __shared__ float slot[2];
   cg::cluster_group cl = cg::this_cluster();
   const int G = (int)cl.num_blocks(), rank = (int)cl.block_rank();
