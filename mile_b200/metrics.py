@@ -32,3 +32,49 @@ def running_lppd(lppd_pointwise: np.ndarray) -> np.ndarray:
     cs = np.cumsum(e, axis=-2)
     cnt = np.arange(1, e.shape[-2] + 1).reshape((1, -1, 1))
     return np.log(cs / cnt).mean(axis=-1).mean(axis=0)
+
+
+# ---- chain diagnostics with the reference's names (metrics.py:226-244, 354-425, 449-523) -------------------------
+# numpy / torch in, numpy out; the arithmetic runs in torch on the GPU when one is present (mile_b200/diagnostics.py).
+def _run(fn, x, *args, **kw):
+    import torch
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+    if not t.is_cuda and torch.cuda.is_available():
+        t = t.cuda()
+    return fn(t, *args, **kw).cpu().numpy()
+
+
+def rank_normalize_array(samples):
+    from . import diagnostics as dg
+    s = np.asarray(samples)
+    return _run(dg.rank_normalize_array, s.reshape(-1, 1)).reshape(s.shape)   # overall ranks of the whole array
+
+
+def between_chain_var(x):
+    from . import diagnostics as dg
+    return _run(dg.between_chain_var, x)
+
+
+def within_chain_var(x):
+    from . import diagnostics as dg
+    return _run(dg.within_chain_var, x)
+
+
+def effective_sample_size(x, rank_normalize: bool = True):
+    from . import diagnostics as dg
+    return _run(dg.chain_effective_sample_size, x, rank_normalize)
+
+
+def running_mean(x, axis: int):
+    from . import diagnostics as dg
+    return _run(dg.running_mean, x, axis)
+
+
+def gelman_split_r_hat(samples, n_splits: int, rank_normalize: bool = True):
+    from . import diagnostics as dg
+    return _run(dg.gelman_split_r_hat, samples, n_splits, rank_normalize)
+
+
+def split_chain_r_hat(samples, n_splits: int, rank_normalize: bool = True):
+    from . import diagnostics as dg
+    return _run(dg.split_chain_r_hat, samples, n_splits, rank_normalize)
