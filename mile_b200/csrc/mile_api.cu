@@ -845,7 +845,19 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
     c->w_woff[l] = wsum; wsum += (long)((M.dims[l] + 7) / 8 * 8) * ((M.dims[l + 1] + 7) / 8 * 8);
   }
   c->w_wstride = wsum; c->w_n8 = N8;
-  c->w_kslices = (int)((N + 1023) / 1024); if (c->w_kslices > 64) c->w_kslices = 64; if (c->w_kslices < 1) c->w_kslices = 1;
+  {
+    // split-K factor of the dW GEMMs (K = rows): the smallest one whose tile count fills whole waves of the persistent
+    // tcgen05 kernel (tiles = m-blocks x n-blocks x chains x slices on n_sms CTAs), at least 256 rows per slice
+    const long mt = (maxw + 127) / 128, nt = (maxw + 255) / 256;
+    int best = 1; double best_eff = 0.0;
+    for (int ks = 1; ks <= 64 && N / ks >= 256; ++ks) {
+      const long tiles = mt * nt * n_chains * ks, waves = (tiles + c->n_sms - 1) / c->n_sms;
+      const double eff = (double)tiles / (double)(waves * c->n_sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
+      if (eff >= 0.95 && waves >= 2) { best = ks; break; }
+    }
+    c->w_kslices = best;
+  }
   c->w_nblk = (int)((N + 255) / 256);
   const size_t actb = (size_t)n_chains * N8 * act_per_row * 4, delb = (size_t)n_chains * N8 * maxw * 4;
   CK(cudaMalloc(&c->w_act, actb));
@@ -874,7 +886,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int tmap_get(mile_ctx* c, const float* ptr, long R, long Ccols, long ld, long bstride, int nbatch, int box_cols, int box_rows,
-                    CUtensorMap* out) {
+                    CUtensorMap* out, int atom32 = 0) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -882,7 +894,7 @@ static int tmap_get(mile_ctx* c, const float* ptr, long R, long Ccols, long ld, 
       return fail("cuTensorMapEncodeTiled is not available");
     g_encode = (EncodeTiledFn)fn;
   }
-  auto key = std::make_tuple((const void*)ptr, R, Ccols, ld, bstride, nbatch, box_cols, box_rows);
+  auto key = std::make_tuple((const void*)ptr, R, Ccols, ld, bstride, nbatch, box_cols, box_rows + 100000 * atom32);
   auto it = c->tmaps.find(key);
   if (it != c->tmaps.end()) { *out = it->second; return 0; }
   alignas(64) CUtensorMap tm;
@@ -892,7 +904,8 @@ static int tmap_get(mile_ctx* c, const float* ptr, long R, long Ccols, long ld, 
   cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   c->tmaps[key] = tm;
   *out = tm;
@@ -907,28 +920,35 @@ static bool tc2_operand_ok(const float* p, long ld, long bstride) {
 static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   const bool a_mn = g.sam == 1 && g.sak != 1, b_mn = g.sbn == 1 && g.sbk != 1;
   const bool a_k = g.sak == 1, b_k = g.sbk == 1;
-  if (!a_k || !b_k) return 0;   // MN-major tf32 operands: handled by the v1 core (transposes while staging)
-  (void)a_mn; (void)b_mn;
+  const bool mn = a_mn && b_mn;                  // dW = a^T delta: both operands MN-major, no packed remainders
+  if (!(a_k && b_k) && !mn) return 0;            // mixed orientations: handled by the v1 core (transposes while staging)
   const long a_ld = a_mn ? g.sak : g.sam, b_ld = b_mn ? g.sbk : g.sbn;
-  if (!tc2_operand_ok(g.A, a_ld, g.a_batch) || !tc2_operand_ok(g.B, b_ld, g.b_batch) || !tc2_operand_ok(g.B_lo, b_ld, g.b_batch)) return 0;
-  if ((g.K & 3) || (a_mn && (g.M & 3)) || (b_mn && (g.N & 3))) return 0;
+  if (!tc2_operand_ok(g.A, a_ld, g.a_batch) || !tc2_operand_ok(g.B, b_ld, g.b_batch)) return 0;
+  if (!mn && !tc2_operand_ok(g.B_lo, b_ld, g.b_batch)) return 0;
+  if (mn ? ((g.M & 3) || (g.N & 3) || g.epi != 0) : (g.K & 3) != 0) return 0;
   Tc2Args t;
   memset(&t, 0, sizeof(t));
-  if (tmap_get(c, g.A, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_hi)) return -1;
-  if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_hi)) return -1;
-  if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_lo)) return -1;
+  if (mn) {   // global [K rows][MN cols]: boxes of 32 MN-floats x 32 K-rows
+    if (tmap_get(c, g.A, g.K, g.M, a_ld, g.a_batch, g.nbatch, 32, T2_BK, &t.a_hi, 1)) return -1;
+    if (tmap_get(c, g.B, g.K, g.N, b_ld, g.b_batch, g.nbatch, 32, T2_BK, &t.b_hi, 1)) return -1;
+  } else {
+    if (tmap_get(c, g.A, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_hi)) return -1;
+    if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_hi)) return -1;
+    if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_lo)) return -1;
+  }
   t.M = g.M; t.N = g.N; t.K = g.K; t.kslices = g.kslices; t.nbatch = g.nbatch;
   t.C = g.C; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
   t.bias = g.bias; t.bias_batch = g.bias_batch; t.aux = g.aux; t.aux_batch = g.aux_batch; t.ldaux = g.ldaux;
   const int ntiles = ((g.M + T2_BM - 1) / T2_BM) * ((g.N + T2_BN - 1) / T2_BN) * g.nbatch * g.kslices;
   const int grid = ntiles < c->n_sms ? ntiles : c->n_sms;      // persistent: one CTA per SM, tiles strided over the grid
   const bool relu = g.act == MILE_ACT_RELU;
-#define T2_LAUNCH(E, R)                                                                                                   \
+#define T2_LAUNCH(...)                                                                                                    \
   do {                                                                                                                    \
-    CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));       \
-    wide_gemm_tc2_kernel<E, R><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(t);                                               \
+    CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES)); \
+    wide_gemm_tc2_kernel<__VA_ARGS__><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(t);                                        \
   } while (0)
-  if (g.epi == 0) T2_LAUNCH(0, false);
+  if (mn) T2_LAUNCH(0, false, true);
+  else if (g.epi == 0) T2_LAUNCH(0, false);
   else if (g.epi == 2) T2_LAUNCH(2, false);
   else if (g.epi == 1) { if (relu) T2_LAUNCH(1, true); else T2_LAUNCH(1, false); }
   else { if (relu) T2_LAUNCH(3, true); else T2_LAUNCH(3, false); }

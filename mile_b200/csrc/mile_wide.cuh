@@ -717,6 +717,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 }
 
 // K-major SWIZZLE_128B descriptor: LBO unused (1), SBO = 1024 B between 8-row groups, layout type 2
+// MN-major tf32 operands: the only shared-memory layout the tensor core accepts is "128-byte swizzle with 32-byte atoms"
+// (UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical ((4,8,m),(4,k)):((1,4,LBO),(32,SBO)) in
+// elements.  The operand tile is a row of [32 K-rows x 128 B] TMA boxes, one per 32 MN-elements: LBO = 4096 B between
+// boxes, SBO = 512 B between the 4-row K-groups inside a box.  One K = 8 instruction consumes two K-groups: k-step = +1024 B.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
@@ -740,7 +748,10 @@ __device__ __forceinline__ float t2_epi(float v, float bias, float aux, int act)
 // main loop of tile t+1:
 //   tmem_full[a]  MMA -> epilogue  (accumulator a complete)
 //   tmem_empty[a] epilogue -> MMA  (accumulator a drained; count = T2_EPI_WARPS)
-template <int EPI, bool RELU>
+// MN = true: both operands are MN-major in global memory (A(m,k) at A[k*lda + m], B(n,k) at B[k*ldb + n]) -- the weight
+// gradients dW = a^T delta with K = data rows.  Each operand tile is then a row of {32 MN-floats x 32 K-rows} TMA boxes,
+// neither operand has a pre-packed remainder, and the converter warps produce A_lo and B_lo.
+template <int EPI, bool RELU, bool MN = false>
 __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __grid_constant__ Tc2Args g) {
   extern __shared__ __align__(1024) char sm2[];
   const uint32_t sbase = smem_u32(sm2);
@@ -790,17 +801,26 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
           const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
           mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
           const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(T2_A_BYTES + 2 * T2_B_BYTES)) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                       "r"((uint32_t)(MN ? T2_A_BYTES + T2_B_BYTES : T2_A_BYTES + 2 * T2_B_BYTES)) : "memory");
           const int k0 = kbeg + kb * T2_BK;
-          tma_load_3d(st, &g.a_hi, k0, m0, b, full);
-          tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0, b, full);
-          tma_load_3d(st + 2 * T2_A_BYTES + T2_B_BYTES, &g.b_lo, k0, n0, b, full);
+          if (MN) {
+#pragma unroll
+            for (int j = 0; j < T2_BM / 32; ++j) tma_load_3d(st + j * 4096, &g.a_hi, m0 + 32 * j, k0, b, full);
+#pragma unroll
+            for (int j = 0; j < T2_BN / 32; ++j) tma_load_3d(st + 2 * T2_A_BYTES + j * 4096, &g.b_hi, n0 + 32 * j, k0, b, full);
+          } else {
+            tma_load_3d(st, &g.a_hi, k0, m0, b, full);
+            tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0, b, full);
+            tma_load_3d(st + 2 * T2_A_BYTES + T2_B_BYTES, &g.b_lo, k0, n0, b, full);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer ----
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24) |
+                             (MN ? ((1u << 15) | (1u << 16)) : 0u);   // bits 15 / 16: A / B are MN-major
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
         int b, ks, m0, n0, kbeg, nkb;
@@ -817,10 +837,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
           const uint32_t ahi = st, alo = st + T2_A_BYTES, bhi = st + 2 * T2_A_BYTES, blo = bhi + T2_B_BYTES;
 #pragma unroll
           for (int j = 0; j < T2_BK / 8; ++j) {   // K = 8 tf32 = 32 B further inside the 128-byte swizzle atom
-            const uint32_t o = j * 32;
-            umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, (kb == 0 && j == 0) ? 0u : 1u);
-            umma_tf32(tacc, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
-            umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+            const uint32_t acc0 = (kb == 0 && j == 0) ? 0u : 1u;
+            if (MN) {
+              const uint32_t o = j * 1024;   // next 8-row K-group of every box
+              umma_tf32(tacc, umma_desc_mn_sw128(ahi + o), umma_desc_mn_sw128(blo + o), idesc, acc0);
+              umma_tf32(tacc, umma_desc_mn_sw128(alo + o), umma_desc_mn_sw128(bhi + o), idesc, 1u);
+              umma_tf32(tacc, umma_desc_mn_sw128(ahi + o), umma_desc_mn_sw128(bhi + o), idesc, 1u);
+            } else {
+              const uint32_t o = j * 32;
+              umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, acc0);
+              umma_tf32(tacc, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
+              umma_tf32(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+            }
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (T2_STAGES + s)) : "memory");
         }
@@ -845,6 +873,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ahi + off));
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(alo + off), "f"(v.x - tf32_hi(v.x)), "f"(v.y - tf32_hi(v.y)),
                        "f"(v.z - tf32_hi(v.z)), "f"(v.w - tf32_hi(v.w)) : "memory");
+        }
+        if (MN) {   // no pre-packed remainder for B either
+          const uint32_t bhi = ahi + 2 * T2_A_BYTES, blo = bhi + T2_B_BYTES;
+#pragma unroll
+          for (int i = 0; i < T2_B_BYTES / 16 / (32 * T2_CVT_WARPS); ++i) {
+            const uint32_t off = (uint32_t)(ct + i * 32 * T2_CVT_WARPS) * 16u;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(bhi + off));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blo + off), "f"(v.x - tf32_hi(v.x)), "f"(v.y - tf32_hi(v.y)),
+                         "f"(v.z - tf32_hi(v.z)), "f"(v.w - tf32_hi(v.w)) : "memory");
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
         __syncwarp();
