@@ -127,7 +127,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
     while (G > 1 && nrows_for_split / G < 64) G >>= 1;
     // few chains: more than 8 CTAs per chain only fit with the global-memory exchange (cooperative launch)
     const int gmax = c->n_sms / n_chains;
-    if (c->opt_sync != 0 && G == 8 && gmax > 9 && nrows_for_split / gmax >= 256) { G = gmax > 16 ? 16 : gmax; sync_mode = 1; }
+    if (c->opt_sync != 0 && G == 8 && gmax > 9 && nrows_for_split / gmax >= 64) { G = gmax > 16 ? 16 : gmax; sync_mode = 1; }
   } else if (c->opt_sync == 1 || (G > 8) || (G & (G - 1))) {
     sync_mode = 1;
   }

@@ -233,6 +233,28 @@ __device__ __forceinline__ float ll_sum(const float2* base, int stride, int G, u
   for (int r = 0; r < 16; ++r) s += __uint_as_float(v[r]);
   return s;
 }
+// two offsets at once (a thread that owns two elements keeps both sets of loads in flight: one L2 round trip, not two)
+__device__ __forceinline__ void ll_sum_pair(const float2* base0, const float2* base1, int stride, int G, unsigned int flag, float& s0, float& s1) {
+  uint32_t v[16], f[16], w[16], h[16];
+  long spin = 0;
+  bool ok;
+  do {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < G) {
+        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v[r]), "=r"(f[r]) : "l"(base0 + (long)r * stride) : "memory");
+        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(w[r]), "=r"(h[r]) : "l"(base1 + (long)r * stride) : "memory");
+      } else { v[r] = 0u; f[r] = flag; w[r] = 0u; h[r] = flag; }
+    }
+    ok = true;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ok = ok && (f[r] == flag) && (h[r] == flag);
+    if (!ok && ++spin > (1L << 24)) __trap();
+  } while (!ok);
+  s0 = 0.f; s1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) { s0 += __uint_as_float(v[r]); s1 += __uint_as_float(w[r]); }
+}
 
 template <int NT, int BAR>
 __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const float2* gslab, unsigned int flag, float& g2, float& ug,
@@ -262,16 +284,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
   const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
-  for (int i = threadIdx.x; i < M.d; i += NT) {
-    float s = 0.f;
-    if (P.sync_mode) s = ll_sum(gslab + i, stride_g, c.G, flag);
-    else {
-      float t[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) s += t[r];
-    }
+  auto consume = [&](int i, float s) {
     const float th = c.th[i];
     float pg, pv;
     if (M.prior == MILE_PRIOR_NORMAL) {
@@ -286,6 +299,28 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     const float g = s + pg * P.prior_weight;
     c.gg[i] = g;
     v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
+  };
+  if (P.sync_mode) {
+    for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
+      const int i2 = i + NT;
+      if (i2 < M.d) {
+        float s0, s1;
+        ll_sum_pair(gslab + i, gslab + i2, stride_g, c.G, flag, s0, s1);
+        consume(i, s0); consume(i2, s1);
+      } else {
+        consume(i, ll_sum(gslab + i, stride_g, c.G, flag));
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < M.d; i += NT) {
+      float t[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += t[r];
+      consume(i, s);
+    }
   }
   PROF(14);
   if (P.sync_mode && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, c.G, flag);
