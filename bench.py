@@ -120,12 +120,13 @@ def load_peaks():
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement (C + OpenMP when built, numpy otherwise)
 # ----------------------------------------------------------------------------------------------
-def cpu_chain_steps_per_s(workload: str, budget_s: float = 12.0, max_steps: int = 200):
+def cpu_chain_steps_per_s(workload: str, budget_s: float = 12.0, max_steps: int = 200, waves: int = 1):
     """Times the CPU restatement of the reference on a bounded sample of the same workload:
     all chains of one wave, one chain per host thread (mirrors one-virtual-device-per-chain pmap,
     train.py:16), as many MCLMC steps as fit the budget."""
     from oracle import mile_oracle as o
     key, C, _ = WORKLOADS[workload]
+    C = C * max(1, waves)          # reference arm at N GPUs: the same N x C chains our arm runs (weak scaling)
     spec = o.make_spec(key)
     X, y, _, _ = o.synthetic_data(key)
     th0 = o.synthetic_theta0(spec, C)
@@ -172,17 +173,19 @@ def run_reference(args):
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        r = cpu_chain_steps_per_s(W, budget_s=max(2.0, 20.0 / max(1, args.steps + args.warmup)))
+        waves = 1 if key == 'covertype_full' else max(1, args.gpus)   # row-sharded workload: the chains do not multiply
+        r = cpu_chain_steps_per_s(W, budget_s=max(2.0, 20.0 / max(1, args.steps + args.warmup)), waves=waves)
         if i >= args.warmup:
             vals.append(r['value'])
         base = r
     v = float(np.mean(vals))
     line = {
         'impl': 'reference', 'metric': 'chain-steps/sec', 'value': v, 'unit': 'chain-steps/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * C * inner / v, 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * C * waves * inner / v, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': W, 'chains_per_gpu': C, 'inner_steps_per_launch': inner, 'n_train': Ntr,
-                   'n_params': spec.n_params, 'note': 'CPU restatement of the reference (JAX/BlackJAX not installable here)'},
+        'config': {'workload': W, 'chains_per_gpu': C, 'chains_total': C * waves, 'inner_steps_per_launch': inner, 'n_train': Ntr,
+                   'n_params': spec.n_params, 'note': 'CPU restatement of the reference (JAX/BlackJAX not installable here); '
+                                                      'one chain per host thread, all chains of the N-GPU job'},
         'grad_evals_per_s': 2 * v,
         'cpu_baseline': dict(base, value=v),
         'e2e': {'value': v, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
