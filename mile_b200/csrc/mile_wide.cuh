@@ -320,21 +320,6 @@ __global__ void wide_slice_reduce_kernel(const float* __restrict__ src, long src
   }
 }
 
-// bias gradient: partial column sums of D [rows x ncols] over a row slice (deterministic two-pass with
-// wide_slice_reduce_kernel); grid (ceil(ncols/256), kslices, chains), thread = column
-__global__ void __launch_bounds__(256) wide_colsum_kernel(const float* __restrict__ D, long d_batch, long N, int ncols,
-                                                          int kslices, float* __restrict__ part, long p_batch) {
-  const int j = blockIdx.x * 256 + threadIdx.x, ks = blockIdx.y, c = blockIdx.z;
-  if (j >= ncols) return;
-  const long per = (N + kslices - 1) / kslices, r0 = ks * per, r1 = min(N, r0 + per);
-  const float* p = D + (long)c * d_batch + j;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  long r = r0;
-  for (; r + 3 < r1; r += 4) { s0 += p[r * ncols]; s1 += p[(r + 1) * ncols]; s2 += p[(r + 2) * ncols]; s3 += p[(r + 3) * ncols]; }
-  for (; r < r1; ++r) s0 += p[r * ncols];
-  part[(long)c * p_batch + (long)ks * ncols + j] = (s0 + s1) + (s2 + s3);
-}
-
 // per (chain, row): log-likelihood term and d/d(out) (probabilistic.py:93-109); block partial sums of ll
 __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const float* __restrict__ out, float* __restrict__ dout,
                                                           const void* __restrict__ y, long N, long N8, float* __restrict__ llpart) {
