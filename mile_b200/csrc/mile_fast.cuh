@@ -266,12 +266,15 @@ struct FastGE {
         float dmu = 0.f, ds = 0.f;
         if (row < nrows) {
           const float yv = reinterpret_cast<const float*>(P.y)[r0 + row];
-          const float e = expf(s);
-          const float sigma = fminf(fmaxf(e, 1e-6f), 1e6f);
-          const float inside = (e > 1e-6f && e < 1e6f) ? 1.f : 0.f;
-          const float s2 = sigma * sigma, res = yv - mu, q = res * res / s2;
-          float ll = (logf(6.283185307179586f * s2) + q) / -2.f;
-          dmu = res / s2; ds = (q - 1.f) * inside;
+          // sigma = clip(exp(s), 1e-6, 1e6) (probabilistic.py:100): with sc = clip(s, ln 1e-6, ln 1e6) this is
+          // log(2 pi sigma^2) = ln(2 pi) + 2 sc and 1 / sigma^2 = exp(-2 sc): one exp, no log, no divide on the
+          // critical path of the pipeline's busiest stage (same values up to fp32 rounding).
+          const float kLnClip = 13.815510557964274f;   // ln 1e6
+          const float sc = fminf(fmaxf(s, -kLnClip), kLnClip);
+          const float inside = (s > -kLnClip && s < kLnClip) ? 1.f : 0.f;
+          const float inv_s2 = expf(-2.f * sc), res = yv - mu, q = res * res * inv_s2;
+          float ll = (1.8378770664093453f + 2.f * sc + q) * -0.5f;
+          dmu = res * inv_s2; ds = (q - 1.f) * inside;
           if (isnan(ll)) { ll = 0.f; dmu = 0.f; ds = 0.f; }
           ll_sum += ll;
           dmu *= nb; ds *= nb;
