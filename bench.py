@@ -390,8 +390,8 @@ def run_ours(args):
                          'note': 'achieved = ALGORITHMIC fp32 FLOPs (12 N W per chain-step); the 3xTF32 split issues 3x that '
                                  'on the tensor pipe, and TF32 dense peak is half the bf16 figure used as denominator'})
         if W == 'bikesharing_2x16' and inner == 500 and not sharded:
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1i_ncu_fastge_bench_config.txt)
-            roof['traffic'] = 1657856 + 121600
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1q_ncu_fastge_final.txt)
+            roof['traffic'] = 1339904 + 109824
             roof['traffic_note'] = 'bytes per launch of mile_mclmc_kernel from the committed ncu capture of this command'
         line['roofline'] = roof
         if world == 1 and not args.no_cpu:
