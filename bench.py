@@ -210,16 +210,15 @@ def run_ours(args):
     from mile_b200 import Ensemble, FCNSpec, capi
     from mile_b200 import build as _b
     _b.build()
-    from oracle import mile_oracle as o   # synthetic inputs + cpu_baseline leg only
+    from mile_b200 import synthetic as syn   # seeded synthetic inputs (the oracle is only used by the cpu_baseline leg)
 
     W = args.workload
     key, C, inner = WORKLOADS[W]
     if args.inner:
         inner = args.inner
-    ospec = o.make_spec(key)
-    X, y, Xt, yt = o.synthetic_data(key, seed=1234)   # same split on every rank; the CHAINS are what shards
-    d = ospec.n_params
-    spec = FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task)
+    spec = ospec = syn.workload_spec(key)
+    X, y, Xt, yt = syn.synthetic_data(key, seed=1234)   # same split on every rank; the CHAINS are what shards
+    d = spec.n_params
     sharded = key == 'covertype_full'
     if sharded:
         from mile_b200 import ShardedEnsemble
@@ -240,7 +239,7 @@ def run_ours(args):
     if fused_lppd:
         ens.set_test(Xt, yt)      # fused posterior-predictive LPPD fold at every kept sample
     crank = 0 if sharded else rank        # sharded: every rank carries the SAME chains (same seeds, same noise)
-    th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 100 * crank, scale=0.3 if key != 'wide_4x256' else 0.05)
+    th0 = syn.synthetic_theta0(d, C, seed0=1000 + 100 * crank, scale=0.3 if key != 'wide_4x256' else 0.05)
     ens.init(th0, seed=17 + crank)
     # short tuning run -> frozen (eps, L); fallback eps=0.02, L=sqrt(d)
     eps = np.full(C, 0.02, np.float32)

@@ -740,16 +740,10 @@ def ess_rank_normalized(x: np.ndarray, rank_normalize: bool = True):
 # Synthetic inputs of the BASELINE shapes
 # --------------------------------------------------------------------------------------
 
-CONFIGS = {
-    # name: (N_train, N_test, F, widths, activation, task)
-    'airfoil_3x16': (1052, 301, 5, (16, 16, 16, 2), 'relu', 'regr'),
-    'airfoil_2x16': (1052, 301, 5, (16, 16, 2), 'relu', 'regr'),
-    'bikesharing_2x16': (12165, 3476, 12, (16, 16, 2), 'relu', 'regr'),
-    'protein_2x16': (32010, 9146, 9, (16, 16, 2), 'relu', 'regr'),
-    'covertype_ref': (3200, 4000, 54, (32, 7), 'sigmoid', 'class'),
-    'covertype_full': (232404, 290506, 54, (32, 7), 'sigmoid', 'class'),
-    'wide_4x256': (12165, 3476, 12, (256, 256, 256, 256, 2), 'relu', 'regr'),
-}
+# Synthetic workloads: one definition for bench.py, smoke() and the tests lives in mile_b200/synthetic.py (numpy only);
+# the oracle re-exports it under its historical names.
+from mile_b200.synthetic import CONFIGS, synthetic_data  # noqa: E402,F401
+from mile_b200 import synthetic as _syn  # noqa: E402
 
 
 def make_spec(name: str) -> ModelSpec:
@@ -757,26 +751,6 @@ def make_spec(name: str) -> ModelSpec:
     return ModelSpec(F, widths, act, task)
 
 
-def synthetic_data(name: str, seed: int = 1234, n_train: int | None = None, n_test: int | None = None):
-    """X ~ N(0,1); regression y = tanh(X w0) + 0.3 eps, z-scored; classification
-    y = argmax(X Wc + Gumbel).  Returns X, y, Xt, yt (fp32 / int32)."""
-    N, Nt, F, widths, _, task = CONFIGS[name]
-    N = n_train or N
-    Nt = n_test or Nt
-    rng = np.random.default_rng(seed)
-    Xall = rng.standard_normal((N + Nt, F)).astype(np.float32)
-    if task == 'regr':
-        w0 = rng.standard_normal(F).astype(np.float32) / np.float32(math.sqrt(F))
-        yall = np.tanh(Xall @ w0) + np.float32(0.3) * rng.standard_normal(N + Nt).astype(np.float32)
-        yall = ((yall - yall.mean()) / yall.std()).astype(np.float32)
-    else:
-        K = widths[-1]
-        Wc = rng.standard_normal((F, K)).astype(np.float32)
-        yall = np.argmax(Xall @ Wc + rng.gumbel(size=(N + Nt, K)).astype(np.float32), axis=1).astype(np.int32)
-    return Xall[:N], yall[:N], Xall[N:], yall[N:]
-
-
 def synthetic_theta0(spec: ModelSpec, n_chains: int, scale: float = 0.3, seed0: int = 1000):
     """Warm-start stand-in: theta0_c ~ N(0, 0.3^2) with chain seed 1000+c."""
-    return np.stack([np.random.default_rng(seed0 + c).standard_normal(spec.n_params).astype(np.float32)
-                     * np.float32(scale) for c in range(n_chains)])
+    return _syn.synthetic_theta0(spec.n_params, n_chains, scale, seed0)
