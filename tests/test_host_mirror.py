@@ -127,3 +127,31 @@ def test_metrics_match_oracle():
     np.testing.assert_allclose(pw, o.pointwise_lppd(spec, lv, y), rtol=1e-12)
     assert abs(metrics.lppd(pw) - o.lppd(pw)) < 1e-12
     np.testing.assert_allclose(metrics.running_lppd(pw), o.running_lppd(pw), rtol=1e-12)
+
+
+def test_shard_rows_partition_is_exact():
+    """Row shards of the data-sharded variant (ShardedEnsemble.shard_rows) tile [0, N) without gaps or overlap."""
+    from mile_b200.engine import ShardedEnsemble
+    for n_rows in (1, 7, 232404, 12165):
+        for world in (1, 2, 3, 8):
+            covered = np.zeros(n_rows, np.int32)
+            for r in range(world):
+                sl = ShardedEnsemble.shard_rows(n_rows, r, world)
+                covered[sl] += 1
+            assert np.all(covered == 1)
+
+
+def test_synthetic_workloads_are_seeded_and_shaped():
+    from mile_b200 import synthetic as syn
+    for name, (N, Nt, F, widths, act, task) in syn.CONFIGS.items():
+        if N > 40000:
+            continue
+        X, y, Xt, yt = syn.synthetic_data(name)
+        assert X.shape == (N, F) and Xt.shape == (Nt, F) and y.shape == (N,) and X.dtype == np.float32
+        assert (y.dtype == np.float32) == (task == 'regr')
+        X2, y2, _, _ = syn.synthetic_data(name)
+        assert np.array_equal(X, X2) and np.array_equal(y, y2)
+        spec = syn.workload_spec(name)
+        assert spec.n_features == F and tuple(spec.widths) == tuple(widths)
+        th = syn.synthetic_theta0(spec.n_params, 3)
+        assert th.shape == (3, spec.n_params) and not np.array_equal(th[0], th[1])
