@@ -37,7 +37,16 @@ __device__ __forceinline__ float act_bwd_from_value(float a) {
   return 1.f;
 }
 
+#ifdef MILE_PROFILE
+// developer build (tools/phase_profile.py): cycles every warp of CTA 0 spends waiting at the per-tick barrier (slots 16 + warp)
+__device__ __forceinline__ void bar_block() {
+  const long long t0 = clock64();
+  asm volatile("bar.sync 0;" ::: "memory");
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_prof[16 + (threadIdx.x >> 5)] += (unsigned long long)(clock64() - t0);
+}
+#else
 __device__ __forceinline__ void bar_block() { asm volatile("bar.sync 0;" ::: "memory"); }
+#endif
 
 template <int NL, int FP, int ACT>
 struct FastGE {

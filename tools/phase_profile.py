@@ -34,4 +34,5 @@ for name, C, steps, opts in [('airfoil_3x16', 12, 200, {}), ('bikesharing_2x16',
           f'resident={ens.get_option("resident")}: {tot / steps:.0f} cycles/step')
     for i, n in NAMES.items():
         print(f'  {n:28s} {prof[i] / steps:10.0f} cycles/step  {100 * prof[i] / tot:5.1f}%')
+    print('  barrier wait per warp (cycles/step):', ' '.join(f'{prof[16 + w] / steps:.0f}' for w in range(16)))
     ens.close()
