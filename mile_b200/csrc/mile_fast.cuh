@@ -61,11 +61,11 @@ struct FastGE {
 
   // ---- warp -> stage tables (compile-time; warp w runs on SMSP w % 4, the tables balance the
   //      FMA work per SMSP) ----
-  //   NL=3, T=64: fwd0 {0,1} fwd1 {2..5} head {6,7} bwd1 {8..11} dW0 {12,13} dW1 {14,15}
+  //   NL=3, T=64: fwd0 {0..3} fwd1 {4,5} head {6,7} bwd1 {8,9} dW0 {10..13} dW1 {14,15}
   //   NL=4, T=32: fwd0 {0} fwd1 {1,2} fwd2 {3,4} head {5} bwd2 {6,7} bwd1 {8,9} dW0 {10} dW1 {11,12} dW2 {13,14} idle {15}
-  static constexpr int DW_STRIDE = 16 * (H + 1) * H;   // scratch floats per dW stage (<= 16 row lanes)
+  static constexpr int DW_STRIDE = (NL == 3 ? 32 : 16) * (H + 1) * H;   // scratch floats per dW stage (<= 32 / 16 row lanes)
   static constexpr int HEAD_STRIDE = 2 * H + 4;
-  static __host__ __device__ constexpr int dw_row_lanes(int l) { return NL == 3 ? 16 : (l == 0 ? 8 : 16); }
+  static __host__ __device__ constexpr int dw_row_lanes(int l) { return NL == 3 ? (l == 0 ? 32 : 16) : (l == 0 ? 8 : 16); }
 
   // buffers inside a ring slot
   static __device__ __forceinline__ float* abuf(float* ring, int slot, int l) {  // a_l, l = 1..NH
@@ -326,11 +326,13 @@ struct FastGE {
     static_assert(NH * DW_STRIDE + T * HEAD_STRIDE <= RING_FLOATS, "reduction scratch does not fit in the ring");
     float ll = 0.f;
     if constexpr (NL == 3) {
-      if (warp < 2) fwd_stage<FP, 0, 0, 2, 0>(c, r0, nrows, ntiles, ring);
-      else if (warp < 6) fwd_stage<H, 1, 2, 4, 1>(c, r0, nrows, ntiles, ring);
+      // the stages that read the X tile get four warps, the hidden-layer GEMM stages two (per-warp barrier-wait timers:
+      // with 2 / 4 / 2 / 4 / 2 / 2 the X stages were the critical roles and the four-warp stages idled ~40 % of a tick)
+      if (warp < 4) fwd_stage<FP, 0, 0, 4, 0>(c, r0, nrows, ntiles, ring);
+      else if (warp < 6) fwd_stage<H, 1, 4, 2, 1>(c, r0, nrows, ntiles, ring);
       else if (warp < 8) ll = head_stage<6, 2>(c, r0, nrows, ntiles, ring, scr_head);
-      else if (warp < 12) bwd_stage<1, 8, 4, 3>(c, ntiles, ring);
-      else if (warp < 14) dw_stage<FP, 0, 12, 2, 4>(c, r0, nrows, ntiles, ring, scr);
+      else if (warp < 10) bwd_stage<1, 8, 2, 3>(c, ntiles, ring);
+      else if (warp < 14) dw_stage<FP, 0, 10, 4, 4>(c, r0, nrows, ntiles, ring, scr);
       else dw_stage<H, 1, 14, 2, 4>(c, r0, nrows, ntiles, ring, scr + DW_STRIDE);
     } else {
       if (warp < 1) fwd_stage<FP, 0, 0, 1, 0>(c, r0, nrows, ntiles, ring);
