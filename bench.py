@@ -234,6 +234,8 @@ def run_ours(args):
         ens.set_option('tile_rows', args.tile_rows)
     if args.tensor >= 0:
         ens.set_option('tensor', args.tensor)
+    if args.fast >= 0:
+        ens.set_option('fast', args.fast)
     ens.set_data(X, y)
     fused_lppd = key != 'wide_4x256' and not sharded
     if fused_lppd:
@@ -412,6 +414,7 @@ def main():
     ap.add_argument('--cluster', type=int, default=0)
     ap.add_argument('--tile-rows', type=int, default=0)
     ap.add_argument('--tensor', type=int, default=-1, help='wide path: 1 = tcgen05 3xTF32 GEMM core, 0 = FP32 SIMT core')
+    ap.add_argument('--fast', type=int, default=-1, help='narrow-MLP evaluator: 2 = 3xTF32 register MMA (default), 1 = FFMA layer pipeline, 0 = generic tiles')
     ap.add_argument('--no-tune', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

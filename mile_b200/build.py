@@ -10,7 +10,6 @@ CSRC = PKG / 'csrc'
 LIBDIR = PKG / '_lib'
 LIB = LIBDIR / 'libmile_b200.so'
 SOURCES = ['mile_api.cu', 'mile_microbench.cu']
-HEADERS = ['mile_device.cuh', 'mile_kernel.cuh', 'mile_fast.cuh', 'mile_sharded.cuh', '../../include/mile_b200.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -26,7 +25,8 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    return any((CSRC / f).resolve().stat().st_mtime > t for f in SOURCES + HEADERS)
+    deps = [CSRC / f for f in SOURCES] + sorted(CSRC.glob('*.cuh')) + sorted((PKG.parent / 'include').glob('*.h'))
+    return any(f.resolve().stat().st_mtime > t for f in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:

@@ -1,7 +1,7 @@
 // mile_api.cu -- host side of the C ABI declared in include/mile_b200.h.
 // Owns the device buffers of one ensemble wave, plans the shared-memory carve-up and the
 // cluster shape, and launches the persistent kernel of mile_kernel.cuh.  Links cudart only.
-#include "mile_fast.cuh"
+#include "mile_mma.cuh"
 #include "mile_sharded.cuh"
 #include "mile_wide.cuh"
 
@@ -59,7 +59,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 1, opt_tensor = 2;   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -139,9 +139,54 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   int S1 = 0;
   for (int l = 1; l <= M.NL; ++l) S1 += M.sA[l];
   const size_t fixed = (size_t)M.psize + 8 * (size_t)dS + 2 * (size_t)(dS + 4) + 2 * dS + 192;
+  // ---- register-chained tensor evaluator (mile_mma.cuh): hidden width 16 + Gaussian head, relu, F <= 16 ----
+  {
+    bool ok = want_resident && c->opt_fast >= 2 && M.task == MILE_TASK_REGRESSION && M.dims[M.NL] == 2 &&
+              (M.NL == 3 || M.NL == 4) && M.act == MILE_ACT_RELU && M.dims[0] <= 16;
+    for (int l = 1; ok && l < M.NL; ++l) ok = M.dims[l] == 16;
+    if (ok) {
+      const int FPm = M.dims[0] <= 8 ? 8 : 16;
+      int tile_f = 0, aux_i = 0;
+      if (M.NL == 3 && FPm == 8) { tile_f = MmaGE<3, 8, 512>::TILE_FLOATS; aux_i = MmaGE<3, 8, 512>::AUX_INTS; }
+      else if (M.NL == 3) { tile_f = MmaGE<3, 16, 512>::TILE_FLOATS; aux_i = MmaGE<3, 16, 512>::AUX_INTS; }
+      else if (FPm == 8) { tile_f = MmaGE<4, 8, 512>::TILE_FLOATS; aux_i = MmaGE<4, 8, 512>::AUX_INTS; }
+      else { tile_f = MmaGE<4, 16, 512>::TILE_FLOATS; aux_i = MmaGE<4, 16, 512>::AUX_INTS; }
+      const int TRg = 64;  // tile of the generic forward used by the fused lppd fold / predict
+      const size_t gen = (size_t)2 * TRg * S1;
+      const size_t tile = (size_t)tile_f > gen ? (size_t)tile_f : gen;
+      // resident slice: 16-row tiles plus one zero guard tile (k-steps may read up to 12 floats past a row's stride)
+      const int rows_res = (int)((rows_cta + 15) / 16) * 16 + 16;
+      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0] + round_up(aux_i, 4)) * 4;
+      const int res = (c->opt_resident != 0 && base_need + (size_t)rows_res * M.sA[0] * 4 <= kSmemLimit) ? 1 : 0;
+      if (base_need <= kSmemLimit) {
+        M.TR = TRg; M.tile_floats = (int)tile;
+        int off = 0;
+        for (int l = 1; l <= M.NL; ++l) { M.a_off[l] = off; off += TRg * M.sA[l]; }
+        for (int l = 0; l < M.NL; ++l) { M.d_off[l] = off; off += TRg * M.sA[l + 1]; }
+        KParams& k = pl.kp;
+        memset(&k, 0, sizeof(k));
+        k.M = M; k.dS = dS;
+        int o = 0;
+        k.off_wp = o; o += round_up(M.psize, 4);
+        k.off_th = o; o += dS; k.off_u = o; o += dS; k.off_g = o; o += dS;
+        k.off_thb = o; o += dS; k.off_ub = o; o += dS; k.off_gb = o; o += dS;
+        k.off_avgx = o; o += dS; k.off_avgx2 = o; o += dS;
+        k.off_gpart = o; o += 2 * (dS + 4);
+        k.off_pmap = o; o += 2 * dS;
+        k.off_red = o; o += 192;
+        k.off_aux = o; o += round_up(aux_i, 4);
+        k.off_tile = o; o += (int)tile + TRg * M.sA[0];
+        k.off_x = o; if (res) o += rows_res * M.sA[0];
+        pl.G = G; pl.TR = 16; pl.resident = res; pl.rows_res = rows_res; pl.fast = 2; pl.fast_fp = FPm; pl.sync_mode = sync_mode;
+        pl.smem = (size_t)o * 4;
+        k.G = G; k.resident = res; k.rows_res = rows_res; k.C = n_chains;
+        return 0;
+      }
+    }
+  }
   // ---- fast path: warp-specialised pipeline (mile_fast.cuh) for hidden width 16 + Gaussian head ----
   {
-    bool ok = want_resident && c->opt_fast && M.task == MILE_TASK_REGRESSION &&
+    bool ok = want_resident && c->opt_fast >= 1 && M.task == MILE_TASK_REGRESSION &&
               M.dims[M.NL] == 2 && (M.NL == 3 || M.NL == 4) && M.act == MILE_ACT_RELU &&
               (M.dimp[0] == 8 || M.dimp[0] == 12);
     for (int l = 1; ok && l < M.NL; ++l) ok = M.dims[l] == 16;
@@ -266,7 +311,13 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   }
   const int NL = c->M.NL;
   int rc;
-  if (pl.fast) {
+  if (pl.fast == 2) {
+    if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>>(pl, n_chains, st);
+    else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>>(pl, n_chains, st);
+    else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>>(pl, n_chains, st);
+    else rc = launch_t<MmaGE<4, 16, 512>>(pl, n_chains, st);
+  }
+  else if (pl.fast) {
     if (NL == 3 && pl.fast_fp == 8) rc = launch_t<FastGE<3, 8, MILE_ACT_RELU>>(pl, n_chains, st);
     else if (NL == 3) rc = launch_t<FastGE<3, 12, MILE_ACT_RELU>>(pl, n_chains, st);
     else if (pl.fast_fp == 8) rc = launch_t<FastGE<4, 8, MILE_ACT_RELU>>(pl, n_chains, st);
@@ -290,7 +341,7 @@ static void fill_common(mile_ctx* c, KParams& k) {
   k.lppd_m = c->lppd_m; k.lppd_s = c->lppd_s;
   k.carry = c->carry; k.carry_valid = c->carry_valid;
   k.refresh_mode = c->opt_refresh; k.thin = 1;
-  k.out_stride = c->d; k.prior_weight = 1.f;
+  k.out_stride = c->d; k.prior_weight = 1.f; k.chain_base = c->opt_chain_base;
 }
 
 // ---- small utility kernels ------------------------------------------------------------------
@@ -356,13 +407,17 @@ int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, m
   build_model(c);
   if (c->d < 2) { delete c; return fail("The target distribution must have more than 1 dimension for MCLMC."); }
   const size_t Cd = (size_t)n_chains * c->d * 4, Cb = (size_t)n_chains * 4;
-  CK(cudaMalloc(&c->theta, Cd)); CK(cudaMalloc(&c->u, Cd)); CK(cudaMalloc(&c->grad, Cd)); CK(cudaMalloc(&c->lp, Cb));
-  CK(cudaMalloc(&c->avg_x, Cd)); CK(cudaMalloc(&c->avg_x2, Cd));
-  CK(cudaMalloc(&c->t_time, Cb)); CK(cudaMalloc(&c->t_xavg, Cb)); CK(cudaMalloc(&c->t_epsmax, Cb));
-  CK(cudaMalloc(&c->t_eps, Cb)); CK(cudaMalloc(&c->t_L, Cb)); CK(cudaMalloc(&c->t_wtot, Cb));
-  CK(cudaMalloc(&c->carry, 2 * Cb));
-  CK(cudaMemset(c->theta, 0, Cd)); CK(cudaMemset(c->u, 0, Cd)); CK(cudaMemset(c->grad, 0, Cd)); CK(cudaMemset(c->lp, 0, Cb));
-  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  auto alloc_all = [&]() -> int {
+    CK(cudaMalloc(&c->theta, Cd)); CK(cudaMalloc(&c->u, Cd)); CK(cudaMalloc(&c->grad, Cd)); CK(cudaMalloc(&c->lp, Cb));
+    CK(cudaMalloc(&c->avg_x, Cd)); CK(cudaMalloc(&c->avg_x2, Cd));
+    CK(cudaMalloc(&c->t_time, Cb)); CK(cudaMalloc(&c->t_xavg, Cb)); CK(cudaMalloc(&c->t_epsmax, Cb));
+    CK(cudaMalloc(&c->t_eps, Cb)); CK(cudaMalloc(&c->t_L, Cb)); CK(cudaMalloc(&c->t_wtot, Cb));
+    CK(cudaMalloc(&c->carry, 2 * Cb));
+    CK(cudaMemset(c->theta, 0, Cd)); CK(cudaMemset(c->u, 0, Cd)); CK(cudaMemset(c->grad, 0, Cd)); CK(cudaMemset(c->lp, 0, Cb));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    return 0;
+  };
+  if (alloc_all()) { const std::string e = g_err; mile_destroy(c); g_err = e; return -1; }
   {  // shapes the shared-memory kernels cannot hold run on the HBM-resident layer-by-layer path
     Plan probe;
     if (make_plan(c, n_chains, 4096, true, probe) != 0) {
@@ -400,6 +455,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "fast")) c->opt_fast = (int)v;
   else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
+  else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
   else return fail(std::string("unknown option ") + key);
   return 0;
 }
@@ -418,6 +474,7 @@ int64_t mile_get_option(const mile_ctx* c, const char* key) {
     return (int64_t)pl.smem;
   }
   if (!strcmp(key, "refresh_mode")) return c->opt_refresh;
+  if (!strcmp(key, "chain_base")) return c->opt_chain_base;
   if (!strcmp(key, "wide")) return c->wide;
   if (!strcmp(key, "tensor")) return c->opt_tensor;
   if (!strcmp(key, "row_stride")) return c->M.sA[0];
@@ -433,7 +490,9 @@ static int set_split(mile_ctx* c, const float* X_dev, const void* y_dev, long N,
   *Nd = N;
   if (N == 0) return 0;
   const int sx = c->M.sA[0];
-  CK(cudaMalloc(Xd, (size_t)N * sx * 4));
+  // 16 zero floats of slack: the k-steps of the tensor evaluator may read up to 12 floats past the last row's stride
+  CK(cudaMalloc(Xd, ((size_t)N * sx + 16) * 4));
+  CK(cudaMemsetAsync(*Xd + (size_t)N * sx, 0, 16 * 4, st));
   CK(cudaMalloc(yd, (size_t)N * 4));
   pad_rows_kernel<<<296, 256, 0, st>>>(X_dev, *Xd, N, c->M.F, sx);
   CK(cudaGetLastError());
@@ -462,7 +521,12 @@ int mile_set_data(mile_ctx* c, const float* X_dev, const void* y_dev, int64_t N,
 int mile_set_test(mile_ctx* c, const float* X_dev, const void* y_dev, int64_t N, void* stream) {
   if (!c) return fail("null ctx");
   if (set_split(c, X_dev, y_dev, (long)N, (cudaStream_t)stream, &c->Xt, &c->yt, &c->Nt)) return -1;
-  return lppd_alloc(c, (cudaStream_t)stream);
+  // the [C, Nt] logsumexp state is allocated on first use (lppd_reset / accumulate / lppd=1 sampling): mile_predict
+  // contexts with thousands of (chain, sample) rows never need it
+  if (c->lppd_m) { CK(cudaFree(c->lppd_m)); c->lppd_m = nullptr; }
+  if (c->lppd_s) { CK(cudaFree(c->lppd_s)); c->lppd_s = nullptr; }
+  c->lppd_count = 0;
+  return 0;
 }
 
 static int set_split_host(mile_ctx* c, const float* X, const void* y, long N, bool test) {
@@ -598,6 +662,7 @@ int mile_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n
   if (lppd && !c->Xt) return fail("lppd requested but mile_set_test has not been called");
   if (!step_size_dev || !L_dev) return fail("step_size / L are required");
   if (n_steps == 0) return 0;
+  if (lppd && !c->wide && !c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
   if (c->wide) {
     if (lppd) return fail("the fused LPPD fold is not available on the wide path");
     if (!c->gl && mile_shard_init(c, nullptr, 0, 1)) return -1;
@@ -747,6 +812,7 @@ int mile_lppd_accumulate(mile_ctx* c, const float* theta_dev, int32_t n, void* s
   if (!c) return fail("null ctx");
   if (!c->Xt) return fail("mile_set_test has not been called");
   if (n < 1 || n > c->C) return fail("n must be in [1, n_chains]");
+  if (!c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
   Plan pl;
   if (make_plan(c, c->C, c->Nt, false, pl)) return -1;
   fill_common(c, pl.kp);
@@ -762,6 +828,8 @@ int mile_lppd_state_host(mile_ctx* c, float* m, float* s, int64_t* count) {
   CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
   const size_t n = (size_t)c->C * c->Nt * 4;
+  if (!c->lppd_m && lppd_alloc(c, nullptr)) return -1;
+  CK(cudaDeviceSynchronize());
   if (m) CK(cudaMemcpy(m, c->lppd_m, n, cudaMemcpyDeviceToHost));
   if (s) CK(cudaMemcpy(s, c->lppd_s, n, cudaMemcpyDeviceToHost));
   if (count) *count = c->lppd_count;
@@ -1150,7 +1218,7 @@ int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_
   const size_t Cd = (size_t)c->C * c->d * 4;
   CK(cudaMemcpyAsync(c->theta, theta0_dev, Cd, cudaMemcpyDeviceToDevice, st));
   if (shard_eval(c, st)) return -1;
-  mile_unit_momentum_kernel<256><<<c->C, 256, 0, st>>>(c->u, z0_dev, seed, c->d);
+  mile_unit_momentum_kernel<256><<<c->C, 256, 0, st>>>(c->u, z0_dev, seed, c->d, c->opt_chain_base);
   CK(cudaGetLastError());
   c->launches++;
   CK(cudaMemcpy2DAsync(c->grad, (size_t)c->d * 4, c->gl, (size_t)(c->d + 1) * 4, (size_t)c->d * 4, c->C, cudaMemcpyDeviceToDevice, st));
@@ -1201,7 +1269,9 @@ int mile_shard_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const
 }
 
 
-// Developer / test hook: C[M,N] = A(M,K) * B(K,N) with chosen operand orientations through the wide-path GEMM cores
+#ifdef MILE_PROFILE
+// Developer hook (only in the -DMILE_PROFILE build of tools/phase_profile.py; not part of the shipped ABI):
+// C[M,N] = A(M,K) * B(K,N) with chosen operand orientations through the wide-path GEMM cores
 // (core: 0 SIMT, 1 tcgen05 v1, 2 tcgen05 v2 TMA).  a_mn: A stored [K x M] (m contiguous) instead of [M x K];
 // b_mn: B stored [K x N] (n contiguous) instead of [N x K].  Host pointers.
 int mile_debug_wide_gemm(int32_t device, int32_t core, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
@@ -1243,6 +1313,7 @@ int mile_debug_wide_gemm(int32_t device, int32_t core, int32_t M, int32_t N, int
   cudaFree(A); cudaFree(Alo); cudaFree(B); cudaFree(Blo); cudaFree(Cd);
   return 0;
 }
+#endif  // MILE_PROFILE
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
 int mile_synchronize(mile_ctx* c) {

@@ -374,7 +374,7 @@ struct FastGE {
     }
     float v[1] = {ll};
     block_sum<1, NT>(v, c.red, c.phase);
-    if (threadIdx.x == 0) gpart[P.dS] = v[0];
+    if (threadIdx.x == 0) gpart[P.dS] = v[0] * M.n_batches;   // probabilistic.py:136
     __syncthreads();   // the ring (== scratch) is reused by the next evaluation / lppd fold
   }
 };

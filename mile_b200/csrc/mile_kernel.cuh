@@ -46,12 +46,15 @@ struct KParams {
   float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)
   int dS, off_wp, off_th, off_u, off_g, off_thb, off_ub, off_gb, off_gpart, off_avgx, off_avgx2,
-      off_pmap, off_red, off_tile, off_x;
+      off_pmap, off_red, off_tile, off_x, off_aux;
+  // global id of local chain 0: the Philox streams are keyed by (seed, chain_base + chain, step, element), so the ranks
+  // of a chain-partitioned ensemble draw independent noise (the reference splits one key per chain, sampling.py:181-184)
+  int chain_base;
 };
 
 struct Ctx {
   const KParams& P;
-  float *wp, *th, *uu, *gg, *thb, *ub, *gb, *gpart, *avgx, *avgx2, *red, *tile, *xbuf, *xstream;
+  float *wp, *th, *uu, *gg, *thb, *ub, *gb, *gpart, *avgx, *avgx2, *red, *tile, *xbuf, *xstream, *aux;
   int* pmap;
   int phase;   // block_sum double-buffer phase (whole block)
   float* red2; int phase2;   // scratch / phase of the integrator thread group (named barrier 1)
@@ -198,7 +201,7 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
   }
   float v[1] = {llpart};
   block_sum<1, NT>(v, c.red, c.phase);
-  if (threadIdx.x == 0) gpart[P.dS] = v[0];
+  if (threadIdx.x == 0) gpart[P.dS] = v[0] * M.n_batches;   // probabilistic.py:136
   PROF(5);
 }
 
@@ -399,7 +402,7 @@ __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
 
 __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step_local, int slot, int nslot, int i) {
   if (P.z) return P.z[(((long)step_local * nslot + slot) * P.C + chain) * P.M.d + i];
-  return philox_normal(P.seed, (uint32_t)chain, (uint64_t)(P.step_base + step_local), (uint32_t)slot + 1u, (uint32_t)i);
+  return philox_normal(P.seed, (uint32_t)(P.chain_base + chain), (uint64_t)(P.step_base + step_local), (uint32_t)slot + 1u, (uint32_t)i);
 }
 
 // partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
@@ -568,12 +571,14 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   c.red = smem + P.off_red; c.red2 = c.red + 128; c.phase2 = 0; c.tile = smem + P.off_tile;
   c.xstream = c.tile + M.tile_floats;              // one streamed X tile [TR][sA[0]]
   c.xbuf = P.resident ? smem + P.off_x : c.xstream;  // resident slice or the streamed tile
+  c.aux = smem + P.off_aux;
   const int d = M.d, ch = c.chain;
   const int tid = threadIdx.x;
 
   // ---- prologue: parameter image, state, resident X slice --------------------------------
   for (int i = tid; i < M.psize; i += NT) c.wp[i] = 0.f;
   build_pmap<NT>(M, c.pmap, P.dS);
+  GE::prepare(c);
   const bool from_input = (P.mode == MODE_EVAL || P.mode == MODE_INIT || P.mode == MODE_LPPD || P.mode == MODE_PREDICT);
   const float* th_src = from_input ? P.theta_in + (long)ch * d : P.theta + (long)ch * d;
   for (int i = tid; i < d; i += NT) {
@@ -706,7 +711,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
           // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
           float v[1] = {0.f};
           for (int i = tid; i < d; i += NI) {
-            const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+            const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)(P.chain_base + ch), 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
             c.uu[i] = zz; v[0] += zz * zz;
           }
           block_sum<1, NI, IB>(v, c.red2, c.phase2);

@@ -1,0 +1,417 @@
+// mile_mma.cuh -- register-chained tensor evaluator for the narrow regression MLPs (hidden width 16, Gaussian
+// head: the airfoil / bikesharing / protein / 1024-chain configs of BASELINE.json).
+//
+// Why this shape (measured on B200, profiles/r2a_mma_microbench.txt): mma.sync.m16n8k8 tf32 issues once per 8 cycles
+// per SM sub-partition (512 FMA/clk/SM = 4x the FFMA rate) with a 20-cycle dependent latency, and its operands are
+// plain registers.  A 16-wide layer is two 8-column accumulator tiles, and the C fragment of one layer IS the A
+// fragment of the next once the contraction index is relabelled (k = t <-> column 2t, k = t+4 <-> column 2t+1; the
+// weight fragments are stored with the same relabelling), so one warp carries 16 rows through every layer forward and
+// backward without shared memory, barriers or pipeline fill.  fp32 accuracy comes from the 3xTF32 split
+// (a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi, 1e-6 relative).  tcgen05 is the wrong tool here: its smallest tile is
+// 128 rows x 16 columns with the accumulator in TMEM, i.e. a shared-memory / TMEM round trip plus an mbarrier wait per
+// 16-wide layer (the wide 4x256 path, mile_wide.cuh, is where it pays).
+//
+// Per 16-row tile and warp:  fwd l=0..NH-1 (MMA)  ->  head 16->2 + Gaussian log-likelihood + delta (FMA, exact fp32)
+//   -> for l = NH-1..0:  dW_l^T += delta_l^T a_l  (MMA, K = rows; both operands transposed through a private
+//   shared-memory patch)  and  delta_{l-1} = (delta_l W_l^T) * relu'(a_l)  (MMA, register-chained).
+// Weight-gradient accumulators stay in registers for all of the warp's tiles; one cross-warp sum per evaluation.
+//
+// Restates the same arithmetic as grad_eval (mile_kernel.cuh): probabilistic.py:92-138 through basic.py:41-61,
+// differentiated by hand.
+#pragma once
+#include "mile_fast.cuh"
+
+// tf32 split by truncation: the tensor core reads the upper 19 bits of a 32-bit operand register (ptxas itself leaves the
+// low 13 bits of a cvt.rna.tf32 result unmasked), so x serves as its own "hi" part and lo = x - trunc(x) is exact in fp32.
+// Two instructions per value (LOP3 + FADD) instead of the nine that cvt.rna.tf32.f32 expands to on sm_100a.  Dropped
+// terms (lo * lo and the truncation of lo) are <= 2^-20 relative per product.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+__device__ __forceinline__ void hmma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct AFrag { uint32_t hi[4], lo[4]; };
+// A fragment (rows g / g+8, k = t / t+4) from four fp32 values in fragment order
+__device__ __forceinline__ void make_afrag(AFrag& A, float v0, float v1, float v2, float v3) {
+  split_tf32(v0, A.hi[0], A.lo[0]); split_tf32(v1, A.hi[1], A.lo[1]);
+  split_tf32(v2, A.hi[2], A.lo[2]); split_tf32(v3, A.hi[3], A.lo[3]);
+}
+// 3xTF32 product, small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const AFrag& A, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  hmma_tf32(c, A.lo, bh0, bh1);
+  hmma_tf32(c, A.hi, bl0, bl1);
+  hmma_tf32(c, A.hi, bh0, bh1);
+}
+
+template <int NL, int FP, int NT_>
+struct MmaGE {
+  static constexpr int NT = NT_;
+  static constexpr int NW = NT / 32;
+  static constexpr int H = 16;
+  static constexpr int NH = NL - 1;              // hidden layers (all H wide); layer NH is the 16 -> 2 head
+  static constexpr int KS0 = FP / 8;             // k-steps of layer 0
+  // ---- weight-fragment image: groups of 4 floats (b0_hi, b1_hi, b0_lo, b1_lo), one group per (k-step, n-tile, lane)
+  static constexpr int GRP_F0 = 0;                                  // layer 0 forward: KS0 * 2 * 32 groups
+  static constexpr int GRP_F1 = KS0 * 64;                           // layers 1..NH-1 forward: 128 groups each
+  static constexpr int GRP_B1 = GRP_F1 + (NH - 1) * 128;            // layers 1..NH-1 backward (W^T as the B operand)
+  static constexpr int NGROUPS = GRP_B1 + (NH - 1) * 128;
+  static constexpr int IMG_HEAD = NGROUPS * 4;                      // head: W[16][2] row-major, then b[2]
+  static constexpr int IMG_FLOATS = IMG_HEAD + 40;
+  // ---- per-warp transposition patches for the weight-gradient operands
+  static constexpr int PT_S = 20;                                   // delta^T  [16 columns][16 rows + 4]
+  static constexpr int PA_S = 24;                                   // a_l      [16 rows][16 columns + 8]
+  static constexpr int PATCH_FLOATS = 16 * PT_S + 16 * PA_S;
+  // ---- cross-warp reduction scratch (aliases the patches): MMA accumulators in fragment order + the FMA-path sums
+  static constexpr int NACC0 = KS0 * 4;                             // dW_0^T: 16 x FP
+  static constexpr int NACC = NACC0 + (NH - 1) * 8;                 // + dW_l^T 16 x 16
+  static constexpr int NSMALL = 8 + 4 * NH + 2 + 1;                 // head kernel, hidden biases, head bias, log-lik
+  static constexpr int SCR_WARP = NACC * 32 + NSMALL * 4;
+  static constexpr int REGION_FLOATS = NW * (PATCH_FLOATS > SCR_WARP ? PATCH_FLOATS : SCR_WARP);
+  static constexpr int TILE_FLOATS = IMG_FLOATS + REGION_FLOATS;
+  // ---- index maps built once per launch (prepare): image group -> two flat parameter indices; scratch slot -> flat
+  static constexpr int AUX_INTS = 2 * NGROUPS + NACC * 32 + NSMALL * 4;
+
+  static __device__ __forceinline__ int* aux(Ctx& c) { return reinterpret_cast<int*>(c.aux); }
+
+  static __device__ __forceinline__ void prepare(Ctx& c) {
+    const DevModel& M = c.P.M;
+    int* imap = aux(c);
+    int* gmapA = imap + 2 * NGROUPS;
+    int* gmapS = gmapA + NACC * 32;
+    const int F = M.dims[0];
+    for (int grp = threadIdx.x; grp < NGROUPS; grp += NT) {
+      int s0, s1;
+      if (grp < GRP_F1) {
+        const int ks = grp >> 6, nt = (grp >> 5) & 1, ln = grp & 31, g = ln >> 2, t = ln & 3;
+        const int i0 = 8 * ks + t, i1 = i0 + 4, j = 8 * nt + g;
+        s0 = i0 < F ? M.kern_off[0] + i0 * H + j : -1;
+        s1 = i1 < F ? M.kern_off[0] + i1 * H + j : -1;
+      } else {
+        const int idx = grp - GRP_F1, which = idx >> 7, rem = idx & 127;
+        const int ks = rem >> 6, nt = (rem >> 5) & 1, ln = rem & 31, g = ln >> 2, t = ln & 3;
+        if (which < NH - 1) {           // forward layer l: B[k][n] = W_l[in = 8ks + 2t (+1)][out = 8nt + g]
+          const int l = which + 1, i0 = 8 * ks + 2 * t, j = 8 * nt + g;
+          s0 = M.kern_off[l] + i0 * H + j; s1 = s0 + H;
+        } else {                        // backward layer l: B[k][n] = W_l[in = 8nt + g][out = 8ks + 2t (+1)]
+          const int l = which - (NH - 1) + 1, j0 = 8 * ks + 2 * t, i = 8 * nt + g;
+          s0 = M.kern_off[l] + i * H + j0; s1 = s0 + 1;
+        }
+      }
+      imap[2 * grp] = s0; imap[2 * grp + 1] = s1;
+    }
+    // accumulator register r of lane ln -> flat gradient index.  dW_l^T C fragment: m = out j = g (+8), n = in i = 8nt + 2t (+1)
+    for (int o = threadIdx.x; o < NACC * 32; o += NT) {
+      const int r = o >> 5, ln = o & 31, g = ln >> 2, t = ln & 3;
+      int l, rr;
+      if (r < NACC0) { l = 0; rr = r; } else { l = 1 + (r - NACC0) / 8; rr = (r - NACC0) % 8; }
+      const int nt = rr >> 2, cc = rr & 3;
+      const int j = g + ((cc >> 1) ? 8 : 0), i = 8 * nt + 2 * t + (cc & 1);
+      gmapA[o] = i < M.dims[l] ? M.kern_off[l] + i * H + j : -1;
+    }
+    for (int o = threadIdx.x; o < NSMALL * 4; o += NT) {
+      const int k = o >> 2, t = o & 3;
+      int dst;
+      if (k < 8) {                      // head kernel: k = (nt*2 + cc)*2 + w  ->  W_head[i = 8nt + 2t + cc][w]
+        const int w = k & 1, cc = (k >> 1) & 1, nt = k >> 2;
+        dst = M.kern_off[NH] + (8 * nt + 2 * t + cc) * 2 + w;
+      } else if (k < 8 + 4 * NH) {      // hidden biases: k' = nt*2 + cc -> b_l[8nt + 2t + cc]
+        const int kk = k - 8, l = kk >> 2, q = kk & 3;
+        dst = M.bias_off[l] + 8 * (q >> 1) + 2 * t + (q & 1);
+      } else if (k < 8 + 4 * NH + 2) {  // head bias (all lanes of a quad hold the same sum: lane t = 0 reports)
+        dst = t == 0 ? M.bias_off[NH] + (k - 8 - 4 * NH) : -1;
+      } else {                          // log-likelihood partial
+        dst = t == 0 ? c.P.dS : -1;
+      }
+      gmapS[o] = dst;
+    }
+  }
+
+  // ---- one gradient evaluation over this CTA's rows [r0, r1) ------------------------------------------------
+  static __device__ __forceinline__ void run(Ctx& c, long r0, long r1, float* gpart) {
+    const KParams& P = c.P;
+    const DevModel& M = P.M;
+    float* img = c.tile;
+    float* region = c.tile + IMG_FLOATS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int* imap = aux(c);
+    const int* gmapA = imap + 2 * NGROUPS;
+    const int* gmapS = gmapA + NACC * 32;
+    // 1. weight-fragment image of the current position (hi / lo tf32 parts), head weights in fp32
+    for (int grp = tid; grp < NGROUPS; grp += NT) {
+      const int s0 = imap[2 * grp], s1 = imap[2 * grp + 1];
+      const float v0 = s0 >= 0 ? c.th[s0] : 0.f, v1 = s1 >= 0 ? c.th[s1] : 0.f;
+      uint32_t h0, l0, h1, l1;
+      split_tf32(v0, h0, l0); split_tf32(v1, h1, l1);
+      reinterpret_cast<uint4*>(img)[grp] = make_uint4(h0, h1, l0, l1);
+    }
+    if (tid < 34) img[IMG_HEAD + tid] = c.th[tid < 32 ? M.kern_off[NH] + tid : M.bias_off[NH] + (tid - 32)];
+    __syncthreads();
+    PROF(0);
+
+    const long nrows = r1 > r0 ? r1 - r0 : 0;
+    const int ntiles = (int)((nrows + 15) >> 4);
+    const int sx = M.sA[0];
+    const float nb = M.n_batches;
+    const float4* img4 = reinterpret_cast<const float4*>(img);
+    float* PT = region + warp * PATCH_FLOATS;
+    float* PA = PT + 16 * PT_S;
+
+    float accW[NH][2][4], accHead[8], db[NH][4], dbHead[2] = {0.f, 0.f}, ll_acc = 0.f;   // accW[0] uses n-tiles < KS0 only
+#pragma unroll
+    for (int l = 0; l < NH; ++l)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) accW[l][i >> 2][i & 3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) accHead[i] = 0.f;
+#pragma unroll
+    for (int l = 0; l < NH; ++l) { db[l][0] = 0.f; db[l][1] = 0.f; db[l][2] = 0.f; db[l][3] = 0.f; }
+
+#pragma unroll 1
+    for (int mt = warp; mt < ntiles; mt += NW) {
+      const int row_a = mt * 16 + g, row_b = row_a + 8;
+      float a[NH][2][4];                         // a[l][nt][*] = activation a_{l+1}, C-fragment layout
+      // ---- layer 0: A operand straight from the X slice (rows beyond the shard are zero / clamped and masked below)
+      {
+        float cf[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const float b0 = c.th[M.bias_off[0] + 8 * nt + 2 * t], b1 = c.th[M.bias_off[0] + 8 * nt + 2 * t + 1];
+          cf[nt][0] = b0; cf[nt][1] = b1; cf[nt][2] = b0; cf[nt][3] = b1;
+        }
+        float xv[KS0][4];
+        if (P.resident) {            // shared-memory slice (explicit LDS: a pointer that may be global or shared compiles to generic loads)
+          const float* xa = c.xbuf + row_a * sx + t;
+#pragma unroll
+          for (int ks = 0; ks < KS0; ++ks) {
+            xv[ks][0] = xa[8 * ks]; xv[ks][1] = xa[8 * sx + 8 * ks]; xv[ks][2] = xa[8 * ks + 4]; xv[ks][3] = xa[8 * sx + 8 * ks + 4];
+          }
+        } else {
+          const long ca = row_a < nrows ? row_a : nrows - 1, cb = row_b < nrows ? row_b : nrows - 1;
+          const float* __restrict__ xa = P.X + (r0 + ca) * sx + t;
+          const float* __restrict__ xb = P.X + (r0 + cb) * sx + t;
+#pragma unroll
+          for (int ks = 0; ks < KS0; ++ks) {
+            xv[ks][0] = __ldg(xa + 8 * ks); xv[ks][1] = __ldg(xb + 8 * ks); xv[ks][2] = __ldg(xa + 8 * ks + 4); xv[ks][3] = __ldg(xb + 8 * ks + 4);
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS0; ++ks) {
+          AFrag A;
+          make_afrag(A, xv[ks][0], xv[ks][1], xv[ks][2], xv[ks][3]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const float4 B = img4[GRP_F0 + (ks * 2 + nt) * 32 + lane];
+            mma3(cf[nt], A, __float_as_uint(B.x), __float_as_uint(B.y), __float_as_uint(B.z), __float_as_uint(B.w));
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[0][nt][e] = fmaxf(cf[nt][e], 0.f);
+      }
+      // ---- hidden layers 1..NH-1: the C fragments of a_l are the A fragments (c0, c2, c1, c3) of the next layer
+#pragma unroll
+      for (int l = 1; l < NH; ++l) {
+        float cf[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const float b0 = c.th[M.bias_off[l] + 8 * nt + 2 * t], b1 = c.th[M.bias_off[l] + 8 * nt + 2 * t + 1];
+          cf[nt][0] = b0; cf[nt][1] = b1; cf[nt][2] = b0; cf[nt][3] = b1;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          AFrag A;
+          make_afrag(A, a[l - 1][ks][0], a[l - 1][ks][2], a[l - 1][ks][1], a[l - 1][ks][3]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const float4 B = img4[GRP_F1 + (l - 1) * 128 + (ks * 2 + nt) * 32 + lane];
+            mma3(cf[nt], A, __float_as_uint(B.x), __float_as_uint(B.y), __float_as_uint(B.z), __float_as_uint(B.w));
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[l][nt][e] = fmaxf(cf[nt][e], 0.f);
+      }
+      // ---- head 16 -> 2 in fp32 FMAs: every lane owns columns {2t, 2t+1, 8+2t, 9+2t} of rows g and g+8
+      const float4 w01 = *reinterpret_cast<const float4*>(img + IMG_HEAD + 4 * t);        // W[2t][0..1], W[2t+1][0..1]
+      const float4 w23 = *reinterpret_cast<const float4*>(img + IMG_HEAD + 16 + 4 * t);   // W[8+2t][..], W[9+2t][..]
+      const float (&an)[2][4] = a[NH - 1];
+      float mu[2], sg[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mu[r] = an[0][2 * r] * w01.x + an[0][2 * r + 1] * w01.z + an[1][2 * r] * w23.x + an[1][2 * r + 1] * w23.z;
+        sg[r] = an[0][2 * r] * w01.y + an[0][2 * r + 1] * w01.w + an[1][2 * r] * w23.y + an[1][2 * r + 1] * w23.w;
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { mu[r] += __shfl_xor_sync(0xffffffffu, mu[r], o); sg[r] += __shfl_xor_sync(0xffffffffu, sg[r], o); }
+      }
+      const float hb0 = img[IMG_HEAD + 32], hb1 = img[IMG_HEAD + 33];
+      float dmu[2], ds[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long row = r ? row_b : row_a;
+        dmu[r] = 0.f; ds[r] = 0.f;
+        if (row < nrows) {
+          const float m_ = mu[r] + hb0, s_ = sg[r] + hb1;
+          const float yv = reinterpret_cast<const float*>(P.y)[r0 + row];
+          // sigma = clip(exp(s), 1e-6, 1e6) (probabilistic.py:100), written through sc = clip(s, ln 1e-6, ln 1e6)
+          const float kLnClip = 13.815510557964274f;
+          const float sc = fminf(fmaxf(s_, -kLnClip), kLnClip);
+          const float inside = (s_ > -kLnClip && s_ < kLnClip) ? 1.f : 0.f;
+          const float inv_s2 = expf(-2.f * sc), res = yv - m_, q = res * res * inv_s2;
+          float ll = (MILE_LOG_2PI + 2.f * sc + q) * -0.5f;
+          float d0 = res * inv_s2, d1 = (q - 1.f) * inside;
+          if (isnan(ll)) { ll = 0.f; d0 = 0.f; d1 = 0.f; }   // jnp.nansum
+          ll_acc += ll;
+          dmu[r] = d0 * nb; ds[r] = d1 * nb;
+        }
+      }
+      dbHead[0] += dmu[0] + dmu[1]; dbHead[1] += ds[0] + ds[1];
+      float dl[2][4];                            // delta_l (pre-activation), C-fragment layout; starts at l = NH-1
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const float w0 = nt == 0 ? (cc ? w01.z : w01.x) : (cc ? w23.z : w23.x);
+          const float w1 = nt == 0 ? (cc ? w01.w : w01.y) : (cc ? w23.w : w23.y);
+          const float a0 = an[nt][cc], a1 = an[nt][2 + cc];
+          accHead[(nt * 2 + cc) * 2 + 0] += a0 * dmu[0] + a1 * dmu[1];
+          accHead[(nt * 2 + cc) * 2 + 1] += a0 * ds[0] + a1 * ds[1];
+          dl[nt][cc] = a0 > 0.f ? fmaf(dmu[0], w0, ds[0] * w1) : 0.f;
+          dl[nt][2 + cc] = a1 > 0.f ? fmaf(dmu[1], w0, ds[1] * w1) : 0.f;
+        }
+      // ---- backward: l = NH-1 .. 0
+#pragma unroll
+      for (int l = NH - 1; l >= 0; --l) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) { db[l][nt * 2] += dl[nt][0] + dl[nt][2]; db[l][nt * 2 + 1] += dl[nt][1] + dl[nt][3]; }
+        // transposed patch of delta_l (PT[column][row]) and row-major patch of a_l (PA[row][column])
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) PT[(8 * nt + 2 * t + (e & 1)) * PT_S + g + ((e >> 1) ? 8 : 0)] = dl[nt][e];
+        if (l >= 1) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            *reinterpret_cast<float2*>(PA + g * PA_S + 8 * nt + 2 * t) = make_float2(a[l - 1][nt][0], a[l - 1][nt][1]);
+            *reinterpret_cast<float2*>(PA + (g + 8) * PA_S + 8 * nt + 2 * t) = make_float2(a[l - 1][nt][2], a[l - 1][nt][3]);
+          }
+        }
+        __syncwarp();
+        // dW_l^T [out j][in i] += sum_r delta_l[r][j] a_l[r][i]:  A[m = j][k = r] from PT, B[k = r][n = i] from PA / X
+        // (the tensor core accumulates with round-toward-zero: a chain over all of the warp's tiles would bias the sum by
+        //  ~n * 2^-24, so every tile starts from zero and is added to the running sum with a rounded FADD)
+        float cw[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          AFrag A;
+          make_afrag(A, PT[g * PT_S + 8 * ks + t], PT[(g + 8) * PT_S + 8 * ks + t], PT[g * PT_S + 8 * ks + t + 4],
+                     PT[(g + 8) * PT_S + 8 * ks + t + 4]);
+          const int nti = l == 0 ? KS0 : 2;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            if (nt < nti) {
+              float v0, v1;
+              if (l == 0) {
+                if (P.resident) {
+                  v0 = c.xbuf[(mt * 16 + 8 * ks + t) * sx + 8 * nt + g];
+                  v1 = c.xbuf[(mt * 16 + 8 * ks + t + 4) * sx + 8 * nt + g];
+                } else {
+                  const long q0 = mt * 16 + 8 * ks + t, q1 = q0 + 4;
+                  v0 = __ldg(P.X + (r0 + (q0 < nrows ? q0 : nrows - 1)) * sx + 8 * nt + g);
+                  v1 = __ldg(P.X + (r0 + (q1 < nrows ? q1 : nrows - 1)) * sx + 8 * nt + g);
+                }
+              } else {
+                v0 = PA[(8 * ks + t) * PA_S + 8 * nt + g];
+                v1 = PA[(8 * ks + t + 4) * PA_S + 8 * nt + g];
+              }
+              uint32_t bh0, bl0, bh1, bl1;
+              split_tf32(v0, bh0, bl0); split_tf32(v1, bh1, bl1);
+              mma3(cw[nt], A, bh0, bh1, bl0, bl1);
+            }
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          if (nt < (l == 0 ? KS0 : 2)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) accW[l][nt][e] += cw[nt][e];
+          }
+        if (l >= 1) {
+          // delta_{l-1} = (delta_l W_l^T) * relu'(a_l)
+          float nd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            AFrag A;
+            make_afrag(A, dl[ks][0], dl[ks][2], dl[ks][1], dl[ks][3]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const float4 B = img4[GRP_B1 + (l - 1) * 128 + (ks * 2 + nt) * 32 + lane];
+              mma3(nd[nt], A, __float_as_uint(B.x), __float_as_uint(B.y), __float_as_uint(B.z), __float_as_uint(B.w));
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dl[nt][e] = a[l - 1][nt][e] > 0.f ? nd[nt][e] : 0.f;
+        }
+        __syncwarp();
+      }
+    }
+
+    PROF(1);
+    // ---- cross-warp sum of the accumulators (the patches are dead: every warp is past its last tile after the barrier)
+    {
+      // FMA-path sums: reduce over the 8 row groups g (lane bits 2..4); lanes g = 0 report
+      float sm[NSMALL];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[i] = accHead[i];
+#pragma unroll
+      for (int l = 0; l < NH; ++l)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sm[8 + 4 * l + q] = db[l][q];
+      sm[8 + 4 * NH] = dbHead[0]; sm[8 + 4 * NH + 1] = dbHead[1]; sm[8 + 4 * NH + 2] = ll_acc;
+#pragma unroll
+      for (int i = 0; i < NSMALL; ++i) {
+        float v = sm[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        sm[i] = v;
+      }
+      __syncthreads();
+      const int nact = ntiles < NW ? ntiles : NW;
+      if (warp < nact) {
+        float* scr = region + warp * SCR_WARP;
+#pragma unroll
+        for (int i = 0; i < NACC0; ++i) scr[i * 32 + lane] = accW[0][i >> 2][i & 3];
+#pragma unroll
+        for (int l = 1; l < NH; ++l)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) scr[(NACC0 + (l - 1) * 8 + i) * 32 + lane] = accW[l][i >> 2][i & 3];
+        if (g == 0) {
+#pragma unroll
+          for (int i = 0; i < NSMALL; ++i) scr[NACC * 32 + i * 4 + t] = sm[i];
+        }
+      }
+      __syncthreads();
+      for (int o = tid; o < SCR_WARP; o += NT) {
+        const int dst = o < NACC * 32 ? gmapA[o] : gmapS[o - NACC * 32];
+        if (dst >= 0) {
+          float s = 0.f;
+          for (int w = 0; w < nact; ++w) s += region[w * SCR_WARP + o];
+          gpart[dst] = dst == P.dS ? s * nb : s;
+        }
+      }
+      __syncthreads();   // scratch (== patches) is reused by the next evaluation / lppd fold
+      PROF(5);
+    }
+  }
+};

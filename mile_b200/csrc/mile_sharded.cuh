@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
 // blackjax generate_unit_vector for all chains: u = z / |z| (z host-supplied or the same Philox draw MODE_INIT uses)
 template <int NT>
 __global__ void __launch_bounds__(NT) mile_unit_momentum_kernel(float* __restrict__ u, const float* __restrict__ z0,
-                                                                unsigned long long seed, int d) {
+                                                                unsigned long long seed, int d, int chain_base) {
   __shared__ __align__(16) float red[64];
   int phase = 0;
   const int ch = blockIdx.x;
   float v[1] = {0.f};
   for (int i = threadIdx.x; i < d; i += NT) {
-    const float zz = z0 ? z0[(long)ch * d + i] : philox_normal(seed, (uint32_t)ch, 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+    const float zz = z0 ? z0[(long)ch * d + i] : philox_normal(seed, (uint32_t)(chain_base + ch), 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
     u[(long)ch * d + i] = zz; v[0] += zz * zz;
   }
   block_sum<1, NT>(v, red, phase);

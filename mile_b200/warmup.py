@@ -24,7 +24,6 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
                fft_params_limit: int = 2000, fft_samples_limit: int = 10000):
     """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C])."""
     import torch
-    from .diagnostics import effective_sample_size
     seed = key_to_seed(rng_key)
     tune1, tune2, tune3 = (int(num_steps * r) for r in PHASE_RATIO)        # warmup.py:555-557
     # blackjax.mcmc.mclmc.init with the SAME key as the tuning (warmup.py:539-541,552)
@@ -54,23 +53,39 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
                                   samples_dev=pos, n_slots=tune3)
                 done += n
             torch.cuda.synchronize(dev)
-            flat = pos
-            if d > fft_params_limit:                                       # warmup.py:442-449
-                g = torch.Generator(device='cpu').manual_seed(part2_key & ((1 << 63) - 1))
-                perm = torch.randperm(d, generator=g)[:fft_params_limit].to(dev)
-                flat = flat[:, :, perm]
-            if tune3 > fft_samples_limit:                                  # warmup.py:450-456
-                idx = torch.linspace(0, tune3 - 1, fft_samples_limit).to(torch.int64).to(dev)
-                flat = flat[idx]
-            n_eff_steps = float(tune3)
-            Ls = []
-            for c in range(C):
-                ess = effective_sample_size(flat[:, c][None])              # [1, samples, dim]
-                Ls.append(LFACTOR * float(eps[c]) * float(torch.mean(n_eff_steps / ess)))
-            L = np.asarray(Ls, np.float32)
+            L = phase3_L(pos, eps, seed=part2_key, fft_params_limit=fft_params_limit,
+                         fft_samples_limit=fft_samples_limit)
         ens.set_tuning(L=L)
         del pos
     return eps.astype(np.float32), L.astype(np.float32)
+
+
+def phase3_L(positions, step_size, seed: int = 0, fft_params_limit: int = 2000, fft_samples_limit: int = 10000,
+             device: int | None = None) -> np.ndarray:
+    """make_adaptation_L's epilogue (warmup.py:442-463) for all chains: positions [tune3, C, d] (torch CUDA tensor
+    or numpy) -> L [C] = 0.4 * eps_c * mean_i(tune3 / ESS_ci), with the reference's subsampling of parameters
+    (> 2000, random permutation) and of samples (> 10000, linspace)."""
+    import torch
+    from .diagnostics import effective_sample_size
+    if not torch.is_tensor(positions):
+        positions = torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float32)).to(
+            f'cuda:{0 if device is None else device}')
+    dev = positions.device
+    tune3, C, d = positions.shape
+    flat = positions
+    if d > fft_params_limit:                                           # warmup.py:442-449
+        g = torch.Generator(device='cpu').manual_seed(int(seed) & ((1 << 63) - 1))
+        perm = torch.randperm(d, generator=g)[:fft_params_limit].to(dev)
+        flat = flat[:, :, perm]
+    if tune3 > fft_samples_limit:                                      # warmup.py:450-456
+        idx = torch.linspace(0, tune3 - 1, fft_samples_limit).to(torch.int64).to(dev)
+        flat = flat[idx]
+    eps = np.broadcast_to(np.asarray(step_size, np.float32), (C,))
+    Ls = []
+    for c in range(C):
+        ess = effective_sample_size(flat[:, c][None])                  # [1, samples, dim]
+        Ls.append(LFACTOR * float(eps[c]) * float(torch.mean(float(tune3) / ess)))
+    return np.asarray(Ls, np.float32)
 
 
 def custom_mclmc_warmup(logdensity_fn, diagonal_preconditioning: bool = True, desired_energy_var_start: float = 5e-4,

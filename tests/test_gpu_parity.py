@@ -26,14 +26,14 @@ def rel(a, b):
 
 @pytest.mark.parametrize('name', CONFIGS)
 @pytest.mark.parametrize('G', [1, 2, 8, 14])   # 14: global-memory exchange + cooperative launch (no cluster)
-@pytest.mark.parametrize('fast', [1, 0])
+@pytest.mark.parametrize('fast', [2, 1, 0])
 def test_value_and_grad_matches_oracle(name, G, fast):
-    """fast=1: warp-specialised pipeline kernel where the shape is eligible (hidden width 16, Gaussian head),
-    fast=0: generic tile kernel."""
+    """fast=2: register-chained 3xTF32 tensor evaluator, fast=1: warp-specialised FFMA pipeline (both where the shape is
+    eligible: hidden width 16, Gaussian head), fast=0: generic tile kernel."""
     C = 3
     ospec, ens, X, y, _, _ = make(name, C, cluster_size=G, fast=fast)
     if fast:
-        assert ens.get_option('fast') == (1 if name != 'covertype_ref' else 0)
+        assert ens.get_option('fast') == (fast if name != 'covertype_ref' else 0)
     th = o.synthetic_theta0(ospec, C)
     lp, g = ens.value_and_grad(th)
     lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
@@ -70,7 +70,7 @@ def test_value_and_grad_activations_tasks_priors(act, task, prior):
 
 def test_ragged_and_tiny_row_counts():
     """Edge cases: N not a multiple of anything, N smaller than a tile, N = 1."""
-    for N, fast in [(n, f) for n in (1, 3, 31, 33, 63, 64, 65, 257, 1000) for f in (1, 0)]:
+    for N, fast in [(n, f) for n in (1, 3, 15, 16, 17, 31, 33, 63, 64, 65, 257, 1000) for f in (2, 1, 0)]:
         ospec, ens, X, y, _, _ = make('airfoil_2x16', 2, n_train=N, fast=fast)
         th = o.synthetic_theta0(ospec, 2)
         lp, g = ens.value_and_grad(th)
@@ -101,7 +101,9 @@ def test_deep_narrow_network():
     ens.close()
 
 
-@pytest.mark.parametrize('name,G,fast', [('airfoil_3x16', 1, 1), ('airfoil_3x16', 8, 1), ('airfoil_3x16', 8, 0),
+@pytest.mark.parametrize('name,G,fast', [('airfoil_3x16', 1, 2), ('airfoil_3x16', 8, 2), ('bikesharing_2x16', 8, 2), ('protein_2x16', 4, 2),
+                                         ('airfoil_2x16', 2, 2), ('bikesharing_2x16', 14, 2), ('airfoil_3x16', 12, 2),
+                                         ('airfoil_3x16', 1, 1), ('airfoil_3x16', 8, 1), ('airfoil_3x16', 8, 0),
                                          ('bikesharing_2x16', 8, 1), ('bikesharing_2x16', 8, 0),
                                          ('covertype_ref', 4, 0), ('protein_2x16', 8, 1), ('airfoil_2x16', 2, 1),
                                          ('bikesharing_2x16', 14, 1), ('covertype_ref', 11, 0), ('bikesharing_2x16', 0, 1)])

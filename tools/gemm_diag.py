@@ -1,6 +1,9 @@
 import sys, ctypes as C; sys.path.insert(0, '.')
 import numpy as np
+from pathlib import Path
 from mile_b200 import capi
+# mile_debug_wide_gemm only exists in the -DMILE_PROFILE build (tools/phase_profile.py builds tools/_prof/)
+capi.lib_path = lambda: Path('tools/_prof/libmile_b200.so').resolve()
 lib = capi.load()
 lib.mile_debug_wide_gemm.argtypes = [C.c_int32]*7 + [C.c_void_p]*3
 rng = np.random.default_rng(0)

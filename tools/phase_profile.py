@@ -17,9 +17,13 @@ from mile_b200 import capi
 capi.lib_path = lambda: lib
 from mile_b200 import Ensemble, FCNSpec
 from oracle import mile_oracle as o
-NAMES = {0: 'x-tile/loop', 1: 'forward', 2: 'loglik', 3: 'backward', 4: 'dW accumulate', 5: 'cross-chunk reduce',
+NAMES = {0: 'x-tile/loop | mma: weight image', 1: 'forward | mma: tile loop (thread 0 = warp 0)', 2: 'loglik', 3: 'backward', 4: 'dW accumulate', 5: 'cross-chunk reduce',
          8: 'esh_update (B)', 9: 'position_update (A)', 10: 'grad_eval total (outer)', 11: 'cluster reduce (rest: block_sum)', 12: 'refresh', 13: 'publish partials', 14: 'wait + sum ranks'}
-for name, C, steps, opts in [('airfoil_3x16', 12, 200, {}), ('bikesharing_2x16', 10, 50, {}), ('protein_2x16', 10, 50, {})]:
+CASES = [('airfoil_3x16', 12, 200, {}), ('airfoil_3x16', 12, 200, {'cluster_size': 8}), ('airfoil_3x16', 12, 200, {'cluster_size': 4}),
+         ('bikesharing_2x16', 10, 50, {}), ('protein_2x16', 10, 50, {}), ('airfoil_3x16', 1024, 20, {})]
+if len(sys.argv) > 1 and sys.argv[1] == 'fast1':
+    CASES = [(n, c, s, dict(o_, fast=1)) for n, c, s, o_ in CASES]
+for name, C, steps, opts in CASES:
     ospec = o.make_spec(name)
     X, y, _, _ = o.synthetic_data(name)
     ens = Ensemble(FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task), C, **opts)
@@ -29,8 +33,8 @@ for name, C, steps, opts in [('airfoil_3x16', 12, 200, {}), ('bikesharing_2x16',
     ens.lib.mile_debug_read_profile(prof, 1)
     ens.sample(steps, 0.02, float(np.sqrt(ospec.n_params)), keep=False, seed=3)
     ens.lib.mile_debug_read_profile(prof, 1)
-    tot = sum(prof[i] for i in (8, 9, 10, 11, 12, 13, 14))
-    print(f'--- {name} C={C} G={ens.get_option("cluster_size")} TR={ens.get_option("tile_rows")} '
+    tot = sum(prof[i] for i in (0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14))
+    print(f'--- {name} C={C} opts={opts} fast={ens.get_option("fast")} sync={ens.get_option("sync_mode")} G={ens.get_option("cluster_size")} TR={ens.get_option("tile_rows")} '
           f'resident={ens.get_option("resident")}: {tot / steps:.0f} cycles/step')
     for i, n in NAMES.items():
         print(f'  {n:28s} {prof[i] / steps:10.0f} cycles/step  {100 * prof[i] / tot:5.1f}%')
