@@ -5,13 +5,16 @@
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement
                                                              # of the reference (oracle/), all host threads
 
-A bench "step" is ONE launch of the persistent sampler kernel: `inner` MCLMC steps for every
-chain of the ensemble wave (two full-batch gradient evaluations per chain-step), thinned samples
-captured in HBM.  Workload (N=1): BASELINE.json configs[1] -- UCI bikesharing shape, FCN 2x16,
-10 chains per split on one B200, synthetic data.  With --gpus N every rank
-runs its own block of 10 chains on the same split (weak scaling: the ensemble shards by chain with no
-data-path collective; the per-chain test-set logsumexp states are merged once at the end over NCCL).
-Prints ONE JSON line on rank 0.
+A bench "step" is ONE launch of the persistent sampler kernel: `inner` MCLMC steps for every chain of the ensemble
+wave (two full-batch gradient evaluations per chain-step), thinned samples captured in HBM and the test-set
+posterior-predictive logsumexp folded in at every kept sample.  Default workload: `airfoil_3x16`, 12 chains -- the
+configuration BASELINE.json's >= 50x target is quoted on (experiments/illustrative_example_readme/mclmc.yaml:31-47 of the
+reference: 12 chains, FCN [16,16,16,2], 1052 x 5 training matrix), synthetic data of that shape.
+With --gpus N every rank runs its own block of chains on the same split (weak scaling: the ensemble shards by chain
+with no data-path collective; the per-chain test-set logsumexp states are merged once at the end over NCCL, timed
+inside `e2e`).  At N = 1 the line also carries `extra.workloads`: the other named shapes of BASELINE.json, each timed the
+same way on a shorter run; at N > 1 it carries the row-sharded covertype step loop (strong scaling, NCCL all-reduce per
+gradient evaluation) with its parity against a single-GPU evaluation.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -30,17 +33,19 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (oracle config key, chains per GPU, inner steps per launch)
-    'bikesharing_2x16': ('bikesharing_2x16', 10, 500),
+    # name: (config key, chains per GPU, inner steps per launch)
     'airfoil_3x16': ('airfoil_3x16', 12, 2000),
+    'bikesharing_2x16': ('bikesharing_2x16', 10, 500),
     'protein_2x16': ('protein_2x16', 10, 200),
     'covertype_ref': ('covertype_ref', 12, 500),
     'airfoil_3x16_1024': ('airfoil_3x16', 1024, 200),
-    'wide_4x256': ('wide_4x256', 8, 10),          # HBM-resident chain-batched GEMM path (no fused LPPD fold)
+    'wide_4x256': ('wide_4x256', 8, 10),          # HBM-resident chain-batched GEMM path
     # BASELINE.json configs[2]: every rank holds all 12 chains and 1/N of the 232 404 rows; one NCCL all-reduce of the
     # packed [C, d+1] (gradient, log-lik) per evaluation.  Strong scaling: total work is fixed as N grows.
     'covertype_full': ('covertype_full', 12, 20),
 }
+DEFAULT_WORKLOAD = 'airfoil_3x16'
+EXTRA_WORKLOADS = ('bikesharing_2x16', 'protein_2x16', 'airfoil_3x16_1024', 'wide_4x256')
 N_THINNING = 10  # every reference MCLMC YAML (experiments/*/mclmc.yaml: n_thinning 10)
 
 
@@ -53,13 +58,38 @@ def load_tensor_peak():
                 return float(pk[k]), f'MEASURED_PEAKS.json {k}'
     except Exception:
         pass
-    return 1626.1, 'fallback: measured cuBLAS bf16 figure quoted in SURVEY.md 8(d)'
+    return 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def load_peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        j = json.loads(p.read_text())
+        return j.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def load_traffic(workload: str, inner: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sampler kernel, from the committed ncu capture of
+    this command (profiles/traffic.json: {workload: {inner, bytes, source}}); None when no capture matches."""
+    try:
+        t = json.loads((ROOT / 'profiles' / 'traffic.json').read_text()).get(workload)
+        if t and int(t.get('inner', -1)) == int(inner):
+            return int(t['bytes']), t.get('source')
+    except Exception:
+        pass
+    return None, None
 
 
 def flops_per_chain_step(n_rows, dims):
     """12*N*W FLOPs per chain-step (two fwd+bwd passes, W = sum in*out)."""
     W = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
     return 12.0 * n_rows * W
+
+
+def flops_executed_per_chain_step(n_rows, dims):
+    """What a gradient evaluation actually needs: no input gradient for layer 0 (12 N W minus 4 N F h1 per step)."""
+    return flops_per_chain_step(n_rows, dims) - 4.0 * n_rows * dims[0] * dims[1]
 
 
 class ClockSampler:
@@ -109,56 +139,92 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def load_peaks():
-    p = ROOT / 'MEASURED_PEAKS.json'
-    if p.exists():
-        j = json.loads(p.read_text())
-        return j.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement.  Three ways of using the host are tried and the fastest is reported:
+#   chains       C port (oracle/mile_oracle.c), one chain per OpenMP thread -- the reference's one-virtual-XLA-device-
+#                per-chain pmap (train.py:16, src/training/sampling.py:181-184)
+#   chains+rows  the same with the spare cores splitting each chain's rows (hosts with more cores than chains)
+#   batched      oracle/torch_batched.py: every layer of all chains as one batched GEMM on torch-CPU, all cores through
+#                the BLAS torch links (mode ii)
+# ----------------------------------------------------------------------------------------------
+def _cpu_modes(C, cores):
+    par = min(C, cores)
+    modes = [('chains', dict(threads=par, row_threads=1))]
+    if cores // par >= 2:
+        modes.append(('chains+rows', dict(threads=par, row_threads=cores // par)))
+    modes.append(('batched', None))
+    return modes
 
 
-# ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle restatement (C + OpenMP when built, numpy otherwise)
-# ----------------------------------------------------------------------------------------------
-def cpu_chain_steps_per_s(workload: str, budget_s: float = 12.0, max_steps: int = 200, waves: int = 1):
-    """Times the CPU restatement of the reference on a bounded sample of the same workload:
-    all chains of one wave, one chain per host thread (mirrors one-virtual-device-per-chain pmap,
-    train.py:16), as many MCLMC steps as fit the budget."""
+def cpu_chain_steps_per_s(workload: str, budget_s: float = 12.0, max_steps: int = 200000, waves: int = 1,
+                          fixed_steps: int | None = None, only_mode: str | None = None):
+    """Times the CPU restatement of the reference on a bounded sample of the same workload: all chains of the job, as
+    many MCLMC steps as fit the budget (or `fixed_steps`), on all the host threads the fastest mode can use."""
     from oracle import mile_oracle as o
     key, C, _ = WORKLOADS[workload]
     C = C * max(1, waves)          # reference arm at N GPUs: the same N x C chains our arm runs (weak scaling)
     spec = o.make_spec(key)
     X, y, _, _ = o.synthetic_data(key)
-    th0 = o.synthetic_theta0(spec, C)
+    th0 = o.synthetic_theta0(spec, C, scale=0.3 if key != 'wide_4x256' else 0.05)
+    cores = os.cpu_count() or 1
+    eps, L = 0.02, float(np.sqrt(spec.n_params))
     try:
         from oracle import c_oracle
         have_c = c_oracle.available()
     except Exception:
         have_c = False
-    if have_c:
-        cores = min(C, os.cpu_count() or 1)
-        n = 2
+
+    def run(mode, kw, n):
         t0 = time.perf_counter()
-        c_oracle.run_sampling_timed(spec, X, y, th0, n, 0.02, float(np.sqrt(spec.n_params)), threads=cores)
+        if mode == 'batched':
+            from oracle import torch_batched as tb
+            dt, _ = tb.run_sampling_timed(spec, X, y, th0, n, eps, L, threads=cores)
+            return dt
+        c_oracle.run_sampling_timed(spec, X, y, th0, n, eps, L, **kw)
+        return time.perf_counter() - t0
+
+    rates = {}
+    for mode, kw in _cpu_modes(C, cores):
+        if only_mode and mode != only_mode:
+            continue
+        if mode != 'batched' and not have_c:
+            continue
+        if mode == 'batched' and spec.n_params > 50000:
+            continue                          # activations of all chains at once would not fit a sensible budget
+        try:
+            n_cal = 2
+            dt = run(mode, kw, n_cal)
+            if dt < 0.2:                      # very fast workloads: calibrate on a longer run
+                n_cal = int(min(200, max(4, 0.5 / max(dt / 2, 1e-6))))
+                dt = run(mode, kw, n_cal)
+            rates[mode] = C * n_cal / dt
+        except Exception as e:   # noqa: BLE001
+            rates[mode] = 0.0
+            print(f'[bench] cpu mode {mode} failed: {e!r}', file=sys.stderr)
+    if not rates or max(rates.values()) <= 0:
+        # numpy port, single process (no C compiler on the host)
+        f = lambda t: o.logpost_value_and_grad(spec, t, X, y)
+        rng = np.random.default_rng(0)
+        d = spec.n_params
+        st = o.mclmc_init(f, th0[0], rng.standard_normal(d).astype(np.float32))
+        n, t0 = 0, time.perf_counter()
+        while n < max_steps and time.perf_counter() - t0 < budget_s:
+            st, _ = o.mclmc_step(f, st, eps, L, rng.standard_normal(d).astype(np.float32))
+            n += 1
         dt = time.perf_counter() - t0
-        n = int(max(2, min(max_steps, budget_s / max(dt / 2, 1e-6))))
-        t0 = time.perf_counter()
-        c_oracle.run_sampling_timed(spec, X, y, th0, n, 0.02, float(np.sqrt(spec.n_params)), threads=cores)
-        dt = time.perf_counter() - t0
-        return {'value': C * n / dt, 'unit': 'chain-steps/s', 'cores': cores, 'kind': 'port',
-                'sample': f'{C} chains x {n} MCLMC steps of {workload} (C restatement, OpenMP one chain per thread)'}
-    # numpy port, single process
-    f = lambda t: o.logpost_value_and_grad(spec, t, X, y)
-    rng = np.random.default_rng(0)
-    d = spec.n_params
-    st = o.mclmc_init(f, th0[0], rng.standard_normal(d).astype(np.float32))
-    n, t0 = 0, time.perf_counter()
-    while n < max_steps and time.perf_counter() - t0 < budget_s:
-        st, _ = o.mclmc_step(f, st, 0.02, float(np.sqrt(d)), rng.standard_normal(d).astype(np.float32))
-        n += 1
-    dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': 'chain-steps/s', 'cores': 1, 'kind': 'port',
-            'sample': f'1 chain x {n} MCLMC steps of {workload} (numpy restatement, BLAS threads as configured)'}
+        return {'value': n / dt, 'unit': 'chain-steps/s', 'cores': 1, 'kind': 'port', 'mode': 'numpy', 'n_steps': n,
+                'seconds': dt, 'sample': f'1 chain x {n} MCLMC steps of {workload} (numpy restatement)'}
+    best = max(rates, key=rates.get)
+    kw = dict(_cpu_modes(C, cores))[best]
+    n = fixed_steps or int(max(2, min(max_steps, budget_s * rates[best] / C)))
+    dt = run(best, kw, n)
+    used = cores if best == 'batched' else kw['threads'] * kw['row_threads']
+    desc = {'chains': 'C restatement, OpenMP, one chain per thread',
+            'chains+rows': f'C restatement, OpenMP, one chain per thread x {kw["row_threads"] if kw else 0} threads sharing its rows',
+            'batched': 'torch-CPU restatement, chain-batched GEMMs on all cores'}[best]
+    return {'value': C * n / dt, 'unit': 'chain-steps/s', 'cores': used, 'host_cores': cores, 'kind': 'port',
+            'mode': best, 'modes_tried': {k: round(v, 1) for k, v in rates.items()}, 'n_steps': n, 'seconds': dt,
+            'sample': f'{C} chains x {n} MCLMC steps of {workload} ({desc}; fastest of the modes tried)'}
 
 
 def run_reference(args):
@@ -170,24 +236,30 @@ def run_reference(args):
     from oracle import mile_oracle as o
     spec = o.make_spec(key)
     Ntr = o.CONFIGS[key][0]
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        waves = 1 if key == 'covertype_full' else max(1, args.gpus)   # row-sharded workload: the chains do not multiply
-        r = cpu_chain_steps_per_s(W, budget_s=max(2.0, 20.0 / max(1, args.steps + args.warmup)), waves=waves)
+    waves = 1 if key == 'covertype_full' else max(1, args.gpus)   # row-sharded workload: the chains do not multiply
+    total = args.warmup + args.steps
+    # one reference "step" = a bounded sample of the workload: ref_inner MCLMC steps of all chains, sized from a short
+    # calibration so that the whole --steps/--warmup run ends within about two minutes
+    cal = cpu_chain_steps_per_s(W, budget_s=3.0, waves=waves)
+    ref_inner = int(max(2, min(inner, cal['value'] * (90.0 / max(1, total)) / (C * waves))))
+    secs, last = [], cal
+    for i in range(total):
+        r = cpu_chain_steps_per_s(W, waves=waves, fixed_steps=ref_inner, only_mode=cal.get('mode'))
         if i >= args.warmup:
-            vals.append(r['value'])
-        base = r
-    v = float(np.mean(vals))
+            secs.append(r['seconds'])
+        last = r
+    t = float(np.sum(secs))
+    v = C * waves * ref_inner * len(secs) / t
     line = {
         'impl': 'reference', 'metric': 'chain-steps/sec', 'value': v, 'unit': 'chain-steps/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * C * waves * inner / v, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': W, 'chains_per_gpu': C, 'chains_total': C * waves, 'inner_steps_per_launch': inner, 'n_train': Ntr,
-                   'n_params': spec.n_params, 'note': 'CPU restatement of the reference (JAX/BlackJAX not installable here); '
-                                                      'one chain per host thread, all chains of the N-GPU job'},
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / max(1, len(secs)), 'higher_is_better': True,
+        'scaling': 'strong' if key == 'covertype_full' else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': W, 'chains_per_gpu': C, 'chains_total': C * waves, 'inner_steps_per_launch': ref_inner,
+                   'n_train': Ntr, 'n_params': spec.n_params,
+                   'note': 'CPU restatement of the reference (JAX/BlackJAX not installable here); all chains of the N-GPU job; '
+                           'a reference step is a bounded sample of ref_inner MCLMC steps (not the GPU arm\'s inner count)'},
         'grad_evals_per_s': 2 * v,
-        'cpu_baseline': dict(base, value=v),
+        'cpu_baseline': dict(last, value=v, modes_tried=cal.get('modes_tried')),
         'e2e': {'value': v, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -197,29 +269,25 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+MMA_PER_TILE = {(4, 8): 84, (4, 16): 96, (3, 8): 48, (3, 16): 60}   # 3xTF32 mma.sync per 16-row tile and evaluation
+
+
+def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
+    """Times one workload; returns the dict of its bench line (rank 0) or None."""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device: there is no CPU fallback'
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-    from mile_b200 import Ensemble, FCNSpec, capi
-    from mile_b200 import build as _b
-    _b.build()
+    from mile_b200 import Ensemble
     from mile_b200 import synthetic as syn   # seeded synthetic inputs (the oracle is only used by the cpu_baseline leg)
+    from mile_b200.distributed import merge_lppd_states
 
-    W = args.workload
     key, C, inner = WORKLOADS[W]
-    if args.inner:
+    if args.inner and W == args.workload:
         inner = args.inner
-    spec = ospec = syn.workload_spec(key)
+    spec = syn.workload_spec(key)
     X, y, Xt, yt = syn.synthetic_data(key, seed=1234)   # same split on every rank; the CHAINS are what shards
     d = spec.n_params
     sharded = key == 'covertype_full'
+    dev = torch.device(f'cuda:{local}')
     if sharded:
         from mile_b200 import ShardedEnsemble
         ens = ShardedEnsemble(spec, C, device=local, rank=rank, world=world)
@@ -228,34 +296,38 @@ def run_ours(args):
         X, y = np.ascontiguousarray(X[rows]), np.ascontiguousarray(y[rows])
     else:
         ens = Ensemble(spec, C, device=local)
-    if args.cluster:
-        ens.set_option('cluster_size', args.cluster)
-    if args.tile_rows:
-        ens.set_option('tile_rows', args.tile_rows)
-    if args.tensor >= 0:
-        ens.set_option('tensor', args.tensor)
-    if args.fast >= 0:
-        ens.set_option('fast', args.fast)
+        ens.set_option('chain_base', rank * C)      # global chain ids: every rank draws its own noise streams
+    if W == args.workload:
+        if args.cluster:
+            ens.set_option('cluster_size', args.cluster)
+        if args.tile_rows:
+            ens.set_option('tile_rows', args.tile_rows)
+        if args.tensor >= 0:
+            ens.set_option('tensor', args.tensor)
+        if args.fast >= 0:
+            ens.set_option('fast', args.fast)
+        if args.steploop >= 0:
+            ens.set_option('steploop', args.steploop)
     ens.set_data(X, y)
-    fused_lppd = key != 'wide_4x256' and not sharded
+    wide = bool(ens.get_option('wide'))
+    fused_lppd = not wide and not sharded
     if fused_lppd:
         ens.set_test(Xt, yt)      # fused posterior-predictive LPPD fold at every kept sample
     crank = 0 if sharded else rank        # sharded: every rank carries the SAME chains (same seeds, same noise)
     th0 = syn.synthetic_theta0(d, C, seed0=1000 + 100 * crank, scale=0.3 if key != 'wide_4x256' else 0.05)
-    ens.init(th0, seed=17 + crank)
+    ens.init(th0, seed=17)
     # short tuning run -> frozen (eps, L); fallback eps=0.02, L=sqrt(d)
     eps = np.full(C, 0.02, np.float32)
     L = np.full(C, np.sqrt(d), np.float32)
     if not args.no_tune:
         ens.tune_reset(0.01)
-        nt1, nt2 = (40, 10) if key in ('wide_4x256', 'covertype_full') else (800, 100)
+        nt1, nt2 = (40, 10) if (wide or sharded) else (800, 100)
         tc = ens.tune_cfg(nt1, nt2, 0.5, 0.1, 1.5, 100)
-        ens.tune(nt1 + nt2, 0, tc, seed=99 + crank)
+        ens.tune(nt1 + nt2, 0, tc, seed=99)
         ens.tune_finish_phase2()
         e, l, _ = ens.get_tuning()
         if np.all(np.isfinite(e)) and np.all(e > 0) and np.all(np.isfinite(l)) and np.all(l > 0):
             eps, L = e, l
-    dev = torch.device(f'cuda:{local}')
     eps_d, L_d = torch.from_numpy(eps).to(dev), torch.from_numpy(L).to(dev)
     n_slots = inner // N_THINNING
     samples_d = torch.empty((n_slots, C, d), dtype=torch.float32, device=dev)
@@ -270,7 +342,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         flush.zero_()
         one_step(i)
     barrier()
@@ -282,11 +354,11 @@ def run_ours(args):
     evs = []
     barrier()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        one_step(args.warmup + i)
+        one_step(warmup + i)
         e1.record()
         evs.append((e0, e1))
     barrier()
@@ -300,23 +372,31 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev = float(t.item())
     nrep = 1 if sharded else world        # sharded: the ranks share one set of chains
-    chain_steps = nrep * C * inner * args.steps
-    value = chain_steps / t_dev
-    # the one exchange step of the path: merge the per-chain online logsumexp states (NCCL all-gather)
-    from mile_b200.distributed import merge_lppd_states
-    t0 = time.perf_counter()
+    value = nrep * C * inner * steps / t_dev
     lppd_val, lppd_total = None, 0
     if fused_lppd:
         m_, s_, cnt_ = ens.lppd_state()
         lppd_val, lppd_total = merge_lppd_states(m_, s_, cnt_, device=dev)
-    lppd_ms = 1e3 * (time.perf_counter() - t0)
 
-    # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside) --------
+    sharded_parity = None
+    if sharded and world > 1:
+        # rank 0 compares the N-rank gradient state with a single-GPU full-data evaluation at the same positions
+        th_s, _, lp_s, g_s = ens.get_state()
+        if rank == 0:
+            ref = Ensemble(spec, C, device=local)
+            ref.set_data(Xfull, yfull)
+            lp_f, g_f = ref.value_and_grad(th_s)
+            ref.close()
+            sharded_parity = {'grad_rel': float(np.linalg.norm(g_s - g_f) / np.linalg.norm(g_f)),
+                              'logdensity_rel': float(np.max(np.abs(lp_s - lp_f) / np.abs(lp_f)))}
+
+    # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside), plus the one exchange step of the
+    #      path at N > 1: the NCCL merge of the per-chain test-set logsumexp states ------------------------------------
     st = ens.get_state()
     Xp = torch.from_numpy(X).pin_memory().numpy()
     h2d = X.nbytes + y.nbytes + 3 * C * d * 4 + C * 4 + 2 * C * 4
     d2h = n_slots * C * d * 4 + 3 * C * d * 4 + C * 4
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(steps, 5))
     # one untimed pass first: the host-buffer entry points allocate their pinned staging buffers on first use
     ens.set_data(Xp, y); ens.set_state(*st)
     ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4320, lppd=False)
@@ -328,6 +408,10 @@ def run_ours(args):
         ens.set_state(*st)
         smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=fused_lppd)
         st = ens.get_state()
+    if fused_lppd and world > 1:
+        m_, s_, cnt_ = ens.lppd_state()
+        merge_lppd_states(m_, s_, cnt_, device=dev)
+        d2h += 2 * m_.nbytes // max(1, e2e_steps)
     barrier()
     t_e2e = time.perf_counter() - t0
     if world > 1:
@@ -337,68 +421,144 @@ def run_ours(args):
     e2e_value = nrep * C * inner * e2e_steps / t_e2e
     finite = bool(np.all(np.isfinite(smp)))
 
+    line = None
     if rank == 0:
-        # FP32 peak measured live (scalar FFMA and packed FFMA2), best of both
-        import ctypes
-        pk = [ctypes.c_double(), ctypes.c_double()]
-        for v in (0, 1):
-            capi.check(ens.lib.mile_measure_fp32_peak(local, v, ctypes.byref(pk[v])))
-        fp32_peak = max(pk[0].value, pk[1].value)
-        hbm_peak, peak_src = load_peaks()
         Ntr = Xfull.shape[0] if sharded else X.shape[0]
-        fl = flops_per_chain_step(Ntr, ospec.dims)
+        fl = flops_per_chain_step(Ntr, spec.dims)
         per_gpu_steps_per_s = value / world     # (sharded: each GPU does 1/world of every chain-step's rows)
         achieved_tf = per_gpu_steps_per_s * fl / 1e12
-        hbm_bytes_per_launch = C * (4 * d * 4 + n_slots * d * 4) + X.nbytes * 0  # state r/w + samples
+        fast = int(ens.get_option('fast'))
+        G = ens.get_option('cluster_size')
+        resident = bool(ens.get_option('resident'))
+        mma_path = fast == 2 and not wide and not sharded
+        if sharded:
+            path = 'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step'
+        elif wide:
+            path = 'wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')
+        else:
+            path = {2: 'MmaGE: register-chained 3xTF32 mma.sync evaluator + integrator-warp step loop',
+                    1: 'FastGE: warp-specialised FFMA layer pipeline', 0: 'GenericGE: 4x4 register tiles'}[fast]
+        hbm_bytes_per_launch = C * (4 * d * 4 + n_slots * d * 4)        # state r/w + kept samples
+        hbm_peak, peak_src = peaks['hbm']
         line = {
             'metric': 'chain-steps/sec', 'value': value, 'unit': 'chain-steps/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * t_dev / steps,
             'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': W, 'chains_per_gpu': C, 'inner_steps_per_launch': inner, 'n_train': int(Ntr),
-                       'n_features': ospec.n_features, 'hidden_structure': list(ospec.widths), 'n_params': d,
-                       'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10',
-                       'cluster_size': ens.get_option('cluster_size'), 'tile_rows': ens.get_option('tile_rows'),
-                       'x_resident_in_smem': bool(ens.get_option('resident')),
-                       'kernel_path': 'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step' if sharded else (('wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')) if ens.get_option('wide') else ('FastGE pipeline' if ens.get_option('fast') else 'GenericGE')),
-                       'l2': 'flushed between timed iterations (256 MiB write); working set is SMEM-resident',
-                       'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()), 'parallelism': (f'rows x{world} + NCCL all-reduce of [C, d+1] per gradient evaluation' if sharded else f'chains x{world}')},
+                       'n_features': spec.n_features, 'hidden_structure': list(spec.widths), 'n_params': d,
+                       'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10, streams keyed by global chain id',
+                       'cluster_size': G, 'sync_mode': ens.get_option('sync_mode'), 'tile_rows': ens.get_option('tile_rows'),
+                       'x_resident_in_smem': resident, 'kernel_path': path,
+                       'l2': 'flushed between timed iterations (256 MiB write); ' +
+                             ('working set is SMEM-resident' if resident else 'X streams from the padded HBM copy through L2 every evaluation'),
+                       'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()),
+                       'parallelism': (f'rows x{world} + NCCL all-reduce of [C, d+1] per gradient evaluation' if sharded else f'chains x{world}')},
             'grad_evals_per_s': 2 * value,
             'samples_finite': finite,
-            'lppd': {'value': lppd_val, 'samples': int(lppd_total), 'merge_ms': lppd_ms,
-                     'note': 'test-set logsumexp folded in-kernel at every kept sample; merged across ranks after the timed region'},
+            'lppd': {'value': lppd_val, 'samples': int(lppd_total),
+                     'note': 'test-set logsumexp folded in-kernel at every kept sample; merged across ranks over NCCL (timed inside e2e)'},
             'wall_s_timed_region': t_wall,
             'gpu_launches': int(launches),
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
-                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers) + get_state'},
+                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers) + get_state'
+                            + (' + NCCL merge of the LPPD states' if fused_lppd and world > 1 else '')},
         }
-        roof = {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': None,
-                'kernel': 'mile_mclmc_kernel', 'flops_per_chain_step': fl,
-                'peak_source': f'live FMA micro-benchmark (FFMA {pk[0].value:.1f}, FFMA2 {pk[1].value:.1f} TFLOP/s)',
-                'note': 'SURVEY.md 8(d): these shapes are bound by the FP32 FMA pipe (working set in SMEM/L2), '
-                        'neither by HBM nor by the tensor pipe; the HBM view is given below for completeness',
+        if sharded_parity is not None:
+            line['sharded_parity_rel'] = sharded_parity
+        traffic, tsrc = load_traffic(W, inner)
+        roof = {'bound': 'fp32', 'achieved': achieved_tf, 'peak': peaks['fp32'], 'unit': 'TFLOP/s',
+                'frac': achieved_tf / peaks['fp32'] if peaks['fp32'] else None, 'traffic': traffic,
+                'kernel': 'mile_mma_step_kernel' if mma_path else 'mile_mclmc_kernel',
+                'flops_per_chain_step': fl, 'flops_executed_per_chain_step': flops_executed_per_chain_step(Ntr, spec.dims),
+                'peak_source': peaks['fp32_src'],
+                'note': 'SURVEY.md 8(d): these shapes are bound by on-chip arithmetic / latency (working set in SMEM/L2), '
+                        'neither by HBM nor by the tcgen05 pipe; achieved = algorithmic fp32 FLOPs (12 N W per chain-step) '
+                        'against the measured FP32 FMA peak; the HBM view is given for completeness',
                 'avg_launch_ms': float(np.mean(kernel_ms)),
                 'hbm': {'achieved_gbs': hbm_bytes_per_launch / (np.mean(kernel_ms) * 1e-3) / 1e9,
                         'peak_gbs': hbm_peak, 'peak_source': peak_src,
                         'note': 'tiny by design: theta/u/g and the X slice stay in shared memory for the whole launch'}}
-        if ens.get_option('wide') and ens.get_option('tensor'):
-            tpk, tsrc = load_tensor_peak()
-            roof.update({'bound': 'tensor', 'peak': tpk, 'frac': achieved_tf / tpk, 'peak_source': tsrc,
-                         'kernel': 'wide_gemm_tc_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32-level accuracy)',
+        if traffic is not None:
+            roof['traffic_note'] = tsrc
+        if mma_path:
+            NL, FP = len(spec.widths), (8 if spec.n_features <= 8 else 16)
+            g_ = max(1, int(G))
+            per = -(-int(Ntr) // g_)
+            tiles = sum(-(-max(0, min(per, Ntr - r * per)) // 16) for r in range(g_))
+            mma_flops = 2.0 * tiles * MMA_PER_TILE[(NL, FP)] * 2048.0          # per chain-step (two evaluations)
+            roof['tensor_pipe'] = {'instruction': 'mma.sync.m16n8k8 tf32 (3 per fp32 product)',
+                                   'issued_tflops': per_gpu_steps_per_s * mma_flops / 1e12, 'peak_tflops': peaks['mma'],
+                                   'frac': per_gpu_steps_per_s * mma_flops / 1e12 / peaks['mma'] if peaks['mma'] else None,
+                                   'peak_source': 'live mma.sync micro-benchmark (mile_measure_fp32_peak variant 2)'}
+        if wide and ens.get_option('tensor'):
+            tpk, tsrc2 = load_tensor_peak()
+            roof.update({'bound': 'tensor', 'peak': tpk, 'frac': achieved_tf / tpk, 'peak_source': tsrc2,
+                         'kernel': 'wide_gemm_tc2_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32-level accuracy)',
                          'note': 'achieved = ALGORITHMIC fp32 FLOPs (12 N W per chain-step); the 3xTF32 split issues 3x that '
                                  'on the tensor pipe, and TF32 dense peak is half the bf16 figure used as denominator'})
-        if W == 'bikesharing_2x16' and inner == 500 and not sharded:
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1q_ncu_fastge_final.txt)
-            roof['traffic'] = 1339904 + 109824
-            roof['traffic_note'] = 'bytes per launch of mile_mclmc_kernel from the committed ncu capture of this command'
         line['roofline'] = roof
-        if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_chain_steps_per_s(W)
-        print(json.dumps(line))
+        if with_cpu:
+            line['cpu_baseline'] = cpu_chain_steps_per_s(W, budget_s=with_cpu)
     ens.close()
+    del flush, samples_d
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device: there is no CPU fallback'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    from mile_b200 import capi
+    from mile_b200 import build as _b
+    _b.build()
+    lib = capi.load()
+    peaks = {'hbm': load_peaks(), 'fp32': None, 'fp32_src': None, 'mma': None}
+    if rank == 0:
+        # FP32 peak measured live (scalar FFMA and packed FFMA2, best of both) + the evaluator's tensor instruction
+        import ctypes
+        pk = [ctypes.c_double(), ctypes.c_double(), ctypes.c_double()]
+        for v in (0, 1, 2):
+            capi.check(lib.mile_measure_fp32_peak(local, v, ctypes.byref(pk[v])))
+        peaks['fp32'] = max(pk[0].value, pk[1].value)
+        peaks['fp32_src'] = f'live FMA micro-benchmark (FFMA {pk[0].value:.1f}, FFMA2 {pk[1].value:.1f} TFLOP/s)'
+        peaks['mma'] = pk[2].value
+    line = measure(args.workload, args, args.steps, args.warmup, rank, world, local,
+                   (0 if (args.no_cpu or world > 1) else 12.0), peaks)
+    extra = {}
+    if not args.no_extra and args.workload == DEFAULT_WORKLOAD:
+        names = EXTRA_WORKLOADS if world == 1 else ('covertype_full',)
+        for W in names:
+            try:
+                sub = measure(W, args, min(args.steps, 3), min(args.warmup, 3), rank, world, local,
+                              (0 if (args.no_cpu or world > 1) else 4.0), peaks)
+            except Exception as e:   # noqa: BLE001
+                sub = {'error': repr(e)} if rank == 0 else None
+            if rank == 0 and sub is not None:
+                keep = ('value', 'unit', 'ms_per_step', 'scaling', 'e2e', 'gpu_launches', 'samples_finite',
+                        'cpu_baseline', 'sharded_parity_rel', 'error')
+                s = {k: sub[k] for k in keep if k in sub}
+                if 'roofline' in sub:
+                    s['roofline'] = {k: sub['roofline'][k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'kernel', 'tensor_pipe')
+                                     if k in sub['roofline']}
+                if 'config' in sub:
+                    s['config'] = {k: sub['config'][k] for k in ('chains_per_gpu', 'inner_steps_per_launch', 'n_train', 'n_params',
+                                                                 'cluster_size', 'kernel_path', 'parallelism')}
+                extra[W] = s
+    if rank == 0:
+        if extra:
+            line['extra'] = {'workloads': extra,
+                             'note': 'the other named shapes of BASELINE.json, same timing method on a shorter run (<= 3 steps)'}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -409,14 +569,16 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='bikesharing_2x16', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--inner', type=int, default=0)
     ap.add_argument('--cluster', type=int, default=0)
     ap.add_argument('--tile-rows', type=int, default=0)
     ap.add_argument('--tensor', type=int, default=-1, help='wide path: 1 = tcgen05 3xTF32 GEMM core, 0 = FP32 SIMT core')
     ap.add_argument('--fast', type=int, default=-1, help='narrow-MLP evaluator: 2 = 3xTF32 register MMA (default), 1 = FFMA layer pipeline, 0 = generic tiles')
+    ap.add_argument('--steploop', type=int, default=-1, help='1 = integrator-warp step loop of the tensor evaluator (default), 0 = generic loop')
     ap.add_argument('--no-tune', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip extra.workloads (the other named shapes)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':

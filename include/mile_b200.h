@@ -82,9 +82,12 @@ int mile_version(void);
 int mile_create(const mile_model_desc* desc, int32_t n_chains, int32_t device, mile_ctx** out);
 void mile_destroy(mile_ctx* ctx);
 int32_t mile_n_params(const mile_ctx* ctx);
-/* Execution knobs: cluster size of the persistent kernel (0 = auto), refresh variant
- * (0 = single post-step refresh, blackjax 1.2.2; 1 = half-step refreshes around the
- * integrator, later blackjax `with_isokinetic_maruyama`). */
+/* Execution knobs: "cluster_size" CTAs per chain of the persistent kernel (0 = auto), "refresh_mode" (0 = single
+ * post-step refresh, blackjax 1.2.2; 1 = half-step refreshes around the integrator, later blackjax
+ * `with_isokinetic_maruyama`), "chain_base" (global id of this context's chain 0: the in-kernel Philox streams are keyed by
+ * chain_base + local chain, so the ranks of a chain-partitioned ensemble draw independent noise, like the reference's
+ * jax.random.split per device, sampling.py:181-184), "fast" (narrow-MLP evaluator: 2 = 3xTF32 register MMA, 1 = FFMA layer
+ * pipeline, 0 = generic tiles), "tensor" (wide path GEMM core), "sync_mode", "resident", "tile_rows", "steploop". */
 int mile_set_option(mile_ctx* ctx, const char* key, int64_t value);
 int64_t mile_get_option(const mile_ctx* ctx, const char* key);
 
@@ -194,7 +197,9 @@ int mile_shard_mclmc_tune(mile_ctx* ctx, int32_t n_steps, int64_t step_base, con
 int64_t mile_launch_count(const mile_ctx* ctx);
 int mile_synchronize(mile_ctx* ctx);
 /* Measured FP32 CUDA-core peak in TFLOP/s (roofline denominator for the narrow-MLP configs,
- * SURVEY.md section 8d): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 (FFMA2). */
+ * SURVEY.md section 8d): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 (FFMA2), 2 = the register-operand tensor
+ * instruction of the narrow-MLP evaluator, mma.sync.m16n8k8 tf32 (TFLOP/s of tf32 products; the evaluator issues three per
+ * fp32 product). */
 int mile_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out);
 
 #ifdef __cplusplus

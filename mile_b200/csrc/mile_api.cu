@@ -59,7 +59,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0, opt_steploop = 1;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -156,7 +156,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
       const size_t tile = (size_t)tile_f > gen ? (size_t)tile_f : gen;
       // resident slice: 16-row tiles plus one zero guard tile (k-steps may read up to 12 floats past a row's stride)
       const int rows_res = (int)((rows_cta + 15) / 16) * 16 + 16;
-      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0] + round_up(aux_i, 4)) * 4;
+      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0] + round_up(aux_i, 4) + 5 * (size_t)dS + 4) * 4;
       const int res = (c->opt_resident != 0 && base_need + (size_t)rows_res * M.sA[0] * 4 <= kSmemLimit) ? 1 : 0;
       if (base_need <= kSmemLimit) {
         M.TR = TRg; M.tile_floats = (int)tile;
@@ -175,6 +175,8 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
         k.off_pmap = o; o += 2 * dS;
         k.off_red = o; o += 192;
         k.off_aux = o; o += round_up(aux_i, 4);
+        k.off_z = o; o += 4 * dS;            // refresh noise of two steps x two slots
+        k.off_gs = o; o += dS + 4;           // slice buffer of the DSMEM reduce-scatter
         k.off_tile = o; o += (int)tile + TRg * M.sA[0];
         k.off_x = o; if (res) o += rows_res * M.sA[0];
         pl.G = G; pl.TR = 16; pl.resident = res; pl.rows_res = rows_res; pl.fast = 2; pl.fast_fp = FPm; pl.sync_mode = sync_mode;
@@ -267,9 +269,10 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   return 0;
 }
 
-template <class GE>
+template <class GE, bool V2 = false>
 static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
-  auto kern = mile_mclmc_kernel<GE>;
+  void (*kern)(const KParams) = mile_mclmc_kernel<GE>;
+  if constexpr (V2) kern = mile_mma_step_kernel<GE>;   // restructured step loop of the tensor evaluator (mile_mma.cuh)
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   if (pl.G > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;
@@ -311,7 +314,13 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   }
   const int NL = c->M.NL;
   int rc;
-  if (pl.fast == 2) {
+  if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0) {
+    if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, true>(pl, n_chains, st);
+    else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, true>(pl, n_chains, st);
+    else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, true>(pl, n_chains, st);
+    else rc = launch_t<MmaGE<4, 16, 512>, true>(pl, n_chains, st);
+  }
+  else if (pl.fast == 2) {
     if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>>(pl, n_chains, st);
     else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>>(pl, n_chains, st);
     else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>>(pl, n_chains, st);
@@ -456,6 +465,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
+  else if (!strcmp(key, "steploop")) c->opt_steploop = (int)v;   // 1: integrator-warp step loop of the tensor evaluator, 0: generic loop
   else return fail(std::string("unknown option ") + key);
   return 0;
 }

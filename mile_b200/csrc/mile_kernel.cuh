@@ -46,7 +46,7 @@ struct KParams {
   float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)
   int dS, off_wp, off_th, off_u, off_g, off_thb, off_ub, off_gb, off_gpart, off_avgx, off_avgx2,
-      off_pmap, off_red, off_tile, off_x, off_aux;
+      off_pmap, off_red, off_tile, off_x, off_aux, off_z, off_gs;
   // global id of local chain 0: the Philox streams are keyed by (seed, chain_base + chain, step, element), so the ranks
   // of a chain-partitioned ensemble draw independent noise (the reference splits one key per chain, sampling.py:181-184)
   int chain_base;
@@ -61,6 +61,7 @@ struct Ctx {
   int rank, G, chain;
   // element-split mode (ES, wide / large-d integrator): the d elements are strided over the CTAs of a cluster
   int e0, estride; float* csum; int csum_phase;
+  bool lead;   // the one thread that reports per-chain scalars (thread 0 of the block; lane 0 of the integrator warp in warp mode)
   __device__ Ctx(const KParams& p) : P(p) {}
 };
 
@@ -358,22 +359,50 @@ __device__ __forceinline__ void cluster_sum(Ctx& c, float (&v)[NV]) {
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = t[k];
 }
+#define MILE_WARP_MODE 99   // BAR value: the caller is ONE warp (elements strided by lane through c.e0 / c.estride, ES = true);
+                            // reductions are xor-shuffles only: no shared memory, no barrier
 template <int NV, int NT, int BAR, bool ES>
 __device__ __forceinline__ void all_sum(Ctx& c, float (&v)[NV]) {
-  block_sum<NV, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
+  if (BAR == MILE_WARP_MODE) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    return;
+  }
+  block_sum<NV, NT, BAR == MILE_WARP_MODE ? 0 : BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   if (ES) cluster_sum<NV>(c, v);
 }
 
 // ESH momentum update B(coef) (blackjax esh_dynamics_momentum_update_one_step, sqrt_diag_cov = 1).
 // delta-small-safe forms: 1-zeta = -expm1(-delta), log(1+p+(1-p)zeta^2) - ln2 = log1p(-(1-p)(1-zeta^2)/2).
-template <int NT, int BAR = 0, bool ES = false>
-__device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
-  const int d = c.P.M.d;
-  const float gn = sqrtf(g2);
-  const float ginv = gn > 1e-13f ? 1.f / gn : 1.f;
+// scalar part: u' = ae * g + au * u; returns the kinetic-energy change of this sub-step
+__device__ __forceinline__ float esh_coeffs(int d, float eps, float coef, float g2, float ug, float& ae, float& au) {
+  // The scalar chain below sits on the critical path of every half step (one thread-serial dependency chain per
+  // evaluation), so the IEEE sqrt / divide / expm1f / log1pf library sequences are replaced on their common range by
+  // MUFU.RSQ + one Newton step and by short Horner series (all <= 1e-9 relative on the stated range); outside it the
+  // library forms are used.
+  float gn, ginv;
+  if (g2 > 1e-26f && g2 < 1e37f) {
+    float y = rsqrtf(g2);
+    y = y * fmaf(-0.5f * g2 * y, y, 1.5f);
+    ginv = y; gn = g2 * y;
+  } else {
+    gn = sqrtf(g2);
+    ginv = gn > 1e-13f ? 1.f / gn : 1.f;
+  }
   const float p = ug * ginv;
   const float delta = eps * coef * gn / (float)(d - 1);
-  const float omz = -expm1f(-delta);   // 1 - zeta without cancellation
+  float omz;                             // 1 - zeta = 1 - exp(-delta) without cancellation
+  if (delta >= 0.f && delta < 0.125f) {
+    float q = fmaf(delta, -1.f / 7.f, 1.f);
+    q = fmaf(delta * (-1.f / 6.f), q, 1.f);
+    q = fmaf(delta * (-1.f / 5.f), q, 1.f);
+    q = fmaf(delta * (-1.f / 4.f), q, 1.f);
+    q = fmaf(delta * (-1.f / 3.f), q, 1.f);
+    q = fmaf(delta * (-1.f / 2.f), q, 1.f);
+    omz = delta * q;
+  } else {
+    omz = -expm1f(-delta);
+  }
   const float zeta = 1.f - omz;
   const float ce = omz * (1.f + zeta + p * omz);
   const float cu = 2.f * zeta;
@@ -381,10 +410,30 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   // B-step; |u| is re-normalised numerically by the partial refresh once per step, so rounding cannot accumulate)
   const float rn2 = ce * ce + cu * cu + 2.f * ce * cu * p;
   const float rinv = rn2 > 1e-26f ? rsqrtf(rn2) : 1.f;
-  const float ae = ce * ginv * rinv, au = cu * rinv;
-  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
+  ae = ce * ginv * rinv; au = cu * rinv;
   const float omz2 = omz * (1.f + zeta);   // 1 - zeta^2
-  return (delta + log1pf(-0.5f * (1.f - p) * omz2)) * (float)(d - 1);
+  const float yy = -0.5f * (1.f - p) * omz2;
+  float l1p;
+  if (fabsf(yy) < 0.0625f) {             // log1p(y) = y (1 - y/2 + y^2/3 - ... + y^6/7)
+    float q = fmaf(yy, 1.f / 7.f, -1.f / 6.f);
+    q = fmaf(yy, q, 1.f / 5.f);
+    q = fmaf(yy, q, -1.f / 4.f);
+    q = fmaf(yy, q, 1.f / 3.f);
+    q = fmaf(yy, q, -1.f / 2.f);
+    q = fmaf(yy, q, 1.f);
+    l1p = yy * q;
+  } else {
+    l1p = log1pf(yy);
+  }
+  return (delta + l1p) * (float)(d - 1);
+}
+template <int NT, int BAR = 0, bool ES = false>
+__device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
+  const int d = c.P.M.d;
+  float ae, au;
+  const float dk = esh_coeffs(d, eps, coef, g2, ug, ae, au);
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
+  return dk;
 }
 
 // A(coef): theta += eps*coef*u and refresh the padded weight image (the caller synchronises the block
@@ -408,7 +457,7 @@ __device__ __forceinline__ float noise_at(const KParams& P, int chain, long step
 // partially_refresh_momentum: u <- normalise(u + nu z); also returns u.g for the next B-step.
 template <int NT, int BAR = 0, bool ES = false>
 __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, long step_local, int slot, int nslot,
-                                                 float& ug_out) {
+                                                 float& ug_out, const float* zsm = nullptr) {
   const KParams& P = c.P;
   const int d = P.M.d;
   if (isinf(L)) {   // no refresh: still re-normalise numerically (the B-steps use the closed-form norm)
@@ -423,7 +472,7 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
   const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
   float v[2] = {0.f, 0.f};
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
-    const float w = c.uu[i] + nu * noise_at(P, c.chain, step_local, slot, nslot, i);
+    const float w = c.uu[i] + nu * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
     c.uu[i] = w;
     v[0] += w * w; v[1] += w * c.gg[i];
   }
@@ -511,7 +560,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         }
         t_wtot += w;
       }
-      if (P.tune_info && c.rank == 0 && tid == 0) {
+      if (P.tune_info && c.rank == 0 && c.lead) {
         float* o = P.tune_info + ((long)s * P.C + ch) * 4;
         o[0] = dE; o[1] = eps_new; o[2] = t_epsmax; o[3] = success ? 1.f : 0.f;
       }
@@ -564,7 +613,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   c.G = P.G;
   c.rank = c.G > 1 ? (P.sync_mode ? (int)(blockIdx.x % c.G) : (int)cluster.block_rank()) : 0;
   c.chain = blockIdx.x / c.G;
-  c.phase = 0;
+  c.phase = 0; c.lead = threadIdx.x == 0;
   c.wp = smem + P.off_wp; c.th = smem + P.off_th; c.uu = smem + P.off_u; c.gg = smem + P.off_g;
   c.thb = smem + P.off_thb; c.ub = smem + P.off_ub; c.gb = smem + P.off_gb; c.gpart = smem + P.off_gpart;
   c.avgx = smem + P.off_avgx; c.avgx2 = smem + P.off_avgx2; c.pmap = reinterpret_cast<int*>(smem + P.off_pmap);

@@ -37,6 +37,26 @@ __global__ void __launch_bounds__(1024, 1) fma_peak_kernel(float* out, int iters
   if (s == 12345.678f) out[0] = s;  // never true; keeps the loop alive
 }
 
+// register-operand tensor instruction of the narrow-MLP evaluator (mile_mma.cuh): 8 independent accumulator chains per warp
+__global__ void __launch_bounds__(1024, 1) mma_peak_kernel(float* out, int iters) {
+  unsigned a[4], b[2];
+  for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(1.0f + 0.001f * (threadIdx.x + i));
+  for (int i = 0; i < 2; ++i) b[i] = __float_as_uint(0.5f + 0.001f * (threadIdx.x + i));
+  float c[8][4];
+  for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) c[j][i] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                   : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  float s = 0.f;
+  for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) s += c[j][i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+// variant 0: scalar FFMA, 1: packed FFMA2, 2: mma.sync m16n8k8 tf32 (TFLOP/s of tf32 products, 2*16*8*8 per warp instruction)
 extern "C" int mile_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out) {
   if (!tflops_out) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
@@ -51,12 +71,14 @@ extern "C" int mile_measure_fp32_peak(int32_t device, int32_t variant, double* t
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0);
     if (variant == 0) fma_peak_kernel<0><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
-    else fma_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    else if (variant == 1) fma_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    else mma_peak_kernel<<<blocks, threads>>>(out, iters / 4);
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -1; }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    const double flops = variant == 2 ? 2048.0 * 8.0 * (double)(iters / 4) * (double)blocks * (threads / 32)
+                                      : 2.0 * 16.0 * (double)iters * (double)blocks * threads;
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }

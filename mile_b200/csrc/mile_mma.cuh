@@ -70,10 +70,16 @@ struct MmaGE {
   static constexpr int NACC = NACC0 + (NH - 1) * 8;                 // + dW_l^T 16 x 16
   static constexpr int NSMALL = 8 + 4 * NH + 2 + 1;                 // head kernel, hidden biases, head bias, log-lik
   static constexpr int SCR_WARP = NACC * 32 + NSMALL * 4;
-  static constexpr int REGION_FLOATS = NW * (PATCH_FLOATS > SCR_WARP ? PATCH_FLOATS : SCR_WARP);
+  // one private region per warp, used first as patches and then as reduction scratch: no cross-warp aliasing, so no
+  // block barrier is needed between a warp's last tile and its scratch writes
+  static constexpr int RSTRIDE = ((PATCH_FLOATS > SCR_WARP ? PATCH_FLOATS : SCR_WARP) + 3) / 4 * 4;
+  static constexpr int REGION_FLOATS = NW * RSTRIDE;
   static constexpr int TILE_FLOATS = IMG_FLOATS + REGION_FLOATS;
   // ---- index maps built once per launch (prepare): image group -> two flat parameter indices; scratch slot -> flat
   static constexpr int AUX_INTS = 2 * NGROUPS + NACC * 32 + NSMALL * 4;
+  // largest parameter count this evaluator serves (F <= FP) and the elements one lane of the integrator warp owns
+  static constexpr int DMAX = FP * H + H + (NH - 1) * (H * H + H) + 2 * H + 2;
+  static constexpr int EMAX = (DMAX + 31) / 32;
 
   static __device__ __forceinline__ int* aux(Ctx& c) { return reinterpret_cast<int*>(c.aux); }
 
@@ -157,7 +163,7 @@ struct MmaGE {
     const int sx = M.sA[0];
     const float nb = M.n_batches;
     const float4* img4 = reinterpret_cast<const float4*>(img);
-    float* PT = region + warp * PATCH_FLOATS;
+    float* PT = region + warp * RSTRIDE;
     float* PA = PT + 16 * PT_S;
 
     float accW[NH][2][4], accHead[8], db[NH][4], dbHead[2] = {0.f, 0.f}, ll_acc = 0.f;   // accW[0] uses n-tiles < KS0 only
@@ -367,29 +373,28 @@ struct MmaGE {
     }
 
     PROF(1);
-    // ---- cross-warp sum of the accumulators (the patches are dead: every warp is past its last tile after the barrier)
+    // ---- cross-warp sum of the accumulators: every warp that owned tiles writes its sums into its own region
     {
-      // FMA-path sums: reduce over the 8 row groups g (lane bits 2..4); lanes g = 0 report
-      float sm[NSMALL];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sm[i] = accHead[i];
-#pragma unroll
-      for (int l = 0; l < NH; ++l)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sm[8 + 4 * l + q] = db[l][q];
-      sm[8 + 4 * NH] = dbHead[0]; sm[8 + 4 * NH + 1] = dbHead[1]; sm[8 + 4 * NH + 2] = ll_acc;
-#pragma unroll
-      for (int i = 0; i < NSMALL; ++i) {
-        float v = sm[i];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        sm[i] = v;
-      }
-      __syncthreads();
       const int nact = ntiles < NW ? ntiles : NW;
       if (warp < nact) {
-        float* scr = region + warp * SCR_WARP;
+        // FMA-path sums: reduce over the 8 row groups g (lane bits 2..4); lanes g = 0 report
+        float sm[NSMALL];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm[i] = accHead[i];
+#pragma unroll
+        for (int l = 0; l < NH; ++l)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sm[8 + 4 * l + q] = db[l][q];
+        sm[8 + 4 * NH] = dbHead[0]; sm[8 + 4 * NH + 1] = dbHead[1]; sm[8 + 4 * NH + 2] = ll_acc;
+#pragma unroll
+        for (int i = 0; i < NSMALL; ++i) {
+          float v = sm[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          sm[i] = v;
+        }
+        float* scr = region + warp * RSTRIDE;
 #pragma unroll
         for (int i = 0; i < NACC0; ++i) scr[i * 32 + lane] = accW[0][i >> 2][i & 3];
 #pragma unroll
@@ -406,12 +411,304 @@ struct MmaGE {
         const int dst = o < NACC * 32 ? gmapA[o] : gmapS[o - NACC * 32];
         if (dst >= 0) {
           float s = 0.f;
-          for (int w = 0; w < nact; ++w) s += region[w * SCR_WARP + o];
+          for (int w = 0; w < nact; ++w) s += region[w * RSTRIDE + o];
           gpart[dst] = dst == P.dS ? s * nb : s;
         }
       }
-      __syncthreads();   // scratch (== patches) is reused by the next evaluation / lppd fold
+      // no trailing barrier: every caller synchronises (block or cluster barrier) before gpart is consumed, and the
+      // regions are next written after further barriers
       PROF(5);
     }
   }
 };
+
+// ------------------------------------------------------------------------------------------------------------
+// Step loop for the tensor evaluator (MODE_SAMPLE / MODE_TUNE).  Same arithmetic as the loop of mile_mclmc_kernel,
+// restructured after two ncu captures (profiles/r2d_*, r2g_*):
+//   * in the generic loop all 16 warps execute every scalar chain of a B-step (sqrt, divide, expm1, log1p, rsqrt; ~100
+//     dependent instructions) and draw the refresh noise in line (Philox + Box-Muller, ~150 instructions per element):
+//     85 % of the issued instructions were this redundant or in-line work;
+//   * a first restructuring with ONE integrator warp owning all d elements removed the redundancy but issued ~2700
+//     dependent instructions per evaluation from a single warp (23 elements per lane): slower.
+// This version keeps the ELEMENT sweeps on all threads (<= 2 elements per thread), runs each SCALAR chain on warp 0
+// only and publishes the coefficients through shared memory, and lets the other 15 warps draw the NEXT step's noise
+// into a double-buffered shared array during exactly those windows, so the draws cost no time on the critical path.
+// Block reductions use a shuffle butterfly over the per-warp partials (36 instead of 80 instructions for four sums).
+// Cluster exchange = reduce-scatter + all-gather over DSMEM (each CTA sums one slice of the partial gradients in rank
+// order, then every CTA gathers the summed slices: 2 x d/G remote floats per CTA instead of (G-1) x d).  The
+// flagged-word exchange through L2 (any G <= 16, cooperative launch) and G = 1 are the other two cases.
+// ------------------------------------------------------------------------------------------------------------
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum_bfly(float (&v)[NV], float* scratch, int& phase) {
+  constexpr int NWARPS = NT / 32;
+  static_assert(NWARPS == 16, "butterfly over 16 per-warp partials");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* buf = scratch + phase * (4 * NWARPS);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float s = warp_sum(v[k]);
+    if (lane == 0) buf[k * NWARPS + warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float s = buf[k * NWARPS + (lane & 15)];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    v[k] = s;
+  }
+  phase ^= 1;
+}
+
+template <class GE>
+__global__ void __launch_bounds__(GE::NT, 1) mile_mma_step_kernel(const __grid_constant__ KParams P) {
+  constexpr int NT = GE::NT;
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = P.M;
+  cg::cluster_group cluster = cg::this_cluster();
+  Ctx c(P);
+  c.G = P.G;
+  c.rank = c.G > 1 ? (P.sync_mode ? (int)(blockIdx.x % c.G) : (int)cluster.block_rank()) : 0;
+  c.chain = blockIdx.x / c.G;
+  c.phase = 0; c.lead = threadIdx.x == 0;
+  c.wp = smem + P.off_wp; c.th = smem + P.off_th; c.uu = smem + P.off_u; c.gg = smem + P.off_g;
+  c.thb = smem + P.off_thb; c.ub = smem + P.off_ub; c.gb = smem + P.off_gb; c.gpart = smem + P.off_gpart;
+  c.avgx = smem + P.off_avgx; c.avgx2 = smem + P.off_avgx2; c.pmap = reinterpret_cast<int*>(smem + P.off_pmap);
+  c.red = smem + P.off_red; c.red2 = c.red + 128; c.phase2 = 0; c.tile = smem + P.off_tile;
+  c.xstream = c.tile + M.tile_floats;
+  c.xbuf = P.resident ? smem + P.off_x : c.xstream;
+  c.aux = smem + P.off_aux;
+  float* zbuf = smem + P.off_z;        // [2 steps][2 slots][dS]
+  float* gslice = smem + P.off_gs;     // this CTA's slice of the summed gradient (cluster exchange)
+  float* sc = c.red + 128;             // scalars published by warp 0: ae, au, dK increment, nu
+  const int d = M.d, ch = c.chain, dS = P.dS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool tune = P.mode == MODE_TUNE;
+  const int nslot = P.refresh_mode ? 2 : 1;
+  const int i0 = tid, i1 = tid + NT;   // the (at most) two elements this thread owns: d <= GE::DMAX <= 2 NT
+  const bool has0 = i0 < d, has1 = i1 < d;
+
+  // ---- prologue ---------------------------------------------------------------------------------------------
+  for (int i = tid; i < M.psize; i += NT) c.wp[i] = 0.f;
+  build_pmap<NT>(M, c.pmap, dS);
+  GE::prepare(c);
+  for (int i = tid; i < d; i += NT) {
+    c.th[i] = P.theta[(long)ch * d + i]; c.uu[i] = P.u[(long)ch * d + i]; c.gg[i] = P.grad[(long)ch * d + i];
+    if (tune) { c.avgx[i] = P.avg_x[(long)ch * d + i]; c.avgx2[i] = P.avg_x2[(long)ch * d + i]; }
+  }
+  const long per = (P.N + c.G - 1) / c.G;
+  const long r0 = per * c.rank < P.N ? per * c.rank : P.N;
+  const long r1 = (r0 + per) < P.N ? (r0 + per) : P.N;
+  if (P.resident) {
+    const int sx = M.sA[0];
+    const long nv4 = (r1 - r0) * (sx >> 2), np4 = (long)P.rows_res * (sx >> 2);
+    const float4* s4 = reinterpret_cast<const float4*>(P.X + r0 * sx);
+    float4* d4 = reinterpret_cast<float4*>(c.xbuf);
+    for (long i = tid; i < np4; i += NT) d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // noise of step s_local into its buffer; `part` of `nparts` (the draws are spread over the idle windows of a step)
+  auto draw_noise = [&](long s_local, int t0, int tstride, int part, int nparts) {
+    float* zs = zbuf + (s_local & 1) * (2 * dS);
+    int j = 0;
+    for (int k = t0; k < nslot * d; k += tstride, ++j) {
+      if (j % nparts != part) continue;
+      const int slot = k >= d ? 1 : 0, i = k - slot * d;
+      zs[slot * dS + i] = noise_at(P, ch, s_local, slot, nslot, i);
+    }
+  };
+  if (P.n_steps > 0) draw_noise(0, tid, NT, 0, 1);
+  __syncthreads();
+
+  // ---- chain scalars, uniform across the block -------------------------------------------------------------------
+  float g2 = 0.f, ug = 0.f, nf = 0.f, lp = P.lp[ch], lp_old = 0.f, dK = 0.f;
+  float eps = tune ? P.t_eps[ch] : P.eps[ch];
+  const float Lc = tune ? P.t_L[ch] : P.L[ch];
+  TuneRegs tr{0.f, 0.f, INFINITY, 0.f};
+  if (tune) { tr.time = P.t_time[ch]; tr.xavg = P.t_xavg[ch]; tr.epsmax = P.t_epsmax[ch]; tr.wtot = P.t_wtot[ch]; }
+  if (P.carry_valid) { g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1]; }
+  else {
+    float v[2] = {0.f, 0.f};
+    if (has0) { v[0] += c.gg[i0] * c.gg[i0]; v[1] += c.uu[i0] * c.gg[i0]; }
+    if (has1) { v[0] += c.gg[i1] * c.gg[i1]; v[1] += c.uu[i1] * c.gg[i1]; }
+    block_sum_bfly<2, NT>(v, c.red, c.phase);
+    g2 = v[0]; ug = v[1];
+  }
+  const float b1 = 0.1931833275037836f, b2 = 1.f - 2.f * 0.1931833275037836f;
+  const float loc = M.prior_loc, scl = M.prior_scale, s2 = scl * scl, inv_s2 = 1.f / s2, inv_scl = 1.f / scl;
+  const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * scl);
+  const int n_evals = 2 * P.n_steps;
+  PROF_DECL;
+#pragma unroll 1
+  for (int e = 0; e < n_evals; ++e) {
+    const int h = e & 1, s = e >> 1;
+    const float* zs = zbuf + (s & 1) * (2 * dS);
+    if (h == 0) {
+      lp_old = lp; dK = 0.f;
+      if (tune) {
+        if (has0) { c.thb[i0] = c.th[i0]; c.ub[i0] = c.uu[i0]; c.gb[i0] = c.gg[i0]; }
+        if (has1) { c.thb[i1] = c.th[i1]; c.ub[i1] = c.uu[i1]; c.gb[i1] = c.gg[i1]; }
+      }
+      if (P.refresh_mode) refresh_momentum<NT>(c, 0.5f * eps, Lc, s, 0, nslot, ug, zs);
+    }
+    // ---- scalar chain of B(b1 | 1 - 2 b1) on warp 0; the other warps draw a part of the next step's noise ----------
+    if (warp == 0) {
+      float ae, au;
+      const float dk = esh_coeffs(d, eps, h == 0 ? b1 : b2, g2, ug, ae, au);
+      if (lane == 0) { sc[0] = ae; sc[1] = au; sc[2] = dk; }
+    } else if (s + 1 < P.n_steps) {
+      draw_noise(s + 1, tid - 32, NT - 32, h, 3);
+    }
+    __syncthreads();
+    {
+      const float ae = sc[0], au = sc[1], st = eps * 0.5f;
+      dK += sc[2];
+      if (has0) { const float un = ae * c.gg[i0] + au * c.uu[i0]; c.uu[i0] = un; c.th[i0] += st * un; }
+      if (has1) { const float un = ae * c.gg[i1] + au * c.uu[i1]; c.uu[i1] = un; c.th[i1] += st * un; }
+    }
+    PROF(8);
+    __syncthreads();                       // the new position is visible to the evaluator
+    float* gp = c.gpart + (e & 1) * (dS + 4);
+    GE::run(c, r0, r1, gp);
+    PROF(10);
+    // ---- exchange: afterwards gsum[0..d) = sum over the chain's CTAs of the likelihood gradient, gp[ll_idx] = sum of ll
+    const float* gsum = c.gg;
+    int ll_idx = dS + 1;
+    if (c.G == 1) {
+      __syncthreads();
+      gsum = gp; ll_idx = dS;
+    } else if (P.sync_mode) {
+      const unsigned int xflag = P.xbase + (unsigned int)e + 1u;
+      float2* slab = P.xchg + ((long)ch * 2 + (e & 1)) * c.G * (dS + 4);
+      float2* mine = slab + c.rank * (dS + 4);
+      __syncthreads();
+      for (int i = tid; i <= dS; i += NT) ll_store(mine + i, gp[i], xflag);
+      PROF(13);
+      const int stride_g = dS + 4;
+      if (has1) {
+        float s0, s1;
+        ll_sum_pair(slab + i0, slab + i1, stride_g, c.G, xflag, s0, s1);
+        c.gg[i0] = s0; c.gg[i1] = s1;
+      } else if (has0) {
+        c.gg[i0] = ll_sum(slab + i0, stride_g, c.G, xflag);
+      }
+      if (tid == NT - 1) gp[dS + 1] = ll_sum(slab + dS, stride_g, c.G, xflag);
+      __syncthreads();
+    } else {
+      // reduce-scatter + all-gather over DSMEM; slices of SL elements over [0, dS] (element dS = log-likelihood)
+      const int SL = (dS + 1 + c.G - 1) / c.G;
+      cluster.sync();                      // every CTA's partial is complete
+      PROF(13);
+      for (int j = tid; j < SL; j += NT) {
+        const int idx = c.rank * SL + j;
+        float sum = 0.f;
+        if (idx <= dS) {
+          float tv[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) tv[r] = r < c.G ? cluster.map_shared_rank(gp, r)[idx] : 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) sum += tv[r];
+        }
+        gslice[j] = sum;
+      }
+      cluster.sync();                      // every slice is summed
+      PROF(2);
+      for (int i = tid; i <= dS; i += NT) {
+        if (i < d || i == dS) {
+          const int owner = i / SL, off = i - owner * SL;
+          const float v = cluster.map_shared_rank(gslice, owner)[off];
+          if (i < d) c.gg[i] = v; else gp[dS + 1] = v;
+        }
+      }
+      __syncthreads();
+    }
+    PROF(14);
+    // ---- prior, full gradient, and the sums the next B-step / handle_nans need -----------------------------------
+    float gk[2] = {0.f, 0.f}, uk[2] = {0.f, 0.f};
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = k ? i1 : i0;
+        if (k ? has1 : has0) {
+          const float th = c.th[i], dlt = th - loc;
+          float pg, pv;
+          if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt * inv_s2) * -0.5f; pg = -dlt * inv_s2; }
+          else { pv = -lognorm - fabsf(dlt) * inv_scl; pg = -((dlt > 0.f) - (dlt < 0.f)) * inv_scl; }
+          const float gi = gsum[i] + pg * P.prior_weight, ui = c.uu[i];
+          c.gg[i] = gi; gk[k] = gi; uk[k] = ui;
+          v[0] += pv * P.prior_weight; v[1] += gi * gi; v[2] += ui * gi; v[3] += isfinite(th) ? 0.f : 1.f;
+        }
+      }
+      block_sum_bfly<4, NT>(v, c.red, c.phase);
+      lp = v[0] + gp[ll_idx]; g2 = v[1]; ug = v[2]; nf = v[3];
+    }
+    PROF(11);
+    if (h == 1) {
+      // ---- end of MCLMC step s: last B and the partial refresh in one sweep (u, g still in registers) ------------
+      const float er = P.refresh_mode ? 0.5f * eps : eps;
+      if (warp == 0) {
+        float ae, au;
+        const float dk = esh_coeffs(d, eps, b1, g2, ug, ae, au);
+        const float nu = isinf(Lc) ? 0.f : sqrtf((expf(2.f * er / Lc) - 1.f) / (float)d);
+        if (lane == 0) { sc[4] = ae; sc[5] = au; sc[6] = dk; sc[7] = nu; }
+      } else if (s + 1 < P.n_steps) {
+        draw_noise(s + 1, tid - 32, NT - 32, 2, 3);
+      }
+      __syncthreads();
+      const float ae = sc[4], au = sc[5], nu = sc[7];
+      dK += sc[6];
+      const float* zl = zs + (nslot - 1) * dS;
+      float w[2] = {0.f, 0.f}, w2[2] = {0.f, 0.f};
+      if (has0) { w[0] = ae * gk[0] + au * uk[0] + nu * zl[i0]; w2[0] += w[0] * w[0]; w2[1] += w[0] * gk[0]; }
+      if (has1) { w[1] = ae * gk[1] + au * uk[1] + nu * zl[i1]; w2[0] += w[1] * w[1]; w2[1] += w[1] * gk[1]; }
+      block_sum_bfly<2, NT>(w2, c.red, c.phase);
+      float inv = rsqrtf(w2[0]);
+      inv = inv * fmaf(-0.5f * w2[0] * inv, inv, 1.5f);
+      if (has0) c.uu[i0] = w[0] * inv;
+      if (has1) c.uu[i1] = w[1] * inv;
+      ug = w2[1] * inv;
+      float dE = dK - lp + lp_old;
+      if (!tune) {
+        if (P.info && c.rank == 0 && tid == 0) {
+          float* o = P.info + ((long)s * P.C + ch) * 3;
+          o[0] = lp; o[1] = dK; o[2] = dE;
+        }
+        const long idx = P.step_base + s;    // thinned sample capture (sampling.py:152-164)
+        if (idx % P.thin == 0) {
+          const long slot = idx / P.thin - P.sample_base;
+          if (P.samples && c.rank == 0 && slot >= 0 && slot < P.n_slots) {
+            if (has0) P.samples[(slot * P.C + ch) * d + i0] = c.th[i0];
+            if (has1) P.samples[(slot * P.C + ch) * d + i1] = c.th[i1];
+          }
+        }
+      } else {
+        __syncthreads();                     // tune_epilogue re-reads u / g of other threads' making through shared memory
+        eps = tune_epilogue<NT, false>(c, tr, eps, lp_old, nf, s, lp, dE, g2, ug);
+      }
+      PROF(12);
+      // fused posterior-predictive fold at every kept position (whole block; needs the padded weight image)
+      if (!tune && P.do_lppd && (P.step_base + s) % P.thin == 0) {
+        __syncthreads();
+        refresh_wp<NT>(c);
+        __syncthreads();
+        lppd_fold<NT>(c, ch);
+      }
+    }
+  }
+  // ---- epilogue: write the state back ----------------------------------------------------------------------------
+  __syncthreads();
+  if (c.rank == 0) {
+    for (int i = tid; i < d; i += NT) {
+      P.theta[(long)ch * d + i] = c.th[i];
+      P.u[(long)ch * d + i] = c.uu[i];
+      P.grad[(long)ch * d + i] = c.gg[i];
+      if (tune) { P.avg_x[(long)ch * d + i] = c.avgx[i]; P.avg_x2[(long)ch * d + i] = c.avgx2[i]; }
+    }
+    if (tid == 0) {
+      P.lp[ch] = lp;
+      P.carry[2 * ch] = g2; P.carry[2 * ch + 1] = ug;
+      if (tune) { P.t_time[ch] = tr.time; P.t_xavg[ch] = tr.xavg; P.t_epsmax[ch] = tr.epsmax; P.t_eps[ch] = eps; P.t_wtot[ch] = tr.wtot; }
+    }
+  }
+  if (c.G > 1 && !P.sync_mode) cluster.sync();
+}

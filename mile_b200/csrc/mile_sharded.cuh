@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
     csize = (int)cl.num_blocks(); crank = (int)cl.block_rank(); ch = blockIdx.x / csize;
   }
   Ctx c(P);
-  c.G = 1; c.rank = crank; c.chain = ch; c.phase = 0; c.phase2 = 0;
+  c.G = 1; c.rank = crank; c.chain = ch; c.phase = 0; c.phase2 = 0; c.lead = tid == 0;
   c.e0 = crank * NT + tid; c.estride = csize * NT; c.csum = csum; c.csum_phase = 0;
   const bool writer = tid == 0 && crank == 0;
   c.th = P.theta + (long)ch * d; c.uu = P.u + (long)ch * d; c.gg = P.grad + (long)ch * d;

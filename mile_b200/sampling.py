@@ -20,6 +20,11 @@ from .warmup import run_warmup
 logger = logging.getLogger(__name__)
 
 CHUNK = 1000  # MCLMC steps per sampling launch (rounded to a multiple of n_thinning)
+# Where the kept positions go: 'npz' = the reference layout samples/{chain}/sample_{n}.npz (default: drop-in),
+# 'store' = one [C, S, d] array under <exp>/samples_store (sample_store.py; `python -m mile_b200.sample_store export`
+# reproduces the npz layout afterwards), 'both'.
+import os as _os
+SAMPLE_FORMAT = _os.environ.get('MILE_SAMPLE_FORMAT', 'npz')
 
 
 def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_params: dict, step_ids,
@@ -51,7 +56,15 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
         logger.info(f'> Starting {config.name.value} Sampling...')
         thin = int(config.n_thinning)
         chunk = max(thin, CHUNK // thin * thin)
-        writer = SampleWriter(spec, saving_path, step_ids)
+        fmt = SAMPLE_FORMAT
+        if fmt not in ('npz', 'store', 'both'):
+            raise ValueError(f'MILE_SAMPLE_FORMAT must be npz, store or both, not {fmt!r}')
+        writer = SampleWriter(spec, saving_path, step_ids) if fmt in ('npz', 'both') else None
+        store = None
+        if fmt in ('store', 'both'):
+            from .sample_store import SampleStore
+            store = SampleStore.create(saving_path.parent / 'samples_store', spec, step_ids,
+                                       -(-int(config.n_samples) // thin))
         fused_lppd = ens.n_test > 0
         if fused_lppd:
             ens.lppd_reset()
@@ -61,9 +74,16 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
             n = min(chunk, config.n_samples - done)
             samples, _ = ens.sample(n, eps, L, step_base=done, n_thinning=thin, seed=seed, lppd=fused_lppd)
             first = -(-done // thin)
-            writer.submit(samples, [(first + k) * thin for k in range(samples.shape[0])])
+            kept = [(first + k) * thin for k in range(samples.shape[0])]
+            if writer is not None:
+                writer.submit(samples, kept)
+            if store is not None:
+                store.append(samples, kept)
             done += n
-        writer.close()
+        if writer is not None:
+            writer.close()
+        if store is not None:
+            store.close()
         if fused_lppd:
             m, s, cnt = ens.lppd_state()
             info['lppd'] = lppd_from_state(m, s, n_devices * cnt)

@@ -38,9 +38,51 @@ def _unflatten(names, arrays) -> dict:
 
 
 def save_tree(dir, tree: dict):
-    """Plain description of the nesting (the reference pickles a jax PyTreeDef here, utils.py:90-93)."""
+    """utils.py:90-93.  The reference pickles a jax PyTreeDef into `<exp>/tree`.  That object can only be built where
+    jax is importable: there the same pickle is written (so `inference.ipynb` loads it unchanged); everywhere a plain
+    description of the nesting goes to `tree.json`, which `load_tree` below turns into a stand-in treedef."""
+    import pickle
+    tree = sorted_tree(tree)
     with open(Path(dir) / 'tree.json', 'w') as f:
-        json.dump(get_flattened_keys(sorted_tree(tree)), f)
+        json.dump(get_flattened_keys(tree), f)
+    try:
+        import jax  # noqa: F401  (absent on this image; present on a host that runs the reference's notebook)
+        with open(Path(dir) / 'tree', 'wb') as f:
+            pickle.dump(jax.tree.structure(tree), f)
+    except Exception:
+        pass
+
+
+class TreeShim:
+    """Stand-in for the pickled PyTreeDef: knows the leaf names in flatten order and rebuilds the nested dict, which is
+    all the reference does with it (`jax.tree.unflatten(tree, leaves)`, utils.py:105-108,127,161)."""
+
+    def __init__(self, names):
+        self.names = list(names)
+        self.num_leaves = len(self.names)
+
+    def unflatten(self, leaves):
+        leaves = list(leaves)
+        if len(leaves) != self.num_leaves:
+            raise ValueError(f'expected {self.num_leaves} leaves, got {len(leaves)}')
+        return _unflatten(self.names, leaves)
+
+    def __repr__(self):
+        return f'TreeShim({self.names})'
+
+
+def load_tree(dir):
+    """utils.py:96-99: the pickled PyTreeDef when it exists and jax can unpickle it, else the tree.json stand-in."""
+    import pickle
+    dir = Path(dir)
+    if (dir / 'tree').exists():
+        try:
+            with open(dir / 'tree', 'rb') as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    with open(dir / 'tree.json') as f:
+        return TreeShim(json.load(f))
 
 
 def save_params(dir, params: dict, idx: int | None = None):
@@ -79,6 +121,11 @@ def load_params_batch(params_path: list, tree_path=None) -> dict:
 def load_samples_from_dir(dir, tree_path=None) -> dict:
     """utils.py:131-161: leaves [n_chains, n_samples, ...] from samples/{chain}/sample_{n}.npz."""
     dir = Path(dir)
+    from .sample_store import SampleStore
+    store = dir.parent / 'samples_store'
+    has_npz = dir.exists() and any(d.is_dir() and any(d.glob('*.npz')) for d in dir.iterdir())
+    if not has_npz and SampleStore.exists(store):          # compact store written by inference_loop (sample_store.py)
+        return SampleStore.open(store).to_tree()
     chain_dirs = sorted([d for d in dir.iterdir() if d.is_dir()], key=lambda x: int(x.stem.split('_')[-1]))
     stacks, names = [], None
     for cd in chain_dirs:

@@ -52,6 +52,7 @@ def load():
     lib.mo_philox_normal.argtypes = [u64, C.c_uint32, u64, C.c_uint32, C.c_uint32]
     lib.mo_philox_normal.restype = f
     lib.mo_max_threads.restype = C.c_int
+    lib.mo_set_row_threads.argtypes = [C.c_int]
     _lib = lib
     return lib
 
@@ -123,8 +124,20 @@ class Chains:
         return samples, inf
 
 
-def run_sampling_timed(ospec, X, y, theta0, n_steps, eps, L, threads=1):
-    """n_steps MCLMC steps for all chains with in-library Philox noise (used by bench.py's CPU legs)."""
-    ch = Chains(ospec, X, y, theta0, seed=1, threads=threads)
-    ch.sample(n_steps, eps, L, seed=2, keep=False)
+def set_row_threads(n: int):
+    """Threads that split the rows of one chain's evaluation (nested under the one-chain-per-thread loop)."""
+    lib = load()
+    lib.mo_max_threads()          # enables two active OpenMP levels
+    lib.mo_set_row_threads(int(n))
+
+
+def run_sampling_timed(ospec, X, y, theta0, n_steps, eps, L, threads=1, row_threads=1):
+    """n_steps MCLMC steps for all chains with in-library Philox noise (used by bench.py's CPU legs).
+    threads = chains in flight (one per OpenMP thread); row_threads = threads sharing the rows of each chain."""
+    set_row_threads(row_threads)
+    try:
+        ch = Chains(ospec, X, y, theta0, seed=1, threads=threads)
+        ch.sample(n_steps, eps, L, seed=2, keep=False)
+    finally:
+        set_row_threads(1)
     return ch

@@ -61,9 +61,10 @@ static inline void act_eval(int act, float z, float* a, float* da) {
   }
 }
 
-/* value_and_grad of log_unnormalized_posterior for one chain; grad [d] overwritten. */
-float mo_logpost_value_and_grad(const mo_spec* s, const float* theta, const float* X, const void* y, int64_t N,
-                                float* grad) {
+/* Likelihood part of value_and_grad over the rows [n0, n1): grad [d] overwritten with the partial gradient, returns the
+ * partial sum of log-likelihood terms. */
+static float mo_loglik_rows(const mo_spec* s, const float* theta, const float* X, const void* y, int64_t n0, int64_t n1,
+                            float* grad) {
   const int NL = s->n_layers, d = mo_nparams(s);
   int dims[MO_MAX_LAYERS + 1];
   dims[0] = s->n_features;
@@ -73,7 +74,7 @@ float mo_logpost_value_and_grad(const mo_spec* s, const float* theta, const floa
   float a[MO_MAX_LAYERS + 1][MO_MAX_WIDTH], da[MO_MAX_LAYERS][MO_MAX_WIDTH], dl[2][MO_MAX_WIDTH];
   float ll_sum = 0.f;
   const int K = dims[NL];
-  for (int64_t n = 0; n < N; ++n) {
+  for (int64_t n = n0; n < n1; ++n) {
     for (int i = 0; i < dims[0]; ++i) a[0][i] = X[n * dims[0] + i];
     for (int l = 0; l < NL; ++l) {
       const int IN = dims[l], OUT = dims[l + 1];
@@ -136,6 +137,47 @@ float mo_logpost_value_and_grad(const mo_spec* s, const float* theta, const floa
         }
       }
     }
+  }
+  return ll_sum;
+}
+
+/* Threads that split the rows of ONE chain's evaluation (bench: host cores / chains when the host has more cores than
+ * chains; 1 = the plain serial evaluation). */
+static int g_row_threads = 1;
+void mo_set_row_threads(int n) { g_row_threads = n < 1 ? 1 : n; }
+
+/* value_and_grad of log_unnormalized_posterior for one chain; grad [d] overwritten. */
+float mo_logpost_value_and_grad(const mo_spec* s, const float* theta, const float* X, const void* y, int64_t N,
+                                float* grad) {
+  const int d = mo_nparams(s);
+  float ll_sum = 0.f;
+  int T = g_row_threads;
+  if (T > 1 && N >= 64 * (int64_t)T) {
+#ifdef _OPENMP
+    float* part = (float*)malloc(sizeof(float) * (size_t)d * (size_t)T);
+    float lls[64];
+    if (T > 64) T = 64;
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+      const int64_t per = (N + nt - 1) / nt, a0 = per * t < N ? per * t : N, a1 = a0 + per < N ? a0 + per : N;
+      lls[t] = mo_loglik_rows(s, theta, X, y, a0, a1, part + (size_t)t * d);
+#pragma omp barrier
+#pragma omp for schedule(static)
+      for (int i = 0; i < d; ++i) {
+        float acc = 0.f;
+        for (int q = 0; q < nt; ++q) acc += part[(size_t)q * d + i];
+        grad[i] = acc;
+      }
+#pragma omp single
+      { for (int q = 0; q < nt; ++q) ll_sum += lls[q]; }
+    }
+    free(part);
+#else
+    ll_sum = mo_loglik_rows(s, theta, X, y, 0, N, grad);
+#endif
+  } else {
+    ll_sum = mo_loglik_rows(s, theta, X, y, 0, N, grad);
   }
   /* prior (priors.py:101-128) */
   float pv = 0.f;
@@ -260,6 +302,7 @@ void mo_run_sampling(const mo_spec* s, const float* X, const void* y, int64_t N,
 
 int mo_max_threads(void) {
 #ifdef _OPENMP
+  omp_set_max_active_levels(2);   /* chains outside, rows of one chain inside (mo_set_row_threads) */
   return omp_get_max_threads();
 #else
   return 1;

@@ -17,8 +17,8 @@ from mile_b200 import capi
 capi.lib_path = lambda: lib
 from mile_b200 import Ensemble, FCNSpec
 from oracle import mile_oracle as o
-NAMES = {0: 'x-tile/loop | mma: weight image', 1: 'forward | mma: tile loop (thread 0 = warp 0)', 2: 'loglik', 3: 'backward', 4: 'dW accumulate', 5: 'cross-chunk reduce',
-         8: 'esh_update (B)', 9: 'position_update (A)', 10: 'grad_eval total (outer)', 11: 'cluster reduce (rest: block_sum)', 12: 'refresh', 13: 'publish partials', 14: 'wait + sum ranks'}
+NAMES = {0: 'x-tile/loop | mma: integrator warp + weight image', 1: 'forward | mma: tile loop (thread 0 = warp 0)', 2: 'loglik | mma: reduce-scatter + 2nd cluster.sync', 3: 'backward', 4: 'dW accumulate', 5: 'cross-chunk reduce',
+         8: 'esh_update (B)', 9: 'position_update (A)', 10: 'grad_eval total (outer)', 11: 'cluster reduce (rest: block_sum)', 12: 'refresh', 13: 'publish partials | 1st cluster.sync', 14: 'wait + sum ranks'}
 CASES = [('airfoil_3x16', 12, 200, {}), ('airfoil_3x16', 12, 200, {'cluster_size': 8}), ('airfoil_3x16', 12, 200, {'cluster_size': 4}),
          ('bikesharing_2x16', 10, 50, {}), ('protein_2x16', 10, 50, {}), ('airfoil_3x16', 1024, 20, {})]
 if len(sys.argv) > 1 and sys.argv[1] == 'fast1':
