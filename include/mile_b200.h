@@ -175,6 +175,31 @@ int mile_lppd_state_host(mile_ctx* ctx, float* m, float* s, int64_t* count);
 int mile_predict(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t which, float* out_dev,
                  void* stream);
 
+/* ---- deep-ensemble warm-start training ---------------------------------------------------- */
+/* src/config/warmstart.py:17-41 (OptimizerConfig -> optax.adamw / adam / sgd with its `parameters`). */
+enum mile_optimizer { MILE_OPT_KIND_ADAMW = 0, MILE_OPT_KIND_ADAM = 1, MILE_OPT_KIND_SGD = 2 };
+typedef struct mile_opt_cfg {
+  int32_t kind;          /* enum mile_optimizer */
+  float learning_rate;
+  float b1, b2, eps;     /* optax defaults 0.9, 0.999, 1e-8 */
+  float weight_decay;    /* optax.adamw default 1e-4 */
+} mile_opt_cfg;
+/* get_initial_state (src/training/trainer.py:870-892) with host-initialised parameters: theta0 [C,d] (one row per ensemble
+ * member), optimizer moments and step counts zeroed. */
+int mile_train_init(mile_ctx* ctx, const float* theta0_dev, void* stream);
+/* One epoch of train_de_member's inner loop (trainer.py:441-460) for all members in ONE launch: for every minibatch
+ * (rows batch_idx[b, 0..B) of the training split set with mile_set_data; the same batches for every member) the mean
+ * Gaussian-NLL / cross-entropy loss, its gradient and the optimizer update (single_step_regr / single_step_class,
+ * trainer.py:662-760).  stopped_dev [C] (or NULL): members whose early-stopping flag is set skip the epoch.
+ * metrics_dev [n_batches, C, 2] (or NULL) = (loss, RMSE | accuracy) of every step before its update, NaN when stopped. */
+int mile_train_epoch(mile_ctx* ctx, const int32_t* batch_idx_dev, int32_t n_batches, int32_t batch_size,
+                     const mile_opt_cfg* opt, const uint8_t* stopped_dev, float* metrics_dev, void* stream);
+/* predict_regr / predict_class (trainer.py:763-868): mean loss and RMSE | accuracy of theta [n,d] (NULL: the training
+ * state of all members) over the train (which = 0) or the mile_set_test (which = 1) split -> out [n,2]. */
+int mile_eval_metrics(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t which, float* out_dev, void* stream);
+/* Parameters, AdamW moments [C,d] and step counts [C] (device buffers; NULLs skipped). */
+int mile_train_get_state(mile_ctx* ctx, float* theta_dev, float* m_dev, float* v_dev, int32_t* t_dev, void* stream);
+
 /* ---- data-sharded variant (covertype, rows split across the GPUs of one box) -------- */
 /* Every rank holds ALL chains and 1/world of the training rows (mile_set_data with the local shard).  Each
  * gradient evaluation = local value_and_grad (prior weighted 1/world) + ncclAllReduce(sum) of the packed

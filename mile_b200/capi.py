@@ -21,6 +21,7 @@ SYMBOLS = [
     'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
+    'mile_train_init', 'mile_train_epoch', 'mile_eval_metrics', 'mile_train_get_state',
     'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
 ]
 
@@ -41,6 +42,14 @@ class TuneCfg(C.Structure):
         ('desired_energy_var_start', C.c_float), ('desired_energy_var_end', C.c_float),
         ('trust_in_estimate', C.c_float), ('num_effective_samples', C.c_float),
     ]
+
+
+class OptCfg(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('learning_rate', C.c_float), ('b1', C.c_float), ('b2', C.c_float), ('eps', C.c_float),
+                ('weight_decay', C.c_float)]
+
+
+OPTIMIZERS = {'adamw': 0, 'adam': 1, 'sgd': 2}
 
 
 class MileError(RuntimeError):
@@ -101,6 +110,10 @@ def load():
     lib.mile_launch_count.restype = i64
     lib.mile_synchronize.argtypes = [vp]
     lib.mile_measure_fp32_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+    lib.mile_train_init.argtypes = [vp, fp, vp]
+    lib.mile_train_epoch.argtypes = [vp, vp, i32, i32, C.POINTER(OptCfg), vp, fp, vp]
+    lib.mile_eval_metrics.argtypes = [vp, fp, i32, i32, fp, vp]
+    lib.mile_train_get_state.argtypes = [vp, fp, fp, fp, vp, vp]
     lib.mile_nccl_unique_id.argtypes = [vp]
     lib.mile_shard_init.argtypes = [vp, vp, i32, i32]
     lib.mile_shard_mclmc_init.argtypes = [vp, fp, fp, u64, vp]

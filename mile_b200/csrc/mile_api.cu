@@ -4,6 +4,7 @@
 #include "mile_mma.cuh"
 #include "mile_sharded.cuh"
 #include "mile_wide.cuh"
+#include "mile_train.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -69,6 +70,7 @@ struct mile_ctx {
         *t_wtot = nullptr, *avg_x = nullptr, *avg_x2 = nullptr;
   float *lppd_m = nullptr, *lppd_s = nullptr; long lppd_count = 0;
   float* carry = nullptr; int carry_valid = 0;
+  float *tr_m = nullptr, *tr_v = nullptr; int* tr_t = nullptr;   // warm-start training: AdamW moments [C,d] and step counts [C]
   float2* xchg = nullptr; unsigned int xepoch = 0; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
   void* nccl_comm = nullptr; int world = 1, rank = 0;
@@ -119,9 +121,9 @@ struct Plan {
   KParams kp;  // offsets + model filled in
 };
 
-static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl) {
+static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g = 0) {
   DevModel M = c->M;
-  int G = c->opt_cluster, sync_mode = 0;
+  int G = force_g > 0 ? force_g : c->opt_cluster, sync_mode = 0;
   if (G <= 0) {
     if (n_chains * 8 <= 128) G = 8; else if (n_chains * 4 <= 148) G = 4; else if (n_chains * 2 <= 148) G = 2; else G = 1;
     while (G > 1 && nrows_for_split / G < 64) G >>= 1;
@@ -390,6 +392,21 @@ static void* scratch(mile_ctx* c, int slot, size_t bytes) {
   return s.first;
 }
 
+template <int NLMAX>
+static int launch_train(const TrainParams& T, int n_chains, size_t smem, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(mile_train_kernel<NLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  mile_train_kernel<NLMAX><<<n_chains, MILE_THREADS, smem, st>>>(T);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <int NLMAX>
+static int launch_metrics(const MetricsParams& T, int n, size_t smem, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(mile_metrics_kernel<NLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  mile_metrics_kernel<NLMAX><<<n, MILE_THREADS, smem, st>>>(T);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" {
 
 static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st);
@@ -444,7 +461,7 @@ void mile_destroy(mile_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
-                  c->gl, c->scal, c->thb, c->ub, c->gb, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
+                  c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
                   c->w_ones, c->w_gl, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
@@ -855,6 +872,102 @@ int mile_predict(mile_ctx* c, const float* theta_dev, int32_t n, int32_t which, 
   fill_common(c, pl.kp);
   pl.kp.C = n; pl.kp.mode = MODE_PREDICT; pl.kp.theta_in = theta_dev; pl.kp.pred_out = out_dev; pl.kp.which = which;
   return launch(c, pl, n, (cudaStream_t)stream);
+}
+
+
+// ---- deep-ensemble warm-start training (mile_train.cuh) ---------------------------------------------------------
+int mile_train_init(mile_ctx* c, const float* theta0_dev, void* stream) {
+  if (!c || !theta0_dev) return fail("null argument");
+  if (c->wide) return fail("warm-start training is implemented for the shared-memory models only");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (!c->tr_m) { CK(cudaMalloc(&c->tr_m, Cd)); CK(cudaMalloc(&c->tr_v, Cd)); CK(cudaMalloc(&c->tr_t, (size_t)c->C * 4)); }
+  CK(cudaMemcpyAsync(c->theta, theta0_dev, Cd, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(c->tr_m, 0, Cd, st)); CK(cudaMemsetAsync(c->tr_v, 0, Cd, st)); CK(cudaMemsetAsync(c->tr_t, 0, (size_t)c->C * 4, st));
+  c->carry_valid = 0;
+  return 0;
+}
+
+int mile_train_epoch(mile_ctx* c, const int32_t* batch_idx_dev, int32_t n_batches, int32_t batch_size, const mile_opt_cfg* opt,
+                     const uint8_t* stopped_dev, float* metrics_dev, void* stream) {
+  if (!c || !batch_idx_dev || !opt) return fail("null argument");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (!c->tr_m) return fail("mile_train_init has not been called");
+  if (n_batches < 0 || batch_size < 1 || batch_size > 256) return fail("batch_size must be in [1, 256] and n_batches >= 0");
+  if (opt->kind < 0 || opt->kind > 2) return fail("unknown optimizer kind");
+  if (n_batches == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  const int keep_fast = c->opt_fast, keep_tr = c->opt_tile_rows;
+  c->opt_fast = 0; c->opt_tile_rows = 0;       // the generic tile evaluator serves any FCN shape
+  Plan pl;
+  const int rc = make_plan(c, c->C, batch_size, false, pl, 1);
+  c->opt_fast = keep_fast; c->opt_tile_rows = keep_tr;
+  if (rc) return -1;
+  fill_common(c, pl.kp);
+  TrainParams T;
+  memset(&T, 0, sizeof(T));
+  T.K = pl.kp; T.K.G = 1; T.K.resident = 0; T.K.C = c->C;
+  T.batch_idx = batch_idx_dev; T.n_batches = n_batches; T.B = batch_size;
+  T.opt_kind = opt->kind; T.lr = opt->learning_rate; T.b1 = opt->b1; T.b2 = opt->b2; T.eps = opt->eps; T.wd = opt->weight_decay;
+  T.stopped = stopped_dev; T.metrics = metrics_dev; T.m = c->tr_m; T.v = c->tr_v; T.t = c->tr_t;
+  T.off_y = (int)(pl.smem / 4);
+  const size_t smem = pl.smem + 256 * 4;
+  if (smem > kSmemLimit) return fail("model too large for the training kernel (shared memory)");
+  const int NL = c->M.NL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r2;
+  if (NL <= 2) r2 = launch_train<2>(T, c->C, smem, st);
+  else if (NL <= 3) r2 = launch_train<3>(T, c->C, smem, st);
+  else if (NL <= 4) r2 = launch_train<4>(T, c->C, smem, st);
+  else if (NL <= 6) r2 = launch_train<6>(T, c->C, smem, st);
+  else if (NL <= 8) r2 = launch_train<8>(T, c->C, smem, st);
+  else r2 = launch_train<12>(T, c->C, smem, st);
+  if (r2 == 0) c->launches++;
+  c->carry_valid = 0;
+  return r2;
+}
+
+int mile_eval_metrics(mile_ctx* c, const float* theta_dev, int32_t n, int32_t which, float* out_dev, void* stream) {
+  if (!c || !out_dev) return fail("null argument");
+  if (which ? !c->Xt : !c->X) return fail("requested split has not been set");
+  if (c->wide) return fail("mile_eval_metrics is implemented for the shared-memory models only");
+  if (!theta_dev) { theta_dev = c->theta; n = c->C; }
+  if (n < 1) return fail("n must be >= 1");
+  CK(cudaSetDevice(c->device));
+  const int keep_fast = c->opt_fast;
+  c->opt_fast = 0;
+  Plan pl;
+  const int rc = make_plan(c, n, which ? c->Nt : c->N, false, pl, 1);
+  c->opt_fast = keep_fast;
+  if (rc) return -1;
+  fill_common(c, pl.kp);
+  MetricsParams T;
+  memset(&T, 0, sizeof(T));
+  T.K = pl.kp; T.K.C = n; T.K.theta_in = theta_dev; T.K.which = which; T.out = out_dev;
+  const int NL = c->M.NL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r2;
+  if (NL <= 2) r2 = launch_metrics<2>(T, n, pl.smem, st);
+  else if (NL <= 3) r2 = launch_metrics<3>(T, n, pl.smem, st);
+  else if (NL <= 4) r2 = launch_metrics<4>(T, n, pl.smem, st);
+  else if (NL <= 6) r2 = launch_metrics<6>(T, n, pl.smem, st);
+  else if (NL <= 8) r2 = launch_metrics<8>(T, n, pl.smem, st);
+  else r2 = launch_metrics<12>(T, n, pl.smem, st);
+  if (r2 == 0) c->launches++;
+  return r2;
+}
+
+int mile_train_get_state(mile_ctx* c, float* theta_dev, float* m_dev, float* v_dev, int32_t* t_dev, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->tr_m) return fail("mile_train_init has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  if (theta_dev) CK(cudaMemcpyAsync(theta_dev, c->theta, Cd, cudaMemcpyDeviceToDevice, st));
+  if (m_dev) CK(cudaMemcpyAsync(m_dev, c->tr_m, Cd, cudaMemcpyDeviceToDevice, st));
+  if (v_dev) CK(cudaMemcpyAsync(v_dev, c->tr_v, Cd, cudaMemcpyDeviceToDevice, st));
+  if (t_dev) CK(cudaMemcpyAsync(t_dev, c->tr_t, (size_t)c->C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 #ifdef MILE_PROFILE

@@ -265,7 +265,11 @@ __device__ __forceinline__ void bwd_layer(const DevModel& M, int l, const float*
 template <int NT>
 __device__ __forceinline__ float loglik_rows(const DevModel& M, const float* __restrict__ Out,
                                              float* __restrict__ Dout, int so, const void* __restrict__ y,
-                                             long row0, int nvalid, int rows_pad) {
+                                             long row0, int nvalid, int rows_pad, float sig_lo = 1e-6f,
+                                             float* metric = nullptr) {
+  // sig_lo: lower clip of sigma (1e-6 in the log-posterior, probabilistic.py:100; 1e-5 in the warm-start training loss,
+  // where GaussianNLLLoss clips once more, src/inference/metrics.py:332).  metric (optional, per-thread accumulator):
+  // sum of squared errors (regression) / number of correct argmax predictions (classification).
   const int K = M.dims[M.NL], KP = M.dimp[M.NL];
   float part = 0.f;
   for (int r = threadIdx.x; r < rows_pad; r += NT) {
@@ -280,14 +284,15 @@ __device__ __forceinline__ float loglik_rows(const DevModel& M, const float* __r
       const float yv = reinterpret_cast<const float*>(y)[row0 + r];
       const float mu = o[0], s = o[1];
       const float e = expf(s);
-      const float sigma = fminf(fmaxf(e, 1e-6f), 1e6f);
-      const float inside = (e > 1e-6f && e < 1e6f) ? 1.f : 0.f;
+      const float sigma = fminf(fmaxf(e, sig_lo), 1e6f);
+      const float inside = (e > sig_lo && e < 1e6f) ? 1.f : 0.f;
       const float s2 = sigma * sigma;
       const float res = yv - mu;
       const float q = res * res / s2;
       ll = (logf(6.283185307179586f * s2) + q) / -2.f;
       float dmu = res / s2, ds = (q - 1.f) * inside;
       if (isnan(ll)) { ll = 0.f; dmu = 0.f; ds = 0.f; }
+      if (metric) *metric += res * res;
       dd[0] = dmu * M.n_batches; dd[1] = ds * M.n_batches;
       for (int k = 2; k < KP; ++k) dd[k] = 0.f;
     } else {
@@ -299,6 +304,7 @@ __device__ __forceinline__ float loglik_rows(const DevModel& M, const float* __r
       const float lse = m + logf(se);
       ll = o[yi] - lse;
       const bool bad = isnan(ll);
+      if (metric) { int am = 0; for (int k = 1; k < K; ++k) if (o[k] > o[am]) am = k; *metric += am == yi ? 1.f : 0.f; }
       const float inv = 1.f / se;
       for (int k = 0; k < K; ++k) {
         float g = -expf(o[k] - m) * inv + (k == yi ? 1.f : 0.f);

@@ -61,6 +61,8 @@ struct Ctx {
   int rank, G, chain;
   // element-split mode (ES, wide / large-d integrator): the d elements are strided over the CTAs of a cluster
   int e0, estride; float* csum; int csum_phase;
+  // warm-start training overrides (mile_train.cuh): labels of the gathered minibatch, X always in c.xbuf, sigma clip, metric
+  const void* y_override = nullptr; int force_resident = 0; float sig_lo = 1e-6f; float* metric = nullptr;
   bool lead;   // the one thread that reports per-chain scalars (thread 0 of the block; lane 0 of the integrator warp in warp mode)
   __device__ Ctx(const KParams& p) : P(p) {}
 };
@@ -139,7 +141,7 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
     const int Q = (((nvalid + 3) >> 2) + 7) & ~7;
     const int rows_pad = Q * 4;
     const float* Xt;
-    if (P.resident) {
+    if (P.resident || c.force_resident) {
       Xt = c.xbuf + (long)t * TR * M.sA[0];
     } else {
       load_x_tile<NT>(c.xbuf, P.X, row0, nvalid, rows_pad, M.sA[0]);
@@ -149,7 +151,8 @@ __device__ __forceinline__ void grad_eval(Ctx& c, long r0, long r1, float* gpart
     PROF(0);
     const float* out = forward_tile<NT>(c, Xt, Q);
     PROF(1);
-    llpart += loglik_rows<NT>(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], P.y, row0, nvalid, rows_pad);
+    llpart += loglik_rows<NT>(M, out, c.tile + M.d_off[M.NL - 1], M.sA[M.NL], c.y_override ? c.y_override : P.y, row0, nvalid,
+                              rows_pad, c.sig_lo, c.metric);
     __syncthreads();
     PROF(2);
     for (int l = M.NL - 1; l >= 1; --l) {

@@ -297,6 +297,66 @@ class Ensemble:
         return out.cpu().numpy()
 
 
+    # ---- deep-ensemble warm-start training (trainer.py:330-538) ----------------------------------------
+    def _to_dev(self, a, dtype=np.float32):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(f'cuda:{self.device}')
+
+    def train_init(self, theta0):
+        """Parameters of all members [C, d]; optimizer moments and step counts are zeroed."""
+        import torch
+        t = self._to_dev(np.reshape(theta0, (self.n_chains, self.d)))
+        capi.check(self.lib.mile_train_init(self.h, _dev_ptr(t), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    @staticmethod
+    def opt_cfg(name='adamw', learning_rate=1e-3, b1=0.9, b2=0.999, eps=1e-8, weight_decay=None, **unknown) -> capi.OptCfg:
+        """optax.<name>(**parameters) of the reference's OptimizerConfig (src/config/warmstart.py:17-41) with optax's
+        defaults (adamw: weight_decay 1e-4; adam / sgd: none)."""
+        if unknown:
+            raise NotImplementedError(f'optimizer parameters {sorted(unknown)} are not supported on the CUDA path')
+        name = str(name).lower()
+        if name not in capi.OPTIMIZERS:
+            raise NotImplementedError(f'optimizer {name!r} is not supported on the CUDA path')
+        wd = (1e-4 if weight_decay is None else weight_decay) if name == 'adamw' else 0.0
+        return capi.OptCfg(capi.OPTIMIZERS[name], learning_rate, b1, b2, eps, wd)
+
+    def train_epoch(self, batch_idx, opt: capi.OptCfg, stopped=None, metrics=True):
+        """One epoch = one launch.  batch_idx [n_batches, B] int32 rows of the training split (shared by all members);
+        stopped [C] bool.  Returns [n_batches, C, 2] = (loss, RMSE | accuracy) per step, NaN for stopped members."""
+        import torch
+        batch_idx = np.ascontiguousarray(batch_idx, dtype=np.int32)
+        nb, B = batch_idx.shape
+        if batch_idx.size and (batch_idx.min() < 0 or batch_idx.max() >= self.n_train):
+            raise ValueError('batch index out of range')
+        bi = self._to_dev(batch_idx, np.int32)
+        st = None if stopped is None else self._to_dev(np.asarray(stopped, dtype=np.uint8), np.uint8)
+        out = torch.empty((nb, self.n_chains, 2), dtype=torch.float32, device=bi.device) if metrics else None
+        capi.check(self.lib.mile_train_epoch(self.h, _dev_ptr(bi), nb, B, C.byref(opt), _dev_ptr(st), _dev_ptr(out),
+                                             _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return None if out is None else out.cpu().numpy()
+
+    def eval_metrics(self, theta=None, which='test'):
+        """predict_regr / predict_class: (mean loss, RMSE | accuracy) per parameter row over a split -> [n, 2]."""
+        import torch
+        t = None if theta is None else self._to_dev(np.reshape(theta, (-1, self.d)))
+        n = self.n_chains if t is None else t.shape[0]
+        out = torch.empty((n, 2), dtype=torch.float32, device=f'cuda:{self.device}')
+        capi.check(self.lib.mile_eval_metrics(self.h, _dev_ptr(t), n, 1 if which == 'test' else 0, _dev_ptr(out), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy()
+
+    def train_state(self):
+        import torch
+        dev = f'cuda:{self.device}'
+        th, m, v = (torch.empty((self.n_chains, self.d), dtype=torch.float32, device=dev) for _ in range(3))
+        t = torch.empty(self.n_chains, dtype=torch.int32, device=dev)
+        capi.check(self.lib.mile_train_get_state(self.h, _dev_ptr(th), _dev_ptr(m), _dev_ptr(v), _dev_ptr(t), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return th.cpu().numpy(), m.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy()
+
+
 class ShardedEnsemble(Ensemble):
     """Data-sharded variant (covertype): every rank holds all chains and 1/world of the
     training rows; gradients are all-reduced over NCCL at every evaluation.  Call `set_data` with the LOCAL shard."""
