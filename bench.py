@@ -308,9 +308,11 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
             ens.set_option('fast', args.fast)
         if args.steploop >= 0:
             ens.set_option('steploop', args.steploop)
+        if args.kslices > 0:
+            ens.set_option('kslices', args.kslices)
     ens.set_data(X, y)
     wide = bool(ens.get_option('wide'))
-    fused_lppd = not wide and not sharded
+    fused_lppd = not sharded          # (the wide path folds through its forward GEMMs, the others inside the sampler kernel)
     if fused_lppd:
         ens.set_test(Xt, yt)      # fused posterior-predictive LPPD fold at every kept sample
     crank = 0 if sharded else rank        # sharded: every rank carries the SAME chains (same seeds, same noise)
@@ -576,6 +578,7 @@ def main():
     ap.add_argument('--tensor', type=int, default=-1, help='wide path: 1 = tcgen05 3xTF32 GEMM core, 0 = FP32 SIMT core')
     ap.add_argument('--fast', type=int, default=-1, help='narrow-MLP evaluator: 2 = 3xTF32 register MMA (default), 1 = FFMA layer pipeline, 0 = generic tiles')
     ap.add_argument('--steploop', type=int, default=-1, help='1 = integrator-warp step loop of the tensor evaluator (default), 0 = generic loop')
+    ap.add_argument('--kslices', type=int, default=0, help='wide path: split-K slices of the dW GEMMs (0 = auto)')
     ap.add_argument('--no-tune', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip extra.workloads (the other named shapes)')

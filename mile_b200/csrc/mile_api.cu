@@ -60,7 +60,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0, opt_steploop = 1;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0, opt_steploop = 1, opt_kslices = 0;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -73,12 +73,14 @@ struct mile_ctx {
   float *tr_m = nullptr, *tr_v = nullptr; int* tr_t = nullptr;   // warm-start training: AdamW moments [C,d] and step counts [C]
   float2* xchg = nullptr; unsigned int xepoch = 0; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
-  void* nccl_comm = nullptr; int world = 1, rank = 0;
+  void* nccl_comm = nullptr; int world = 1, rank = 0; int shard_lppd = 0;
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
   // wide / large-d path (mile_wide.cuh): HBM-resident activations, chain-batched GEMMs
   int wide = 0; long w_rows = 0; int w_chains = 0, w_kslices = 1, w_nblk = 0;
   float *w_act = nullptr, *w_delta[2] = {nullptr, nullptr}, *w_part = nullptr, *w_llpart = nullptr, *w_ones = nullptr;
   float* w_gl = nullptr;   // packed [n, d+1] output of a stand-alone value_and_grad call
+  float* wp_act = nullptr; size_t wp_act_floats = 0;   // activations of a forward-only pass over a split (mile_predict / LPPD)
+  float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
   float *w_wpk = nullptr, *w_wpk_lo = nullptr, *w_wpkT = nullptr,
@@ -300,7 +302,8 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   CK(cudaSetDevice(c->device));
   pl.kp.sync_mode = pl.sync_mode;
   if (pl.sync_mode) {
-    const size_t need = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4) * sizeof(float2);
+    const size_t nA = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4), nB = (size_t)n_chains * 2 * (pl.kp.dS + 4);
+    const size_t need = (nA + nB) * sizeof(float2);   // partials of every rank + the summed slices (reduce-scatter form)
     const unsigned int adv = 2u * (unsigned int)(pl.kp.n_steps > 0 ? pl.kp.n_steps : 0) + 2u;
     if (need > c->xchg_bytes || c->xepoch > 0xF0000000u - adv) {   // (re)allocate, or restart the flag epoch before it wraps
       if (need > c->xchg_bytes) {
@@ -312,6 +315,7 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
       c->xepoch = 0;
     }
     pl.kp.xchg = c->xchg; pl.kp.xbase = c->xepoch;   // flags of this launch: xbase+1 .. xbase+n_evals (never 0, never reused)
+    pl.kp.xchg2 = c->xchg + nA;
     c->xepoch += adv;
   }
   const int NL = c->M.NL;
@@ -409,6 +413,10 @@ static int launch_metrics(const MetricsParams& T, int n, size_t smem, cudaStream
 
 extern "C" {
 
+static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st);
+static int wide_predict(mile_ctx* c, const float* theta, int n, int which, float* out, cudaStream_t st);
+static int wide_lppd_fold(mile_ctx* c, const float* theta, int n, cudaStream_t st);
+static int wide_alloc(mile_ctx* c, int n_chains);
 static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st);
 
 const char* mile_last_error(void) { return g_err.c_str(); }
@@ -462,7 +470,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
+                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -482,6 +490,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
+  else if (!strcmp(key, "kslices")) { c->opt_kslices = (int)v; c->w_rows = -1; }   // wide path: split-K slices of the dW GEMMs (0 = auto)
   else if (!strcmp(key, "steploop")) c->opt_steploop = (int)v;   // 1: integrator-warp step loop of the tensor evaluator, 0: generic loop
   else return fail(std::string("unknown option ") + key);
   return 0;
@@ -691,10 +700,18 @@ int mile_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n
   if (n_steps == 0) return 0;
   if (lppd && !c->wide && !c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
   if (c->wide) {
-    if (lppd) return fail("the fused LPPD fold is not available on the wide path");
     if (!c->gl && mile_shard_init(c, nullptr, 0, 1)) return -1;
-    return mile_shard_mclmc_sample(c, n_steps, step_base, n_thinning, sample_base, step_size_dev, L_dev, z_dev, seed,
-                                   samples_dev, n_slots, info_dev, stream);
+    if (lppd && !c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
+    c->shard_lppd = lppd ? 1 : 0;      // shard_run folds every kept position through the wide forward pass
+    const int rc = mile_shard_mclmc_sample(c, n_steps, step_base, n_thinning, sample_base, step_size_dev, L_dev, z_dev, seed,
+                                           samples_dev, n_slots, info_dev, stream);
+    c->shard_lppd = 0;
+    if (rc) return rc;
+    if (lppd) {
+      const long first = (step_base + n_thinning - 1) / n_thinning, last = (step_base + n_steps - 1) / n_thinning;
+      c->lppd_count += (last >= first) ? (last - first + 1) : 0;
+    }
+    return 0;
   }
   Plan pl;
   if (make_plan(c, c->C, c->N, true, pl)) return -1;
@@ -840,6 +857,11 @@ int mile_lppd_accumulate(mile_ctx* c, const float* theta_dev, int32_t n, void* s
   if (!c->Xt) return fail("mile_set_test has not been called");
   if (n < 1 || n > c->C) return fail("n must be in [1, n_chains]");
   if (!c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
+  if (c->wide) {
+    if (wide_lppd_fold(c, theta_dev, n, (cudaStream_t)stream)) return -1;
+    c->lppd_count += 1;
+    return 0;
+  }
   Plan pl;
   if (make_plan(c, c->C, c->Nt, false, pl)) return -1;
   fill_common(c, pl.kp);
@@ -867,6 +889,7 @@ int mile_predict(mile_ctx* c, const float* theta_dev, int32_t n, int32_t which, 
   if (!c) return fail("null ctx");
   if (which ? !c->Xt : !c->X) return fail("requested split has not been set");
   if (n < 1) return fail("n must be >= 1");
+  if (c->wide) return wide_predict(c, theta_dev, n, which, out_dev, (cudaStream_t)stream);
   Plan pl;
   if (make_plan(c, n, which ? c->Nt : c->N, false, pl)) return -1;
   fill_common(c, pl.kp);
@@ -1047,10 +1070,11 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
       if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
       if (eff >= 0.95 && waves >= 2) { best = ks; break; }
     }
-    c->w_kslices = best;
+    c->w_kslices = c->opt_kslices > 0 ? c->opt_kslices : best;
   }
   c->w_nblk = (int)((N + 255) / 256);
-  const size_t actb = (size_t)n_chains * N8 * act_per_row * 4, delb = (size_t)n_chains * N8 * maxw * 4;
+  // (+64: a context that only predicts has no training rows yet; the cache check above needs non-null buffers)
+  const size_t actb = (size_t)n_chains * N8 * act_per_row * 4 + 64, delb = (size_t)n_chains * N8 * maxw * 4 + 64;
   CK(cudaMalloc(&c->w_act, actb));
   CK(cudaMalloc(&c->w_delta[0], delb)); CK(cudaMalloc(&c->w_delta[1], delb));
   CK(cudaMalloc(&c->w_wpk, (size_t)n_chains * wsum * 4)); CK(cudaMalloc(&c->w_wpk_lo, (size_t)n_chains * wsum * 4));
@@ -1061,8 +1085,8 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
   CK(cudaMemset(c->w_wpk, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpk_lo, 0, (size_t)n_chains * wsum * 4));
   c->w_part_per_chain = (long)c->w_kslices * maxio;
   CK(cudaMalloc(&c->w_part, (size_t)n_chains * c->w_kslices * maxio * 4));
-  CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4));
-  CK(cudaMalloc(&c->w_ones, (size_t)N * 4));
+  CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4 + 64));
+  CK(cudaMalloc(&c->w_ones, (size_t)N * 4 + 64));
   CK(cudaMalloc(&c->w_gl, (size_t)n_chains * (c->d + 1) * 4));
   fill_kernel<<<148, 256>>>(c->w_ones, N, 1.f);
   CK(cudaGetLastError());
@@ -1196,16 +1220,13 @@ static int wide_rowreduce(mile_ctx* c, const float* Wd, long wd_batch, long wd_l
   return 0;
 }
 
-// value_and_grad of n chains (theta [n,d]) over the local rows into the packed buffer gl [n, d+1]
-static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st) {
-  if (wide_alloc(c, n > c->C ? n : c->C)) return -1;
-  if (!gl) gl = c->w_gl;
+// forward pass of n chains over the rows of one split: activations a_1..a_NL into actbuf ([n][N8][dims[l]] each, a_NL last)
+static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st) {
   const DevModel& M = c->M;
-  const long N = c->N, N8 = c->w_n8;          // buffers hold N8 rows per chain (pad rows stay zero)
   const int d = c->d, NL = M.NL;
-  std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N8][dims[l]]
+  std::vector<long> aoff(NL + 2, 0);
   for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
-  auto act = [&](int l) { return c->w_act + aoff[l]; };
+  auto act = [&](int l) { return actbuf + aoff[l]; };
   const bool tc2 = c->opt_tensor >= 2;
   if (tc2) {                                  // aligned packed copies of the weights + their tf32 remainders
     for (int l = 0; l < NL; ++l) {
@@ -1218,7 +1239,7 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   for (int l = 0; l < NL; ++l) {              // forward
     GemmArgs g; memset(&g, 0, sizeof(g));
     const int IN = M.dims[l], OUT = M.dims[l + 1];
-    if (l == 0) { g.A = c->X; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
+    if (l == 0) { g.A = Xs; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
     else { g.A = act(l); g.a_batch = N8 * IN; g.sam = IN; g.sak = 1; }
     if (tc2) {   // W^T [OUT x IN]: K-major B for the TMA-fed core (MN-major tf32 operands are not used)
       g.B = c->w_wpkT + c->w_woff[l]; g.B_lo = c->w_wpkT_lo + c->w_woff[l]; g.b_batch = c->w_wstride; g.sbk = 1; g.sbn = IN;
@@ -1231,6 +1252,59 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
       if (wide_skinny(c, g, st)) return -1;
     } else if (wide_gemm(c, g, st)) return -1;
   }
+  return 0;
+}
+
+// forward-only pass of n chains over a split (which: 0 train, 1 test) -> out [n][N][K]
+static int wide_predict(mile_ctx* c, const float* theta, int n, int which, float* out, cudaStream_t st) {
+  if (wide_alloc(c, n > c->C ? n : c->C)) return -1;        // packed-weight buffers and their offsets
+  const DevModel& M = c->M;
+  const float* Xs = which ? c->Xt : c->X;
+  const long N = which ? c->Nt : c->N, N8 = (N + 7) / 8 * 8;
+  long per_row = 0, before_last = 0;
+  for (int l = 1; l <= M.NL; ++l) { if (l == M.NL) before_last = per_row; per_row += M.dims[l]; }
+  const size_t need = (size_t)n * N8 * per_row;
+  if (need > c->wp_act_floats) {
+    if (c->wp_act) { CK(cudaFree(c->wp_act)); c->wp_act = nullptr; c->wp_act_floats = 0; }
+    c->tmaps.clear();
+    CK(cudaMalloc(&c->wp_act, need * 4));
+    c->wp_act_floats = need;
+  }
+  CK(cudaMemsetAsync(c->wp_act, 0, need * 4, st));            // pad rows (N..N8) must stay finite for the tensor tiles
+  if (wide_forward(c, theta, n, Xs, N, N8, c->wp_act, st)) return -1;
+  const int K = M.dims[M.NL];
+  const float* last = c->wp_act + (size_t)n * N8 * before_last;
+  CK(cudaMemcpy2DAsync(out, (size_t)N * K * 4, last, (size_t)N8 * K * 4, (size_t)N * K * 4, n, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// fold theta [n,d] (row c = chain c) into the per-chain online logsumexp state through the wide forward pass
+static int wide_lppd_fold(mile_ctx* c, const float* theta, int n, cudaStream_t st) {
+  const size_t need = (size_t)n * c->Nt * c->M.dims[c->M.NL];
+  if (need > c->wp_out_floats) {
+    if (c->wp_out) { CK(cudaFree(c->wp_out)); c->wp_out = nullptr; c->wp_out_floats = 0; }
+    CK(cudaMalloc(&c->wp_out, need * 4));
+    c->wp_out_floats = need;
+  }
+  if (wide_predict(c, theta, n, 1, c->wp_out, st)) return -1;
+  wide_lppd_fold_kernel<<<296, 256, 0, st>>>(c->M, c->wp_out, c->yt, c->lppd_m, c->lppd_s, n, c->Nt);
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// value_and_grad of n chains (theta [n,d]) over the local rows into the packed buffer gl [n, d+1]
+static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st) {
+  if (wide_alloc(c, n > c->C ? n : c->C)) return -1;
+  if (!gl) gl = c->w_gl;
+  const DevModel& M = c->M;
+  const long N = c->N, N8 = c->w_n8;          // buffers hold N8 rows per chain (pad rows stay zero)
+  const int d = c->d, NL = M.NL;
+  std::vector<long> aoff(NL + 2, 0);          // activation buffers a_1..a_NL, each [n][N8][dims[l]]
+  for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
+  auto act = [&](int l) { return c->w_act + aoff[l]; };
+  const bool tc2 = c->opt_tensor >= 2;
+  if (wide_forward(c, theta, n, c->X, N, N8, c->w_act, st)) return -1;
   float* dcur = c->w_delta[(NL - 1) & 1];
   wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, N8, c->w_llpart);
   CK(cudaGetLastError());
@@ -1357,6 +1431,7 @@ static int shard_run(mile_ctx* c, ShardParams& S, int n_steps, cudaStream_t st) 
     if (shard_integ(c, S, SH_MID, s, st)) return -1;
     if (shard_eval(c, st)) return -1;
     if (shard_integ(c, S, SH_END, s, st)) return -1;
+    if (c->shard_lppd && c->wide && !S.tune && (S.K.step_base + s) % S.K.thin == 0 && wide_lppd_fold(c, c->theta, c->C, st)) return -1;
   }
   c->carry_valid = 0;
   return 0;

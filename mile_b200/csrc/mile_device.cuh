@@ -118,17 +118,26 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// One standard normal for (seed, chain, step, stream, element) via Box-Muller.
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t chain, uint64_t step,
-                                               uint32_t stream, uint32_t elem) {
+// Two standard normals for (seed, chain, step, stream, element pair) via Box-Muller: elements 2p and 2p + 1 of a
+// noise vector are the cosine and sine branches of ONE Philox draw (counter word 0 = p).
+__device__ __forceinline__ void philox_normal2(uint64_t seed, uint32_t chain, uint64_t step, uint32_t stream, uint32_t pair,
+                                               float& z0, float& z1) {
   uint32_t r[4];
-  philox4x32_10(elem, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed ^ (chain * 0x9E3779B9u),
+  philox4x32_10(pair, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed ^ (chain * 0x9E3779B9u),
                 (uint32_t)(seed >> 32) + chain, r);
   const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
   const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   float s, c;
   sincospif(2.0f * u2, &s, &c);
-  return sqrtf(-2.0f * logf(u1)) * c;
+  const float rad = sqrtf(-2.0f * logf(u1));
+  z0 = rad * c; z1 = rad * s;
+}
+// One standard normal for (seed, chain, step, stream, element).
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t chain, uint64_t step,
+                                               uint32_t stream, uint32_t elem) {
+  float z0, z1;
+  philox_normal2(seed, chain, step, stream, elem >> 1, z0, z1);
+  return (elem & 1u) ? z1 : z0;
 }
 
 // activation value and derivative (src/config/models/base.py:24-37; jax.nn semantics)

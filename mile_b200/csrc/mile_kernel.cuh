@@ -42,6 +42,7 @@ struct KParams {
   // Exchange words are {value, epoch flag} pairs written with one 8-byte store each (the NCCL "LL" idea): a reader
   // spins on the data word itself, so there is no fence, no atomic counter and no separate barrier on the critical path.
   int sync_mode; float2* xchg; unsigned int xbase;   // xchg [C][2][G][dS+4] (value, flag); flag = xbase + eval + 1
+  float2* xchg2;         // [C][2][dS+4] summed slices of the reduce-scatter form of the exchange (mile_mma_step_kernel)
   int out_stride;        // row stride of grad_out / lp_out (d, or d+1 for the packed [C,d+1] all-reduce buffer)
   float prior_weight;    // 1, or 1/world when the rows are sharded across ranks (the sum over ranks counts the prior once)
   // shared-memory carve-up (float offsets)

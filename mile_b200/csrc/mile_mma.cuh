@@ -410,8 +410,13 @@ struct MmaGE {
       for (int o = tid; o < SCR_WARP; o += NT) {
         const int dst = o < NACC * 32 ? gmapA[o] : gmapS[o - NACC * 32];
         if (dst >= 0) {
+          // all partials of this slot in flight at once (predicated), then summed in warp order
+          float pv[NW];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) pv[w] = w < nact ? region[w * RSTRIDE + o] : 0.f;
           float s = 0.f;
-          for (int w = 0; w < nact; ++w) s += region[w * RSTRIDE + o];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) s += pv[w];
           gpart[dst] = dst == P.dS ? s * nb : s;
         }
       }
@@ -509,11 +514,20 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mma_step_kernel(const __grid_c
   // noise of step s_local into its buffer; `part` of `nparts` (the draws are spread over the idle windows of a step)
   auto draw_noise = [&](long s_local, int t0, int tstride, int part, int nparts) {
     float* zs = zbuf + (s_local & 1) * (2 * dS);
+    const int npair = (d + 1) >> 1;            // one Philox call yields the normals of elements 2p and 2p + 1
     int j = 0;
-    for (int k = t0; k < nslot * d; k += tstride, ++j) {
+    for (int k = t0; k < nslot * npair; k += tstride, ++j) {
       if (j % nparts != part) continue;
-      const int slot = k >= d ? 1 : 0, i = k - slot * d;
-      zs[slot * dS + i] = noise_at(P, ch, s_local, slot, nslot, i);
+      const int slot = k >= npair ? 1 : 0, p2 = (k - slot * npair) * 2;
+      if (P.z) {
+        zs[slot * dS + p2] = noise_at(P, ch, s_local, slot, nslot, p2);
+        if (p2 + 1 < d) zs[slot * dS + p2 + 1] = noise_at(P, ch, s_local, slot, nslot, p2 + 1);
+      } else {
+        float z0, z1;
+        philox_normal2(P.seed, (uint32_t)(P.chain_base + ch), (uint64_t)(P.step_base + s_local), (uint32_t)slot + 1u, (uint32_t)(p2 >> 1), z0, z1);
+        zs[slot * dS + p2] = z0;
+        if (p2 + 1 < d) zs[slot * dS + p2 + 1] = z1;
+      }
     }
   };
   if (P.n_steps > 0) draw_noise(0, tid, NT, 0, 1);
@@ -583,15 +597,24 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mma_step_kernel(const __grid_c
       __syncthreads();
       for (int i = tid; i <= dS; i += NT) ll_store(mine + i, gp[i], xflag);
       PROF(13);
+      // reduce-scatter + all-gather through L2: every CTA sums ONE slice of the G partials (G flagged words per element of
+      // its slice) and republishes the sums; everybody then reads d + 1 summed words.  The all-to-all form (every CTA
+      // polls all G x d words) costs ~770 LSU wavefronts per poll and CTA at G = 12, this form ~60 + ~45.
       const int stride_g = dS + 4;
+      const int SL = (dS + 1 + c.G - 1) / c.G;
+      float2* sums = P.xchg2 + ((long)ch * 2 + (e & 1)) * (dS + 4);
+      for (int j = tid; j < SL; j += NT) {
+        const int idx = c.rank * SL + j;
+        if (idx <= dS) ll_store(sums + idx, ll_sum(slab + idx, stride_g, c.G, xflag), xflag);
+      }
       if (has1) {
         float s0, s1;
-        ll_sum_pair(slab + i0, slab + i1, stride_g, c.G, xflag, s0, s1);
+        ll_sum_pair(sums + i0, sums + i1, 0, 1, xflag, s0, s1);
         c.gg[i0] = s0; c.gg[i1] = s1;
       } else if (has0) {
-        c.gg[i0] = ll_sum(slab + i0, stride_g, c.G, xflag);
+        c.gg[i0] = ll_sum(sums + i0, 0, 1, xflag);
       }
-      if (tid == NT - 1) gp[dS + 1] = ll_sum(slab + dS, stride_g, c.G, xflag);
+      if (tid == NT - 1) gp[dS + 1] = ll_sum(sums + dS, 0, 1, xflag);
       __syncthreads();
     } else {
       // reduce-scatter + all-gather over DSMEM; slices of SL elements over [0, dS] (element dS = log-likelihood)

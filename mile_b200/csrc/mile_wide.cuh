@@ -143,6 +143,14 @@ __global__ void __launch_bounds__(256) wide_smallk_kernel(const GemmArgs g) {
   const bool vec = n + 3 < g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                    (g.epi != 3 || ((g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0));
   const int mend = min(g.M, (int)(blockIdx.x + 1) * 64);
+  // the thread's [K][4] slab of B stays in registers for all of its rows (the kernel was bound by re-reading it from
+  // shared memory once per row: profiles/r1k_launches_wide_4x256.csv, 100 us for a 100 MB output)
+  float wreg[WS_KMAX][4];
+#pragma unroll
+  for (int k = 0; k < WS_KMAX; ++k) {
+    const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    wreg[k][0] = w.x; wreg[k][1] = w.y; wreg[k][2] = w.z; wreg[k][3] = w.w;
+  }
   for (int m = blockIdx.x * 64 + ty; m < mend; m += 4) {
     float a[WS_KMAX];
 #pragma unroll
@@ -150,8 +158,10 @@ __global__ void __launch_bounds__(256) wide_smallk_kernel(const GemmArgs g) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < WS_KMAX; ++k) {
-      const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      o[0] = fmaf(a[k], w.x, o[0]); o[1] = fmaf(a[k], w.y, o[1]); o[2] = fmaf(a[k], w.z, o[2]); o[3] = fmaf(a[k], w.w, o[3]);
+      if (k < g.K) {
+        o[0] = fmaf(a[k], wreg[k][0], o[0]); o[1] = fmaf(a[k], wreg[k][1], o[1]);
+        o[2] = fmaf(a[k], wreg[k][2], o[2]); o[3] = fmaf(a[k], wreg[k][3], o[3]);
+      }
     }
     float x[4] = {0.f, 0.f, 0.f, 0.f};
     if (g.epi == 3) {
@@ -361,6 +371,22 @@ __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const floa
 // gl[c][0..d) += prior gradient * w ; gl[c][d] = n_batches * sum(ll partials) + w * log prior   (one CTA per chain)
 // launched as clusters of WF_CLUSTER CTAs per chain: the d elements are strided over the cluster's threads and the two
 // partial sums are combined over DSMEM in rank order (one CTA per chain would be a latency-bound 200k-element loop)
+// Online logsumexp fold of forward outputs out [n][Nt][K] into the per-chain state (same update as lppd_fold, mile_kernel.cuh)
+__global__ void __launch_bounds__(256) wide_lppd_fold_kernel(DevModel M, const float* __restrict__ out, const void* __restrict__ yt,
+                                                             float* __restrict__ lm, float* __restrict__ ls, int n, long Nt) {
+  const int K = M.dims[M.NL];
+  const long total = (long)n * Nt;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx % Nt;
+    const float lp = pointwise_lppd_row(M, out + idx * K, yt, r);
+    const float m = lm[idx], s = ls[idx];
+    const float nm = fmaxf(m, lp);
+    const float safe = isfinite(nm) ? nm : 0.f;
+    lm[idx] = nm;
+    ls[idx] = s * expf((isfinite(m) ? m : -INFINITY) - safe) + expf(lp - safe);
+  }
+}
+
 #define WF_CLUSTER 8
 __global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
                                                             const float* __restrict__ llpart, int nblk, float prior_weight) {

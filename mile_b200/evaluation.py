@@ -53,6 +53,9 @@ def _forward_rows(spec: FCNSpec, theta: np.ndarray, x: np.ndarray, device: int |
     n, K = theta.shape[0], spec.widths[-1]
     out = np.empty((n, x.shape[0], K), np.float32)
     chunk = max(1, min(chunk, n, max(1, (1 << 28) // max(1, x.shape[0] * K))))   # <= 1 GiB of outputs per launch
+    if spec.n_params > 20000:
+        # wide models run layer by layer with HBM-resident activations [chunk, rows, sum(widths)]: keep them under ~2 GiB
+        chunk = max(1, min(chunk, (1 << 29) // max(1, x.shape[0] * sum(spec.widths))))
     ens = Ensemble(spec, chunk, device=device)
     try:
         dummy_y = np.zeros(x.shape[0], np.float32 if spec.task.startswith('regr') else np.int32)

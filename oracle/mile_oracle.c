@@ -201,12 +201,14 @@ static inline void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 float mo_philox_normal(uint64_t seed, uint32_t chain, uint64_t step, uint32_t stream, uint32_t elem) {
+  /* elements 2p and 2p + 1 are the cosine and sine branches of one draw (counter word 0 = p), as on the device */
   uint32_t r[4];
-  philox(elem, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed ^ (chain * 0x9E3779B9u),
+  philox(elem >> 1, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed ^ (chain * 0x9E3779B9u),
          (uint32_t)(seed >> 32) + chain, r);
   const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+  const float rad = sqrtf(-2.0f * logf(u1)), ang = 6.283185307179586f * u2;
+  return (elem & 1u) ? rad * sinf(ang) : rad * cosf(ang);
 }
 
 /* B-step (literal blackjax formula, fp32). Returns the kinetic-energy change of this sub-step. */

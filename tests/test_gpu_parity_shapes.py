@@ -290,3 +290,44 @@ def test_chain_base_decorrelates_partitioned_ensembles():
     np.testing.assert_array_equal(outs[3][0][:2], outs[0][0])        # block 0 of the 4-chain ensemble
     np.testing.assert_array_equal(outs[3][0][2:], outs[2][0])        # block 1 == the chain_base = 2 context
     np.testing.assert_array_equal(outs[3][1][2:], outs[2][1])
+
+
+def test_wide_path_predict_and_lppd_match_oracle():
+    """models on the HBM-resident wide path (here 2 x 256) are evaluated through the same entry points as the
+    shared-memory ones: mile_predict, mile_lppd_accumulate and the lppd=1 fold during sampling."""
+    from mile_b200 import Ensemble, FCNSpec, lppd_from_state
+    from mile_b200.evaluation import _forward_rows
+    F, N, Nt, C, S = 12, 700, 333, 3, 3
+    widths = (256, 256, 2)
+    ospec = o.ModelSpec(F, widths, 'relu', 'regr')
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, F)).astype(np.float32); y = rng.standard_normal(N).astype(np.float32)
+    Xt = rng.standard_normal((Nt, F)).astype(np.float32); yt = rng.standard_normal(Nt).astype(np.float32)
+    d = ospec.n_params
+    thetas = (rng.standard_normal((S, C, d)) * 0.04).astype(np.float32)
+    spec = FCNSpec(F, widths, 'relu', 'regr')
+    ens = Ensemble(spec, C)
+    ens.set_data(X, y); ens.set_test(Xt, yt)
+    assert ens.get_option('wide') == 1
+    out = ens.predict(thetas[0], 'test')
+    ref = np.stack([o.forward(ospec, thetas[0, c].astype(np.float64), Xt.astype(np.float64)) for c in range(C)])
+    assert rel(out, ref) <= 1e-5
+    assert rel(_forward_rows(spec, thetas.reshape(-1, d), Xt, None, 4096), np.stack(
+        [o.forward(ospec, t.astype(np.float64), Xt.astype(np.float64)) for t in thetas.reshape(-1, d)])) <= 1e-5
+    for s in range(S):
+        ens.lppd_accumulate(thetas[s])
+    m, sst, cnt = ens.lppd_state()
+    assert cnt == S
+    lv = np.stack([[o.forward(ospec, thetas[s, c].astype(np.float64), Xt.astype(np.float64)) for s in range(S)] for c in range(C)])
+    want = o.lppd(o.pointwise_lppd(ospec, lv, yt.astype(np.float64)))
+    assert abs(lppd_from_state(m, sst, C * S) - want) <= 1e-5 * abs(want)
+    # fused fold during sampling == post-hoc fold of the kept positions
+    ens.lppd_reset()
+    ens.init(thetas[0], seed=3)
+    samples, _ = ens.sample(6, 0.005, float(np.sqrt(d)), n_thinning=3, seed=7, lppd=True)
+    m, sst, cnt = ens.lppd_state()
+    assert cnt == 2 and samples.shape[0] == 2
+    lv = np.stack([[o.forward(ospec, samples[k, c].astype(np.float64), Xt.astype(np.float64)) for k in range(2)] for c in range(C)])
+    want = o.lppd(o.pointwise_lppd(ospec, lv, yt.astype(np.float64)))
+    assert abs(lppd_from_state(m, sst, C * 2) - want) <= 1e-5 * abs(want)
+    ens.close()
