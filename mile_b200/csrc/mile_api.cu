@@ -1068,7 +1068,7 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
       const long tiles = mt * nt * n_chains * ks, waves = (tiles + c->n_sms - 1) / c->n_sms;
       const double eff = (double)tiles / (double)(waves * c->n_sms);
       if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
-      if (eff >= 0.95 && waves >= 2) { best = ks; break; }
+      if (eff >= 0.95) { best = ks; break; }   // (measured: one full wave of 9 slices beats four waves of 37: fewer epilogues, 4x smaller slice reduction)
     }
     c->w_kslices = c->opt_kslices > 0 ? c->opt_kslices : best;
   }

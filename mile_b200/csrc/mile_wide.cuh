@@ -137,14 +137,24 @@ __global__ void __launch_bounds__(256) wide_smallk_kernel(const GemmArgs g) {
     Bs[k][nn] = (k < g.K && n0 + nn < g.N) ? __ldg(B + (long)k * g.sbk + (long)(n0 + nn) * g.sbn) : 0.f;
   }
   bs[tid] = (bias && n0 + tid < g.N) ? __ldg(bias + n0 + tid) : 0.f;
+  __shared__ __align__(16) float As[64][WS_KMAX];
+  {
+    const int m0 = blockIdx.x * 64;
+    for (int e = tid; e < 64 * WS_KMAX; e += 256) {
+      const int r = e / WS_KMAX, k = e % WS_KMAX;
+      As[r][k] = (m0 + r < g.M && k < g.K) ? __ldg(A + (long)(m0 + r) * g.sam + (long)k * g.sak) : 0.f;
+    }
+  }
   __syncthreads();
   const int tx = tid & 63, ty = tid >> 6, n = n0 + tx * 4;
   if (n >= g.N) return;
   const bool vec = n + 3 < g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                    (g.epi != 3 || ((g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0));
   const int mend = min(g.M, (int)(blockIdx.x + 1) * 64);
-  // the thread's [K][4] slab of B stays in registers for all of its rows (the kernel was bound by re-reading it from
-  // shared memory once per row: profiles/r1k_launches_wide_4x256.csv, 100 us for a 100 MB output)
+  // The thread's [K][4] slab of B stays in registers for all of its rows and the CTA's 64 rows of A are staged once in
+  // shared memory (coalesced), so a row costs 4 broadcast LDS.128 + 4 K FMAs + one 16-byte store: the kernel is then
+  // bound by writing C.  (Before: 16 LDS.128 of B + 16 uniform global loads of A per row, 100 us for a 100 MB output,
+  // profiles/r1k_launches_wide_4x256.csv.)
   float wreg[WS_KMAX][4];
 #pragma unroll
   for (int k = 0; k < WS_KMAX; ++k) {
@@ -153,8 +163,9 @@ __global__ void __launch_bounds__(256) wide_smallk_kernel(const GemmArgs g) {
   }
   for (int m = blockIdx.x * 64 + ty; m < mend; m += 4) {
     float a[WS_KMAX];
+    const float4* ar = reinterpret_cast<const float4*>(&As[m - blockIdx.x * 64][0]);
 #pragma unroll
-    for (int k = 0; k < WS_KMAX; ++k) a[k] = k < g.K ? __ldg(A + (long)m * g.sam + (long)k * g.sak) : 0.f;
+    for (int k4 = 0; k4 < WS_KMAX / 4; ++k4) { const float4 t = ar[k4]; a[4 * k4] = t.x; a[4 * k4 + 1] = t.y; a[4 * k4 + 2] = t.z; a[4 * k4 + 3] = t.w; }
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < WS_KMAX; ++k) {
@@ -324,9 +335,17 @@ __global__ void wide_slice_reduce_kernel(const float* __restrict__ src, long src
   const long total = n * nbatch;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const long b = t / n, e = t % n;
-    float s = 0.f;
-    for (int k = 0; k < kslices; ++k) s += src[b * src_batch + k * slice + e];
-    dst[b * dst_batch + e] = s;
+    // four interleaved partial sums so that the slice loads are in flight together (148 dependent L2 loads per
+    // element took 15 us for a 1 MB reduction); fixed association, so the result is run-to-run deterministic
+    const float* p = src + b * src_batch + e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 3 < kslices; k += 4) {
+      s0 += p[(long)k * slice]; s1 += p[(long)(k + 1) * slice]; s2 += p[(long)(k + 2) * slice]; s3 += p[(long)(k + 3) * slice];
+    }
+    for (; k < kslices; ++k) s0 += p[(long)k * slice];
+    dst[b * dst_batch + e] = (s0 + s1) + (s2 + s3);
   }
 }
 

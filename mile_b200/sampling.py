@@ -44,6 +44,9 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     if theta0.shape[0] != n_devices:
         raise ValueError(f'init_params carry {theta0.shape[0]} chains but step_ids has {n_devices}')
     ens = model.make_ensemble(n_devices, x, y)
+    # global chain ids key the noise streams (the reference splits one key per chain, sampling.py:181-184): waves / ranks
+    # that own different step_ids never share a stream even with the same rng_key
+    ens.set_option('chain_base', min(step_ids))
     try:
         logger.info('> Starting Warmup sampling...')
         eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens)
