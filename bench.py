@@ -434,7 +434,9 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
         resident = bool(ens.get_option('resident'))
         mma_path = fast == 2 and not wide and not sharded
         if sharded:
-            path = 'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step'
+            path = ('data-sharded: gradient kernel -> integrator kernel that sums the ranks\' [C, d+1] partials out of peer memory (CUDA IPC over NVLink), twice per step'
+                    if ens.get_option('p2p') == 1 else
+                    'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step')
         elif wide:
             path = 'wide: HBM-resident chain-batched GEMMs, ' + ('tcgen05 3xTF32' if ens.get_option('tensor') else 'FP32 SIMT')
         else:
@@ -451,7 +453,7 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
                        'n_features': spec.n_features, 'hidden_structure': list(spec.widths), 'n_params': d,
                        'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10, streams keyed by global chain id',
                        'cluster_size': G, 'sync_mode': ens.get_option('sync_mode'), 'tile_rows': ens.get_option('tile_rows'),
-                       'x_resident_in_smem': resident, 'kernel_path': path,
+                       'x_resident_in_smem': resident, 'kernel_path': path, 'peer_memory_allreduce': bool(ens.get_option('p2p') == 1),
                        'l2': 'flushed between timed iterations (256 MiB write); ' +
                              ('working set is SMEM-resident' if resident else 'X streams from the padded HBM copy through L2 every evaluation'),
                        'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()),

@@ -209,6 +209,12 @@ int mile_train_get_state(mile_ctx* ctx, float* theta_dev, float* m_dev, float* v
  * mile_mclmc_sample / mile_mclmc_tune.  NCCL is resolved with dlopen at run time. */
 int mile_nccl_unique_id(void* out128);   /* rank 0: 128-byte ncclUniqueId to broadcast to the other ranks */
 int mile_shard_init(mile_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world);
+/* Optional peer-memory all-reduce (one box, 2..8 ranks, NVLink): every rank exports the CUDA-IPC handle of its exchange
+ * region (64 bytes), the host all-gathers them, and after mile_shard_p2p_open the step loop's integrator kernel sums the
+ * ranks' partial [C, d+1] buffers straight out of peer memory (flag + data, rank order) instead of waiting for an
+ * ncclAllReduce: compute step and collective in one kernel.  mile_get_option("p2p") reports whether it is active. */
+int mile_shard_p2p_handle(mile_ctx* ctx, void* out64);
+int mile_shard_p2p_open(mile_ctx* ctx, const void* handles64 /* [world][64] */);
 int mile_shard_mclmc_init(mile_ctx* ctx, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream);
 int mile_shard_mclmc_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning,
                             int64_t sample_base, const float* step_size_dev, const float* L_dev,

@@ -22,7 +22,7 @@ SYMBOLS = [
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
     'mile_train_init', 'mile_train_epoch', 'mile_eval_metrics', 'mile_train_get_state',
-    'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
+    'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_p2p_handle', 'mile_shard_p2p_open', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
 ]
 
 
@@ -116,6 +116,8 @@ def load():
     lib.mile_train_get_state.argtypes = [vp, fp, fp, fp, vp, vp]
     lib.mile_nccl_unique_id.argtypes = [vp]
     lib.mile_shard_init.argtypes = [vp, vp, i32, i32]
+    lib.mile_shard_p2p_handle.argtypes = [vp, vp]
+    lib.mile_shard_p2p_open.argtypes = [vp, vp]
     lib.mile_shard_mclmc_init.argtypes = [vp, fp, fp, u64, vp]
     lib.mile_shard_mclmc_sample.argtypes = [vp, i32, i64, i32, i64, fp, fp, fp, u64, fp, i64, fp, vp]
     lib.mile_shard_mclmc_tune.argtypes = [vp, i32, i64, C.POINTER(TuneCfg), fp, u64, fp, vp]

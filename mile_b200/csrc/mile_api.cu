@@ -74,6 +74,8 @@ struct mile_ctx {
   float2* xchg = nullptr; unsigned int xepoch = 0; size_t xchg_bytes = 0; int n_sms = 148, opt_sync = -1;
   // data-sharded variant (rows split across ranks, NCCL all-reduce per gradient evaluation)
   void* nccl_comm = nullptr; int world = 1, rank = 0; int shard_lppd = 0;
+  // peer-memory all-reduce (mile_sharded.cuh): own exchange region [2 parities][xr_n floats] + 2 flags, peers' regions via CUDA IPC
+  float* xr = nullptr; size_t xr_n = 0; unsigned int xr_epoch = 0; int p2p = 0; float* xr_peer[8] = {nullptr};
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
   // wide / large-d path (mile_wide.cuh): HBM-resident activations, chain-batched GEMMs
   int wide = 0; long w_rows = 0; int w_chains = 0, w_kslices = 1, w_nblk = 0;
@@ -473,6 +475,8 @@ void mile_destroy(mile_ctx* c) {
                   c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
+  for (int r = 0; r < 8; ++r) if (c->xr_peer[r] && c->xr_peer[r] != c->xr) cudaIpcCloseMemHandle(c->xr_peer[r]);
+  if (c->xr) cudaFree(c->xr);
   if (c->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -512,6 +516,7 @@ int64_t mile_get_option(const mile_ctx* c, const char* key) {
   if (!strcmp(key, "refresh_mode")) return c->opt_refresh;
   if (!strcmp(key, "chain_base")) return c->opt_chain_base;
   if (!strcmp(key, "wide")) return c->wide;
+  if (!strcmp(key, "p2p")) return c->p2p;
   if (!strcmp(key, "tensor")) return c->opt_tensor;
   if (!strcmp(key, "row_stride")) return c->M.sA[0];
   return -1;
@@ -1363,27 +1368,40 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   return 0;
 }
 
-// local value_and_grad of the rank's row shard into the packed buffer, then all-reduce over the ranks
-static int shard_eval(mile_ctx* c, cudaStream_t st) {
+// local value_and_grad of the rank's row shard into the packed buffer, then all-reduce over the ranks: through NCCL, or
+// (use_p2p, step loop with an open peer mapping) left in this rank's exchange region for the integrator kernel to sum out
+// of peer memory
+static float* xr_slot(mile_ctx* c, float* region, unsigned int epoch) { return region + (size_t)(epoch & 1u) * c->xr_n; }
+static unsigned int* xr_flag(mile_ctx* c, float* region, unsigned int epoch) {
+  return reinterpret_cast<unsigned int*>(region + 2 * c->xr_n) + (epoch & 1u);
+}
+static int shard_eval(mile_ctx* c, cudaStream_t st, bool use_p2p = false) {
+  const bool p2p = use_p2p && c->p2p && c->world > 1;
+  float* target = c->gl;
+  if (p2p) { c->xr_epoch++; target = xr_slot(c, c->xr, c->xr_epoch); }
   if (c->wide) {
-    if (wide_eval(c, c->theta, c->C, c->gl, 1.f / (float)c->world, st)) return -1;
-    if (c->world > 1)
-      NCK(g_nccl.AllReduce(c->gl, c->gl, (size_t)c->C * (c->d + 1), ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, st));
-    return 0;
+    if (wide_eval(c, c->theta, c->C, target, 1.f / (float)c->world, st)) return -1;
+  } else {
+    Plan pl;
+    if (make_plan(c, c->C, c->N, true, pl)) return -1;
+    fill_common(c, pl.kp);
+    pl.kp.mode = MODE_EVAL; pl.kp.theta_in = c->theta; pl.kp.grad_out = target; pl.kp.lp_out = target + c->d;
+    pl.kp.out_stride = c->d + 1; pl.kp.prior_weight = 1.f / (float)c->world; pl.kp.n_eval = c->C;
+    if (launch(c, pl, c->C, st)) return -1;
   }
-  Plan pl;
-  if (make_plan(c, c->C, c->N, true, pl)) return -1;
-  fill_common(c, pl.kp);
-  pl.kp.mode = MODE_EVAL; pl.kp.theta_in = c->theta; pl.kp.grad_out = c->gl; pl.kp.lp_out = c->gl + c->d;
-  pl.kp.out_stride = c->d + 1; pl.kp.prior_weight = 1.f / (float)c->world; pl.kp.n_eval = c->C;
-  if (launch(c, pl, c->C, st)) return -1;
-  if (c->world > 1)
+  if (c->world > 1 && !p2p)
     NCK(g_nccl.AllReduce(c->gl, c->gl, (size_t)c->C * (c->d + 1), ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, st));
   return 0;
 }
 
-static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st) {
+static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cudaStream_t st, bool use_p2p = false) {
   S.stage = stage; S.s_local = s_local;
+  S.p2p = (use_p2p && c->p2p && c->world > 1) ? 1 : 0; S.world = c->world; S.rank = c->rank; S.epoch = c->xr_epoch;
+  if (S.p2p)
+    for (int r = 0; r < c->world; ++r) {
+      float* region = r == c->rank ? c->xr : c->xr_peer[r];
+      S.peer_data[r] = xr_slot(c, region, c->xr_epoch); S.peer_flag[r] = xr_flag(c, region, c->xr_epoch);
+    }
   if (c->d > 8192) {   // large d: a cluster of 8 CTAs per chain, elements strided over its 8192 threads (DSMEM reductions)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1407,6 +1425,39 @@ static int shard_params(mile_ctx* c, ShardParams& S) {
   return 0;
 }
 
+// ---- peer-memory all-reduce over NVLink (CUDA IPC) --------------------------------------------------------------
+int mile_shard_p2p_handle(mile_ctx* c, void* out64) {
+  if (!c || !out64) return fail("null argument");
+  if (!c->gl) return fail("mile_shard_init has not been called");
+  CK(cudaSetDevice(c->device));
+  if (!c->xr) {
+    c->xr_n = ((size_t)c->C * (c->d + 1) + 31) / 32 * 32;
+    CK(cudaMalloc(&c->xr, (2 * c->xr_n + 32) * 4));
+    CK(cudaMemset(c->xr, 0, (2 * c->xr_n + 32) * 4));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->xr));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  memcpy(out64, &h, 64);
+  return 0;
+}
+int mile_shard_p2p_open(mile_ctx* c, const void* handles64) {
+  if (!c || !handles64) return fail("null argument");
+  if (!c->xr) return fail("mile_shard_p2p_handle has not been called");
+  if (c->world < 2 || c->world > 8) return fail("the peer-memory all-reduce serves 2..8 ranks of one box");
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->xr_peer[r] = c->xr; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles64 + 64 * r, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xr_peer[r] = (float*)p;
+  }
+  c->p2p = 1;
+  return 0;
+}
+
 int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_dev, uint64_t seed, void* stream) {
   if (!c) return fail("null ctx");
   if (!c->X) return fail("mile_set_data has not been called");
@@ -1427,10 +1478,10 @@ int mile_shard_mclmc_init(mile_ctx* c, const float* theta0_dev, const float* z0_
 static int shard_run(mile_ctx* c, ShardParams& S, int n_steps, cudaStream_t st) {
   for (int s = 0; s < n_steps; ++s) {
     if (shard_integ(c, S, SH_BEGIN, s, st)) return -1;
-    if (shard_eval(c, st)) return -1;
-    if (shard_integ(c, S, SH_MID, s, st)) return -1;
-    if (shard_eval(c, st)) return -1;
-    if (shard_integ(c, S, SH_END, s, st)) return -1;
+    if (shard_eval(c, st, true)) return -1;
+    if (shard_integ(c, S, SH_MID, s, st, true)) return -1;
+    if (shard_eval(c, st, true)) return -1;
+    if (shard_integ(c, S, SH_END, s, st, true)) return -1;
     if (c->shard_lppd && c->wide && !S.tune && (S.K.step_base + s) % S.K.thin == 0 && wide_lppd_fold(c, c->theta, c->C, st)) return -1;
   }
   c->carry_valid = 0;

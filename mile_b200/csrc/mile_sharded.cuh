@@ -17,7 +17,32 @@ struct ShardParams {
   float* thb; float* ub; float* gb;   // [C,d] state backups for handle_nans (tune mode)
   int stage, tune;
   long s_local;           // index of the step inside this call (noise / info / tune_info addressing)
+  // Peer-memory all-reduce (world > 1, CUDA IPC over NVLink): instead of an ncclAllReduce between the gradient kernel and
+  // this one, every rank's gradient kernel leaves its partial [C, d+1] in its own exchange buffer, and this kernel --
+  // the consumer -- publishes "my partial of evaluation `epoch` is complete", waits for the same flag of every peer and
+  // sums the partials straight out of peer memory in rank order (identical on every rank, so the replicas stay
+  // bit-identical).  Compute step and collective in one kernel: no NCCL launch, no extra pass over the buffer.
+  int p2p, world, rank;
+  unsigned int epoch;
+  const float* peer_data[8];        // rank r's partial of this evaluation (peer pointer; own buffer for r == rank)
+  unsigned int* peer_flag[8];       // rank r's completion flag for this parity
 };
+
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");   // peer memory must not be served by L1
+  return v;
+}
+// sum of the world's partials at packed index k (rank order; all loads in flight)
+__device__ __forceinline__ float p2p_sum(const ShardParams& S, long k) {
+  float t[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) t[r] = r < S.world ? ld_peer(S.peer_data[r] + k) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += t[r];
+  return s;
+}
 
 // ES = element split: a cluster of CTAs per chain, the d elements strided over all of its threads and every reduction
 // completed over DSMEM -- the large-d (wide) path, where one CTA per chain would be a latency-bound 200k-element loop.
@@ -43,12 +68,51 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 2 * 4 * (NT / 32);
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
-  float lp = fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch];
+  const bool p2p = S.p2p && fresh;
+  if (p2p) {
+    // (the gradient kernel of this rank finished before this kernel started: stream order)
+    if (blockIdx.x == 0 && tid == 0) {
+      __threadfence_system();
+      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(S.peer_flag[S.rank]), "r"(S.epoch) : "memory");
+    }
+    if (tid < S.world && tid != S.rank) {
+      unsigned int f;
+      long spin = 0;
+      do {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(f) : "l"(S.peer_flag[tid]) : "memory");
+        if ((int)(f - S.epoch) < 0 && ++spin > (1L << 26)) __trap();     // a dead peer must not hang the GPU
+      } while ((int)(f - S.epoch) < 0);
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+  float lp = p2p ? p2p_sum(S, (long)ch * (d + 1) + d) : (fresh ? S.gl[(long)ch * (d + 1) + d] : P.lp[ch]);
+  if (p2p) {
+    // sum the ranks' partial gradients out of peer memory into the chain's gradient array, four elements x world loads in
+    // flight per thread (an NVLink round trip is ~2 us: one element at a time would serialise d / NT of them)
+    const int IS = MILE_IS(c, ES, NT);
+    for (int i = MILE_I0(c, ES); i < d; i += 4 * IS) {
+      float t[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          t[k][r] = (i + k * IS < d && r < S.world) ? ld_peer(S.peer_data[r] + (long)ch * (d + 1) + i + k * IS) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i + k * IS < d) {
+          float sum = 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) sum += t[k][r];
+          c.gg[i + k * IS] = sum;
+        }
+    }
+  }
   // (the copy and the sums touch the same elements in the same thread: no barrier needed in between)
   float v[3] = {0.f, 0.f, 0.f};
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
-    const float gi = fresh ? S.gl[(long)ch * (d + 1) + i] : c.gg[i];
-    if (fresh) c.gg[i] = gi;
+    const float gi = (fresh && !p2p) ? S.gl[(long)ch * (d + 1) + i] : c.gg[i];   // (p2p: this thread just wrote c.gg[i])
+    if (fresh && !p2p) c.gg[i] = gi;
     v[0] += gi * gi; v[1] += c.uu[i] * gi; v[2] += isfinite(c.th[i]) ? 0.f : 1.f;
   }
   all_sum<3, NT, 0, ES>(c, v);

@@ -134,8 +134,12 @@ class Ensemble:
 
     def close(self):
         if getattr(self, 'h', None):
+            self._pre_close()
             self.lib.mile_destroy(self.h)
             self.h = None
+
+    def _pre_close(self):
+        pass
 
     def __del__(self):
         try:
@@ -378,6 +382,27 @@ class ShardedEnsemble(Ensemble):
             dist.broadcast(t, 0)
             uid = np.ascontiguousarray(t.cpu().numpy())
         capi.check(self.lib.mile_shard_init(self.h, capi.host_ptr(uid), rank, world))
+        # peer-memory all-reduce over NVLink (CUDA IPC) for the step loop; MILE_SHARD_P2P=0 keeps ncclAllReduce
+        import os
+        if 1 < world <= 8 and os.environ.get('MILE_SHARD_P2P', '1') != '0' and dist.get_backend() == 'nccl':
+            h = np.zeros(64, np.uint8)
+            capi.check(self.lib.mile_shard_p2p_handle(self.h, capi.host_ptr(h)))
+            t = torch.from_numpy(h).to(f'cuda:{device}')
+            allh = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allh, t)
+            hs = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
+            capi.check(self.lib.mile_shard_p2p_open(self.h, capi.host_ptr(hs)))
+
+    def _pre_close(self):
+        # no rank may free its exchange region while a peer can still read it
+        try:
+            import torch
+            import torch.distributed as dist
+            if self.world > 1 and self.get_option('p2p') == 1 and dist.is_initialized():
+                torch.cuda.synchronize()
+                dist.barrier()
+        except Exception:
+            pass
 
     @staticmethod
     def shard_rows(n_rows: int, rank: int, world: int) -> slice:

@@ -120,27 +120,15 @@ def test_inference_loop_outputs_and_layout(tmp_path):
 
 def test_statistical_parity_with_cpu_restatement():
     """Full-run parity (north star): same data / split / warm-start / (eps, L); GPU (Philox noise) vs the C
-    restatement (its own noise).  LPPD and RMSE on the test split and the per-chain mean log-density must agree
-    within 4 standard errors (SE from chain-to-chain spread) / stated absolute tolerances."""
+    restatement (its own noise), THREE seeds (the reference replicates over rng: [1, 2, 3],
+    experiments/replicate_uci/repl_uci_search.yaml:1-4).  Stated tolerances: LPPD on the test split |mean difference| <=
+    3 SE (SE from the chain-to-chain spread, pooled over the seeds) + 0.01; RMSE within 0.05; mean log-density within
+    3 SE + 2; effective sample size of the log-density trace within a factor 2; parameter-space split-R-hat (rank
+    normalised, 4 splits, median over the parameters) within 0.15."""
     from oracle import c_oracle
     name, C, n, thin = 'airfoil_2x16', 8, 3000, 10
     ospec, module, pm, X, y, Xt, yt = setup_problem(name, n_train=400, n_test=200)
     pm.attach_test_split(Xt, yt)
-    th0 = o.synthetic_theta0(ospec, C)
-    ens = pm.make_ensemble(C, X, y)
-    ens.init(th0, seed=1)
-    ens.tune_reset(0.01)
-    tc = ens.tune_cfg(1600, 200, 0.5, 0.1, 1.5, 100)
-    ens.tune(1800, 0, tc, seed=2)
-    ens.tune_finish_phase2()
-    eps, L, _ = ens.get_tuning()
-    assert np.all(np.isfinite(eps)) and np.all(np.isfinite(L))
-    start = ens.get_state()
-    g_samples, g_info = ens.sample(n, eps, L, n_thinning=thin, seed=3, info=True)
-    ens.close()
-    ch = c_oracle.Chains(ospec, X, y, start[0], threads=8)
-    ch.u[:], ch.lp[:], ch.g[:] = start[1], start[2], start[3]
-    c_samples, c_info = ch.sample(n, eps, L, thin=thin, seed=4, info=True)
 
     def metrics(samples):
         S = samples.shape[0]
@@ -151,15 +139,39 @@ def test_statistical_parity_with_cpu_restatement():
         rmse = np.sqrt(np.mean((lv[..., 0].mean(axis=(0, 1)) - yt) ** 2))
         return o.lppd(pw), per_chain, rmse
 
-    gl, gpc, grmse = metrics(g_samples)
-    cl, cpc, crmse = metrics(c_samples)
-    se = np.sqrt(gpc.var(ddof=1) / C + cpc.var(ddof=1) / C)
-    assert abs(gl - cl) <= 4 * se + 0.02, (gl, cl, se)
-    assert abs(grmse - crmse) <= 0.05, (grmse, crmse)
-    glp, clp = g_info[n // 2:, :, 0].mean(axis=0), c_info[n // 2:, :, 0].mean(axis=0)
-    se_lp = np.sqrt(glp.var(ddof=1) / C + clp.var(ddof=1) / C)
-    assert abs(glp.mean() - clp.mean()) <= 4 * se_lp + 2.0, (glp.mean(), clp.mean(), se_lp)
-    # chain-wise split-R-hat of the log-density trace is in the same range for both implementations
-    gr = o.split_chain_r_hat(g_info[n // 2:, :, 0].T[:, :, None], 4, rank_normalize=False)
-    cr = o.split_chain_r_hat(c_info[n // 2:, :, 0].T[:, :, None], 4, rank_normalize=False)
-    assert abs(np.median(gr) - np.median(cr)) < 0.3, (np.median(gr), np.median(cr))
+    d_lppd, v_lppd, d_lp, v_lp = [], [], [], []
+    for seed in (0, 1, 2):
+        th0 = o.synthetic_theta0(ospec, C, seed0=1000 + 50 * seed)
+        ens = pm.make_ensemble(C, X, y)
+        ens.init(th0, seed=1 + 10 * seed)
+        ens.tune_reset(0.01)
+        tc = ens.tune_cfg(1600, 200, 0.5, 0.1, 1.5, 100)
+        ens.tune(1800, 0, tc, seed=2 + 10 * seed)
+        ens.tune_finish_phase2()
+        eps, L, _ = ens.get_tuning()
+        assert np.all(np.isfinite(eps)) and np.all(np.isfinite(L))
+        start = ens.get_state()
+        g_samples, g_info = ens.sample(n, eps, L, n_thinning=thin, seed=3 + 10 * seed, info=True)
+        ens.close()
+        ch = c_oracle.Chains(ospec, X, y, start[0], threads=8)
+        ch.u[:], ch.lp[:], ch.g[:] = start[1], start[2], start[3]
+        c_samples, c_info = ch.sample(n, eps, L, thin=thin, seed=4 + 10 * seed, info=True)
+        gl, gpc, grmse = metrics(g_samples)
+        cl, cpc, crmse = metrics(c_samples)
+        d_lppd.append(gl - cl); v_lppd.append(gpc.var(ddof=1) / C + cpc.var(ddof=1) / C)
+        assert abs(grmse - crmse) <= 0.05, (seed, grmse, crmse)
+        glp, clp = g_info[n // 2:, :, 0].mean(axis=0), c_info[n // 2:, :, 0].mean(axis=0)
+        d_lp.append(glp.mean() - clp.mean()); v_lp.append(glp.var(ddof=1) / C + clp.var(ddof=1) / C)
+        # effective sample size of the log-density trace (all chains), same estimator for both
+        g_ess = o.ess_rank_normalized(g_info[n // 2:, :, 0].T[:, :, None], rank_normalize=False)
+        c_ess = o.ess_rank_normalized(c_info[n // 2:, :, 0].T[:, :, None], rank_normalize=False)
+        assert 0.5 <= float(np.mean(g_ess)) / float(np.mean(c_ess)) <= 2.0, (seed, np.mean(g_ess), np.mean(c_ess))
+        # parameter-space split-R-hat over the kept samples of the second half: [C, S/2, d]
+        gs, cs = np.transpose(g_samples[g_samples.shape[0] // 2:], (1, 0, 2)), np.transpose(c_samples[c_samples.shape[0] // 2:], (1, 0, 2))
+        gr, cr = o.split_chain_r_hat(gs, 4), o.split_chain_r_hat(cs, 4)
+        assert abs(np.median(gr) - np.median(cr)) <= 0.15, (seed, np.median(gr), np.median(cr))
+    k = len(d_lppd)
+    se = np.sqrt(np.sum(v_lppd)) / k
+    assert abs(np.mean(d_lppd)) <= 3 * se + 0.01, (d_lppd, se)
+    se_lp = np.sqrt(np.sum(v_lp)) / k
+    assert abs(np.mean(d_lp)) <= 3 * se_lp + 2.0, (d_lp, se_lp)
