@@ -391,6 +391,7 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
             ref.close()
             sharded_parity = {'grad_rel': float(np.linalg.norm(g_s - g_f) / np.linalg.norm(g_f)),
                               'logdensity_rel': float(np.max(np.abs(lp_s - lp_f) / np.abs(lp_f)))}
+        barrier()      # (the ranks of the fused step loop wait on each other inside the kernel: start the next phase together)
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside), plus the one exchange step of the
     #      path at N > 1: the NCCL merge of the per-chain test-set logsumexp states ------------------------------------
@@ -434,7 +435,9 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
         resident = bool(ens.get_option('resident'))
         mma_path = fast == 2 and not wide and not sharded
         if sharded:
-            path = ('data-sharded: gradient kernel -> integrator kernel that sums the ranks\' [C, d+1] partials out of peer memory (CUDA IPC over NVLink), twice per step'
+            path = ('data-sharded: ONE persistent kernel per rank for the whole step loop; per gradient evaluation a local reduce-scatter through L2, then every CTA pushes its summed slice as flagged 8-byte words into every rank\'s exchange region (CUDA IPC peer memory over NVLink) and polls its own copy'
+                    if ens.get_option('shard_fused') == 1 else
+                    'data-sharded: gradient kernel -> integrator kernel that sums the ranks\' [C, d+1] partials out of peer memory (CUDA IPC over NVLink), twice per step'
                     if ens.get_option('p2p') == 1 else
                     'data-sharded: gradient kernel -> ncclAllReduce([C, d+1]) -> integrator kernel, twice per step')
         elif wide:
@@ -453,11 +456,11 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
                        'n_features': spec.n_features, 'hidden_structure': list(spec.widths), 'n_params': d,
                        'n_thinning': N_THINNING, 'noise': 'in-kernel Philox4x32-10, streams keyed by global chain id',
                        'cluster_size': G, 'sync_mode': ens.get_option('sync_mode'), 'tile_rows': ens.get_option('tile_rows'),
-                       'x_resident_in_smem': resident, 'kernel_path': path, 'peer_memory_allreduce': bool(ens.get_option('p2p') == 1),
+                       'x_resident_in_smem': resident, 'kernel_path': path, 'peer_memory_allreduce': bool(ens.get_option('p2p') == 1), 'fused_multi_rank_step_loop': bool(ens.get_option('shard_fused') == 1),
                        'l2': 'flushed between timed iterations (256 MiB write); ' +
                              ('working set is SMEM-resident' if resident else 'X streams from the padded HBM copy through L2 every evaluation'),
                        'step_size_mean': float(eps.mean()), 'L_mean': float(L.mean()),
-                       'parallelism': (f'rows x{world} + NCCL all-reduce of [C, d+1] per gradient evaluation' if sharded else f'chains x{world}')},
+                       'parallelism': (f'rows x{world} + all-reduce of [C, d+1] per gradient evaluation (peer memory over NVLink inside the kernel; NCCL when the peer mapping is unavailable)' if sharded else f'chains x{world}')},
             'grad_evals_per_s': 2 * value,
             'samples_finite': finite,
             'lppd': {'value': lppd_val, 'samples': int(lppd_total),

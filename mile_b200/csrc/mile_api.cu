@@ -76,6 +76,9 @@ struct mile_ctx {
   void* nccl_comm = nullptr; int world = 1, rank = 0; int shard_lppd = 0;
   // peer-memory all-reduce (mile_sharded.cuh): own exchange region [2 parities][xr_n floats] + 2 flags, peers' regions via CUDA IPC
   float* xr = nullptr; size_t xr_n = 0; unsigned int xr_epoch = 0; int p2p = 0; float* xr_peer[8] = {nullptr};
+  // multi-rank exchange of the fused step loop (KParams::mr_*): float offset of the [C][2][world][dS+4] float2 area inside
+  // the exchange region, flag epoch (advanced identically on every rank), option switch (mile_set_option "shard_fused")
+  size_t mr_off = 0; unsigned int mr_epoch = 0; int opt_shard_fused = 1;
   float *gl = nullptr, *scal = nullptr, *thb = nullptr, *ub = nullptr, *gb = nullptr;
   // wide / large-d path (mile_wide.cuh): HBM-resident activations, chain-batched GEMMs
   int wide = 0; long w_rows = 0; int w_chains = 0, w_kslices = 1, w_nblk = 0;
@@ -125,7 +128,8 @@ struct Plan {
   KParams kp;  // offsets + model filled in
 };
 
-static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g = 0) {
+static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g = 0,
+                     bool force_sync = false) {
   DevModel M = c->M;
   int G = force_g > 0 ? force_g : c->opt_cluster, sync_mode = 0;
   if (G <= 0) {
@@ -137,6 +141,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
   } else if (c->opt_sync == 1 || (G > 8) || (G & (G - 1))) {
     sync_mode = 1;
   }
+  if (force_sync) sync_mode = 1;    // (multi-rank step loop: the exchange is flagged words only, every CTA co-resident)
   if (G < 1 || G > 16) return fail("cluster_size must be in [1, 16]");
   if (sync_mode && (long)G * n_chains > c->n_sms) return fail("cluster_size x chains exceeds the SM count (cooperative launch)");
   if (G == 1) sync_mode = 0;
@@ -420,6 +425,7 @@ static int wide_predict(mile_ctx* c, const float* theta, int n, int which, float
 static int wide_lppd_fold(mile_ctx* c, const float* theta, int n, cudaStream_t st);
 static int wide_alloc(mile_ctx* c, int n_chains);
 static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float prior_weight, cudaStream_t st);
+static int shard_fused_plan(mile_ctx* c, Plan& pl);
 
 const char* mile_last_error(void) { return g_err.c_str(); }
 int mile_version(void) { return 100; }
@@ -495,6 +501,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
   else if (!strcmp(key, "kslices")) { c->opt_kslices = (int)v; c->w_rows = -1; }   // wide path: split-K slices of the dW GEMMs (0 = auto)
+  else if (!strcmp(key, "shard_fused")) c->opt_shard_fused = (int)v;   // 1: multi-rank step loop as ONE persistent kernel per rank (needs the peer mapping), 0: one launch per phase
   else if (!strcmp(key, "steploop")) c->opt_steploop = (int)v;   // 1: integrator-warp step loop of the tensor evaluator, 0: generic loop
   else return fail(std::string("unknown option ") + key);
   return 0;
@@ -517,6 +524,10 @@ int64_t mile_get_option(const mile_ctx* c, const char* key) {
   if (!strcmp(key, "chain_base")) return c->opt_chain_base;
   if (!strcmp(key, "wide")) return c->wide;
   if (!strcmp(key, "p2p")) return c->p2p;
+  if (!strcmp(key, "shard_fused")) {   // is the multi-rank step loop the fused persistent kernel?
+    Plan pl;
+    return shard_fused_plan(const_cast<mile_ctx*>(c), pl) == 0 ? 1 : 0;
+  }
   if (!strcmp(key, "tensor")) return c->opt_tensor;
   if (!strcmp(key, "row_stride")) return c->M.sA[0];
   return -1;
@@ -1432,8 +1443,11 @@ int mile_shard_p2p_handle(mile_ctx* c, void* out64) {
   CK(cudaSetDevice(c->device));
   if (!c->xr) {
     c->xr_n = ((size_t)c->C * (c->d + 1) + 31) / 32 * 32;
-    CK(cudaMalloc(&c->xr, (2 * c->xr_n + 32) * 4));
-    CK(cudaMemset(c->xr, 0, (2 * c->xr_n + 32) * 4));
+    c->mr_off = 2 * c->xr_n + 32;
+    // + the flagged-word area of the fused multi-rank step loop: [C][2][world][dS+4] float2
+    const size_t mr_floats = c->wide ? 0 : (size_t)c->C * 2 * c->world * (round_up(c->d, 4) + 4) * 2;
+    CK(cudaMalloc(&c->xr, (c->mr_off + mr_floats) * 4));
+    CK(cudaMemset(c->xr, 0, (c->mr_off + mr_floats) * 4));
   }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, c->xr));
@@ -1488,12 +1502,48 @@ static int shard_run(mile_ctx* c, ShardParams& S, int n_steps, cudaStream_t st) 
   return 0;
 }
 
+// Fused multi-rank step loop: when the peer mapping is open and the model runs on the shared-memory kernels, the whole
+// call is ONE launch of mile_mclmc_kernel per rank (rows of this rank, flagged-word exchange over NVLink inside the
+// kernel, KParams::mr_*).  Returns 1 when the plan does not qualify (the caller then runs the launch-per-phase loop).
+static int shard_fused_plan(mile_ctx* c, Plan& pl) {
+  if (!(c->p2p && c->world > 1 && !c->wide && c->opt_shard_fused && c->mr_off)) return 1;
+  const int save_fast = c->opt_fast;
+  c->opt_fast = save_fast < 1 ? save_fast : 1;       // the exchange lives in mile_mclmc_kernel (generic / FastGE evaluators)
+  const int rc = make_plan(c, c->C, c->N, true, pl, 0, true);
+  c->opt_fast = save_fast;
+  if (rc) return 1;
+  if ((long)pl.G * c->C > c->n_sms) return 1;      // every CTA of every rank must be resident: the ranks wait on each other
+  if (pl.G == 1) pl.sync_mode = 0;
+  return 0;
+}
+static int shard_fused_launch(mile_ctx* c, Plan& pl, cudaStream_t st) {
+  KParams& k = pl.kp;
+  k.mr_world = c->world; k.mr_rank = c->rank; k.mr_base = c->mr_epoch;
+  for (int r = 0; r < c->world; ++r) k.mr_sums[r] = reinterpret_cast<float2*>((r == c->rank ? c->xr : c->xr_peer[r]) + c->mr_off);
+  c->mr_epoch += 2u * (unsigned int)k.n_steps + 2u;     // same sequence of calls on every rank -> same epochs
+  if (launch(c, pl, c->C, st)) return -1;
+  c->carry_valid = 1;
+  return 0;
+}
+
 int mile_shard_mclmc_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
                             const float* step_size_dev, const float* L_dev, const float* z_dev, uint64_t seed,
                             float* samples_dev, int64_t n_slots, float* info_dev, void* stream) {
   if (!c) return fail("null ctx");
   if (!c->gl) return fail("mile_shard_init has not been called");
   if (!step_size_dev || !L_dev) return fail("step_size / L are required");
+  if (n_steps <= 0) return 0;
+  {
+    Plan pl;
+    if (shard_fused_plan(c, pl) == 0) {
+      fill_common(c, pl.kp);
+      KParams& k = pl.kp;
+      k.mode = MODE_SAMPLE; k.n_steps = n_steps; k.step_base = step_base; k.thin = n_thinning; k.sample_base = sample_base;
+      k.n_slots = n_slots; k.eps = step_size_dev; k.L = L_dev; k.z = z_dev; k.seed = seed; k.samples = samples_dev;
+      k.info = info_dev; k.do_lppd = 0;
+      return shard_fused_launch(c, pl, (cudaStream_t)stream);
+    }
+  }
   ShardParams S;
   shard_params(c, S);
   KParams& k = S.K;
@@ -1507,6 +1557,18 @@ int mile_shard_mclmc_tune(mile_ctx* c, int32_t n_steps, int64_t step_base, const
                           uint64_t seed, float* tune_info_dev, void* stream) {
   if (!c || !cfg) return fail("null argument");
   if (!c->gl) return fail("mile_shard_init has not been called");
+  if (n_steps <= 0) return 0;
+  {
+    Plan pl;
+    if (shard_fused_plan(c, pl) == 0) {
+      fill_common(c, pl.kp);
+      KParams& k = pl.kp;
+      k.mode = MODE_TUNE; k.n_steps = n_steps; k.step_base = step_base; k.z = z_dev; k.seed = seed; k.tune_info = tune_info_dev;
+      k.tune1 = cfg->tune1_steps; k.tune2 = cfg->tune2_steps; k.ev_start = cfg->desired_energy_var_start;
+      k.ev_end = cfg->desired_energy_var_end; k.trust = cfg->trust_in_estimate; k.neff = cfg->num_effective_samples;
+      return shard_fused_launch(c, pl, (cudaStream_t)stream);
+    }
+  }
   ShardParams S;
   shard_params(c, S);
   KParams& k = S.K;

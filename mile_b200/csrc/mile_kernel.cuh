@@ -51,6 +51,12 @@ struct KParams {
   // global id of local chain 0: the Philox streams are keyed by (seed, chain_base + chain, step, element), so the ranks
   // of a chain-partitioned ensemble draw independent noise (the reference splits one key per chain, sampling.py:181-184)
   int chain_base;
+  // multi-rank exchange (rows sharded across the GPUs of one box, mile_shard_*): the step loop stays ONE persistent kernel
+  // per rank.  After the local reduce-scatter every CTA pushes its summed slice as flagged 8-byte words into the
+  // `mr_sums` region of EVERY rank (peer memory mapped with CUDA IPC, stores travel over NVLink), and all CTAs then poll
+  // only their own GPU's copy: one NVLink store hop per evaluation, no NCCL call, no kernel boundary.
+  int mr_world, mr_rank; unsigned int mr_base;   // flag = mr_base + eval + 1 (advanced identically on every rank)
+  float2* mr_sums[8];    // rank r's region [C][2 parities][world][dS+4] (own region for r == mr_rank)
 };
 
 struct Ctx {
@@ -266,7 +272,9 @@ __device__ __forceinline__ void ll_sum_pair(const float2* base0, const float2* b
 
 template <int NT, int BAR>
 __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const float2* gslab, unsigned int flag, float& g2, float& ug,
-                                                     float& nonfinite) {
+                                                     float& nonfinite, const bool use_ll, const int ng) {
+  // use_ll: the partials arrive as `ng` flagged words per element at gslab (+ r * (dS + 4)): the G CTAs of the chain
+  // (sync_mode 1), or the `world` ranks' summed slices of the multi-rank exchange
   // (DSMEM mode: the caller has already executed the cluster / block barrier that publishes every CTA's gpart;
   //  global mode: gslab = this chain's parity slab of flagged words, waited on element by element)
   const KParams& P = c.P;
@@ -277,9 +285,9 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
   const float* rp[16];
   const int stride_g = P.dS + 4;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) rp[r] = (!P.sync_mode && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
+  for (int r = 0; r < 16; ++r) rp[r] = (!use_ll && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
   float ll = 0.f;
-  if (P.sync_mode) {
+  if (use_ll) {
     // only one thread fetches the log-likelihood partials (it folds them into its v[0] below): a second serial L2
     // round trip for every thread would sit on the critical path
   } else {
@@ -308,15 +316,15 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     c.gg[i] = g;
     v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
   };
-  if (P.sync_mode) {
+  if (use_ll) {
     for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
       const int i2 = i + NT;
       if (i2 < M.d) {
         float s0, s1;
-        ll_sum_pair(gslab + i, gslab + i2, stride_g, c.G, flag, s0, s1);
+        ll_sum_pair(gslab + i, gslab + i2, stride_g, ng, flag, s0, s1);
         consume(i, s0); consume(i2, s1);
       } else {
-        consume(i, ll_sum(gslab + i, stride_g, c.G, flag));
+        consume(i, ll_sum(gslab + i, stride_g, ng, flag));
       }
     }
   } else {
@@ -331,7 +339,7 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     }
   }
   PROF(14);
-  if (P.sync_mode && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, c.G, flag);
+  if (use_ll && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, ng, flag);
   block_sum<4, NT, BAR>(v, MILE_RED(c, BAR), MILE_PH(c, BAR));
   g2 = v[1]; ug = v[2]; nonfinite = v[3];
   return v[0] + ll;
@@ -735,7 +743,9 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     GE::run(c, r0, r1, gp);
     PROF(10);
     const float2* gslab = nullptr;
-    const unsigned int xflag = P.xbase + (unsigned int)e + 1u;
+    unsigned int xflag = P.xbase + (unsigned int)e + 1u;
+    bool use_ll = c.G > 1 && P.sync_mode;
+    int ng = c.G;
     if (c.G > 1 && P.sync_mode) {
       // global exchange: publish this CTA's partial as flagged 8-byte words; readers wait on the words themselves.
       // Two parity slabs suffice: a CTA can only publish eval e+2 after it has read every rank's eval e+1, which
@@ -751,8 +761,30 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
     } else {
       __syncthreads();
     }
+    if (P.mr_world > 1) {
+      // multi-rank exchange: local reduce-scatter (CTA j sums slice j of the G local partials in rank order), push of the
+      // summed slice into every rank's region over NVLink, then everybody polls its own GPU's copy of the world's slices.
+      // Every rank adds the same `world` values in the same order, so the replicas of a chain stay bit-identical.
+      // Two parities suffice by the same argument as for the local slabs: a CTA pushes eval e+2 only after it has read
+      // every rank's eval e+1, which each CTA of each rank pushes after it finished reading eval e.
+      const int W = P.mr_world, stride_g = P.dS + 4;
+      const int SL = (P.dS + 1 + c.G - 1) / c.G;
+      const unsigned int rflag = P.mr_base + (unsigned int)e + 1u;
+      const long roff = (((long)ch * 2 + (e & 1)) * W + P.mr_rank) * stride_g;
+      for (int j = tid; j < SL; j += NT) {
+        const int idx = c.rank * SL + j;
+        if (idx <= P.dS) {
+          const float sl = c.G > 1 ? ll_sum(gslab + idx, stride_g, c.G, xflag) : gp[idx];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < W) ll_store(P.mr_sums[r] + roff + idx, sl, rflag);
+        }
+      }
+      gslab = P.mr_sums[P.mr_rank] + ((long)ch * 2 + (e & 1)) * W * stride_g;
+      xflag = rflag; use_ll = true; ng = W;
+    }
     if (integ) {
-      const float lp_new = cluster_reduce_grad<NI, IB>(c, gp, gslab, xflag, g2, ug, nf);
+      const float lp_new = cluster_reduce_grad<NI, IB>(c, gp, gslab, xflag, g2, ug, nf, use_ll, ng);
       PROF(11);
       if (!stepping) {
         if (P.mode == MODE_EVAL) {

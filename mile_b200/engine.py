@@ -392,6 +392,10 @@ class ShardedEnsemble(Ensemble):
             dist.all_gather(allh, t)
             hs = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
             capi.check(self.lib.mile_shard_p2p_open(self.h, capi.host_ptr(hs)))
+            # with the mapping open the whole step loop is one persistent kernel per rank (flagged-word exchange over
+            # NVLink inside it); MILE_SHARD_FUSED=0 keeps one launch per phase
+            if os.environ.get('MILE_SHARD_FUSED', '1') == '0':
+                self.set_option('shard_fused', 0)
 
     def _pre_close(self):
         # no rank may free its exchange region while a peer can still read it

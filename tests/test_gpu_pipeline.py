@@ -167,7 +167,8 @@ def test_statistical_parity_with_cpu_restatement():
         c_ess = o.ess_rank_normalized(c_info[n // 2:, :, 0].T[:, :, None], rank_normalize=False)
         assert 0.5 <= float(np.mean(g_ess)) / float(np.mean(c_ess)) <= 2.0, (seed, np.mean(g_ess), np.mean(c_ess))
         # parameter-space split-R-hat over the kept samples of the second half: [C, S/2, d]
-        gs, cs = np.transpose(g_samples[g_samples.shape[0] // 2:], (1, 0, 2)), np.transpose(c_samples[c_samples.shape[0] // 2:], (1, 0, 2))
+        half = g_samples.shape[0] // 2 // 4 * 4          # second half, trimmed to a multiple of the 4 splits
+        gs, cs = np.transpose(g_samples[-half:], (1, 0, 2)), np.transpose(c_samples[-half:], (1, 0, 2))
         gr, cr = o.split_chain_r_hat(gs, 4), o.split_chain_r_hat(cs, 4)
         assert abs(np.median(gr) - np.median(cr)) <= 0.15, (seed, np.median(gr), np.median(cr))
     k = len(d_lppd)
