@@ -88,6 +88,9 @@ struct mile_ctx {
   float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
+  float* w_fin = nullptr;     // finalize scratch: [chains][32 CTAs][2] partial scalars, then [chains] arrival tickets
+  float* w_arena = nullptr; size_t w_arena_floats = 0;   // partial sums of one evaluation, summed by wide_finalize_kernel (WideJobs)
+  int opt_head_fused = 1;                                 // wide path: fused output-layer kernel (0 = separate streaming kernels)
   float *w_wpk = nullptr, *w_wpk_lo = nullptr, *w_wpkT = nullptr,
         *w_wpkT_lo = nullptr;
   long w_n8 = 0, w_wstride = 0; long w_woff[MILE_MAX_LAYERS] = {0};
@@ -420,7 +423,7 @@ static int launch_metrics(const MetricsParams& T, int n, size_t smem, cudaStream
 
 extern "C" {
 
-static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st);
+static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st, int n_layers = -1);
 static int wide_predict(mile_ctx* c, const float* theta, int n, int which, float* out, cudaStream_t st);
 static int wide_lppd_fold(mile_ctx* c, const float* theta, int n, cudaStream_t st);
 static int wide_alloc(mile_ctx* c, int n_chains);
@@ -478,7 +481,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo};
+                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   for (int r = 0; r < 8; ++r) if (c->xr_peer[r] && c->xr_peer[r] != c->xr) cudaIpcCloseMemHandle(c->xr_peer[r]);
@@ -501,6 +504,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
   else if (!strcmp(key, "kslices")) { c->opt_kslices = (int)v; c->w_rows = -1; }   // wide path: split-K slices of the dW GEMMs (0 = auto)
+  else if (!strcmp(key, "head_fused")) c->opt_head_fused = (int)v;   // wide path: fused output-layer kernel on / off
   else if (!strcmp(key, "shard_fused")) c->opt_shard_fused = (int)v;   // 1: multi-rank step loop as ONE persistent kernel per rank (needs the peer mapping), 0: one launch per phase
   else if (!strcmp(key, "steploop")) c->opt_steploop = (int)v;   // 1: integrator-warp step loop of the tensor evaluator, 0: generic loop
   else return fail(std::string("unknown option ") + key);
@@ -1100,7 +1104,26 @@ static int wide_alloc(mile_ctx* c, int n_chains) {
   CK(cudaMemset(c->w_delta[0], 0, delb)); CK(cudaMemset(c->w_delta[1], 0, delb));
   CK(cudaMemset(c->w_wpk, 0, (size_t)n_chains * wsum * 4)); CK(cudaMemset(c->w_wpk_lo, 0, (size_t)n_chains * wsum * 4));
   c->w_part_per_chain = (long)c->w_kslices * maxio;
-  CK(cudaMalloc(&c->w_part, (size_t)n_chains * c->w_kslices * maxio * 4));
+  CK(cudaMalloc(&c->w_part, 64));      // (legacy scratch; the partial sums of an evaluation live in the arena below)
+  {
+    // arena of partial sums, per chain and layer: split-K slices (GEMM layers) or 148 row slices (skinny layers) of dW,
+    // and row-group column sums (<= 4 per 128-row block, or 148 row slices) for the bias; + the fused head's partials
+    size_t per_chain = 0;
+    const long nmb = (N + 127) / 128;
+    for (int l = 0; l < M.NL; ++l) {
+      const long IN = M.dims[l], OUT = M.dims[l + 1];
+      const long ns_w = (IN <= WS_KMAX || OUT <= WS_KMAX) ? 148 : c->w_kslices;
+      per_chain += (size_t)ns_w * IN * OUT + 32;
+      per_chain += (size_t)(4 * nmb > 148 ? 4 * nmb : 148) * OUT + 32;
+    }
+    per_chain += (size_t)4 * 148 * ((size_t)maxw * 9 + 16) + 128;      // fused head: <= 592 CTAs x (IN*K + IN + K + 1), K <= 8
+    if (c->w_arena) { cudaFree(c->w_arena); c->w_arena = nullptr; }
+    if (c->w_fin) { cudaFree(c->w_fin); c->w_fin = nullptr; }
+    CK(cudaMalloc(&c->w_fin, (size_t)n_chains * (64 + 1) * 4 + 64));
+    CK(cudaMemset(c->w_fin, 0, (size_t)n_chains * (64 + 1) * 4 + 64));
+    c->w_arena_floats = per_chain * n_chains + 1024;
+    CK(cudaMalloc(&c->w_arena, c->w_arena_floats * 4));
+  }
   CK(cudaMalloc(&c->w_llpart, (size_t)n_chains * c->w_nblk * 4 + 64));
   CK(cudaMalloc(&c->w_ones, (size_t)N * 4 + 64));
   CK(cudaMalloc(&c->w_gl, (size_t)n_chains * (c->d + 1) * 4));
@@ -1170,6 +1193,7 @@ static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   t.M = g.M; t.N = g.N; t.K = g.K; t.kslices = g.kslices; t.nbatch = g.nbatch;
   t.C = g.C; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
   t.bias = g.bias; t.bias_batch = g.bias_batch; t.aux = g.aux; t.aux_batch = g.aux_batch; t.ldaux = g.ldaux;
+  t.csum = g.csum;
   const int ntiles = ((g.M + T2_BM - 1) / T2_BM) * ((g.N + T2_BN - 1) / T2_BN) * g.nbatch * g.kslices;
   const int grid = ntiles < c->n_sms ? ntiles : c->n_sms;      // persistent: one CTA per SM, tiles strided over the grid
   const bool relu = g.act == MILE_ACT_RELU;
@@ -1211,48 +1235,91 @@ static int wide_gemm(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
 
 // skinny GEMM (K <= 16 or N <= 8): streaming kernels, no tile padding
 static int wide_skinny(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
-  if (g.K <= WS_KMAX) wide_smallk_kernel<<<dim3((g.M + 63) / 64, (g.N + 255) / 256, g.nbatch), 256, 0, st>>>(g);
+  if (g.K <= WS_KMAX && g.epi == 1 && g.sak == 1 && (g.N & 3) == 0 && (g.ldc & 3) == 0 && (g.c_batch & 3) == 0 &&
+      ((uintptr_t)g.C & 15) == 0) {            // forward of the first layer: dedicated register-stationary kernel
+    const dim3 grid((g.M + 127) / 128, (g.N + 255) / 256, g.nbatch);
+    const int KQ = (g.K + 3) / 4;
+    const bool relu = g.act == MILE_ACT_RELU;
+#define FIRST_LAUNCH(KQv) do { if (relu) wide_first_kernel<KQv, true><<<grid, 256, 0, st>>>(g); else wide_first_kernel<KQv, false><<<grid, 256, 0, st>>>(g); } while (0)
+    if (KQ == 1) FIRST_LAUNCH(1); else if (KQ == 2) FIRST_LAUNCH(2); else if (KQ == 3) FIRST_LAUNCH(3); else FIRST_LAUNCH(4);
+#undef FIRST_LAUNCH
+  }
+  else if (g.K <= WS_KMAX) wide_smallk_kernel<<<dim3((g.M + 63) / 64, (g.N + 255) / 256, g.nbatch), 256, 0, st>>>(g);
   else wide_smalln_kernel<<<dim3((g.M + 63) / 64, 1, g.nbatch), 256, 0, st>>>(g);
   CK(cudaGetLastError());
   c->launches++;
   return 0;
 }
 
-// dst[b][...] = sum_r Wd(r, t) S(r, q) (S == nullptr: column sums) through row slices + the fixed-order slice reduction
-static int wide_rowreduce(mile_ctx* c, const float* Wd, long wd_batch, long wd_ld, int WD, const float* S, long s_batch, long s_ld,
-                          int s, int small_is_row, long rows, int n, float* dst, long dst_batch, long n_out, cudaStream_t st) {
-  RowReduceArgs a;
-  a.Wd = Wd; a.wd_batch = wd_batch; a.wd_ld = wd_ld; a.WD = WD; a.S = S; a.s_batch = s_batch; a.s_ld = s_ld; a.s = s;
-  a.small_is_row = small_is_row; a.rows = rows;
-  long nsl = 148;   // with 8 chains: 1184 CTAs = 8 per SM
-  if (nsl * n_out > c->w_part_per_chain) nsl = c->w_part_per_chain / n_out;
-  if (nsl < 1) return fail("wide path: partial buffer too small");
-  if (nsl > rows) nsl = rows;
-  a.nslices = (int)nsl; a.part = c->w_part; a.p_slice = n_out; a.p_batch = nsl * n_out;
-  wide_rowreduce_kernel<<<dim3((unsigned)nsl, (WD + 255) / 256, n), 256, 0, st>>>(a);
-  wide_slice_reduce_kernel<<<n_out * n >= 148 * 256 ? 148 : 32, 256, 0, st>>>(c->w_part, a.p_batch, a.p_slice, (int)nsl, dst, dst_batch, n_out, n);
-  CK(cudaGetLastError());
-  c->launches += 2;
+// ---- partial-sum arena + reduction jobs of one evaluation (summed by wide_finalize_kernel) -----------------------
+struct WideEvalState { WideJobs J; size_t used; };
+static float* arena_take(mile_ctx* c, WideEvalState& E, size_t floats) {
+  floats = (floats + 31) / 32 * 32;
+  if (E.used + floats > c->w_arena_floats) return nullptr;
+  float* p = c->w_arena + E.used;
+  E.used += floats;
+  return p;
+}
+static int add_job(WideEvalState& E, const float* src, long src_batch, long slice, int nslices, int dst_off, int len) {
+  if (E.J.n >= WJ_MAX) return fail("wide path: too many reduction jobs");
+  const int j = E.J.n++;
+  E.J.src[j] = src; E.J.src_batch[j] = src_batch; E.J.slice[j] = slice; E.J.nslices[j] = nslices; E.J.dst_off[j] = dst_off; E.J.len[j] = len;
   return 0;
 }
 
+// partials of  sum_r Wd(r, t) S(r, q)  (S == nullptr: column sums) over row slices; the sum over the slices is a finalize job
+static int wide_rowreduce(mile_ctx* c, WideEvalState& E, const float* Wd, long wd_batch, long wd_ld, int WD, const float* S, long s_batch,
+                          long s_ld, int s, int small_is_row, long rows, int n, int dst_off, long n_out, cudaStream_t st) {
+  RowReduceArgs a;
+  a.Wd = Wd; a.wd_batch = wd_batch; a.wd_ld = wd_ld; a.WD = WD; a.S = S; a.s_batch = s_batch; a.s_ld = s_ld; a.s = s;
+  a.small_is_row = small_is_row; a.rows = rows;
+  // dW of a layer with few inputs (S = its input rows): float4-streaming kernel with S staged in shared memory
+  const bool dw_small = S && small_is_row && (WD & 3) == 0 && (wd_ld & 3) == 0 && (wd_batch & 3) == 0 && ((uintptr_t)Wd & 15) == 0;
+  long nsl = dw_small ? (4 * c->n_sms + n - 1) / n : 148;   // with 8 chains: 592 / 1184 CTAs
+  if (nsl > 148) nsl = 148;
+  if (nsl > rows) nsl = rows;
+  float* part = arena_take(c, E, (size_t)n * nsl * n_out);
+  if (!part) return fail("wide path: partial arena too small");
+  a.nslices = (int)nsl; a.part = part; a.p_slice = n_out; a.p_batch = nsl * n_out;
+  const dim3 grid((unsigned)nsl, (WD + 255) / 256, n);
+  if (dw_small) {
+    const int KQ = (s + 3) / 4;
+    if (KQ == 1) wide_dw_small_kernel<1><<<grid, 256, 0, st>>>(a);
+    else if (KQ == 2) wide_dw_small_kernel<2><<<grid, 256, 0, st>>>(a);
+    else if (KQ == 3) wide_dw_small_kernel<3><<<grid, 256, 0, st>>>(a);
+    else wide_dw_small_kernel<4><<<grid, 256, 0, st>>>(a);
+  } else wide_rowreduce_kernel<<<grid, 256, 0, st>>>(a);
+  CK(cudaGetLastError());
+  c->launches++;
+  return add_job(E, part, a.p_batch, a.p_slice, (int)nsl, dst_off, (int)n_out);
+}
+
 // forward pass of n chains over the rows of one split: activations a_1..a_NL into actbuf ([n][N8][dims[l]] each, a_NL last)
-static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st) {
+static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs, long N, long N8, float* actbuf, cudaStream_t st, int n_layers) {
   const DevModel& M = c->M;
   const int d = c->d, NL = M.NL;
+  if (n_layers < 0) n_layers = NL;
   std::vector<long> aoff(NL + 2, 0);
   for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
   auto act = [&](int l) { return actbuf + aoff[l]; };
   const bool tc2 = c->opt_tensor >= 2;
-  if (tc2) {                                  // aligned packed copies of the weights + their tf32 remainders
-    for (int l = 0; l < NL; ++l) {
-      wide_pack_weights_kernel<<<148, 256, 0, st>>>(theta, d, M.kern_off[l], M.dims[l], M.dims[l + 1], c->w_wpk, c->w_wpk_lo, c->w_wpkT,
-                                                    c->w_wpkT_lo, c->w_woff[l], c->w_wstride, n);
+  if (tc2) {                                  // aligned packed copies of the weights + their tf32 remainders (GEMM layers only)
+    PackArgs pa; memset(&pa, 0, sizeof(pa));
+    for (int l = 0; l < NL && pa.n_layers < 13; ++l) {
+      // layers whose forward AND backward products are skinny stream their weights from theta (first layer with few
+      // features: no input delta is ever formed; output layer with few outputs)
+      if ((l == 0 && M.dims[0] <= WS_KMAX) || (M.dims[l + 1] <= WS_NMAX && M.dims[l] <= 1024)) continue;
+      const int k = pa.n_layers++;
+      pa.kern_off[k] = M.kern_off[l]; pa.IN[k] = M.dims[l]; pa.OUT[k] = M.dims[l + 1]; pa.pack_off[k] = c->w_woff[l];
+    }
+    if (pa.n_layers > 0) {
+      wide_pack_weights_kernel<<<dim3(74, pa.n_layers), 256, 0, st>>>(theta, d, pa, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo,
+                                                                      c->w_wstride, n);
+      CK(cudaGetLastError());
       c->launches++;
     }
-    CK(cudaGetLastError());
   }
-  for (int l = 0; l < NL; ++l) {              // forward
+  for (int l = 0; l < n_layers; ++l) {        // forward
     GemmArgs g; memset(&g, 0, sizeof(g));
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     if (l == 0) { g.A = Xs; g.a_batch = 0; g.sam = M.sA[0]; g.sak = 1; }
@@ -1320,34 +1387,69 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
   for (int l = 1; l <= NL; ++l) aoff[l + 1] = aoff[l] + (long)n * N8 * M.dims[l];
   auto act = [&](int l) { return c->w_act + aoff[l]; };
   const bool tc2 = c->opt_tensor >= 2;
-  if (wide_forward(c, theta, n, c->X, N, N8, c->w_act, st)) return -1;
-  float* dcur = c->w_delta[(NL - 1) & 1];
-  wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), dcur, c->y, N, N8, c->w_llpart);
-  CK(cudaGetLastError());
-  c->launches++;
-  for (int l = NL - 1; l >= 0; --l) {         // dW_l, db_l, then the delta of the layer below
+  WideEvalState E; memset(&E, 0, sizeof(E));
+  // fused output layer: last hidden width 128 or 256, <= 8 outputs, activation whose derivative follows from its value
+  const int HIN = NL >= 2 ? M.dims[NL - 1] : 0, HK = M.dims[NL];
+  const bool head_fused = c->opt_head_fused && NL >= 2 && (HIN == 128 || HIN == 256) && HK <= 8;
+  if (wide_forward(c, theta, n, c->X, N, N8, c->w_act, st, head_fused ? NL - 1 : NL)) return -1;
+  const float* llpart = c->w_llpart; int n_llpart = c->w_nblk;
+  bool have_colsum = false;                   // the column sums (bias gradient) of the current delta are already a job
+  if (head_fused) {
+    int nblk = (4 * c->n_sms + n - 1) / n;
+    if (nblk > (N + 31) / 32) nblk = (int)((N + 31) / 32);
+    const int KP = HK <= 2 ? 2 : 8;
+    HeadArgs h; memset(&h, 0, sizeof(h));
+    h.a_last = act(NL - 1); h.a_batch = N8 * HIN; h.D = c->w_delta[(NL - 2) & 1]; h.d_batch = N8 * HIN;
+    h.theta = theta; h.d = d; h.kern_off = M.kern_off[NL - 1]; h.bias_off = M.bias_off[NL - 1];
+    h.y = c->y; h.N = N; h.rows_per_cta = (int)((N + nblk - 1) / nblk);
+    h.pW = arena_take(c, E, (size_t)n * nblk * HIN * HK); h.pb = arena_take(c, E, (size_t)n * nblk * HK);
+    h.pcol = arena_take(c, E, (size_t)n * nblk * HIN); h.pll = arena_take(c, E, (size_t)n * nblk);
+    if (!h.pW || !h.pb || !h.pcol || !h.pll) return fail("wide path: partial arena too small");
+    const size_t smem = ((size_t)HIN * KP + KP + 8 * ((size_t)HIN * KP + HIN + KP + 1)) * 4;
+#define HEAD_LAUNCH(NV, KPv)                                                                                              \
+    do {                                                                                                                  \
+      CK(cudaFuncSetAttribute(wide_head_kernel<NV, KPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+      wide_head_kernel<NV, KPv><<<dim3(nblk, n), 256, smem, st>>>(M, h);                                                  \
+    } while (0)
+    if (HIN == 128) { if (KP == 2) HEAD_LAUNCH(1, 2); else HEAD_LAUNCH(1, 8); }
+    else { if (KP == 2) HEAD_LAUNCH(2, 2); else HEAD_LAUNCH(2, 8); }
+#undef HEAD_LAUNCH
+    CK(cudaGetLastError());
+    c->launches++;
+    if (add_job(E, h.pW, (long)nblk * HIN * HK, (long)HIN * HK, nblk, M.kern_off[NL - 1], HIN * HK)) return -1;
+    if (add_job(E, h.pb, (long)nblk * HK, HK, nblk, M.bias_off[NL - 1], HK)) return -1;
+    if (add_job(E, h.pcol, (long)nblk * HIN, HIN, nblk, M.bias_off[NL - 2], HIN)) return -1;
+    llpart = h.pll; n_llpart = nblk;
+    have_colsum = true;
+  } else {
+    wide_loglik_kernel<<<dim3(c->w_nblk, n), 256, 0, st>>>(M, act(NL), c->w_delta[(NL - 1) & 1], c->y, N, N8, c->w_llpart);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  for (int l = head_fused ? NL - 2 : NL - 1; l >= 0; --l) {         // dW_l, db_l, then the delta of the layer below
     const int IN = M.dims[l], OUT = M.dims[l + 1];
     float* D = c->w_delta[l & 1];
     const float* Aop = l == 0 ? c->X : act(l);
     const long a_bs = l == 0 ? 0 : N8 * IN, a_ld = l == 0 ? M.sA[0] : IN;
     if (IN <= WS_KMAX) {          // dW[i][j] = sum_r A(r,i) D(r,j), few rows i: thread = column j of D
-      if (wide_rowreduce(c, D, N8 * OUT, OUT, OUT, Aop, a_bs, a_ld, IN, 1, N, n, gl + M.kern_off[l], d + 1, (long)IN * OUT, st)) return -1;
+      if (wide_rowreduce(c, E, D, N8 * OUT, OUT, OUT, Aop, a_bs, a_ld, IN, 1, N, n, M.kern_off[l], (long)IN * OUT, st)) return -1;
     } else if (OUT <= WS_KMAX) {  // few columns j: thread = column i of A
-      if (wide_rowreduce(c, Aop, a_bs, a_ld, IN, D, N8 * OUT, OUT, OUT, 0, N, n, gl + M.kern_off[l], d + 1, (long)IN * OUT, st)) return -1;
+      if (wide_rowreduce(c, E, Aop, a_bs, a_ld, IN, D, N8 * OUT, OUT, OUT, 0, N, n, M.kern_off[l], (long)IN * OUT, st)) return -1;
     } else {
       GemmArgs g; memset(&g, 0, sizeof(g));
       g.A = Aop; g.a_batch = a_bs; g.sam = 1; g.sak = a_ld;
       g.B = D; g.b_batch = N8 * OUT; g.sbk = OUT; g.sbn = 1;
       g.M = IN; g.N = OUT; g.K = (int)N8; g.kslices = c->w_kslices; g.nbatch = n; g.epi = 0;
-      g.C = c->w_part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
+      float* part = arena_take(c, E, (size_t)n * c->w_kslices * IN * OUT);
+      if (!part) return fail("wide path: partial arena too small");
+      g.C = part; g.c_slice = (long)IN * OUT; g.c_batch = (long)c->w_kslices * IN * OUT; g.ldc = OUT;
       if (wide_gemm(c, g, st)) return -1;
-      wide_slice_reduce_kernel<<<148, 256, 0, st>>>(c->w_part, g.c_batch, g.c_slice, c->w_kslices, gl + M.kern_off[l],
-                                                   d + 1, (long)IN * OUT, n);
-      CK(cudaGetLastError());
-      c->launches++;
+      if (add_job(E, part, g.c_batch, g.c_slice, c->w_kslices, M.kern_off[l], IN * OUT)) return -1;
     }
-    // bias gradient = column sums of D
-    if (wide_rowreduce(c, D, N8 * OUT, OUT, OUT, nullptr, 0, 0, 1, 1, N, n, gl + M.bias_off[l], d + 1, (long)OUT, st)) return -1;
+    // bias gradient = column sums of D (already a job when the kernel that produced D summed its columns)
+    if (!have_colsum &&
+        wide_rowreduce(c, E, D, N8 * OUT, OUT, OUT, nullptr, 0, 0, 1, 1, N, n, M.bias_off[l], (long)OUT, st)) return -1;
+    have_colsum = false;
     if (l > 0) {
       GemmArgs w; memset(&w, 0, sizeof(w));
       w.A = D; w.a_batch = N8 * OUT; w.sam = OUT; w.sak = 1;
@@ -1360,19 +1462,31 @@ static int wide_eval(mile_ctx* c, const float* theta, int n, float* gl, float pr
       if (OUT <= WS_KMAX) {
         w.B = theta + M.kern_off[l]; w.B_lo = nullptr; w.b_batch = d;
         if (wide_skinny(c, w, st)) return -1;
-      } else if (wide_gemm(c, w, st)) return -1;
+      } else {
+        // TMA core with a full-width epilogue: it also leaves the column sums of the new delta (bias gradient of layer l-1)
+        const long nmb = (N + T2_BM - 1) / T2_BM;
+        const bool cs_ok = tc2 && OUT >= 32 && IN >= 64 && N >= 64 && (IN % T2_BN) == 0 && (OUT & 3) == 0 &&
+                           tc2_operand_ok(w.A, OUT, w.a_batch) && tc2_operand_ok(w.B, OUT, w.b_batch) && tc2_operand_ok(w.B_lo, OUT, w.b_batch) &&
+                           tc2_operand_ok(w.C, IN, w.c_batch) && tc2_operand_ok(w.aux, IN, w.aux_batch);
+        if (cs_ok) {
+          w.csum = arena_take(c, E, (size_t)n * nmb * 4 * IN);
+          if (!w.csum) return fail("wide path: partial arena too small");
+        }
+        if (wide_gemm(c, w, st)) return -1;
+        if (cs_ok) {
+          if (add_job(E, w.csum, nmb * 4 * IN, IN, (int)(nmb * 4), M.bias_off[l - 1], IN)) return -1;
+          have_colsum = true;
+        }
+      }
     }
   }
   {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)n * WF_CLUSTER, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = WF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const float* th_c = theta; const float* ll_c = c->w_llpart; int nblk = c->w_nblk;
-    CK(cudaLaunchKernelEx(&cfg, wide_finalize_kernel, M, th_c, gl, ll_c, nblk, prior_weight));
+    int NB = c->n_sms / n;       // CTAs per chain: the pass over the partials (89 MB for 4x256 x 8 chains) needs every SM
+    if (NB < 1) NB = 1;
+    if (NB > 32) NB = 32;
+    const int wc = c->w_chains > n ? c->w_chains : n;
+    wide_finalize_kernel<<<dim3(NB, n), 1024, 0, st>>>(M, theta, gl, llpart, n_llpart, prior_weight, c->w_fin,
+                                                       reinterpret_cast<unsigned int*>(c->w_fin + (size_t)wc * 64), E.J);
   }
   CK(cudaGetLastError());
   c->launches++;

@@ -22,6 +22,7 @@ struct GemmArgs {
   const float* bias; long bias_batch;
   const float* aux; long aux_batch; long ldaux;
   int act, nbatch;
+  float* csum;                                     // TMA core, epi 3: optional column-sum partials of C (see Tc2Args)
 };
 
 __device__ __forceinline__ float act_value(int act, float z) {
@@ -387,9 +388,6 @@ __global__ void __launch_bounds__(256) wide_loglik_kernel(DevModel M, const floa
   if (threadIdx.x == 0) llpart[(long)c * gridDim.x + blockIdx.x] = v[0];
 }
 
-// gl[c][0..d) += prior gradient * w ; gl[c][d] = n_batches * sum(ll partials) + w * log prior   (one CTA per chain)
-// launched as clusters of WF_CLUSTER CTAs per chain: the d elements are strided over the cluster's threads and the two
-// partial sums are combined over DSMEM in rank order (one CTA per chain would be a latency-bound 200k-element loop)
 // Online logsumexp fold of forward outputs out [n][Nt][K] into the per-chain state (same update as lppd_fold, mile_kernel.cuh)
 __global__ void __launch_bounds__(256) wide_lppd_fold_kernel(DevModel M, const float* __restrict__ out, const void* __restrict__ yt,
                                                              float* __restrict__ lm, float* __restrict__ ls, int n, long Nt) {
@@ -407,35 +405,408 @@ __global__ void __launch_bounds__(256) wide_lppd_fold_kernel(DevModel M, const f
 }
 
 #define WF_CLUSTER 8
+// Every parameter-gradient block of an evaluation (kernel / bias of each layer) is left by its producer as `nslices`
+// partial sums (split-K slices of the dW GEMMs, per-CTA partials of the streaming kernels, per-row-group column sums of
+// the delta epilogues).  The finalize kernel adds them in slice order -- ONE pass instead of a slice-reduction launch
+// behind every producer (8 launches and 20 % of the kernel time of an evaluation, profiles/r2n_launches_wide_4x256.csv).
+#define WJ_MAX 32
+struct WideJobs {
+  int n;
+  const float* src[WJ_MAX]; long src_batch[WJ_MAX]; long slice[WJ_MAX];
+  int nslices[WJ_MAX], dst_off[WJ_MAX], len[WJ_MAX];
+};
+
+// gl[c][i] = sum of the partials of element i + w * prior gradient;  gl[c][d] = n_batches * sum(ll partials) + w * log prior
+// grid (NB, chains): the d elements of a chain are strided over the NB x 1024 threads of its CTAs (the partials of the
+// 4x256 config are 89 MB: the pass needs every SM).  The two per-chain scalars go through per-CTA partials; the CTA that
+// arrives last (atomic ticket) adds them in CTA order, so the value does not depend on which CTA that was.
 __global__ void __launch_bounds__(1024) wide_finalize_kernel(DevModel M, const float* __restrict__ theta, float* __restrict__ gl,
-                                                            const float* __restrict__ llpart, int nblk, float prior_weight) {
+                                                            const float* __restrict__ llpart, int nblk, float prior_weight,
+                                                            float* __restrict__ fin_part, unsigned int* __restrict__ fin_count,
+                                                            const __grid_constant__ WideJobs J) {
   __shared__ __align__(16) float red[256];
-  __shared__ float slot[2];
-  cg::cluster_group cl = cg::this_cluster();
-  const int G = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  __shared__ int is_last;
+  const int G = (int)gridDim.x, rank = (int)blockIdx.x;
   int phase = 0;
-  const int c = blockIdx.x / G, d = M.d;
+  const int c = blockIdx.y, d = M.d;
   const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
   const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
   float v[2] = {0.f, 0.f};
-  for (int i = rank * 1024 + threadIdx.x; i < d; i += G * 1024) {
-    const float dlt = theta[(long)c * d + i] - loc;
-    float pv, pg;
-    if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
-    else { pv = -lognorm - fabsf(dlt) / sc; pg = -((dlt > 0.f) - (dlt < 0.f)) / sc; }
-    gl[(long)c * (d + 1) + i] += pg * prior_weight;
-    v[0] += pv;
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < J.n; ++j) {
+    const float* __restrict__ src = J.src[j] + (long)c * J.src_batch[j];
+    const long slice = J.slice[j];
+    const int ns = J.nslices[j], len = J.len[j], off = J.dst_off[j];
+    // TPE threads (a power of two <= 32, consecutive lanes) share one element: lane t adds slices t, t + TPE, ... and the
+    // group finishes with an xor-shuffle tree.  Many-slice jobs (row-group column sums: 4 per 128-row block, per-CTA
+    // partials of the streaming kernels) would otherwise be a serial chain of hundreds of L2 round trips on a handful of
+    // threads.  The association is fixed by (ns, TPE): run-to-run deterministic.
+    int tpe = 1;
+    while (tpe < 32 && tpe * 8 <= ns) tpe <<= 1;
+    if (tpe == 1 && (len & 3) == 0 && (slice & 3) == 0 && (J.src_batch[j] & 3) == 0 && (reinterpret_cast<uintptr_t>(J.src[j]) & 15) == 0) {
+      // few slices, long block (split-K partials of a weight matrix): four consecutive elements per thread, 16-byte loads
+      for (int e4 = rank * 1024 + threadIdx.x; e4 < (len >> 2); e4 += G * 1024) {
+        const float4* p = reinterpret_cast<const float4*>(src) + e4;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        int k = 0;
+#pragma unroll 4
+        for (; k + 1 < ns; k += 2) {
+          const float4 a = p[(long)k * (slice >> 2)], b = p[(long)(k + 1) * (slice >> 2)];
+          s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+        }
+        if (k < ns) { const float4 a = p[(long)k * (slice >> 2)]; s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; }
+        const float sum4[4] = {s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = off + 4 * e4 + q;
+          const float dlt = theta[(long)c * d + i] - loc;
+          float pv, pg;
+          if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
+          else { pv = -lognorm - fabsf(dlt) / sc; pg = -((dlt > 0.f) - (dlt < 0.f)) / sc; }
+          gl[(long)c * (d + 1) + i] = sum4[q] + pg * prior_weight;
+          v[0] += pv;
+        }
+      }
+      continue;
+    }
+    const int sub = lane & (tpe - 1);
+    const int per_pass = (G * 1024) / tpe;
+    const int npass = (len + per_pass - 1) / per_pass;
+    for (int ps = 0; ps < npass; ++ps) {      // (uniform trip count: the shuffles below need whole warps)
+      const int e = ps * per_pass + (rank * 1024 + (int)threadIdx.x) / tpe;
+      const bool on = e < len;
+      const float* p = src + (on ? e : 0);
+      float s0 = 0.f, s1 = 0.f, s2_ = 0.f, s3 = 0.f;
+      int k = sub;
+      if (on) {
+#pragma unroll 2
+        for (; k + 3 * tpe < ns; k += 4 * tpe) {
+          s0 += p[(long)k * slice]; s1 += p[(long)(k + tpe) * slice]; s2_ += p[(long)(k + 2 * tpe) * slice]; s3 += p[(long)(k + 3 * tpe) * slice];
+        }
+        for (; k < ns; k += tpe) s0 += p[(long)k * slice];
+      }
+      float sum = (s0 + s1) + (s2_ + s3);
+      for (int o = tpe >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (on && sub == 0) {
+        const int i = off + e;
+        const float dlt = theta[(long)c * d + i] - loc;
+        float pv, pg;
+        if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
+        else { pv = -lognorm - fabsf(dlt) / sc; pg = -((dlt > 0.f) - (dlt < 0.f)) / sc; }
+        gl[(long)c * (d + 1) + i] = sum + pg * prior_weight;
+        v[0] += pv;
+      }
+    }
   }
   for (int i = rank * 1024 + threadIdx.x; i < nblk; i += G * 1024) v[1] += llpart[(long)c * nblk + i];
   block_sum<2, 1024>(v, red, phase);
-  if (threadIdx.x == 0) { slot[0] = v[0]; slot[1] = v[1]; }
-  cl.sync();
-  if (rank == 0 && threadIdx.x == 0) {
-    float p = 0.f, l = 0.f;
-    for (int r = 0; r < G; ++r) { const float* rs = cl.map_shared_rank(slot, r); p += rs[0]; l += rs[1]; }
-    gl[(long)c * (d + 1) + d] = l * M.n_batches + p * prior_weight;
+  if (threadIdx.x == 0) {
+    fin_part[((long)c * G + rank) * 2] = v[0]; fin_part[((long)c * G + rank) * 2 + 1] = v[1];
+    __threadfence();
+    is_last = atomicAdd(fin_count + c, 1u) == (unsigned int)(G - 1);
   }
-  cl.sync();
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float p = 0.f, l = 0.f;
+    for (int r = 0; r < G; ++r) {
+      p += *reinterpret_cast<volatile float*>(fin_part + ((long)c * G + r) * 2);
+      l += *reinterpret_cast<volatile float*>(fin_part + ((long)c * G + r) * 2 + 1);
+    }
+    gl[(long)c * (d + 1) + d] = l * M.n_batches + p * prior_weight;
+    fin_count[c] = 0u;      // ready for the next launch (stream order)
+  }
+}
+
+// =====================================================================================================
+// First layer (K = n_features <= 16).  Forward  C = act(A B + bias):  the thread's [K][4] slab of B and its bias stay in
+// registers, the CTA's 128 rows of A are staged once in shared memory, a row costs KQ broadcast LDS.128 + 4 K FMAs + one
+// 16-byte store (the generic wide_smallk_kernel spent 41 % of the issue slots for 0.9 TB/s: runtime activation switch,
+// predicated K loop, 64-row CTAs at two CTAs per SM; ncu in profiles/r2v_ncu_wide_small_kernels.txt).
+// grid (ceil(M/128), ceil(N/256), batch), 256 threads; requires A rows contiguous (sak == 1), N % 4 == 0, aligned C.
+// =====================================================================================================
+template <int KQ, bool RELU>
+__global__ void __launch_bounds__(256) wide_first_kernel(const GemmArgs g) {
+  constexpr int KP = 4 * KQ, ROWS = 128;
+  __shared__ __align__(16) float As[ROWS][KP];
+  const int b = blockIdx.z, n0 = blockIdx.y * 256, m0 = blockIdx.x * ROWS, tid = threadIdx.x;
+  const float* A = g.A + (long)b * g.a_batch;
+  const float* B = g.B + (long)b * g.b_batch;
+  const float* bias = g.bias + (long)b * g.bias_batch;
+  float* C = g.C + (long)b * g.c_batch;
+  for (int e = tid; e < ROWS * KP; e += 256) {
+    const int r = e / KP, k = e % KP;
+    As[r][k] = (m0 + r < g.M && k < g.K) ? __ldg(A + (long)(m0 + r) * g.sam + k) : 0.f;
+  }
+  const int tx = tid & 63, ty = tid >> 6, n = n0 + tx * 4;
+  float wreg[KP][4], bs[4];
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wreg[k][e] = (k < g.K && n + e < g.N) ? __ldg(B + (long)k * g.sbk + (long)(n + e) * g.sbn) : 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) bs[e] = n + e < g.N ? __ldg(bias + n + e) : 0.f;
+  __syncthreads();
+  if (n >= g.N) return;
+  const int mend = min(g.M - m0, ROWS);
+#pragma unroll 2
+  for (int r = ty; r < mend; r += 4) {
+    float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = fmaf(a.x, wreg[4 * q][e], o[e]); o[e] = fmaf(a.y, wreg[4 * q + 1][e], o[e]);
+        o[e] = fmaf(a.z, wreg[4 * q + 2][e], o[e]); o[e] = fmaf(a.w, wreg[4 * q + 3][e], o[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = RELU ? fmaxf(o[e], 0.f) : act_value(g.act, o[e]);
+    *reinterpret_cast<float4*>(C + (long)(m0 + r) * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Weight gradient of a layer with few inputs:  part[b][slice][i * WD + j] = sum_{r in slice} S(r, i) Wd(r, j),  i < K <= 4 KQ.
+// Thread = 4 columns j of the wide operand (one LDG.128 per row, four rows in flight), S rows staged in shared memory;
+// the four row phases of a CTA are added through shared memory.  grid (nslices, ceil(WD/256), batch), 256 threads;
+// requires WD % 4 == 0, wd_ld % 4 == 0, aligned Wd.
+template <int KQ>
+__global__ void __launch_bounds__(256) wide_dw_small_kernel(const RowReduceArgs g) {
+  constexpr int KP = 4 * KQ, CH = 128;
+  __shared__ __align__(16) float Ss[CH][KP];
+  __shared__ __align__(16) float red[KP][256];
+  const int b = blockIdx.z, sl = blockIdx.x, tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  const int j = blockIdx.y * 256 + tx * 4;
+  const long per = (g.rows + g.nslices - 1) / g.nslices, r0 = sl * per, r1 = min(g.rows, r0 + per);
+  const float* W = g.Wd + (long)b * g.wd_batch + j;
+  const float* S = g.S + (long)b * g.s_batch;
+  float acc[KP][4];
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
+  const bool on = j < g.WD;
+  for (long c0 = r0; c0 < r1; c0 += CH) {
+    const int nr = (int)min((long)CH, r1 - c0);
+    __syncthreads();
+    for (int e = tid; e < CH * KP; e += 256) {
+      const int r = e / KP, k = e % KP;
+      Ss[r][k] = (r < nr && k < g.s) ? __ldg(S + (c0 + r) * g.s_ld + k) : 0.f;
+    }
+    __syncthreads();
+    if (on) {
+      for (int r = ty; r < nr; r += 16) {
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          w[u] = r + 4 * u < nr ? __ldg(reinterpret_cast<const float4*>(W + (c0 + r + 4 * u) * g.wd_ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r + 4 * u >= nr) break;
+#pragma unroll
+          for (int q = 0; q < KQ; ++q) {
+            const float4 sv = *reinterpret_cast<const float4*>(&Ss[r + 4 * u][4 * q]);
+            const float s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              acc[4 * q + kk][0] = fmaf(s4[kk], w[u].x, acc[4 * q + kk][0]); acc[4 * q + kk][1] = fmaf(s4[kk], w[u].y, acc[4 * q + kk][1]);
+              acc[4 * q + kk][2] = fmaf(s4[kk], w[u].z, acc[4 * q + kk][2]); acc[4 * q + kk][3] = fmaf(s4[kk], w[u].w, acc[4 * q + kk][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // row phases 1..3 -> shared memory one after the other, phase 0 adds them in order
+#pragma unroll 1
+  for (int p = 1; p < 4; ++p) {
+    if (ty == p) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) *reinterpret_cast<float4*>(&red[k][tx * 4]) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const float4 o = *reinterpret_cast<const float4*>(&red[k][tx * 4]);
+        acc[k][0] += o.x; acc[k][1] += o.y; acc[k][2] += o.z; acc[k][3] += o.w;
+      }
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && on) {
+    float* out = g.part + (long)b * g.p_batch + (long)sl * g.p_slice;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (k >= g.s) break;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (j + e < g.WD) out[(long)k * g.WD + j + e] = acc[k][e];
+    }
+  }
+}
+
+// =====================================================================================================
+// Fused output layer (IN = 128 NV wide last hidden activation, K <= KP outputs): ONE pass over a_last does the head
+// forward, the log-likelihood and d/d(out) (probabilistic.py:93-109), the partial sums of dW_head / db_head / ll, and
+// writes the delta of the last hidden layer  D = (dout W_head^T) .* act'(a_last)  together with its column sums (the bias
+// gradient of that layer).  Replaces five streaming passes over the same 100 MB activation matrix (head forward, log-lik,
+// dW_head row-reduction, db_head row-reduction, delta back-propagation: 326 us of a 1.87 ms evaluation in
+// profiles/r2n_launches_wide_4x256.csv) by one that reads a_last and writes D once.
+// One warp per row: lane owns columns {128 v + 4 lane + e}.  grid (nblk, chains), 256 threads; CTA = contiguous row range.
+// Partials per (chain, CTA): [IN*K] dW_head (theta order: in-major), [K] db_head, [IN] column sums of D, [1] ll.
+// =====================================================================================================
+struct HeadArgs {
+  const float* a_last; long a_batch;        // [n][N8][IN]
+  float* D; long d_batch;                   // [n][N8][IN]
+  const float* theta; int d, kern_off, bias_off;
+  const void* y; long N; int rows_per_cta;
+  float* pW; float* pb; float* pcol; float* pll;     // partial areas: [n][nblk][IN*K], [n][nblk][K], [n][nblk][IN], [n][nblk]
+};
+
+template <int NV, int KP>
+__global__ void __launch_bounds__(256) wide_head_kernel(DevModel M, const HeadArgs g) {
+  constexpr int IN = 128 * NV, NW = 8, RU = 4;        // RU rows of a warp in flight together
+  extern __shared__ __align__(16) float hsm[];
+  float* Wh = hsm;                    // [KP][IN] (transposed: a lane's four columns are one conflict-free LDS.128)
+  float* bh = Wh + IN * KP;           // [KP]
+  float* scr = bh + KP;               // [NW][IN*KP + IN + KP + 1] cross-warp reduction
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.y, K = M.dims[M.NL], nblk = gridDim.x;
+  const float* th = g.theta + (long)c * g.d;
+  for (int e = tid; e < IN * KP; e += 256) { const int k = e / IN, i = e % IN; Wh[e] = k < K ? th[g.kern_off + i * K + k] : 0.f; }
+  if (tid < KP) bh[tid] = tid < K ? th[g.bias_off + tid] : 0.f;
+  __syncthreads();
+  const float* A = g.a_last + (long)c * g.a_batch;
+  float* D = g.D + (long)c * g.d_batch;
+  // two outputs: the lane's slab of W_head lives in registers; more: it is re-read from shared memory per row
+  constexpr bool WREG = KP == 2;
+  float4 wreg[WREG ? NV : 1][KP];
+  if (WREG) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < KP; ++k) wreg[v][k] = reinterpret_cast<const float4*>(Wh + k * IN + v * 128)[lane];
+  }
+  auto wld = [&](int v, int k) -> float4 { return WREG ? wreg[WREG ? v : 0][k] : reinterpret_cast<const float4*>(Wh + k * IN + v * 128)[lane]; };
+  float accW[NV * 4][KP], accC[NV * 4], accB[KP], ll_acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV * 4; ++i) { accC[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) accW[i][k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) accB[k] = 0.f;
+  const long r_beg = (long)blockIdx.x * g.rows_per_cta, r_end = min(g.N, r_beg + g.rows_per_cta);
+  for (long rb = r_beg + warp * RU; rb < r_end; rb += NW * RU) {
+    float4 a4[RU][NV];
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        a4[u][v] = rb + u < r_end ? __ldg(reinterpret_cast<const float4*>(A + (rb + u) * IN + v * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long r = rb + u;
+      if (r >= r_end) break;           // (warp-uniform)
+      float a[NV * 4];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { a[4 * v] = a4[u][v].x; a[4 * v + 1] = a4[u][v].y; a[4 * v + 2] = a4[u][v].z; a[4 * v + 3] = a4[u][v].w; }
+      float o[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) o[k] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const float4 w = wld(v, k);
+          o[k] = fmaf(a[4 * v], w.x, o[k]); o[k] = fmaf(a[4 * v + 1], w.y, o[k]);
+          o[k] = fmaf(a[4 * v + 2], w.z, o[k]); o[k] = fmaf(a[4 * v + 3], w.w, o[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) o[k] += __shfl_xor_sync(0xffffffffu, o[k], s);
+        o[k] += bh[k];
+      }
+      // log-likelihood term and d/d(out): same arithmetic as wide_loglik_kernel (every lane, redundantly)
+      float dd[KP], ll;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) dd[k] = 0.f;
+      if (M.task == MILE_TASK_REGRESSION) {
+        const float yv = reinterpret_cast<const float*>(g.y)[r], mu = o[0], sg = o[1];
+        const float ex = expf(sg), sigma = fminf(fmaxf(ex, 1e-6f), 1e6f);
+        const float inside = (ex > 1e-6f && ex < 1e6f) ? 1.f : 0.f;
+        const float s2 = sigma * sigma, res = yv - mu, q = res * res / s2;
+        ll = (logf(6.283185307179586f * s2) + q) / -2.f;
+        float dmu = res / s2, ds = (q - 1.f) * inside;
+        if (isnan(ll)) { ll = 0.f; dmu = 0.f; ds = 0.f; }
+        dd[0] = dmu * M.n_batches; dd[1] = ds * M.n_batches;
+      } else {
+        const int yi = reinterpret_cast<const int*>(g.y)[r];
+        float m = o[0];
+#pragma unroll
+        for (int k = 1; k < KP; ++k) if (k < K) m = fmaxf(m, o[k]);
+        float se = 0.f, oy = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) if (k < K) { se += expf(o[k] - m); if (k == yi) oy = o[k]; }
+        ll = oy - (m + logf(se));
+        const bool bad = isnan(ll);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) if (k < K) dd[k] = bad ? 0.f : (-expf(o[k] - m) / se + (k == yi ? 1.f : 0.f)) * M.n_batches;
+        if (bad) ll = 0.f;
+      }
+      ll_acc += ll;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) accB[k] += dd[k];
+      float dl[NV * 4];
+#pragma unroll
+      for (int i = 0; i < NV * 4; ++i) dl[i] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const float4 w = wld(v, k);
+          dl[4 * v] = fmaf(dd[k], w.x, dl[4 * v]); dl[4 * v + 1] = fmaf(dd[k], w.y, dl[4 * v + 1]);
+          dl[4 * v + 2] = fmaf(dd[k], w.z, dl[4 * v + 2]); dl[4 * v + 3] = fmaf(dd[k], w.w, dl[4 * v + 3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) accW[4 * v + e][k] = fmaf(a[4 * v + e], dd[k], accW[4 * v + e][k]);
+        }
+#pragma unroll
+      for (int i = 0; i < NV * 4; ++i) { dl[i] *= act_deriv_from_value(M.act, a[i]); accC[i] += dl[i]; }
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        reinterpret_cast<float4*>(D + r * IN + v * 128)[lane] = make_float4(dl[4 * v], dl[4 * v + 1], dl[4 * v + 2], dl[4 * v + 3]);
+    }
+  }
+  // cross-warp sums (warp order), then this CTA's partials
+  constexpr int SW = IN * KP + IN + KP + 1;
+  float* my = scr + warp * SW;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = v * 128 + lane * 4 + e;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) my[col * KP + k] = accW[4 * v + e][k];
+      my[IN * KP + col] = accC[4 * v + e];
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) my[IN * KP + IN + k] = accB[k];
+    my[IN * KP + IN + KP] = ll_acc;
+  }
+  __syncthreads();
+  const long pidx = (long)c * nblk + blockIdx.x;
+  for (int e = tid; e < SW; e += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += scr[w * SW + e];
+    if (e < IN * KP) { const int i = e / KP, k = e % KP; if (k < K) g.pW[pidx * (IN * K) + i * K + k] = s; }
+    else if (e < IN * KP + IN) g.pcol[pidx * IN + (e - IN * KP)] = s;
+    else if (e < IN * KP + IN + KP) { const int k = e - IN * KP - IN; if (k < K) g.pb[pidx * K + k] = s; }
+    else g.pll[pidx] = s;
+  }
 }
 
 // =====================================================================================================
@@ -726,6 +1097,10 @@ struct Tc2Args {
   int epi, act;
   const float* bias; long bias_batch;
   const float* aux; long aux_batch, ldaux;
+  // EPI 3 only (optional): column sums of the produced delta tile = partial bias gradient of the layer below, one partial
+  // per (batch, m-block, 32-row group): csum[((b * nmb + mb) * 4 + q) * N + n].  Fused here, the bias gradients cost no
+  // extra pass over the 100 MB delta matrices (wide_rowreduce_kernel: 21 us + a slice reduction per layer before).
+  float* csum;
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -744,6 +1119,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// L2 prefetch of a TMA box (no shared-memory destination): issued a tile / several k-blocks ahead by the producer so that
+// the later cp.async.bulk.tensor of the same box is an L2 hit.  With two 96 KB stages the producer can run only ONE
+// k-block (1536 tensor-pipe cycles) ahead of the MMAs -- less than an HBM round trip plus the conversion pass, which left
+// the tensor pipe idle ~40 % of every k-block (profiles/r1i_ncu_wide_tc2.txt: 58 % active).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // K-major SWIZZLE_128B descriptor: LBO unused (1), SBO = 1024 B between 8-row groups, layout type 2
@@ -824,10 +1207,38 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer ----
       int it = 0;
+      constexpr int PF = 6;          // MN flavour (both operands stream from HBM): prefetch distance in k-blocks
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int b, ks, m0, n0, kbeg, nkb;
         tile_coords(t, b, ks, m0, n0, kbeg, nkb);
+        // coordinates of the CTA's next tile (its first k-blocks are prefetched while this tile's last ones load)
+        int nb_ = 0, nks = 0, nm0 = 0, nn0 = 0, nkbeg = 0, nnkb = 0;
+        const bool has_next = t + (int)gridDim.x < ntiles;
+        if (has_next) tile_coords(t + gridDim.x, nb_, nks, nm0, nn0, nkbeg, nnkb);
+        if (MN && t == (int)blockIdx.x) {
+          for (int kb = 0; kb < PF && kb < nkb; ++kb) {
+            const int k0 = kbeg + kb * T2_BK;
+#pragma unroll
+            for (int j = 0; j < T2_BM / 32; ++j) tma_prefetch_3d(&g.a_hi, m0 + 32 * j, k0, b);
+#pragma unroll
+            for (int j = 0; j < T2_BN / 32; ++j) tma_prefetch_3d(&g.b_hi, n0 + 32 * j, k0, b);
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
+          if (MN) {   // k-block kb + PF of this tile, or the matching early k-block of the next one
+            int pb = b, pm0 = m0, pn0 = n0, pk0 = kbeg + (kb + PF) * T2_BK;
+            bool ok = kb + PF < nkb;
+            if (!ok && has_next && kb + PF - nkb < nnkb) { pb = nb_; pm0 = nm0; pn0 = nn0; pk0 = nkbeg + (kb + PF - nkb) * T2_BK; ok = true; }
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < T2_BM / 32; ++j) tma_prefetch_3d(&g.a_hi, pm0 + 32 * j, pk0, pb);
+#pragma unroll
+              for (int j = 0; j < T2_BN / 32; ++j) tma_prefetch_3d(&g.b_hi, pn0 + 32 * j, pk0, pb);
+            }
+          } else if (has_next && kb < nnkb) {
+            // the A rows of the next tile (HBM; the weights are L2-resident anyway), one k-block per k-block of this tile
+            tma_prefetch_3d(&g.a_hi, nkbeg + kb * T2_BK, nm0, nb_);
+          }
           const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
           mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
           const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
@@ -929,6 +1340,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       int pb, pks, pm0, pn0, pkbeg, pnkb;
       tile_coords(t, pb, pks, pm0, pn0, pkbeg, pnkb);
+      if (EPI == 3) {
+        // act'(aux) operand of this tile: pull this warp's 32 rows x 128 columns into L2 while the main loop still runs
+        const float* aux = g.aux + (long)pb * g.aux_batch;
+        const int c0 = pn0 + half * (T2_BN / 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = pm0 + q * 32 + i * 8 + (lane >> 2), n = c0 + (lane & 3) * 32;
+          if (m < g.M && n < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + (long)m * g.ldaux + n));
+        }
+      }
       {
         const int el = tl - 1, acc = el & 1, aph = (el >> 1) & 1;
         mbar_wait(bar0 + 8 * (3 * T2_STAGES + acc), aph);
@@ -968,6 +1389,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
               x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (EPI == 3 && m < g.M) x4[i] = *reinterpret_cast<const float4*>(aux + (long)m * g.ldaux + n);
             }
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = i * 8 + (lane >> 2), m = pm0 + q * 32 + row;
@@ -975,7 +1397,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
               float4 o4;
               o4.x = t2_epi<EPI, RELU>(t4.x, b4.x, x4[i].x, g.act); o4.y = t2_epi<EPI, RELU>(t4.y, b4.y, x4[i].y, g.act);
               o4.z = t2_epi<EPI, RELU>(t4.z, b4.z, x4[i].z, g.act); o4.w = t2_epi<EPI, RELU>(t4.w, b4.w, x4[i].w, g.act);
-              if (m < g.M) *reinterpret_cast<float4*>(C + (long)m * g.ldc + n) = o4;
+              if (m < g.M) {
+                *reinterpret_cast<float4*>(C + (long)m * g.ldc + n) = o4;
+                if (EPI == 3) { cs.x += o4.x; cs.y += o4.y; cs.z += o4.z; cs.w += o4.w; }
+              }
+            }
+            if (EPI == 3 && g.csum) {   // column sums over the 32 rows of this warp's lane quarter (fixed shuffle order)
+#pragma unroll
+              for (int o = 4; o <= 16; o <<= 1) {
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+              }
+              if (lane < 4)
+                *reinterpret_cast<float4*>(g.csum + (((long)pb * nmb + pm0 / T2_BM) * 4 + q) * g.N + n) = cs;
             }
           } else {
 #pragma unroll 1
@@ -1004,11 +1438,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
 }
 
 // lo = v - tf32(v) of the layer weights into 16-byte aligned packed buffers (theta's own offsets / chain stride are not
-// TMA-aligned): wpk_hi[c][off_l + e] = W_l[e], wpk_lo = W_l[e] - tf32(W_l[e])
-__global__ void wide_pack_weights_kernel(const float* __restrict__ theta, int d, int kern_off, int IN, int OUT, float* __restrict__ hi,
-                                         float* __restrict__ lo, float* __restrict__ hiT, float* __restrict__ loT, long pack_off,
-                                         long pack_stride, int nbatch) {
+// TMA-aligned): wpk_hi[c][off_l + e] = W_l[e], wpk_lo = W_l[e] - tf32(W_l[e]).  One launch for all layers that run on the
+// TMA core: grid (x, layer).
+struct PackArgs {
+  int n_layers, kern_off[13], IN[13], OUT[13];
+  long pack_off[13];
+};
+__global__ void wide_pack_weights_kernel(const float* __restrict__ theta, int d, const __grid_constant__ PackArgs P,
+                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ hiT,
+                                         float* __restrict__ loT, long pack_stride, int nbatch) {
   // W [IN x OUT] row-major (K-major B of the backward GEMM) and W^T [OUT x IN] (K-major B of the forward GEMM)
+  const int L = blockIdx.y, IN = P.IN[L], OUT = P.OUT[L], kern_off = P.kern_off[L];
+  const long pack_off = P.pack_off[L];
   const long n_elem = (long)IN * OUT, total = n_elem * nbatch;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const long b = t / n_elem, e = t % n_elem;

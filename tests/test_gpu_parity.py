@@ -355,6 +355,8 @@ def test_errors_are_loud():
 
 @pytest.mark.parametrize('widths,act,task', [((256, 256, 256, 256, 2), 'relu', 'regr'), ((96, 80, 3), 'tanh', 'class'),
                                              ((48, 48, 48, 2), 'relu', 'regr'),
+                                             # fused output-layer kernel with a classification head: 128- and 256-wide last hidden layer
+                                             ((128, 128, 7), 'sigmoid', 'class'), ((64, 256, 3), 'tanh', 'class'),
                                              # more than one 256-column block, K not a multiple of the 32-wide k-block
                                              ((272, 264, 2), 'sigmoid', 'regr')])
 def test_wide_path_value_and_grad_and_step(widths, act, task):

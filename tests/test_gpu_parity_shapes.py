@@ -69,6 +69,7 @@ def test_wide_4x256_full_shape_all_tensor_cores():
     th = o.synthetic_theta0(ospec, C, scale=0.05)
     lp64, g64 = o.logpost_batch(ospec, th.astype(np.float64), X.astype(np.float64), y)
     _, g32 = o.logpost_batch(ospec, th, X, y)
+
     worst = {}
     for tensor in (2, 1, 0):
         ens = Ensemble(FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task), C, tensor=tensor)
@@ -84,8 +85,17 @@ def test_wide_4x256_full_shape_all_tensor_cores():
             # accumulator (K = 256 x 3 passes, or one 330-row split-K slice) leave a SYSTEMATIC ~6e-6 relative error on
             # every delta / dW element, which the bias gradients (column sums of delta over 12 165 rows with heavy
             # cancellation) amplify; measured 2.0e-4 norm-wise, bounded here at 3e-4.
-            tol = (2e-5 if tensor == 0 else 3e-4) + 2 * rel(g32[c], g64[c])
+            #
+            # ReLU kink: every chain has 2-12 (row, unit) pairs whose pre-activation lies within 1e-7 relative of zero;
+            # which side an fp32 implementation takes there is decided by its summation order, and ONE flip moves the
+            # gradient blocks of the layers below it by about a row's share of the sum (measured 1.2e-4 on those blocks,
+            # 6e-5 on the whole gradient; tools/wide_grad_blocks.py -- chains without a flip sit at 1e-7 on the SIMT core).
+            # A flip is chain-specific, an arithmetic error is not: the MEDIAN over the chains must hold the tight bar,
+            # every chain the bar with 2e-4 of kink allowance.
+            tol = (2e-5 if tensor == 0 else 3e-4) + 2 * rel(g32[c], g64[c]) + 2e-4
             assert rel(g[c], g64[c]) <= tol, (tensor, c, rel(g[c], g64[c]), rel(g32[c], g64[c]))
+        errs = sorted(rel(g[c], g64[c]) for c in range(C))
+        assert errs[C // 2] <= (2e-5 if tensor == 0 else 3e-4), (tensor, errs)
         if tensor == 2:
             # what the sampler consumes: one MCLMC step at the full shape holds the 1e-5 bar on position and log-density
             rng = np.random.default_rng(3)
