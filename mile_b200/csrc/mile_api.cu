@@ -60,7 +60,7 @@ struct mile_ctx {
   DevModel M;
   int C = 0, device = 0, d = 0;
   // options
-  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0, opt_steploop = 1, opt_kslices = 0;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 tcgen05 TMA-fed for K-major GEMMs
+  int opt_cluster = 0, opt_tile_rows = 0, opt_refresh = 0, opt_resident = -1, opt_fast = 2, opt_tensor = 2, opt_chain_base = 0, opt_steploop = 1, opt_kslices = 0;   // fast: 0 generic tiles, 1 FFMA layer pipeline (mile_fast.cuh), 2 register-chained 3xTF32 MMA evaluator (mile_mma.cuh);   // tensor: 0 SIMT, 1 tcgen05 (staged), 2 (default) tcgen05 TMA-fed, one CTA per tile, 3 = 2 + CTA pairs (cta_group::2) for the K-major GEMMs (measured 5 % slower, profiles/r3a_*)
   // data
   float* X = nullptr; void* y = nullptr; long N = 0;
   float* Xt = nullptr; void* yt = nullptr; long Nt = 0;
@@ -88,6 +88,7 @@ struct mile_ctx {
   float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
+  int integ_cluster = 8;      // cluster size of the large-d integrator kernel (16 = non-portable size: measured slower, 69 vs 55 us)
   float* w_fin = nullptr;     // finalize scratch: [chains][32 CTAs][2] partial scalars, then [chains] arrival tickets
   float* w_arena = nullptr; size_t w_arena_floats = 0;   // partial sums of one evaluation, summed by wide_finalize_kernel (WideJobs)
   int opt_head_fused = 1;                                 // wide path: fused output-layer kernel (0 = separate streaming kernels)
@@ -1180,15 +1181,18 @@ static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   if (!tc2_operand_ok(g.A, a_ld, g.a_batch) || !tc2_operand_ok(g.B, b_ld, g.b_batch)) return 0;
   if (!mn && !tc2_operand_ok(g.B_lo, b_ld, g.b_batch)) return 0;
   if (mn ? ((g.M & 3) || (g.N & 3) || g.epi != 0) : (g.K & 3) != 0) return 0;
+  // K-major products on CTA pairs (tcgen05.mma.cta_group::2, wide_gemm_tc2x_kernel) unless tensor == 2 asks for one CTA per tile
+  const bool pairs = !mn && c->opt_tensor >= 3 && g.kslices == 1 && g.M > T2_BM;
   Tc2Args t;
   memset(&t, 0, sizeof(t));
   if (mn) {   // global [K rows][MN cols]: boxes of 32 MN-floats x 32 K-rows
     if (tmap_get(c, g.A, g.K, g.M, a_ld, g.a_batch, g.nbatch, 32, T2_BK, &t.a_hi, 1)) return -1;
     if (tmap_get(c, g.B, g.K, g.N, b_ld, g.b_batch, g.nbatch, 32, T2_BK, &t.b_hi, 1)) return -1;
   } else {
+    const int brows = pairs ? 128 : T2_BN;      // CTA pairs: every CTA stages its half of the weight tile
     if (tmap_get(c, g.A, g.M, g.K, a_ld, g.a_batch, g.nbatch, T2_BK, T2_BM, &t.a_hi)) return -1;
-    if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_hi)) return -1;
-    if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, T2_BN, &t.b_lo)) return -1;
+    if (tmap_get(c, g.B, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, brows, &t.b_hi)) return -1;
+    if (tmap_get(c, g.B_lo, g.N, g.K, b_ld, g.b_batch, g.nbatch, T2_BK, brows, &t.b_lo)) return -1;
   }
   t.M = g.M; t.N = g.N; t.K = g.K; t.kslices = g.kslices; t.nbatch = g.nbatch;
   t.C = g.C; t.c_batch = g.c_batch; t.c_slice = g.c_slice; t.ldc = g.ldc; t.epi = g.epi; t.act = g.act;
@@ -1197,6 +1201,31 @@ static int wide_gemm_tc2(mile_ctx* c, const GemmArgs& g, cudaStream_t st) {
   const int ntiles = ((g.M + T2_BM - 1) / T2_BM) * ((g.N + T2_BN - 1) / T2_BN) * g.nbatch * g.kslices;
   const int grid = ntiles < c->n_sms ? ntiles : c->n_sms;      // persistent: one CTA per SM, tiles strided over the grid
   const bool relu = g.act == MILE_ACT_RELU;
+  if (pairs) {
+    const int ntiles2 = ((g.M + 2 * T2_BM - 1) / (2 * T2_BM)) * ((g.N + T2_BN - 1) / T2_BN) * g.nbatch;
+    const int npairs = ntiles2 < c->n_sms / 2 ? ntiles2 : c->n_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * npairs), 1, 1); cfg.blockDim = dim3(T2_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = X2_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define X2_LAUNCH(...)                                                                                                      \
+    do {                                                                                                                    \
+      CK(cudaFuncSetAttribute(wide_gemm_tc2x_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_SMEM_BYTES)); \
+      CK(cudaLaunchKernelEx(&cfg, wide_gemm_tc2x_kernel<__VA_ARGS__>, t));                                                  \
+    } while (0)
+    if (g.epi == 0) X2_LAUNCH(0, false);
+    else if (g.epi == 2) X2_LAUNCH(2, false);
+    else if (g.epi == 1) { if (relu) X2_LAUNCH(1, true); else X2_LAUNCH(1, false); }
+    else { if (relu) X2_LAUNCH(3, true); else X2_LAUNCH(3, false); }
+#undef X2_LAUNCH
+    CK(cudaGetLastError());
+    c->launches++;
+    return 1;
+  }
 #define T2_LAUNCH(...)                                                                                                    \
   do {                                                                                                                    \
     CK(cudaFuncSetAttribute(wide_gemm_tc2_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES)); \
@@ -1313,8 +1342,13 @@ static int wide_forward(mile_ctx* c, const float* theta, int n, const float* Xs,
       pa.kern_off[k] = M.kern_off[l]; pa.IN[k] = M.dims[l]; pa.OUT[k] = M.dims[l + 1]; pa.pack_off[k] = c->w_woff[l];
     }
     if (pa.n_layers > 0) {
-      wide_pack_weights_kernel<<<dim3(74, pa.n_layers), 256, 0, st>>>(theta, d, pa, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo,
-                                                                      c->w_wstride, n);
+      int max_tiles = 1;
+      for (int k = 0; k < pa.n_layers; ++k) {
+        const int tiles = ((pa.IN[k] + 31) / 32) * ((pa.OUT[k] + 31) / 32);
+        if (tiles > max_tiles) max_tiles = tiles;
+      }
+      wide_pack_weights_kernel<<<dim3(max_tiles, n, pa.n_layers), 256, 0, st>>>(theta, d, pa, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo,
+                                                                               c->w_wstride);
       CK(cudaGetLastError());
       c->launches++;
     }
@@ -1530,12 +1564,21 @@ static int shard_integ(mile_ctx* c, ShardParams& S, int stage, long s_local, cud
   if (c->d > 8192) {   // large d: a cluster of 8 CTAs per chain, elements strided over its 8192 threads (DSMEM reductions)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)c->C * 8, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, mile_integrator_kernel<1024, true>, S));
+    // 16-CTA clusters (non-portable size) when all of them fit at once: twice the threads per chain for a pass that is
+    // bound by the latency of its element loops and cluster reductions; 8 otherwise (or when the device refuses 16)
+    int cs = (c->integ_cluster == 16 && (long)c->C * 16 <= c->n_sms) ? 16 : 8;
+    for (;;) {
+      cfg.gridDim = dim3((unsigned)c->C * cs, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (cs == 16) cudaFuncSetAttribute(mile_integrator_kernel<1024, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, mile_integrator_kernel<1024, true>, S);
+      if (e == cudaSuccess) break;
+      if (cs == 16) { cudaGetLastError(); cs = 8; c->integ_cluster = 8; continue; }
+      CK(e);
+    }
   } else mile_integrator_kernel<256><<<c->C, 256, 0, st>>>(S);
   CK(cudaGetLastError());
   c->launches++;

@@ -1124,7 +1124,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 // L2 prefetch of a TMA box (no shared-memory destination): issued a tile / several k-blocks ahead by the producer so that
 // the later cp.async.bulk.tensor of the same box is an L2 hit.  With two 96 KB stages the producer can run only ONE
 // k-block (1536 tensor-pipe cycles) ahead of the MMAs -- less than an HBM round trip plus the conversion pass, which left
-// the tensor pipe idle ~40 % of every k-block (profiles/r1i_ncu_wide_tc2.txt: 58 % active).
+// the tensor pipe idle ~40 % of every k-block (profiles/r1i_ncu_wide_tc2.txt: 58 % active).  OUTCOME: no gain (72 -> 72 us,
+// profiles/r2x_launches_wide_4x256.csv), removed from the kernels again; the helper stays for the record.
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
@@ -1154,6 +1155,113 @@ __device__ __forceinline__ float t2_epi(float v, float bias, float aux, int act)
   if (EPI == 2) return v + bias;
   if (EPI == 3) return RELU ? (aux > 0.f ? v : 0.f) : v * act_deriv_from_value(act, aux);
   return v;
+}
+
+// Epilogue of one 128 x 256 accumulator tile for one epilogue warp (TMEM lane quarter q, column half `half`): 8 passes of
+// 16 columns, tcgen05.ld -> per-warp shared tile (transposition: a lane holds a row, the stores want a lane per column
+// group) -> bias / activation / act' -> 64-byte row segments.  (A software-pipelined variant -- bias slab hoisted, aux
+// and tcgen05.ld of pass cc+1 in flight during pass cc -- measured 10 % SLOWER on the act' flavour and equal on the
+// others, profiles/r3c_launches_wide_4x256.csv: the epilogue is not on the critical path.)
+#define T2_LD16(r, taddr)                                                                                                  \
+  asm volatile(                                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n" \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                        \
+      : "r"(taddr))
+
+template <int EPI, bool RELU, class WaitFn>
+__device__ __forceinline__ void t2_epilogue_tile(const Tc2Args& g, uint32_t tmem, int acc, float* tile, int q, int half, int lane,
+                                                 int pb, int pks, int pm0, int pn0, int nmb, bool have_k, WaitFn wait_full) {
+  constexpr int TS = T2_TS, NP = T2_BN / 32;
+  float* C = g.C + (long)pb * g.c_batch + (long)pks * g.c_slice;
+  const float* bias = g.bias ? g.bias + (long)pb * g.bias_batch : nullptr;
+  const float* aux = g.aux ? g.aux + (long)pb * g.aux_batch : nullptr;
+  const bool fast = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && pn0 + T2_BN <= g.N &&
+                    (EPI != 3 || ((g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0));
+  const int cq = lane & 3, rsub = lane >> 2;
+  const int nbase = pn0 + half * (T2_BN / 2) + cq * 4;
+  const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + half * (T2_BN / 2));
+  if (fast) {
+    wait_full();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int cc = 0; cc < NP; ++cc) {     // 16 accumulator columns per pass
+      uint32_t r[16];
+      T2_LD16(r, tbase + (uint32_t)(cc * 16));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      __syncwarp();   // the previous pass has been read out of the tile
+      float* trow = tile + lane * TS;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(trow + j) = have_k ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      // 4 lanes cover one 64-byte row segment: sector-aligned stores and aux loads, no per-element branches
+      const int n = nbase + cc * 16;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == 1 || EPI == 2) b4 = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));   // (theta offsets are not 16-byte aligned)
+      float4 x4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = pm0 + q * 32 + i * 8 + rsub;
+        x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == 3 && m < g.M) x4[i] = *reinterpret_cast<const float4*>(aux + (long)m * g.ldaux + n);
+      }
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 8 + rsub, m = pm0 + q * 32 + row;
+        const float4 t4 = *reinterpret_cast<const float4*>(tile + row * TS + cq * 4);
+        float4 o4;
+        o4.x = t2_epi<EPI, RELU>(t4.x, b4.x, x4[i].x, g.act); o4.y = t2_epi<EPI, RELU>(t4.y, b4.y, x4[i].y, g.act);
+        o4.z = t2_epi<EPI, RELU>(t4.z, b4.z, x4[i].z, g.act); o4.w = t2_epi<EPI, RELU>(t4.w, b4.w, x4[i].w, g.act);
+        if (m < g.M) {
+          *reinterpret_cast<float4*>(C + (long)m * g.ldc + n) = o4;
+          if (EPI == 3) { cs.x += o4.x; cs.y += o4.y; cs.z += o4.z; cs.w += o4.w; }
+        }
+      }
+      if (EPI == 3 && g.csum) {   // column sums over the 32 rows of this warp's lane quarter (fixed shuffle order)
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
+        if (lane < 4 && pm0 < g.M)
+          *reinterpret_cast<float4*>(g.csum + (((long)pb * nmb + pm0 / T2_BM) * 4 + q) * g.N + n) = cs;
+      }
+    }
+  } else {
+    wait_full();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int cc = 0; cc < NP; ++cc) {
+      uint32_t r[16];
+      T2_LD16(r, tbase + (uint32_t)(cc * 16));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      __syncwarp();
+      float* trow = tile + lane * TS;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(trow + j) = have_k ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      const int n = nbase + cc * 16;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 8 + rsub, m = pm0 + q * 32 + row;
+        if (m >= g.M) continue;
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+          if (n + e >= g.N) break;
+          const float v = tile[row * TS + cq * 4 + e];
+          C[(long)m * g.ldc + n + e] = t2_epi<EPI, RELU>(v, (EPI == 1 || EPI == 2) ? bias[n + e] : 0.f,
+                                                         EPI == 3 ? aux[(long)m * g.ldaux + n + e] : 0.f, g.act);
+        }
+      }
+    }
+  }
 }
 
 // Persistent: CTA i works on tiles i, i + gridDim.x, ... (tile = (batch*kslice, m-block); N <= 256 is one n-block per
@@ -1207,38 +1315,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer ----
       int it = 0;
-      constexpr int PF = 6;          // MN flavour (both operands stream from HBM): prefetch distance in k-blocks
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int b, ks, m0, n0, kbeg, nkb;
         tile_coords(t, b, ks, m0, n0, kbeg, nkb);
-        // coordinates of the CTA's next tile (its first k-blocks are prefetched while this tile's last ones load)
-        int nb_ = 0, nks = 0, nm0 = 0, nn0 = 0, nkbeg = 0, nnkb = 0;
-        const bool has_next = t + (int)gridDim.x < ntiles;
-        if (has_next) tile_coords(t + gridDim.x, nb_, nks, nm0, nn0, nkbeg, nnkb);
-        if (MN && t == (int)blockIdx.x) {
-          for (int kb = 0; kb < PF && kb < nkb; ++kb) {
-            const int k0 = kbeg + kb * T2_BK;
-#pragma unroll
-            for (int j = 0; j < T2_BM / 32; ++j) tma_prefetch_3d(&g.a_hi, m0 + 32 * j, k0, b);
-#pragma unroll
-            for (int j = 0; j < T2_BN / 32; ++j) tma_prefetch_3d(&g.b_hi, n0 + 32 * j, k0, b);
-          }
-        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          if (MN) {   // k-block kb + PF of this tile, or the matching early k-block of the next one
-            int pb = b, pm0 = m0, pn0 = n0, pk0 = kbeg + (kb + PF) * T2_BK;
-            bool ok = kb + PF < nkb;
-            if (!ok && has_next && kb + PF - nkb < nnkb) { pb = nb_; pm0 = nm0; pn0 = nn0; pk0 = nkbeg + (kb + PF - nkb) * T2_BK; ok = true; }
-            if (ok) {
-#pragma unroll
-              for (int j = 0; j < T2_BM / 32; ++j) tma_prefetch_3d(&g.a_hi, pm0 + 32 * j, pk0, pb);
-#pragma unroll
-              for (int j = 0; j < T2_BN / 32; ++j) tma_prefetch_3d(&g.b_hi, pn0 + 32 * j, pk0, pb);
-            }
-          } else if (has_next && kb < nnkb) {
-            // the A rows of the next tile (HBM; the weights are L2-resident anyway), one k-block per k-block of this tile
-            tma_prefetch_3d(&g.a_hi, nkbeg + kb * T2_BK, nm0, nb_);
-          }
           const int s = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
           mbar_wait(bar0 + 8 * (T2_STAGES + s), ph ^ 1);
           const uint32_t full = bar0 + 8 * s, st = sbase + s * T2_STAGE_BYTES;
@@ -1340,16 +1420,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       int pb, pks, pm0, pn0, pkbeg, pnkb;
       tile_coords(t, pb, pks, pm0, pn0, pkbeg, pnkb);
-      if (EPI == 3) {
-        // act'(aux) operand of this tile: pull this warp's 32 rows x 128 columns into L2 while the main loop still runs
-        const float* aux = g.aux + (long)pb * g.aux_batch;
-        const int c0 = pn0 + half * (T2_BN / 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = pm0 + q * 32 + i * 8 + (lane >> 2), n = c0 + (lane & 3) * 32;
-          if (m < g.M && n < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + (long)m * g.ldaux + n));
-        }
-      }
       {
         const int el = tl - 1, acc = el & 1, aph = (el >> 1) & 1;
         mbar_wait(bar0 + 8 * (3 * T2_STAGES + acc), aph);
@@ -1408,7 +1478,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
                 cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
                 cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
               }
-              if (lane < 4)
+              if (lane < 4 && pm0 < g.M)
                 *reinterpret_cast<float4*>(g.csum + (((long)pb * nmb + pm0 / T2_BM) * 4 + q) * g.N + n) = cs;
             }
           } else {
@@ -1437,6 +1507,191 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2_kernel(const __gr
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * T2_BN));
 }
 
+// =====================================================================================================
+// tcgen05 GEMM, version 3: CTA PAIRS (cta_group::2) for the K-major products (forward  act(a W + b)  and backward
+// (delta W^T) .* act').  Why: in the one-CTA kernel every tcgen05.mma M128 N256 K8 reads 4 KB of A and 8 KB of B from
+// shared memory, three of them per product (3xTF32), and every k-block brings 64 KB of weights (hi + lo) into the SM: per
+// k-block 144 KB of operand reads + 80 KB of TMA writes + 32 KB of conversion + the epilogue staging = ~290 KB against
+// 128 B/clk -> ~2250 cycles for 1536 cycles of tensor work (measured 2640, tensor pipe 58 % busy,
+// profiles/r1i_ncu_wide_tc2.txt; an L2 prefetch of the operands changed nothing, profiles/r2x_*: not latency).
+// A pair of SMs shares one 256-row tile: each CTA stages ITS 128 rows of A and ITS half (128 of the 256 output columns)
+// of the weights; one tcgen05.mma.cta_group::2 M256 N256 K8 issued by the leader reads A from both and the two weight
+// halves from both.  Per SM that halves the weight bytes on every path (TMA writes 48 KB, operand reads 96 KB per
+// k-block) and shrinks a stage to 64 KB, so three stages fit.
+//   per CTA : warp 0 TMA producer (own A rows, own half of W_hi / W_lo) -> local full[s]
+//             warps 2-5 converters (A_lo = A - tf32(A) in shared memory) -> arrive on the LEADER's conv[s]
+//             warps 6-13 epilogue of the CTA's own 128 accumulator rows (TMEM lanes) -> arrive on the LEADER's tmem_empty[a]
+//   leader  : warp 1 issues the MMAs once conv[s] has both CTAs' arrivals; tcgen05.commit multicasts to empty[s] /
+//             tmem_full[a] of both CTAs
+// =====================================================================================================
+#define X2_STAGES 3
+#define X2_B_BYTES (128 * T2_BK * 4)                       // this CTA's half of the weight tile
+#define X2_STAGE_BYTES (2 * T2_A_BYTES + 2 * X2_B_BYTES)   // A, A_lo, W_hi half, W_lo half = 64 KB
+#define X2_SMEM_BYTES (X2_STAGES * X2_STAGE_BYTES + T2_EPI_WARPS * 32 * T2_TS * 4 + 256)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1L << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3) : "memory");
+}
+
+template <int EPI, bool RELU>
+__global__ void __launch_bounds__(T2_THREADS, 1) wide_gemm_tc2x_kernel(const __grid_constant__ Tc2Args g) {
+  extern __shared__ __align__(1024) char sm2[];
+  const uint32_t sbase = smem_u32(sm2);
+  constexpr int TS = T2_TS, S = X2_STAGES;
+  float* tiles = reinterpret_cast<float*>(sm2 + S * X2_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm2 + S * X2_STAGE_BYTES + T2_EPI_WARPS * 32 * TS * 4);
+  // full[s] = bar0 + 8 s, empty[s] = +8 (S + s), conv[s] = +8 (2S + s), tmem_full[a] = +8 (3S + a), tmem_empty[a] = +8 (3S + 2 + a)
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nmb2 = (g.M + 2 * T2_BM - 1) / (2 * T2_BM), nnb = (g.N + T2_BN - 1) / T2_BN;
+  const int nmb = (g.M + T2_BM - 1) / T2_BM;
+  const int ntiles = nmb2 * nnb * g.nbatch;
+  const int nkb = (g.K + T2_BK - 1) / T2_BK;
+  if (tid == 0) {
+    for (int s = 0; s < 3 * S + 4; ++s) {
+      const int cnt = (s >= 2 * S && s < 3 * S) ? 2 * T2_CVT_WARPS : (s >= 3 * S + 2 ? 2 * T2_EPI_WARPS : 1);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(cnt));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * T2_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  // both CTAs' barriers are initialised before anybody arrives remotely
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lead0 = mapa_rank0(bar0);      // the leader's barrier block in the shared::cluster window
+  auto tile_coords = [&](int t, int& b, int& m0, int& n0) {
+    const int nb = t % nnb; t /= nnb;
+    const int mb2 = t % nmb2; b = t / nmb2;
+    m0 = mb2 * 2 * T2_BM + rank * T2_BM; n0 = nb * T2_BN;
+  };
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer: this CTA's rows of A, this CTA's half of the weights ----
+      int it = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        int b, m0, n0;
+        tile_coords(t, b, m0, n0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S, ph = (it / S) & 1;
+          mbar_wait_cluster(bar0 + 8 * (S + s), ph ^ 1);
+          const uint32_t full = bar0 + 8 * s, st = sbase + s * X2_STAGE_BYTES;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(T2_A_BYTES + 2 * X2_B_BYTES)) : "memory");
+          const int k0 = kb * T2_BK;
+          tma_load_3d(st, &g.a_hi, k0, m0, b, full);
+          tma_load_3d(st + 2 * T2_A_BYTES, &g.b_hi, k0, n0 + rank * 128, b, full);
+          tma_load_3d(st + 2 * T2_A_BYTES + X2_B_BYTES, &g.b_lo, k0, n0 + rank * 128, b, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {   // ---- MMA issuer (leader CTA only) ----
+      // D = F32, A = B = TF32, both K-major, N = 256, M = 256 (128 rows per CTA)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)((2 * T2_BM) >> 4) << 24);
+      int it = 0, tl = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++tl) {
+        const int acc = tl & 1, aph = (tl >> 1) & 1;
+        mbar_wait_cluster(bar0 + 8 * (3 * S + 2 + acc), aph ^ 1);      // accumulator drained by BOTH epilogues of tile tl-2
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem + (uint32_t)(acc * T2_BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S, ph = (it / S) & 1;
+          mbar_wait_cluster(bar0 + 8 * (2 * S + s), ph);     // both CTAs: boxes landed and remainder tile written
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = sbase + s * X2_STAGE_BYTES;
+          const uint32_t ahi = st, alo = st + T2_A_BYTES, bhi = st + 2 * T2_A_BYTES, blo = bhi + X2_B_BYTES;
+#pragma unroll
+          for (int j = 0; j < T2_BK / 8; ++j) {
+            const uint32_t acc0 = (kb == 0 && j == 0) ? 0u : 1u, o = j * 32;
+            umma_tf32_2cta(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(blo + o), idesc, acc0);
+            umma_tf32_2cta(tacc, umma_desc_sw128(alo + o), umma_desc_sw128(bhi + o), idesc, 1u);
+            umma_tf32_2cta(tacc, umma_desc_sw128(ahi + o), umma_desc_sw128(bhi + o), idesc, 1u);
+          }
+          umma_commit_2cta(bar0 + 8 * (S + s));
+        }
+        umma_commit_2cta(bar0 + 8 * (3 * S + acc));
+      }
+    }
+  } else if (warp < 2 + T2_CVT_WARPS) {
+    // ---- converter warps: remainder tile of this CTA's A rows, then tell the leader ----
+    const int ct = tid - 64;
+    int it = 0;
+    for (int t = pair; t < ntiles; t += npairs) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S, ph = (it / S) & 1;
+        mbar_wait(bar0 + 8 * s, ph);
+        const uint32_t ahi = sbase + s * X2_STAGE_BYTES, alo = ahi + T2_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < T2_A_BYTES / 16 / (32 * T2_CVT_WARPS); ++i) {
+          const uint32_t off = (uint32_t)(ct + i * 32 * T2_CVT_WARPS) * 16u;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ahi + off));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(alo + off), "f"(v.x - tf32_hi(v.x)), "f"(v.y - tf32_hi(v.y)),
+                       "f"(v.z - tf32_hi(v.z)), "f"(v.w - tf32_hi(v.w)) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead0 + 8 * (2 * S + s));
+      }
+    }
+  } else {
+    // ---- epilogue warps: this CTA's 128 accumulator rows of tile tl while the main loop of tile tl+1 runs ----
+    const int ew = warp - 2 - T2_CVT_WARPS;
+    const int q = warp & 3, half = ew >> 2;
+    float* tile = tiles + ew * (32 * TS);
+    int tl = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++tl) {
+      int pb, pm0, pn0;
+      tile_coords(t, pb, pm0, pn0);
+      const int acc = tl & 1, aph = (tl >> 1) & 1;
+      t2_epilogue_tile<EPI, RELU>(g, tmem, acc, tile, q, half, lane, pb, 0, pm0, pn0, nmb, true,
+                                  [&]() { mbar_wait_cluster(bar0 + 8 * (3 * S + acc), aph); });
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead0 + 8 * (3 * S + 2 + acc));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * T2_BN));
+}
+
 // lo = v - tf32(v) of the layer weights into 16-byte aligned packed buffers (theta's own offsets / chain stride are not
 // TMA-aligned): wpk_hi[c][off_l + e] = W_l[e], wpk_lo = W_l[e] - tf32(W_l[e]).  One launch for all layers that run on the
 // TMA core: grid (x, layer).
@@ -1444,20 +1699,39 @@ struct PackArgs {
   int n_layers, kern_off[13], IN[13], OUT[13];
   long pack_off[13];
 };
-__global__ void wide_pack_weights_kernel(const float* __restrict__ theta, int d, const __grid_constant__ PackArgs P,
-                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ hiT,
-                                         float* __restrict__ loT, long pack_stride, int nbatch) {
-  // W [IN x OUT] row-major (K-major B of the backward GEMM) and W^T [OUT x IN] (K-major B of the forward GEMM)
-  const int L = blockIdx.y, IN = P.IN[L], OUT = P.OUT[L], kern_off = P.kern_off[L];
-  const long pack_off = P.pack_off[L];
-  const long n_elem = (long)IN * OUT, total = n_elem * nbatch;
-  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const long b = t / n_elem, e = t % n_elem;
-    const int i = (int)(e / OUT), j = (int)(e % OUT);
-    const float v = theta[b * d + kern_off + e], l = v - tf32_hi(v);
-    hi[b * pack_stride + pack_off + e] = v;
-    lo[b * pack_stride + pack_off + e] = l;
-    hiT[b * pack_stride + pack_off + (long)j * IN + i] = v;
-    loT[b * pack_stride + pack_off + (long)j * IN + i] = l;
+__global__ void __launch_bounds__(256) wide_pack_weights_kernel(const float* __restrict__ theta, int d, const __grid_constant__ PackArgs P,
+                                                                float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ hiT,
+                                                                float* __restrict__ loT, long pack_stride) {
+  // W [IN x OUT] row-major (K-major B of the backward GEMM) and W^T [OUT x IN] (K-major B of the forward GEMM);
+  // 32 x 32 tiles through shared memory so that both orientations are written in 128-byte rows.
+  // grid (tiles, chains, layers), 256 threads = 32 x 8
+  __shared__ float tl[32][33];
+  const int L = blockIdx.z, IN = P.IN[L], OUT = P.OUT[L], b = blockIdx.y;
+  const int tj = (OUT + 31) / 32, ti = (IN + 31) / 32;
+  if ((int)blockIdx.x >= ti * tj) return;
+  const int i0 = (blockIdx.x / tj) * 32, j0 = (blockIdx.x % tj) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* W = theta + (long)b * d + P.kern_off[L];
+  const long base = (long)b * pack_stride + P.pack_off[L];
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;
+    float v = 0.f;
+    if (i < IN && j < OUT) {
+      v = W[(long)i * OUT + j];
+      hi[base + (long)i * OUT + j] = v;
+      lo[base + (long)i * OUT + j] = v - tf32_hi(v);
+    }
+    tl[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + tx;
+    if (i < IN && j < OUT) {
+      const float v = tl[tx][r];
+      hiT[base + (long)j * IN + i] = v;
+      loT[base + (long)j * IN + i] = v - tf32_hi(v);
+    }
   }
 }
