@@ -300,6 +300,8 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
     if W == args.workload:
         if args.cluster:
             ens.set_option('cluster_size', args.cluster)
+        if args.sync_mode >= 0:
+            ens.set_option('sync_mode', args.sync_mode)
         if args.tile_rows:
             ens.set_option('tile_rows', args.tile_rows)
         if args.tensor >= 0:
@@ -579,6 +581,7 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--inner', type=int, default=0)
     ap.add_argument('--cluster', type=int, default=0)
+    ap.add_argument('--sync-mode', type=int, default=-1, help='CTAs of a chain exchange through: 0 = DSMEM (thread-block cluster), 1 = flagged words in L2')
     ap.add_argument('--tile-rows', type=int, default=0)
     ap.add_argument('--tensor', type=int, default=-1, help='wide path: 1 = tcgen05 3xTF32 GEMM core, 0 = FP32 SIMT core')
     ap.add_argument('--fast', type=int, default=-1, help='narrow-MLP evaluator: 2 = 3xTF32 register MMA (default), 1 = FFMA layer pipeline, 0 = generic tiles')

@@ -132,8 +132,8 @@ struct Plan {
   KParams kp;  // offsets + model filled in
 };
 
-static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g = 0,
-                     bool force_sync = false) {
+static int make_plan_impl(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g,
+                          int force_sync) {
   DevModel M = c->M;
   int G = force_g > 0 ? force_g : c->opt_cluster, sync_mode = 0;
   if (G <= 0) {
@@ -142,10 +142,10 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
     // few chains: more than 8 CTAs per chain only fit with the global-memory exchange (cooperative launch)
     const int gmax = c->n_sms / n_chains;
     if (c->opt_sync != 0 && G == 8 && gmax > 9 && nrows_for_split / gmax >= 64) { G = gmax > 16 ? 16 : gmax; sync_mode = 1; }
-  } else if (c->opt_sync == 1 || (G > 8) || (G & (G - 1))) {
-    sync_mode = 1;
+  } else if (c->opt_sync == 1 || (c->opt_sync != 0 && force_sync != 0 && ((G > 8) || (G & (G - 1))))) {
+    sync_mode = 1;      // (sync_mode 0 asked for explicitly: a thread-block cluster of any size <= 16, non-portable above 8)
   }
-  if (force_sync) sync_mode = 1;    // (multi-rank step loop: the exchange is flagged words only, every CTA co-resident)
+  if (force_sync == 1) sync_mode = 1;    // (multi-rank step loop: the exchange is flagged words only, every CTA co-resident)
   if (G < 1 || G > 16) return fail("cluster_size must be in [1, 16]");
   if (sync_mode && (long)G * n_chains > c->n_sms) return fail("cluster_size x chains exceeds the SM count (cooperative launch)");
   if (G == 1) sync_mode = 0;
@@ -171,7 +171,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
       const size_t tile = (size_t)tile_f > gen ? (size_t)tile_f : gen;
       // resident slice: 16-row tiles plus one zero guard tile (k-steps may read up to 12 floats past a row's stride)
       const int rows_res = (int)((rows_cta + 15) / 16) * 16 + 16;
-      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0] + round_up(aux_i, 4) + 5 * (size_t)dS + 4) * 4;
+      const size_t base_need = (fixed + tile + (size_t)TRg * M.sA[0] + round_up(aux_i, 4) + 6 * (size_t)dS + 32) * 4;
       const int res = (c->opt_resident != 0 && base_need + (size_t)rows_res * M.sA[0] * 4 <= kSmemLimit) ? 1 : 0;
       if (base_need <= kSmemLimit) {
         M.TR = TRg; M.tile_floats = (int)tile;
@@ -191,7 +191,7 @@ static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool
         k.off_red = o; o += 192;
         k.off_aux = o; o += round_up(aux_i, 4);
         k.off_z = o; o += 4 * dS;            // refresh noise of two steps x two slots
-        k.off_gs = o; o += dS + 4;           // slice buffer of the DSMEM reduce-scatter
+        k.off_gs = o; o += 2 * (dS + 16);    // DSMEM push exchange: recv[G][SL] slots, then the gathered sums
         k.off_tile = o; o += (int)tile + TRg * M.sA[0];
         k.off_x = o; if (res) o += rows_res * M.sA[0];
         pl.G = G; pl.TR = 16; pl.resident = res; pl.rows_res = rows_res; pl.fast = 2; pl.fast_fp = FPm; pl.sync_mode = sync_mode;
@@ -306,6 +306,58 @@ static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
   }
   cfg.attrs = attr; cfg.numAttrs = 1;
   CK(cudaLaunchKernelEx(&cfg, kern, pl.kp));
+  return 0;
+}
+
+// Can `n_chains` clusters of `G` CTAs of the tensor evaluator's step kernel be resident at the same time?  (cached)
+static bool mma_clusters_fit(const mile_ctx* c, const Plan& pl, int n_chains) {
+  static std::map<std::tuple<int, int, int, size_t, int, int>, bool> cache;
+  const auto key = std::make_tuple(c->device, c->M.NL, pl.fast_fp, pl.smem, pl.G, n_chains);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  void (*kern)(const KParams) = nullptr;
+  const int NL = c->M.NL;
+  if (NL == 3 && pl.fast_fp == 8) kern = mile_mma_step_kernel<MmaGE<3, 8, 512>>;
+  else if (NL == 3) kern = mile_mma_step_kernel<MmaGE<3, 16, 512>>;
+  else if (pl.fast_fp == 8) kern = mile_mma_step_kernel<MmaGE<4, 8, 512>>;
+  else kern = mile_mma_step_kernel<MmaGE<4, 16, 512>>;
+  bool ok = false;
+  if (cudaSetDevice(c->device) == cudaSuccess &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) == cudaSuccess &&
+      (pl.G <= 8 || cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(n_chains * pl.G), 1, 1); cfg.blockDim = dim3(512, 1, 1); cfg.dynamicSmemBytes = pl.smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) ok = n >= n_chains;
+    else cudaGetLastError();
+  }
+  cache[key] = ok;
+  return ok;
+}
+
+// Plan of a launch.  Automatic choice for FEW chains on the tensor evaluator: the L2 flagged-word exchange lets a chain use
+// up to 16 CTAs, but when the row slice of a CTA is at most one wave of 16-row tiles either way (latency-bound regime:
+// airfoil) a thread-block cluster with the DSMEM push exchange is faster even with fewer CTAs (9 x 12 chains: 834 k
+// chain-steps/s against 769 k for 12 x 12 through L2, profiles/r3h_*).  The largest cluster size (<= 16, non-portable
+// above 8) whose clusters are all co-resident is taken.
+static int make_plan(const mile_ctx* c, int n_chains, long nrows_for_split, bool want_resident, Plan& pl, int force_g = 0,
+                     bool force_sync = false) {
+  const int rc = make_plan_impl(c, n_chains, nrows_for_split, want_resident, pl, force_g, force_sync ? 1 : -1);
+  if (rc || force_g > 0 || force_sync || c->opt_cluster > 0 || c->opt_sync >= 0 || pl.fast != 2 || !pl.sync_mode) return rc;
+  const std::string keep_err = g_err;
+  for (int gc = pl.G < 16 ? pl.G : 16; gc >= 9; --gc) {
+    const long rows_cta = (nrows_for_split + gc - 1) / gc;
+    if ((rows_cta + 15) / 16 > 8) break;             // more than two tiles per scheduler: the extra CTAs of the L2 form pay
+    Plan alt;
+    if (make_plan_impl(c, n_chains, nrows_for_split, want_resident, alt, gc, 0) || alt.fast != 2 || alt.sync_mode) continue;
+    if (mma_clusters_fit(c, alt, n_chains)) { pl = alt; break; }
+  }
+  g_err = keep_err;
   return 0;
 }
 

@@ -443,6 +443,32 @@ struct MmaGE {
 // order, then every CTA gathers the summed slices: 2 x d/G remote floats per CTA instead of (G-1) x d).  The
 // flagged-word exchange through L2 (any G <= 16, cooperative launch) and G = 1 are the other two cases.
 // ------------------------------------------------------------------------------------------------------------
+// ---- DSMEM push exchange (cluster of G <= 16 CTAs per chain) -------------------------------------------------------------
+// st.async: a 4-byte store into another CTA's shared memory that signals the DESTINATION's mbarrier with the bytes written;
+// the receiver sleeps on its own barrier (mbarrier.try_wait) until the expected byte count has arrived.  One DSMEM store
+// latency per hop and no cluster-wide barrier (cluster.sync costs ~380 cycles and the pull form needs two of them plus two
+// dependent remote-load round trips per evaluation).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(__float_as_uint(v)),
+               "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void xbar_arm(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1L << 22)) __trap();     // a lost store must not hang the GPU
+  }
+}
+
 template <int NV, int NT>
 __device__ __forceinline__ void block_sum_bfly(float (&v)[NV], float* scratch, int& phase) {
   constexpr int NWARPS = NT / 32;
@@ -531,6 +557,19 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mma_step_kernel(const __grid_c
     }
   };
   if (P.n_steps > 0) draw_noise(0, tid, NT, 0, 1);
+  // push exchange: recv[G][SL] + gfull[dS + 4] live in the gslice area; two mbarriers behind the published scalars
+  const bool push = c.G > 1 && !P.sync_mode;
+  const uint32_t xb1 = (uint32_t)__cvta_generic_to_shared(c.red + 160), xb2 = xb1 + 8;
+  float* recv = gslice;
+  float* gfull = gslice + (dS + 16);
+  if (push) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xb1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xb2));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();      // every CTA's barriers exist before the first remote store
+  }
   __syncthreads();
 
   // ---- chain scalars, uniform across the block -------------------------------------------------------------------
@@ -617,31 +656,42 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mma_step_kernel(const __grid_c
       if (tid == NT - 1) gp[dS + 1] = ll_sum(sums + dS, 0, 1, xflag);
       __syncthreads();
     } else {
-      // reduce-scatter + all-gather over DSMEM; slices of SL elements over [0, dS] (element dS = log-likelihood)
+      // reduce-scatter + all-gather over DSMEM by PUSH; slices of SL elements over [0, dS] (element dS = log-likelihood).
+      //   hop 1: every CTA stores element i of its partial into the owner's recv[rank][i - owner SL]  (owner = i / SL)
+      //   owner: waits for G x |slice| x 4 bytes on its barrier 1, adds the G partials in rank order
+      //   hop 2: the owner stores each sum into every CTA's gfull[i]; everybody waits for (dS + 1) x 4 bytes on barrier 2
+      // Buffer reuse is safe without further barriers: a CTA can only start hop 1 of evaluation e+1 after it passed
+      // barrier 2 of e, i.e. after EVERY owner finished reading its recv slots of e; an owner can only start hop 2 of e+1
+      // after it received hop 1 of e+1 from everybody, i.e. after everybody consumed gfull of e.
       const int SL = (dS + 1 + c.G - 1) / c.G;
-      cluster.sync();                      // every CTA's partial is complete
-      PROF(13);
-      for (int j = tid; j < SL; j += NT) {
-        const int idx = c.rank * SL + j;
-        float sum = 0.f;
-        if (idx <= dS) {
-          float tv[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) tv[r] = r < c.G ? cluster.map_shared_rank(gp, r)[idx] : 0.f;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) sum += tv[r];
-        }
-        gslice[j] = sum;
-      }
-      cluster.sync();                      // every slice is summed
-      PROF(2);
+      const int my0 = c.rank * SL;
+      const int mySL = my0 > dS ? 0 : (my0 + SL > dS + 1 ? dS + 1 - my0 : SL);
+      const uint32_t par = (uint32_t)(e & 1);
+      __syncthreads();                     // this CTA's partial is complete
+      if (tid == 0) { xbar_arm(xb1, (uint32_t)(c.G * mySL * 4)); xbar_arm(xb2, (uint32_t)((dS + 1) * 4)); }
+      const uint32_t recv_s = (uint32_t)__cvta_generic_to_shared(recv), gfull_s = (uint32_t)__cvta_generic_to_shared(gfull);
       for (int i = tid; i <= dS; i += NT) {
-        if (i < d || i == dS) {
-          const int owner = i / SL, off = i - owner * SL;
-          const float v = cluster.map_shared_rank(gslice, owner)[off];
-          if (i < d) c.gg[i] = v; else gp[dS + 1] = v;
-        }
+        const int owner = i / SL, off = i - owner * SL;
+        st_async_f32(mapa_u32(recv_s + (uint32_t)(c.rank * SL + off) * 4u, (uint32_t)owner), gp[i], mapa_u32(xb1, (uint32_t)owner));
       }
+      PROF(13);
+      xbar_wait(xb1, par);
+      for (int j = tid; j < mySL; j += NT) {
+        float tv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tv[r] = r < c.G ? recv[r * SL + j] : 0.f;
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sum += tv[r];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+          if (r < c.G) st_async_f32(mapa_u32(gfull_s + (uint32_t)(my0 + j) * 4u, (uint32_t)r), sum, mapa_u32(xb2, (uint32_t)r));
+      }
+      PROF(2);
+      xbar_wait(xb2, par);
+      if (has0) c.gg[i0] = gfull[i0];
+      if (has1) c.gg[i1] = gfull[i1];
+      if (tid == NT - 1) gp[dS + 1] = gfull[dS];
       __syncthreads();
     }
     PROF(14);

@@ -9,8 +9,10 @@ out = ROOT / 'tools' / '_prof'
 out.mkdir(exist_ok=True)
 lib = out / 'libmile_b200.so'
 src = ROOT / 'mile_b200' / 'csrc'
-subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-DMILE_PROFILE',
-                '-shared', '-Xcompiler', '-fPIC', '-o', str(lib), str(src / 'mile_api.cu'), str(src / 'mile_microbench.cu')], check=True)
+import os
+if not (os.environ.get('MILE_PROF_NOBUILD') == '1' and lib.exists()):   # (build here, run on the GPU box with MILE_PROF_NOBUILD=1)
+    subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-DMILE_PROFILE',
+                    '-shared', '-Xcompiler', '-fPIC', '-o', str(lib), str(src / 'mile_api.cu'), str(src / 'mile_microbench.cu')], check=True)
 if len(sys.argv) > 1 and sys.argv[1] == 'build':
     sys.exit(0)
 from mile_b200 import capi
@@ -21,6 +23,8 @@ NAMES = {0: 'x-tile/loop | mma: integrator warp + weight image', 1: 'forward | m
          8: 'esh_update (B)', 9: 'position_update (A)', 10: 'grad_eval total (outer)', 11: 'cluster reduce (rest: block_sum)', 12: 'refresh', 13: 'publish partials | 1st cluster.sync', 14: 'wait + sum ranks'}
 CASES = [('airfoil_3x16', 12, 200, {}), ('airfoil_3x16', 12, 200, {'cluster_size': 8}), ('airfoil_3x16', 12, 200, {'cluster_size': 4}),
          ('bikesharing_2x16', 10, 50, {}), ('protein_2x16', 10, 50, {}), ('airfoil_3x16', 1024, 20, {})]
+if len(sys.argv) > 1 and sys.argv[1] == 'airfoil':
+    CASES = CASES[:2]
 if len(sys.argv) > 1 and sys.argv[1] == 'fast1':
     CASES = [(n, c, s, dict(o_, fast=1)) for n, c, s, o_ in CASES]
 for name, C, steps, opts in CASES:
