@@ -201,6 +201,17 @@ int mile_eval_metrics(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t 
 int mile_train_get_state(mile_ctx* ctx, float* theta_dev, float* m_dev, float* v_dev, int32_t* t_dev, void* stream);
 
 /* ---- data-sharded variant (covertype, rows split across the GPUs of one box) -------- */
+/* ---- diagonal preconditioning: src/training/warmup.py:385-401 (`diagonal_preconditioning=True`, the reference's default,
+ * off in every MCLMC YAML) and blackjax's `sqrt_diag_cov` argument of mclmc.build_kernel / isokinetic_mclachlan.
+ * With a preconditioner m set, the B-steps see the scaled gradient m .* g and the A-steps move by eps * m .* u in every
+ * following mile_mclmc_tune / mile_mclmc_sample / mile_shard_* call (generic step loop; gradients still come from the
+ * fastest evaluator).  mile_precondition_from_moments: m = sqrt(E[x^2] - E[x]^2) from the streaming moments of tuning
+ * phase 2 and L = sqrt(d) (warmup.py:388-394).  NULL clears it.  The reference DROPS m after warmup (sampling.py:291:
+ * only step_size and L are returned), so its sampling phase runs unpreconditioned; the mirror does the same. */
+int mile_precondition_from_moments(mile_ctx* ctx, void* stream);
+int mile_set_sqrt_diag_cov_host(mile_ctx* ctx, const float* sqrt_diag_cov /* [C,d] host, or NULL = identity */);
+int mile_get_sqrt_diag_cov_host(mile_ctx* ctx, float* out /* [C,d] host */);
+
 /* Every rank holds ALL chains and 1/world of the training rows (mile_set_data with the local shard).  Each
  * gradient evaluation = local value_and_grad (prior weighted 1/world) + ncclAllReduce(sum) of the packed
  * [C, d+1] (gradient | log-density) buffer + an integrator-only kernel; all ranks apply identical updates, so

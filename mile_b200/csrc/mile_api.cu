@@ -88,6 +88,7 @@ struct mile_ctx {
   float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
+  float* sdc = nullptr; int sdc_on = 0;      // diagonal preconditioner [C][d] (warmup.py:391-393); used when sdc_on
   int integ_cluster = 8;      // cluster size of the large-d integrator kernel (16 = non-portable size: measured slower, 69 vs 55 us)
   float* w_fin = nullptr;     // finalize scratch: [chains][32 CTAs][2] partial scalars, then [chains] arrival tickets
   float* w_arena = nullptr; size_t w_arena_floats = 0;   // partial sums of one evaluation, summed by wide_finalize_kernel (WideJobs)
@@ -383,7 +384,8 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   }
   const int NL = c->M.NL;
   int rc;
-  if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0) {
+  // (the preconditioned dynamics live in the generic step loop; the tensor evaluator still computes the gradients)
+  if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0 && !pl.kp.sdc) {
     if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, true>(pl, n_chains, st);
     else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, true>(pl, n_chains, st);
     else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, true>(pl, n_chains, st);
@@ -420,6 +422,7 @@ static void fill_common(mile_ctx* c, KParams& k) {
   k.carry = c->carry; k.carry_valid = c->carry_valid;
   k.refresh_mode = c->opt_refresh; k.thin = 1;
   k.out_stride = c->d; k.prior_weight = 1.f; k.chain_base = c->opt_chain_base;
+  k.sdc = c->sdc_on ? c->sdc : nullptr;
 }
 
 // ---- small utility kernels ------------------------------------------------------------------
@@ -445,6 +448,17 @@ __global__ void tune_L_kernel(const float* __restrict__ ax, const float* __restr
   }
   block_sum<1, MILE_THREADS>(v, red, phase);
   if (threadIdx.x == 0) L[c] = sqrtf(v[0]);
+}
+
+__global__ void precond_from_moments_kernel(const float* __restrict__ ax, const float* __restrict__ ax2, float* __restrict__ sdc,
+                                            float* __restrict__ L, int d) {
+  // sqrt_diag_cov = sqrt(E[x^2] - E[x]^2), L = sqrt(d)  (warmup.py:388-394); a variance that rounds below zero gives 0
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    const float m = ax[(long)c * d + i];
+    sdc[(long)c * d + i] = sqrtf(fmaxf(ax2[(long)c * d + i] - m * m, 0.f));
+  }
+  if (threadIdx.x == 0) L[c] = sqrtf((float)d);
 }
 
 static void* scratch(mile_ctx* c, int slot, size_t bytes) {
@@ -534,7 +548,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin};
+                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin, c->sdc};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   for (int r = 0; r < 8; ++r) if (c->xr_peer[r] && c->xr_peer[r] != c->xr) cudaIpcCloseMemHandle(c->xr_peer[r]);
@@ -889,6 +903,42 @@ int mile_tune_finish_phase2(mile_ctx* c, void* stream) {
   tune_L_kernel<<<c->C, MILE_THREADS, 0, (cudaStream_t)stream>>>(c->avg_x, c->avg_x2, c->t_L, c->d);
   CK(cudaGetLastError());
   c->launches++;
+  return 0;
+}
+
+// ---- diagonal preconditioning -------------------------------------------------------------------------------------
+static int sdc_alloc(mile_ctx* c) {
+  if (!c->sdc) CK(cudaMalloc(&c->sdc, (size_t)c->C * c->d * 4));
+  return 0;
+}
+int mile_precondition_from_moments(mile_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  if (sdc_alloc(c)) return -1;
+  precond_from_moments_kernel<<<c->C, 256, 0, (cudaStream_t)stream>>>(c->avg_x, c->avg_x2, c->sdc, c->t_L, c->d);
+  CK(cudaGetLastError());
+  c->launches++;
+  c->sdc_on = 1; c->carry_valid = 0;     // the carried (sum g^2, u.g) refer to the unscaled gradient
+  return 0;
+}
+int mile_set_sqrt_diag_cov_host(mile_ctx* c, const float* sdc) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  c->carry_valid = 0;
+  if (!sdc) { c->sdc_on = 0; return 0; }
+  if (sdc_alloc(c)) return -1;
+  CK(cudaMemcpy(c->sdc, sdc, (size_t)c->C * c->d * 4, cudaMemcpyHostToDevice));
+  c->sdc_on = 1;
+  return 0;
+}
+int mile_get_sqrt_diag_cov_host(mile_ctx* c, float* out) {
+  if (!c || !out) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  const size_t n = (size_t)c->C * c->d;
+  if (c->sdc_on) CK(cudaMemcpy(out, c->sdc, n * 4, cudaMemcpyDeviceToHost));
+  else for (size_t i = 0; i < n; ++i) out[i] = 1.f;
   return 0;
 }
 

@@ -55,6 +55,9 @@ struct KParams {
   // per rank.  After the local reduce-scatter every CTA pushes its summed slice as flagged 8-byte words into the
   // `mr_sums` region of EVERY rank (peer memory mapped with CUDA IPC, stores travel over NVLink), and all CTAs then poll
   // only their own GPU's copy: one NVLink store hop per evaluation, no NCCL call, no kernel boundary.
+  // diagonal preconditioning (warmup.py:391-393, blackjax `sqrt_diag_cov`): [C][d] or null.  The B-steps see the scaled
+  // gradient m .* g, the A-steps move by eps * m .* u.  Served by the generic step loop and the integrator kernel.
+  const float* sdc;
   int mr_world, mr_rank; unsigned int mr_base;   // flag = mr_base + eval + 1 (advanced identically on every rank)
   float2* mr_sums[8];    // rank r's region [C][2 parities][world][dS+4] (own region for r == mr_rank)
 };
@@ -70,9 +73,13 @@ struct Ctx {
   int e0, estride; float* csum; int csum_phase;
   // warm-start training overrides (mile_train.cuh): labels of the gathered minibatch, X always in c.xbuf, sigma clip, metric
   const void* y_override = nullptr; int force_resident = 0; float sig_lo = 1e-6f; float* metric = nullptr;
+  const float* sdc = nullptr;   // this chain's sqrt_diag_cov [d] (global memory) or null = identity
   bool lead;   // the one thread that reports per-chain scalars (thread 0 of the block; lane 0 of the integrator warp in warp mode)
   __device__ Ctx(const KParams& p) : P(p) {}
 };
+
+// element i of the preconditioner (1 when none is set)
+__device__ __forceinline__ float sdc_at(const Ctx& c, int i) { return c.sdc ? __ldg(c.sdc + i) : 1.f; }
 
 // flat element i -> position in the padded parameter image (pmap) and in the transposed image
 // (pmap + dS; biases and layer 0, which need no transpose, point at their pmap slot again)
@@ -314,7 +321,8 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
     }
     const float g = s + pg * P.prior_weight;
     c.gg[i] = g;
-    v[0] += pv * P.prior_weight; v[1] += g * g; v[2] += c.uu[i] * g; v[3] += isfinite(th) ? 0.f : 1.f;
+    const float gs = g * sdc_at(c, i);
+    v[0] += pv * P.prior_weight; v[1] += gs * gs; v[2] += c.uu[i] * gs; v[3] += isfinite(th) ? 0.f : 1.f;
   };
   if (use_ll) {
     for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
@@ -444,7 +452,7 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const int d = c.P.M.d;
   float ae, au;
   const float dk = esh_coeffs(d, eps, coef, g2, ug, ae, au);
-  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * c.gg[i] + au * c.uu[i];
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * (c.gg[i] * sdc_at(c, i)) + au * c.uu[i];
   return dk;
 }
 
@@ -455,7 +463,7 @@ __device__ __forceinline__ void position_update(Ctx& c, float eps, float coef) {
   const int d = c.P.M.d;
   const float s = eps * coef;
   for (int i = threadIdx.x; i < d; i += NT) {
-    const float t = c.th[i] + s * c.uu[i];
+    const float t = c.th[i] + s * sdc_at(c, i) * c.uu[i];
     c.th[i] = t;
     store_param(c, i, t);
   }
@@ -474,7 +482,7 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
   const int d = P.M.d;
   if (isinf(L)) {   // no refresh: still re-normalise numerically (the B-steps use the closed-form norm)
     float v[2] = {0.f, 0.f};
-    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.uu[i] * c.uu[i]; v[1] += c.uu[i] * c.gg[i]; }
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.uu[i] * c.uu[i]; v[1] += c.uu[i] * (c.gg[i] * sdc_at(c, i)); }
     all_sum<2, NT, BAR, ES>(c, v);
     const float inv = 1.f / sqrtf(v[0]);
     for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] *= inv;
@@ -486,7 +494,7 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
     const float w = c.uu[i] + nu * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
     c.uu[i] = w;
-    v[0] += w * w; v[1] += w * c.gg[i];
+    v[0] += w * w; v[1] += w * (c.gg[i] * sdc_at(c, i));
   }
   all_sum<2, NT, BAR, ES>(c, v);
   const float inv = 1.f / sqrtf(v[0]);
@@ -520,7 +528,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         t_epsmax = eps * 0.8f;
         dE = 0.f;
         float v[2] = {0.f, 0.f};
-        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+        for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { const float gs = c.gg[i] * sdc_at(c, i); v[0] += gs * gs; v[1] += c.uu[i] * gs; }
         all_sum<2, NT, BAR, ES>(c, v);
         g2 = v[0]; ug = v[1];
       } else {
@@ -537,7 +545,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         all_sum<1, NT, BAR, ES>(c, chv);
         if (chv[0] != 0.f) {
           float v[2] = {0.f, 0.f};
-          for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+          for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) { const float gs = c.gg[i] * sdc_at(c, i); v[0] += gs * gs; v[1] += c.uu[i] * gs; }
           all_sum<2, NT, BAR, ES>(c, v);
           g2 = v[0]; ug = v[1];
         }
@@ -635,6 +643,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   c.aux = smem + P.off_aux;
   const int d = M.d, ch = c.chain;
   const int tid = threadIdx.x;
+  c.sdc = P.sdc ? P.sdc + (long)ch * d : nullptr;
 
   // ---- prologue: parameter image, state, resident X slice --------------------------------
   for (int i = tid; i < M.psize; i += NT) c.wp[i] = 0.f;
@@ -715,7 +724,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
       g2 = P.carry[2 * ch]; ug = P.carry[2 * ch + 1];
     } else {  // cached gradient: sum g^2 and u.g for the first B-step
       float v[2] = {0.f, 0.f};
-      for (int i = tid; i < d; i += NI) { v[0] += c.gg[i] * c.gg[i]; v[1] += c.uu[i] * c.gg[i]; }
+      for (int i = tid; i < d; i += NI) { const float gs = c.gg[i] * sdc_at(c, i); v[0] += gs * gs; v[1] += c.uu[i] * gs; }
       block_sum<2, NI, IB>(v, c.red2, c.phase2);
       g2 = v[0]; ug = v[1];
     }

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   c.thb = S.thb + (long)ch * d; c.ub = S.ub + (long)ch * d; c.gb = S.gb + (long)ch * d;
   c.avgx = P.avg_x + (long)ch * d; c.avgx2 = P.avg_x2 + (long)ch * d; c.red = red; c.red2 = red + 2 * 4 * (NT / 32);
   c.wp = nullptr; c.pmap = nullptr; c.gpart = nullptr; c.tile = nullptr; c.xbuf = nullptr; c.xstream = nullptr;
+  c.sdc = P.sdc ? P.sdc + (long)ch * d : nullptr;
   const bool fresh = S.stage != SH_BEGIN;      // a newly all-reduced gradient arrives with MID / END
   const bool p2p = S.p2p && fresh;
   if (p2p) {
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
     const float gi = (fresh && !p2p) ? S.gl[(long)ch * (d + 1) + i] : c.gg[i];   // (p2p: this thread just wrote c.gg[i])
     if (fresh && !p2p) c.gg[i] = gi;
-    v[0] += gi * gi; v[1] += c.uu[i] * gi; v[2] += isfinite(c.th[i]) ? 0.f : 1.f;
+    const float gs = gi * sdc_at(c, i);
+    v[0] += gs * gs; v[1] += c.uu[i] * gs; v[2] += isfinite(c.th[i]) ? 0.f : 1.f;
   }
   all_sum<3, NT, 0, ES>(c, v);
   float g2 = v[0], ug = v[1];
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   if (S.stage != SH_END) {
     dK += esh_update<NT, 0, ES>(c, eps, S.stage == SH_BEGIN ? b1 : b2, g2, ug);
     const float st = eps * 0.5f;
-    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.th[i] += st * c.uu[i];
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.th[i] += st * sdc_at(c, i) * c.uu[i];
   } else {
     dK += esh_update<NT, 0, ES>(c, eps, b1, g2, ug);
     refresh_momentum<NT, 0, ES>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, S.s_local, nslot - 1, nslot, ug);

@@ -267,6 +267,22 @@ class Ensemble:
         l = None if L is None else _f32(np.broadcast_to(L, (C_,)))
         capi.check(self.lib.mile_set_tuning_host(self.h, capi.host_ptr(e), capi.host_ptr(l)))
 
+    # ---- diagonal preconditioning (warmup.py:385-401; blackjax sqrt_diag_cov) -----------------
+    def precondition_from_moments(self):
+        """sqrt_diag_cov = sqrt(E[x^2] - E[x]^2) from the phase-2 streaming moments, L = sqrt(d); active from now on."""
+        capi.check(self.lib.mile_precondition_from_moments(self.h, None))
+        self.synchronize()
+
+    def set_sqrt_diag_cov(self, sdc):
+        """[C,d] (or [d], broadcast) preconditioner; None clears it."""
+        a = None if sdc is None else _f32(np.broadcast_to(sdc, (self.n_chains, self.d)))
+        capi.check(self.lib.mile_set_sqrt_diag_cov_host(self.h, capi.host_ptr(a)))
+
+    def get_sqrt_diag_cov(self):
+        out = np.empty((self.n_chains, self.d), np.float32)
+        capi.check(self.lib.mile_get_sqrt_diag_cov_host(self.h, capi.host_ptr(out)))
+        return out
+
     # ---- LPPD / predict -----------------------------------------------------------------
     def lppd_reset(self):
         capi.check(self.lib.mile_lppd_reset(self.h, None))

@@ -111,11 +111,13 @@ def warmup_mclmc(config: SamplerConfig, rng_key, init_params: dict, unnorm_log_p
     kw = dict(desired_energy_var_start=config.desired_energy_var_start,
               desired_energy_var_end=config.desired_energy_var_end, trust_in_estimate=config.trust_in_estimate,
               num_effective_samples=config.num_effective_samples, step_size_init=config.step_size_init)
-    if config.diagonal_preconditioning:
-        raise NotImplementedError('diagonal_preconditioning is not implemented on the CUDA path')
+    dp = bool(config.diagonal_preconditioning)
     if _ensemble is not None:
-        return run_warmup(_ensemble, theta0, rng_key, config.warmup_steps, **kw)
+        out = run_warmup(_ensemble, theta0, rng_key, config.warmup_steps, diagonal_preconditioning=dp, **kw)
+        # sampling.py:291 returns only step_size and L: the sampling phase of the reference runs WITHOUT the preconditioner
+        _ensemble.set_sqrt_diag_cov(None)
+        return out
     from .warmup import custom_mclmc_warmup
-    res = custom_mclmc_warmup(unnorm_log_posterior, diagonal_preconditioning=False, **kw).run(
+    res = custom_mclmc_warmup(unnorm_log_posterior, diagonal_preconditioning=dp, **kw).run(
         rng_key, init_params, config.warmup_steps)
     return res.state, {'step_size': res.parameters.step_size, 'L': res.parameters.L}

@@ -21,8 +21,10 @@ CHUNK = 10000                      # MCLMC steps per kernel launch
 
 def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, desired_energy_var_start,
                desired_energy_var_end, trust_in_estimate, num_effective_samples, step_size_init,
-               fft_params_limit: int = 2000, fft_samples_limit: int = 10000):
-    """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C])."""
+               fft_params_limit: int = 2000, fft_samples_limit: int = 10000, diagonal_preconditioning: bool = False):
+    """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C]); with
+    `diagonal_preconditioning` the preconditioner stays set on `ens` (read it with `ens.get_sqrt_diag_cov()`, clear it
+    with `ens.set_sqrt_diag_cov(None)` -- the reference's sampling phase does not use it, sampling.py:291)."""
     import torch
     seed = key_to_seed(rng_key)
     tune1, tune2, tune3 = (int(num_steps * r) for r in PHASE_RATIO)        # warmup.py:555-557
@@ -39,6 +41,18 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
         done += n
     if tune2 != 0:
         ens.tune_finish_phase2()                                           # L = sqrt(sum var), warmup.py:387-390
+        if diagonal_preconditioning:                                       # warmup.py:391-401
+            eps, _, _ = ens.get_tuning()
+            ens.precondition_from_moments()                                # sqrt_diag_cov = sqrt(var), L = sqrt(d)
+            _, Ld, _ = ens.get_tuning()
+            # "readjust the stepsize": tune2 // 3 steps of phase-1 style adaptation (mask = 1) with the preconditioned
+            # kernel; run_steps restarts the adaptive state (0, 0, inf), the streaming averages and the step counter
+            steps = tune2 // 3
+            ens.tune_reset(0.0)
+            ens.set_tuning(step_size=eps, L=Ld)
+            final_key = split(part1_key, 2)[1]
+            if steps > 0:
+                ens.tune(steps, 0, cfg, seed=final_key)
     eps, L, _ = ens.get_tuning()
     if tune3 != 0:                                                         # HOT LOOP B, warmup.py:408-465
         dev = torch.device(f'cuda:{ens.device}')
@@ -92,9 +106,6 @@ def custom_mclmc_warmup(logdensity_fn, diagonal_preconditioning: bool = True, de
                         desired_energy_var_end: float = 5e-4, trust_in_estimate: float = 1.5,
                         num_effective_samples: int = 100, step_size_init: float = 0.005) -> AdaptationAlgorithm:
     """warmup.py:486-568 (same argument names and defaults)."""
-    if diagonal_preconditioning:
-        raise NotImplementedError('diagonal_preconditioning=True is off in every MCLMC YAML of the reference and is '
-                                  'not implemented on the CUDA path (SURVEY.md section 3.2)')
     model, x, y = unwrap_posterior(logdensity_fn)
     spec = model.spec
 
@@ -106,14 +117,15 @@ def custom_mclmc_warmup(logdensity_fn, diagonal_preconditioning: bool = True, de
         try:
             eps, L = run_warmup(ens, theta0, rng_key, num_steps, desired_energy_var_start=desired_energy_var_start,
                                 desired_energy_var_end=desired_energy_var_end, trust_in_estimate=trust_in_estimate,
-                                num_effective_samples=num_effective_samples, step_size_init=step_size_init)
+                                num_effective_samples=num_effective_samples, step_size_init=step_size_init,
+                                diagonal_preconditioning=diagonal_preconditioning)
             th, u, lp, g = ens.get_state()
+            sdc = ens.get_sqrt_diag_cov()
         finally:
             ens.close()
         un = (lambda a: spec.unravel(a)) if batched else (lambda a: spec.unravel(a[0]))
         state = IntegratorState(un(th), un(u), lp if batched else lp[0], un(g))
-        params = MCLMCAdaptationState(L if batched else L[0], eps if batched else eps[0],
-                                      np.ones(spec.n_params, np.float32))
+        params = MCLMCAdaptationState(L if batched else L[0], eps if batched else eps[0], sdc if batched else sdc[0])
         return AdaptationResults(state, params)
 
     return AdaptationAlgorithm(run)

@@ -473,9 +473,9 @@ def tune_update(cfg: TuneConfig, ts: TuneState, x: np.ndarray, de, success: bool
 
 
 def tune_step(logdensity_and_grad, cfg: TuneConfig, state: IntegratorState, ts: TuneState,
-              z, step_number: int, refresh='post'):
+              z, step_number: int, refresh='post', sqrt_diag_cov=1.0):
     """One iteration of HOT LOOP A: warmup.py:276-352 (`predictor` + `step`)."""
-    new, info = mclmc_step(logdensity_and_grad, state, ts.step_size, ts.L, z, refresh=refresh)
+    new, info = mclmc_step(logdensity_and_grad, state, ts.step_size, ts.L, z, sqrt_diag_cov=sqrt_diag_cov, refresh=refresh)
     success, state, step_size_max, de = handle_nans(state, new, ts.step_size, ts.step_size_max,
                                                     info.energy_change)
     ts = tune_update(cfg, ts._replace(step_size_max=step_size_max), state.position, de, success, step_number)
@@ -583,11 +583,12 @@ def subsample_for_fft(samples: np.ndarray, perm: np.ndarray | None,
     return samples
 
 
-def run_warmup(logdensity_and_grad, cfg: TuneConfig, position, z0, z_steps, refresh='post'):
+def run_warmup(logdensity_and_grad, cfg: TuneConfig, position, z0, z_steps, refresh='post',
+               diagonal_preconditioning=False):
     """custom_mclmc_warmup(...).run for one chain (warmup.py:533-566).
 
-    z_steps: [tune1+tune2+tune3, d] normal draws (host supplied).  Returns
-    (state, step_size, L, info dict).
+    z_steps: [tune1+tune2 (+ tune2//3 with diagonal_preconditioning) + tune3, d] normal draws (host supplied).
+    Returns (state, step_size, L, TuneState) and, with diagonal_preconditioning, sqrt_diag_cov as a fifth value.
     """
     state = mclmc_init(logdensity_and_grad, position, z0)
     d = position.shape[0]
@@ -598,14 +599,25 @@ def run_warmup(logdensity_and_grad, cfg: TuneConfig, position, z0, z_steps, refr
         state, ts, _, _ = tune_step(logdensity_and_grad, cfg, state, ts, z_steps[k], i, refresh)
         k += 1
     ts = tune_finish_phase2(cfg, ts)
+    sdc = 1.0
+    if diagonal_preconditioning and cfg.tune2 != 0:                      # warmup.py:391-401
+        var = ts.avg_x2 - np.square(ts.avg_x)
+        sdc = np.sqrt(np.maximum(var, 0)).astype(position.dtype)
+        ts2 = tune_init(cfg, d, dt)._replace(step_size=ts.step_size, L=dt(np.sqrt(dt(d))))
+        for i in range(cfg.tune2 // 3):                                  # run_steps restarts adaptive state and counter
+            state, ts2, _, _ = tune_step(logdensity_and_grad, cfg, state, ts2, z_steps[k], i, refresh, sqrt_diag_cov=sdc)
+            k += 1
+        ts = ts2
     L, eps = ts.L, ts.step_size
     if cfg.tune3 != 0:
         pos = np.empty((cfg.tune3, d), position.dtype)
         for i in range(cfg.tune3):
-            state, _ = mclmc_step(logdensity_and_grad, state, eps, L, z_steps[k], refresh=refresh)
+            state, _ = mclmc_step(logdensity_and_grad, state, eps, L, z_steps[k], sqrt_diag_cov=sdc, refresh=refresh)
             pos[i] = state.position
             k += 1
         L = adaptation_L(eps, pos)
+    if diagonal_preconditioning:
+        return state, eps, L, ts, sdc
     return state, eps, L, ts
 
 

@@ -57,8 +57,6 @@ def test_custom_mclmc_warmup_reaches_desired_energy_variance():
     C = 4
     pos = [module.init(rng, ospec.n_features, scale=0.5) for _ in range(C)]
     posb = {'fcn': {k: {kk: np.stack([p['fcn'][k][kk] for p in pos]) for kk in v} for k, v in pos[0]['fcn'].items()}}
-    with pytest.raises(NotImplementedError):
-        custom_mclmc_warmup(log_post)            # reference default diagonal_preconditioning=True is not on the CUDA path
     algo = custom_mclmc_warmup(log_post, diagonal_preconditioning=False, desired_energy_var_start=0.5,
                                desired_energy_var_end=0.1, trust_in_estimate=1.5, num_effective_samples=100,
                                step_size_init=0.01)
@@ -66,7 +64,7 @@ def test_custom_mclmc_warmup_reaches_desired_energy_variance():
     assert params.step_size.shape == (C,) and params.L.shape == (C,)
     assert np.all(np.isfinite(params.step_size)) and np.all(params.step_size > 0)
     assert np.all(np.isfinite(params.L)) and np.all(params.L > 0)
-    assert params.sqrt_diag_cov.shape == (ospec.n_params,)
+    assert params.sqrt_diag_cov.shape == (C, ospec.n_params) and np.all(params.sqrt_diag_cov == 1.0)   # (preconditioning: tests/test_gpu_preconditioning.py)
     # Var[dE]/d with the tuned step size is of the order of the target (the predictor's premise)
     from mile_b200 import Ensemble, FCNSpec
     ens = pm.make_ensemble(C, X, y)
