@@ -248,39 +248,8 @@ def test_tuning_matches_oracle():
     ens.close()
 
 
-def test_tuning_handle_nans_path():
-    """A poisoned step (inf in the noise -> non-finite position) must keep the previous state,
-    set step_size_max = 0.8 * eps and report dE = 0 (warmup.py:468-483)."""
-    name, C = 'airfoil_2x16', 2
-    ospec, ens, X, y, _, _ = make(name, C)
-    d = ospec.n_params
-    th0 = o.synthetic_theta0(ospec, C)
-    rng = np.random.default_rng(4)
-    z0 = rng.standard_normal((C, d)).astype(np.float32)
-    z = rng.standard_normal((3, C, d)).astype(np.float32)
-    ens.init(th0, z0)
-    ens.tune_reset(0.01)
-    tc = ens.tune_cfg(3, 0, 0.5, 0.1, 1.5, 100)
-    ens.tune(1, 0, tc, z=z[:1])
-    before = ens.get_state()
-    eps_before = ens.get_tuning()[0]
-    # poison chain 1 by making its state blow up: a huge momentum refresh is not enough (u is
-    # normalised), so poison the position through the state instead
-    th_bad = before[0].copy()
-    th_bad[1, 0] = np.float32(3e38)   # next A-step overflows -> inf
-    ens.set_state(theta=th_bad)
-    info = ens.tune(1, 1, tc, z=z[1:2], info=True)
-    after = ens.get_state()
-    e, L, emax = ens.get_tuning()
-    assert info[0, 0, 3] == 1.0
-    if info[0, 1, 3] == 0.0:   # chain 1 failed: previous state kept, eps_max shrunk, dE = 0
-        np.testing.assert_array_equal(after[0][1], th_bad[1])
-        assert abs(emax[1] - 0.8 * eps_before[1]) <= 1e-6 * eps_before[1]
-        assert info[0, 1, 0] == 0.0
-        assert e[1] <= emax[1]
-    else:                       # stayed finite: nothing to check beyond finiteness
-        assert np.all(np.isfinite(after[0][1]))
-    ens.close()
+# (handle_nans: the deterministic failure case is compared field by field with the oracle in
+#  tests/test_gpu_parity_shapes.py::test_handle_nans_failure_matches_oracle)
 
 
 def test_lppd_and_predict_match_oracle():
