@@ -406,12 +406,15 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
     ens.set_data(Xp, y); ens.set_state(*st)
     ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4320, lppd=False)
     ens.set_state(*st)
+    # the step's result is read back into pinned host memory (the sample tensor is the bulk of the D2H bytes)
+    out_pinned = None if sharded else torch.empty(n_slots * C * d, dtype=torch.float32, pin_memory=True).numpy()
+    skw = {} if sharded else {'out': out_pinned}
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         ens.set_data(Xp, y)
         ens.set_state(*st)
-        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=fused_lppd)
+        smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=fused_lppd, **skw)
         st = ens.get_state()
     if fused_lppd and world > 1:
         m_, s_, cnt_ = ens.lppd_state()
@@ -472,7 +475,7 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
-                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers) + get_state'
+                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers; X and the kept-sample buffer are pinned) + get_state'
                             + (' + NCCL merge of the LPPD states' if fused_lppd and world > 1 else '')},
         }
         if sharded_parity is not None:

@@ -206,15 +206,22 @@ class Ensemble:
 
     # ---- sampling -----------------------------------------------------------------------
     def sample(self, n_steps, step_size, L, *, step_base=0, n_thinning=1, z=None, seed=0, keep=True, info=False,
-               lppd=False):
-        """Host-buffer sampling call (the e2e path): returns (samples [S,C,d] | None, info [n,C,3] | None)."""
+               lppd=False, out=None):
+        """Host-buffer sampling call (the e2e path): returns (samples [S,C,d] | None, info [n,C,3] | None).
+        `out`: optional caller-owned float32 host array of at least S*C*d elements for the kept samples (e.g. the numpy
+        view of a pinned torch tensor: the device-to-host copy then runs at PCIe speed instead of through a staging
+        buffer); the returned samples are a view of it."""
         C_, d = self.n_chains, self.d
         eps = _f32(np.broadcast_to(step_size, (C_,)))
         Ls = _f32(np.broadcast_to(L, (C_,)))
         first = -(-step_base // n_thinning)
         last = (step_base + n_steps - 1) // n_thinning
         n_slots = max(0, last - first + 1) if keep and n_steps > 0 else 0
-        samples = np.empty((n_slots, C_, d), np.float32) if keep else None
+        if keep and out is not None:
+            assert out.dtype == np.float32 and out.flags['C_CONTIGUOUS'] and out.size >= n_slots * C_ * d
+            samples = out.reshape(-1)[:n_slots * C_ * d].reshape(n_slots, C_, d)
+        else:
+            samples = np.empty((n_slots, C_, d), np.float32) if keep else None
         inf = np.empty((n_steps, C_, 3), np.float32) if info else None
         z = None if z is None else _f32(z)
         capi.check(self.lib.mile_mclmc_sample_host(self.h, n_steps, step_base, n_thinning, capi.host_ptr(eps),
