@@ -409,13 +409,18 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
     # the step's result is read back into pinned host memory (the sample tensor is the bulk of the D2H bytes)
     out_pinned = None if sharded else torch.empty(n_slots * C * d, dtype=torch.float32, pin_memory=True).numpy()
     skw = {} if sharded else {'out': out_pinned}
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    st_pinned = (pin(C, d), pin(C, d), pin(C), pin(C, d))        # chain state travels through pinned buffers as well
+    for dst, src in zip(st_pinned, st):
+        dst[...] = src
+    st = st_pinned
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         ens.set_data(Xp, y)
         ens.set_state(*st)
         smp, _ = ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4321 + i, lppd=fused_lppd, **skw)
-        st = ens.get_state()
+        st = ens.get_state(out=st_pinned)
     if fused_lppd and world > 1:
         m_, s_, cnt_ = ens.lppd_state()
         merge_lppd_states(m_, s_, cnt_, device=dev)
@@ -475,7 +480,7 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'chain-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
-                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers; X and the kept-sample buffer are pinned) + get_state'
+                    'path': 'Ensemble.set_data + set_state + sample (mile_*_host C-ABI calls, host numpy buffers; X, the chain state and the kept-sample buffer are pinned) + get_state'
                             + (' + NCCL merge of the LPPD states' if fused_lppd and world > 1 else '')},
         }
         if sharded_parity is not None:

@@ -192,10 +192,17 @@ class Ensemble:
         z0 = None if z0 is None else _f32(z0).reshape(self.n_chains, self.d)
         capi.check(self.lib.mile_mclmc_init_host(self.h, capi.host_ptr(theta0), capi.host_ptr(z0), seed))
 
-    def get_state(self):
+    def get_state(self, out=None):
+        """(theta [C,d], u [C,d], logdensity [C], grad [C,d]) as host arrays; `out` = caller-owned float32 arrays of these
+        shapes (e.g. pinned) to be filled instead of fresh ones."""
         C_, d = self.n_chains, self.d
-        th, u, g = (np.empty((C_, d), np.float32) for _ in range(3))
-        lp = np.empty(C_, np.float32)
+        if out is not None:
+            th, u, lp, g = out
+            assert all(a.dtype == np.float32 and a.flags['C_CONTIGUOUS'] for a in out)
+            assert th.shape == u.shape == g.shape == (C_, d) and lp.shape == (C_,)
+        else:
+            th, u, g = (np.empty((C_, d), np.float32) for _ in range(3))
+            lp = np.empty(C_, np.float32)
         capi.check(self.lib.mile_get_state_host(self.h, capi.host_ptr(th), capi.host_ptr(u), capi.host_ptr(lp),
                                                 capi.host_ptr(g)))
         return th, u, lp, g
