@@ -571,6 +571,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
   else if (!strcmp(key, "kslices")) { c->opt_kslices = (int)v; c->w_rows = -1; }   // wide path: split-K slices of the dW GEMMs (0 = auto)
+  else if (!strcmp(key, "p2p")) { if (v == 0) c->p2p = 0; else if (!c->xr_peer[c->rank == 0 ? 1 : 0]) return fail("p2p: the peer mapping has not been opened"); else c->p2p = 1; }
   else if (!strcmp(key, "head_fused")) c->opt_head_fused = (int)v;   // wide path: fused output-layer kernel on / off
   else if (!strcmp(key, "shard_fused")) c->opt_shard_fused = (int)v;   // 1: multi-rank step loop as ONE persistent kernel per rank (needs the peer mapping), 0: one launch per phase
   else if (!strcmp(key, "steploop")) c->opt_steploop = (int)v;   // 1: integrator-warp step loop of the tensor evaluator, 0: generic loop

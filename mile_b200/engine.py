@@ -421,7 +421,14 @@ class ShardedEnsemble(Ensemble):
             allh = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(allh, t)
             hs = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
-            capi.check(self.lib.mile_shard_p2p_open(self.h, capi.host_ptr(hs)))
+            ok = self.lib.mile_shard_p2p_open(self.h, capi.host_ptr(hs)) == 0
+            # all ranks or none: a rank without peer access to everybody sends the whole job back to ncclAllReduce
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f'cuda:{device}')
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    self.set_option('p2p', 0)
+                return
             # with the mapping open the whole step loop is one persistent kernel per rank (flagged-word exchange over
             # NVLink inside it); MILE_SHARD_FUSED=0 keeps one launch per phase
             if os.environ.get('MILE_SHARD_FUSED', '1') == '0':
