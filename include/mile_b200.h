@@ -201,6 +201,13 @@ int mile_eval_metrics(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t 
 int mile_train_get_state(mile_ctx* ctx, float* theta_dev, float* m_dev, float* v_dev, int32_t* t_dev, void* stream);
 
 /* ---- data-sharded variant (covertype, rows split across the GPUs of one box) -------- */
+/* ---- partition sampling: src/training/partition_sampling.py:32-330 with trainer.py:613-659
+ * (`log_unnormalized_posterior_partition`): only the first and the last layer are sampled, the hidden layers stay at their
+ * warm-start values.  frozen[i] != 0 freezes flat parameter i for ALL chains: it keeps its value, contributes no prior
+ * term, and gets zero gradient / momentum / noise; the dimension of the dynamics (ESH normalisation d - 1, refresh,
+ * tuning, L_0) becomes the number of sampled parameters.  NULL clears the mask.  Generic step loop; rejected on the wide path. */
+int mile_set_frozen_mask_host(mile_ctx* ctx, const uint8_t* frozen /* [d] host, or NULL */);
+
 /* ---- diagonal preconditioning: src/training/warmup.py:385-401 (`diagonal_preconditioning=True`, the reference's default,
  * off in every MCLMC YAML) and blackjax's `sqrt_diag_cov` argument of mclmc.build_kernel / isokinetic_mclachlan.
  * With a preconditioner m set, the B-steps see the scaled gradient m .* g and the A-steps move by eps * m .* u in every

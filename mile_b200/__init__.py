@@ -13,8 +13,9 @@ from .priors import Prior, PriorDist  # noqa: F401
 from .probabilistic import ProbabilisticModel  # noqa: F401
 from .sampling import inference_loop, warmup_mclmc  # noqa: F401
 from .warmup import custom_mclmc_warmup  # noqa: F401
+from .partition_sampling import partition_inference_loop, partition_params  # noqa: F401
 from .evaluation import evaluate_bde, predict_bde  # noqa: F401
 
 __all__ = ['Ensemble', 'FCNSpec', 'ShardedEnsemble', 'lppd_from_state', 'PriorConfig', 'Sampler', 'SamplerConfig', 'KERNELS', 'mclmc',
            'FCN', 'Prior', 'PriorDist', 'ProbabilisticModel', 'inference_loop', 'warmup_mclmc', 'custom_mclmc_warmup',
-           'evaluate_bde', 'predict_bde']
+           'evaluate_bde', 'predict_bde', 'partition_inference_loop', 'partition_params']

@@ -88,6 +88,7 @@ struct mile_ctx {
   float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
+  float* pmask = nullptr; int pmask_on = 0, d_eff = 0;   // partition sampling: 1 = sampled / 0 = frozen per parameter
   float* sdc = nullptr; int sdc_on = 0;      // diagonal preconditioner [C][d] (warmup.py:391-393); used when sdc_on
   int integ_cluster = 8;      // cluster size of the large-d integrator kernel (16 = non-portable size: measured slower, 69 vs 55 us)
   float* w_fin = nullptr;     // finalize scratch: [chains][32 CTAs][2] partial scalars, then [chains] arrival tickets
@@ -385,7 +386,7 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   const int NL = c->M.NL;
   int rc;
   // (the preconditioned dynamics live in the generic step loop; the tensor evaluator still computes the gradients)
-  if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0 && !pl.kp.sdc) {
+  if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0 && !pl.kp.sdc && !pl.kp.pmask) {
     if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, true>(pl, n_chains, st);
     else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, true>(pl, n_chains, st);
     else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, true>(pl, n_chains, st);
@@ -423,6 +424,7 @@ static void fill_common(mile_ctx* c, KParams& k) {
   k.refresh_mode = c->opt_refresh; k.thin = 1;
   k.out_stride = c->d; k.prior_weight = 1.f; k.chain_base = c->opt_chain_base;
   k.sdc = c->sdc_on ? c->sdc : nullptr;
+  k.pmask = c->pmask_on ? c->pmask : nullptr; k.d_eff = c->pmask_on ? c->d_eff : c->d;
 }
 
 // ---- small utility kernels ------------------------------------------------------------------
@@ -451,14 +453,14 @@ __global__ void tune_L_kernel(const float* __restrict__ ax, const float* __restr
 }
 
 __global__ void precond_from_moments_kernel(const float* __restrict__ ax, const float* __restrict__ ax2, float* __restrict__ sdc,
-                                            float* __restrict__ L, int d) {
+                                            float* __restrict__ L, int d, int d_eff) {
   // sqrt_diag_cov = sqrt(E[x^2] - E[x]^2), L = sqrt(d)  (warmup.py:388-394); a variance that rounds below zero gives 0
   const int c = blockIdx.x;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     const float m = ax[(long)c * d + i];
     sdc[(long)c * d + i] = sqrtf(fmaxf(ax2[(long)c * d + i] - m * m, 0.f));
   }
-  if (threadIdx.x == 0) L[c] = sqrtf((float)d);
+  if (threadIdx.x == 0) L[c] = sqrtf((float)d_eff);
 }
 
 static void* scratch(mile_ctx* c, int slot, size_t bytes) {
@@ -548,7 +550,7 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin, c->sdc};
+                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin, c->sdc, c->pmask};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   for (int r = 0; r < 8; ++r) if (c->xr_peer[r] && c->xr_peer[r] != c->xr) cudaIpcCloseMemHandle(c->xr_peer[r]);
@@ -596,6 +598,7 @@ int64_t mile_get_option(const mile_ctx* c, const char* key) {
   if (!strcmp(key, "chain_base")) return c->opt_chain_base;
   if (!strcmp(key, "wide")) return c->wide;
   if (!strcmp(key, "p2p")) return c->p2p;
+  if (!strcmp(key, "d_eff")) return c->pmask_on ? c->d_eff : c->d;
   if (!strcmp(key, "shard_fused")) {   // is the multi-rank step loop the fused persistent kernel?
     Plan pl;
     return shard_fused_plan(const_cast<mile_ctx*>(c), pl) == 0 ? 1 : 0;
@@ -851,7 +854,7 @@ int mile_tune_reset(mile_ctx* c, float step_size_init, void* stream) {
   fill_kernel<<<8, 256, 0, st>>>(c->t_xavg, C, 0.f);
   fill_kernel<<<8, 256, 0, st>>>(c->t_epsmax, C, INFINITY);
   fill_kernel<<<8, 256, 0, st>>>(c->t_eps, C, step_size_init);
-  fill_kernel<<<8, 256, 0, st>>>(c->t_L, C, fmaxf(sqrtf((float)c->d), 15.0f));
+  fill_kernel<<<8, 256, 0, st>>>(c->t_L, C, fmaxf(sqrtf((float)(c->pmask_on ? c->d_eff : c->d)), 15.0f));
   fill_kernel<<<8, 256, 0, st>>>(c->t_wtot, C, 0.f);
   fill_kernel<<<148, 256, 0, st>>>(c->avg_x, Cd, 0.f);
   fill_kernel<<<148, 256, 0, st>>>(c->avg_x2, Cd, 0.f);
@@ -916,7 +919,7 @@ int mile_precondition_from_moments(mile_ctx* c, void* stream) {
   if (!c) return fail("null ctx");
   CK(cudaSetDevice(c->device));
   if (sdc_alloc(c)) return -1;
-  precond_from_moments_kernel<<<c->C, 256, 0, (cudaStream_t)stream>>>(c->avg_x, c->avg_x2, c->sdc, c->t_L, c->d);
+  precond_from_moments_kernel<<<c->C, 256, 0, (cudaStream_t)stream>>>(c->avg_x, c->avg_x2, c->sdc, c->t_L, c->d, c->pmask_on ? c->d_eff : c->d);
   CK(cudaGetLastError());
   c->launches++;
   c->sdc_on = 1; c->carry_valid = 0;     // the carried (sum g^2, u.g) refer to the unscaled gradient
@@ -940,6 +943,24 @@ int mile_get_sqrt_diag_cov_host(mile_ctx* c, float* out) {
   const size_t n = (size_t)c->C * c->d;
   if (c->sdc_on) CK(cudaMemcpy(out, c->sdc, n * 4, cudaMemcpyDeviceToHost));
   else for (size_t i = 0; i < n; ++i) out[i] = 1.f;
+  return 0;
+}
+
+// ---- partition sampling ---------------------------------------------------------------------------------------------
+int mile_set_frozen_mask_host(mile_ctx* c, const uint8_t* frozen) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  c->carry_valid = 0;
+  if (!frozen) { c->pmask_on = 0; return 0; }
+  if (c->wide) return fail("partition sampling is served by the shared-memory kernels only (this model runs on the wide path)");
+  std::vector<float> m((size_t)c->d);
+  int n = 0;
+  for (int i = 0; i < c->d; ++i) { m[i] = frozen[i] ? 0.f : 1.f; n += frozen[i] ? 0 : 1; }
+  if (n < 2) return fail("partition sampling needs at least two sampled parameters");
+  if (!c->pmask) CK(cudaMalloc(&c->pmask, (size_t)c->d * 4));
+  CK(cudaMemcpy(c->pmask, m.data(), (size_t)c->d * 4, cudaMemcpyHostToDevice));
+  c->pmask_on = 1; c->d_eff = n;
   return 0;
 }
 

@@ -58,6 +58,11 @@ struct KParams {
   // diagonal preconditioning (warmup.py:391-393, blackjax `sqrt_diag_cov`): [C][d] or null.  The B-steps see the scaled
   // gradient m .* g, the A-steps move by eps * m .* u.  Served by the generic step loop and the integrator kernel.
   const float* sdc;
+  // partition sampling (src/training/partition_sampling.py, trainer.py:613-659): pmask [d] = 1 for sampled parameters, 0
+  // for frozen ones (shared by all chains), d_eff = number of sampled parameters (the dimension of the MCLMC dynamics:
+  // ESH normalisation, refresh, tuning).  Frozen parameters keep their value, see no prior and get zero gradient,
+  // momentum and noise.  Null = everything is sampled (d_eff = d).  Generic step loop only.
+  const float* pmask; int d_eff;
   int mr_world, mr_rank; unsigned int mr_base;   // flag = mr_base + eval + 1 (advanced identically on every rank)
   float2* mr_sums[8];    // rank r's region [C][2 parities][world][dS+4] (own region for r == mr_rank)
 };
@@ -74,12 +79,17 @@ struct Ctx {
   // warm-start training overrides (mile_train.cuh): labels of the gathered minibatch, X always in c.xbuf, sigma clip, metric
   const void* y_override = nullptr; int force_resident = 0; float sig_lo = 1e-6f; float* metric = nullptr;
   const float* sdc = nullptr;   // this chain's sqrt_diag_cov [d] (global memory) or null = identity
+  const float* pmask = nullptr; // partition mask [d] or null; deff = dimension of the sampled sub-space
+  int deff = 0;
   bool lead;   // the one thread that reports per-chain scalars (thread 0 of the block; lane 0 of the integrator warp in warp mode)
   __device__ Ctx(const KParams& p) : P(p) {}
 };
 
 // element i of the preconditioner (1 when none is set)
 __device__ __forceinline__ float sdc_at(const Ctx& c, int i) { return c.sdc ? __ldg(c.sdc + i) : 1.f; }
+// 1 for a sampled parameter, 0 for a frozen one (partition sampling)
+__device__ __forceinline__ float pm_at(const Ctx& c, int i) { return c.pmask ? __ldg(c.pmask + i) : 1.f; }
+__device__ __forceinline__ int dim_eff(const Ctx& c) { return c.pmask ? c.deff : c.P.M.d; }
 
 // flat element i -> position in the padded parameter image (pmap) and in the transposed image
 // (pmap + dS; biases and layer 0, which need no transpose, point at their pmap slot again)
@@ -319,10 +329,11 @@ __device__ __forceinline__ float cluster_reduce_grad(Ctx& c, float* gpart, const
       pv = -lognorm - fabsf(dlt) / sc;
       pg = -((dlt > 0.f) - (dlt < 0.f)) / sc;
     }
-    const float g = s + pg * P.prior_weight;
+    const float mk = pm_at(c, i);
+    const float g = (s + pg * P.prior_weight) * mk;
     c.gg[i] = g;
     const float gs = g * sdc_at(c, i);
-    v[0] += pv * P.prior_weight; v[1] += gs * gs; v[2] += c.uu[i] * gs; v[3] += isfinite(th) ? 0.f : 1.f;
+    v[0] += pv * P.prior_weight * mk; v[1] += gs * gs; v[2] += c.uu[i] * gs; v[3] += isfinite(th) ? 0.f : 1.f;
   };
   if (use_ll) {
     for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
@@ -451,7 +462,7 @@ template <int NT, int BAR = 0, bool ES = false>
 __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float g2, float ug) {
   const int d = c.P.M.d;
   float ae, au;
-  const float dk = esh_coeffs(d, eps, coef, g2, ug, ae, au);
+  const float dk = esh_coeffs(dim_eff(c), eps, coef, g2, ug, ae, au);
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * (c.gg[i] * sdc_at(c, i)) + au * c.uu[i];
   return dk;
 }
@@ -489,10 +500,10 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
     ug_out = v[1] * inv;
     return;
   }
-  const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)d);
+  const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)dim_eff(c));
   float v[2] = {0.f, 0.f};
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
-    const float w = c.uu[i] + nu * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
+    const float w = c.uu[i] + nu * pm_at(c, i) * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
     c.uu[i] = w;
     v[0] += w * w; v[1] += w * (c.gg[i] * sdc_at(c, i));
   }
@@ -562,7 +573,7 @@ __device__ __forceinline__ float tune_epilogue(Ctx& c, TuneRegs& t, float eps, f
         target = P.ev_start - (P.ev_start - P.ev_end) * progress;
       }
       const float decay = (P.neff - 1.f) / (P.neff + 1.f);
-      const float xi = dE * dE / ((float)d * target) + 1e-8f;
+      const float xi = dE * dE / ((float)dim_eff(c) * target) + 1e-8f;
       const float lx = logf(xi) / (6.f * P.trust);
       const float wgt = expf(-0.5f * lx * lx);
       t_xavg = decay * t_xavg + wgt * (xi / powf(eps, 6.f));
@@ -644,6 +655,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
   const int d = M.d, ch = c.chain;
   const int tid = threadIdx.x;
   c.sdc = P.sdc ? P.sdc + (long)ch * d : nullptr;
+  c.pmask = P.pmask; c.deff = P.d_eff;
 
   // ---- prologue: parameter image, state, resident X slice --------------------------------
   for (int i = tid; i < M.psize; i += NT) c.wp[i] = 0.f;
@@ -805,7 +817,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_mclmc_kernel(const __grid_cons
           // blackjax.mcmc.mclmc.init: generate_unit_vector u = z / |z|
           float v[1] = {0.f};
           for (int i = tid; i < d; i += NI) {
-            const float zz = P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)(P.chain_base + ch), 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i);
+            const float zz = pm_at(c, i) * (P.z ? P.z[(long)ch * d + i] : philox_normal(P.seed, (uint32_t)(P.chain_base + ch), 0xFFFFFFFFFFFFFFFFull, 0u, (uint32_t)i));
             c.uu[i] = zz; v[0] += zz * zz;
           }
           block_sum<1, NI, IB>(v, c.red2, c.phase2);

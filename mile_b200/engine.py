@@ -58,6 +58,17 @@ class FCNSpec:
             off += d[l] * d[l + 1]
         return bias_off, kern_off
 
+    def hidden_layer_mask(self) -> np.ndarray:
+        """bool [d]: True for the parameters of the hidden layers (everything except layer0 and the last layer) -- the
+        ones `partition_params` (partition_sampling.py:290-302) freezes."""
+        b, k = self.offsets()
+        dims = self.dims
+        m = np.zeros(self.n_params, bool)
+        for l in range(1, len(self.widths) - 1):
+            m[b[l]:b[l] + dims[l + 1]] = True
+            m[k[l]:k[l] + dims[l] * dims[l + 1]] = True
+        return m
+
     def to_desc(self) -> capi.ModelDesc:
         m = capi.ModelDesc()
         m.n_features = self.n_features
@@ -280,6 +291,13 @@ class Ensemble:
         e = None if step_size is None else _f32(np.broadcast_to(step_size, (C_,)))
         l = None if L is None else _f32(np.broadcast_to(L, (C_,)))
         capi.check(self.lib.mile_set_tuning_host(self.h, capi.host_ptr(e), capi.host_ptr(l)))
+
+    # ---- partition sampling (partition_sampling.py; trainer.py:613-659) ------------------------
+    def set_frozen_mask(self, frozen):
+        """frozen: bool [d] (True = the parameter keeps its value, sees no prior, gets no gradient / momentum / noise) or
+        None to clear.  The dimension of the MCLMC dynamics becomes the number of sampled parameters."""
+        a = None if frozen is None else np.ascontiguousarray(np.asarray(frozen).reshape(self.d), dtype=np.uint8)
+        capi.check(self.lib.mile_set_frozen_mask_host(self.h, capi.host_ptr(a)))
 
     # ---- diagonal preconditioning (warmup.py:385-401; blackjax sqrt_diag_cov) -----------------
     def precondition_from_moments(self):

@@ -66,6 +66,20 @@ class ProbabilisticModel:
             ens.set_test(*self._test)
         return ens
 
+    def log_unnormalized_posterior_partition(self, input_output_layers, hidden_layers, x, y, **kwargs):
+        """trainer.py:651-659: log prior of the SAMPLED layers (first and last) + log-likelihood of the merged network."""
+        spec = self.spec
+        theta = spec.ravel(merge_partition(input_output_layers, hidden_layers))
+        batched = theta.ndim == 2
+        theta = theta.reshape(-1, spec.n_params)
+        ens = self.make_ensemble(theta.shape[0], x, y)
+        try:
+            ens.set_frozen_mask(spec.hidden_layer_mask())
+            lp, _ = ens.value_and_grad(theta)
+        finally:
+            ens.close()
+        return lp if batched else lp[0]
+
     def log_unnormalized_posterior(self, position, x, y, **kwargs):
         """probabilistic.py:115-138.  position: ParamTree (optionally with a leading chain axis)."""
         spec = self.spec
@@ -80,6 +94,11 @@ class ProbabilisticModel:
         return lp if batched else lp[0]
 
 
+def merge_partition(input_output_layers: dict, hidden_layers: dict) -> dict:
+    """{'fcn': {**input_output['fcn'], **hidden['fcn']}} (partition_sampling.py:117,144)."""
+    return {'fcn': {**input_output_layers['fcn'], **hidden_layers['fcn']}}
+
+
 def unwrap_posterior(fn):
     """Recognise `partial(prob_model.log_unnormalized_posterior, x=train_x, y=train_y)`
     (src/training/trainer.py:576-580) and return (prob_model, x, y).  Anything else cannot be routed to the
@@ -87,7 +106,8 @@ def unwrap_posterior(fn):
     if isinstance(fn, functools.partial):
         target = fn.func
         owner = getattr(target, '__self__', None)
-        if isinstance(owner, ProbabilisticModel) and getattr(target, '__name__', '') == 'log_unnormalized_posterior':
+        if isinstance(owner, ProbabilisticModel) and getattr(target, '__name__', '') in (
+                'log_unnormalized_posterior', 'log_unnormalized_posterior_partition'):
             kw = fn.keywords or {}
             if 'x' in kw and 'y' in kw:
                 return owner, kw['x'], kw['y']

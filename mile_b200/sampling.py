@@ -28,8 +28,9 @@ SAMPLE_FORMAT = _os.environ.get('MILE_SAMPLE_FORMAT', 'npz')
 
 
 def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_params: dict, step_ids,
-                   saving_path: Path, saving_path_warmup: Path | None = None):
-    """sampling.py:32-216: warmup -> warmup_params.txt -> n_samples steps with thinned saves -> info.pkl."""
+                   saving_path: Path, saving_path_warmup: Path | None = None, _frozen=None):
+    """sampling.py:32-216: warmup -> warmup_params.txt -> n_samples steps with thinned saves -> info.pkl.
+    (`_frozen`: bool [d] mask of parameters that are not sampled -- partition_sampling.partition_inference_loop.)"""
     info = {}
     step_ids = [int(s) for s in np.atleast_1d(np.asarray(step_ids))]
     n_devices = len(step_ids)
@@ -47,9 +48,12 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     # global chain ids key the noise streams (the reference splits one key per chain, sampling.py:181-184): waves / ranks
     # that own different step_ids never share a stream even with the same rng_key
     ens.set_option('chain_base', min(step_ids))
+    if _frozen is not None:
+        ens.set_frozen_mask(_frozen)
     try:
         logger.info('> Starting Warmup sampling...')
-        eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens)
+        eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens,
+                              _active=None if _frozen is None else np.flatnonzero(~np.asarray(_frozen, bool)))
         saving_path.mkdir(parents=True, exist_ok=True)
         with open(saving_path.parent / 'warmup_params.txt', 'w') as f:      # sampling.py:92-97
             f.write(','.join(str(np.float32(v)) for v in eps) + '\n')
@@ -102,7 +106,7 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
 
 
 def warmup_mclmc(config: SamplerConfig, rng_key, init_params: dict, unnorm_log_posterior, n_devices: int,
-                 _ensemble=None):
+                 _ensemble=None, _active=None):
     """sampling.py:258-292.  Returns (step_size [n_devices], L [n_devices]); the warmed-up chain state stays
     in the ensemble (`use_warmup_as_init`) when one is passed in, else (state, parameters) like the reference."""
     model, x, y = unwrap_posterior(unnorm_log_posterior)
@@ -113,7 +117,8 @@ def warmup_mclmc(config: SamplerConfig, rng_key, init_params: dict, unnorm_log_p
               num_effective_samples=config.num_effective_samples, step_size_init=config.step_size_init)
     dp = bool(config.diagonal_preconditioning)
     if _ensemble is not None:
-        out = run_warmup(_ensemble, theta0, rng_key, config.warmup_steps, diagonal_preconditioning=dp, **kw)
+        out = run_warmup(_ensemble, theta0, rng_key, config.warmup_steps, diagonal_preconditioning=dp,
+                         active=_active, **kw)
         # sampling.py:291 returns only step_size and L: the sampling phase of the reference runs WITHOUT the preconditioner
         _ensemble.set_sqrt_diag_cov(None)
         return out

@@ -21,7 +21,8 @@ CHUNK = 10000                      # MCLMC steps per kernel launch
 
 def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, desired_energy_var_start,
                desired_energy_var_end, trust_in_estimate, num_effective_samples, step_size_init,
-               fft_params_limit: int = 2000, fft_samples_limit: int = 10000, diagonal_preconditioning: bool = False):
+               fft_params_limit: int = 2000, fft_samples_limit: int = 10000, diagonal_preconditioning: bool = False,
+               active=None):
     """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C]); with
     `diagonal_preconditioning` the preconditioner stays set on `ens` (read it with `ens.get_sqrt_diag_cov()`, clear it
     with `ens.set_sqrt_diag_cov(None)` -- the reference's sampling phase does not use it, sampling.py:291)."""
@@ -67,6 +68,8 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
                                   samples_dev=pos, n_slots=tune3)
                 done += n
             torch.cuda.synchronize(dev)
+            if active is not None:     # partition sampling: the ESS is taken over the sampled parameters only
+                pos = pos[:, :, torch.as_tensor(np.asarray(active), device=dev)]
             L = phase3_L(pos, eps, seed=part2_key, fft_params_limit=fft_params_limit,
                          fft_samples_limit=fft_samples_limit)
         ens.set_tuning(L=L)
