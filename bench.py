@@ -407,7 +407,7 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
     ens.sample(inner, eps, L, step_base=0, n_thinning=N_THINNING, seed=4320, lppd=False)
     ens.set_state(*st)
     # the step's result is read back into pinned host memory (the sample tensor is the bulk of the D2H bytes)
-    out_pinned = None if sharded else torch.empty(n_slots * C * d, dtype=torch.float32, pin_memory=True).numpy()
+    out_pinned = None if sharded else torch.empty(max(1, -(-inner // N_THINNING)) * C * d, dtype=torch.float32, pin_memory=True).numpy()
     skw = {} if sharded else {'out': out_pinned}
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
     st_pinned = (pin(C, d), pin(C, d), pin(C), pin(C, d))        # chain state travels through pinned buffers as well

@@ -612,15 +612,17 @@ static int set_split(mile_ctx* c, const float* X_dev, const void* y_dev, long N,
                      void** yd, long* Nd) {
   if (N < 0) return fail("n_rows < 0");
   CK(cudaSetDevice(c->device));
-  if (*Xd) { CK(cudaFree(*Xd)); *Xd = nullptr; }
-  if (*yd) { CK(cudaFree(*yd)); *yd = nullptr; }
-  *Nd = N;
-  if (N == 0) return 0;
   const int sx = c->M.sA[0];
-  // 16 zero floats of slack: the k-steps of the tensor evaluator may read up to 12 floats past the last row's stride
-  CK(cudaMalloc(Xd, ((size_t)N * sx + 16) * 4));
+  if (!(*Xd && *yd && *Nd == N && N > 0)) {      // a split of the same size reuses its buffers (cudaFree / cudaMalloc of tens
+    if (*Xd) { CK(cudaFree(*Xd)); *Xd = nullptr; }   // of MB cost 20-600 ms per call: tools/time_e2e_phases.py)
+    if (*yd) { CK(cudaFree(*yd)); *yd = nullptr; }
+    *Nd = N;
+    if (N == 0) return 0;
+    // 16 zero floats of slack: the k-steps of the tensor evaluator may read up to 12 floats past the last row's stride
+    CK(cudaMalloc(Xd, ((size_t)N * sx + 16) * 4));
+    CK(cudaMalloc(yd, (size_t)N * 4));
+  }
   CK(cudaMemsetAsync(*Xd + (size_t)N * sx, 0, 16 * 4, st));
-  CK(cudaMalloc(yd, (size_t)N * 4));
   pad_rows_kernel<<<296, 256, 0, st>>>(X_dev, *Xd, N, c->M.F, sx);
   CK(cudaGetLastError());
   c->launches++;

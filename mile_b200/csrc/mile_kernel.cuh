@@ -463,7 +463,12 @@ __device__ __forceinline__ float esh_update(Ctx& c, float eps, float coef, float
   const int d = c.P.M.d;
   float ae, au;
   const float dk = esh_coeffs(dim_eff(c), eps, coef, g2, ug, ae, au);
-  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] = ae * (c.gg[i] * sdc_at(c, i)) + au * c.uu[i];
+  // (restrict + unroll: in the element-split / global-memory form every access is an L2 round trip; the loads of four
+  //  elements must be in flight together)
+  float* __restrict__ uu = c.uu;
+  const float* __restrict__ gg = c.gg;
+#pragma unroll 4
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) uu[i] = ae * (gg[i] * sdc_at(c, i)) + au * uu[i];
   return dk;
 }
 
@@ -502,14 +507,18 @@ __device__ __forceinline__ void refresh_momentum(Ctx& c, float eps, float L, lon
   }
   const float nu = sqrtf((expf(2.f * eps / L) - 1.f) / (float)dim_eff(c));
   float v[2] = {0.f, 0.f};
+  float* __restrict__ uu = c.uu;
+  const float* __restrict__ gg = c.gg;
+#pragma unroll 4
   for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
-    const float w = c.uu[i] + nu * pm_at(c, i) * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
-    c.uu[i] = w;
-    v[0] += w * w; v[1] += w * (c.gg[i] * sdc_at(c, i));
+    const float w = uu[i] + nu * pm_at(c, i) * (zsm ? zsm[i] : noise_at(P, c.chain, step_local, slot, nslot, i));
+    uu[i] = w;
+    v[0] += w * w; v[1] += w * (gg[i] * sdc_at(c, i));
   }
   all_sum<2, NT, BAR, ES>(c, v);
   const float inv = 1.f / sqrtf(v[0]);
-  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.uu[i] *= inv;
+#pragma unroll 4
+  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) uu[i] *= inv;
   ug_out = v[1] * inv;
 }
 

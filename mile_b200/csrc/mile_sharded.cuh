@@ -111,11 +111,19 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   }
   // (the copy and the sums touch the same elements in the same thread: no barrier needed in between)
   float v[3] = {0.f, 0.f, 0.f};
-  for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
-    const float gi = (fresh && !p2p) ? S.gl[(long)ch * (d + 1) + i] : c.gg[i];   // (p2p: this thread just wrote c.gg[i])
-    if (fresh && !p2p) c.gg[i] = gi;
-    const float gs = gi * sdc_at(c, i);
-    v[0] += gs * gs; v[1] += c.uu[i] * gs; v[2] += isfinite(c.th[i]) ? 0.f : 1.f;
+  {
+    float* __restrict__ gg = c.gg;
+    const float* __restrict__ uu = c.uu;
+    const float* __restrict__ th = c.th;
+    const float* __restrict__ gl = S.gl + (long)ch * (d + 1);
+    const bool copy = fresh && !p2p;
+#pragma unroll 4
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) {
+      const float gi = copy ? gl[i] : gg[i];   // (p2p: this thread just wrote gg[i])
+      if (copy) gg[i] = gi;
+      const float gs = gi * sdc_at(c, i);
+      v[0] += gs * gs; v[1] += uu[i] * gs; v[2] += isfinite(th[i]) ? 0.f : 1.f;
+    }
   }
   all_sum<3, NT, 0, ES>(c, v);
   float g2 = v[0], ug = v[1];
@@ -134,7 +142,10 @@ __global__ void __launch_bounds__(NT, 1) mile_integrator_kernel(const __grid_con
   if (S.stage != SH_END) {
     dK += esh_update<NT, 0, ES>(c, eps, S.stage == SH_BEGIN ? b1 : b2, g2, ug);
     const float st = eps * 0.5f;
-    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) c.th[i] += st * sdc_at(c, i) * c.uu[i];
+    float* __restrict__ th = c.th;
+    const float* __restrict__ uu = c.uu;
+#pragma unroll 4
+    for (int i = MILE_I0(c, ES); i < d; i += MILE_IS(c, ES, NT)) th[i] += st * sdc_at(c, i) * uu[i];
   } else {
     dK += esh_update<NT, 0, ES>(c, eps, b1, g2, ug);
     refresh_momentum<NT, 0, ES>(c, P.refresh_mode ? 0.5f * eps : eps, Lc, S.s_local, nslot - 1, nslot, ug);
