@@ -201,6 +201,15 @@ int mile_eval_metrics(mile_ctx* ctx, const float* theta_dev, int32_t n, int32_t 
 int mile_train_get_state(mile_ctx* ctx, float* theta_dev, float* m_dev, float* v_dev, int32_t* t_dev, void* stream);
 
 /* ---- data-sharded variant (covertype, rows split across the GPUs of one box) -------- */
+/* ---- sample files: src/training/callbacks.py:17-44 (`save_position`: one compressed npz per chain and kept position).
+ * Writes n_files archives with the same n_members members each: member m of file i = header bytes (the .npy header of
+ * its shape) followed by member_floats[m] fp32 values taken from data[i][offset of m] (members back to back in leaf
+ * order, i.e. a flat position vector when the leaves are in ravel order).  Deflated by n_threads host threads; plain zip
+ * archives that np.load / load_samples_from_dir (utils.py:131-161) read unchanged.  Host memory only; 0 on success. */
+int mile_write_npz_batch(const char* const* paths, int32_t n_files, const char* const* member_names,
+                         const uint8_t* const* member_headers, const int32_t* header_lens, const int64_t* member_floats,
+                         int32_t n_members, const float* data /* [n_files][sum member_floats] host */, int32_t n_threads);
+
 /* ---- partition sampling: src/training/partition_sampling.py:32-330 with trainer.py:613-659
  * (`log_unnormalized_posterior_partition`): only the first and the last layer are sampled, the hidden layers stay at their
  * warm-start values.  frozen[i] != 0 freezes flat parameter i for ALL chains: it keeps its value, contributes no prior

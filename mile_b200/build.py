@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 LIBDIR = PKG / '_lib'
 LIB = LIBDIR / 'libmile_b200.so'
-SOURCES = ['mile_api.cu', 'mile_microbench.cu']
+SOURCES = ['mile_api.cu', 'mile_microbench.cu', 'mile_npz.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     LIBDIR.mkdir(exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, '-o', str(LIB), *[str(CSRC / s) for s in SOURCES], '-ldl']
+    cmd = [_nvcc(), *NVCC_FLAGS, '-o', str(LIB), *[str(CSRC / s) for s in SOURCES], '-ldl', '-lz']
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, capture_output=True, text=True)

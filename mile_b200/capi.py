@@ -21,7 +21,7 @@ SYMBOLS = [
     'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
-    'mile_set_frozen_mask_host', 'mile_precondition_from_moments', 'mile_set_sqrt_diag_cov_host', 'mile_get_sqrt_diag_cov_host',
+    'mile_write_npz_batch', 'mile_set_frozen_mask_host', 'mile_precondition_from_moments', 'mile_set_sqrt_diag_cov_host', 'mile_get_sqrt_diag_cov_host',
     'mile_train_init', 'mile_train_epoch', 'mile_eval_metrics', 'mile_train_get_state',
     'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_p2p_handle', 'mile_shard_p2p_open', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
 ]
@@ -115,6 +115,7 @@ def load():
     lib.mile_train_epoch.argtypes = [vp, vp, i32, i32, C.POINTER(OptCfg), vp, fp, vp]
     lib.mile_eval_metrics.argtypes = [vp, fp, i32, i32, fp, vp]
     lib.mile_train_get_state.argtypes = [vp, fp, fp, fp, vp, vp]
+    lib.mile_write_npz_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32]
     lib.mile_set_frozen_mask_host.argtypes = [vp, vp]
     lib.mile_precondition_from_moments.argtypes = [vp, vp]
     lib.mile_set_sqrt_diag_cov_host.argtypes = [vp, fp]

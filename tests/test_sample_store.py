@@ -63,3 +63,27 @@ def test_tree_shim_rebuilds_nesting(tmp_path):
     with np.load(tmp_path / 'warmstart' / 'params_0.npz') as z:
         rebuilt = tree.unflatten([z[k] for k in z.files])
     _same_tree(rebuilt, {'fcn': {'layer0': params['fcn']['layer0'], 'layer1': params['fcn']['layer1']}})
+
+
+def test_native_npz_writer_matches_savez_compressed(tmp_path):
+    """mile_write_npz_batch (csrc/mile_npz.cu) against np.savez_compressed, the call of the reference's save_position
+    (src/training/callbacks.py:40-44): same member names in the same order, same dtypes/shapes/values, valid zip CRCs."""
+    import zipfile
+    from mile_b200.callbacks import save_position
+    spec = FCNSpec(3, (8, 1))
+    rng = np.random.default_rng(1)
+    samples = rng.standard_normal((4, 2, spec.n_params)).astype(np.float32)
+    samples[0, 0, :5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
+    w = SampleWriter(spec, tmp_path / 'a', [0, 1], max_workers=3)
+    w.submit(samples, [0, 10, 20, 30])
+    w.close()
+    for c in range(2):
+        for k, n in enumerate([0, 10, 20, 30]):
+            save_position(spec.unravel(samples[k, c]), tmp_path / 'b', np.asarray(c), n)
+            pa, pb = tmp_path / 'a' / str(c) / f'sample_{n}.npz', tmp_path / 'b' / str(c) / f'sample_{n}.npz'
+            assert zipfile.ZipFile(pa).testzip() is None
+            with np.load(pa) as za, np.load(pb) as zb:
+                assert za.files == zb.files
+                for m in za.files:
+                    assert za[m].dtype == zb[m].dtype and za[m].shape == zb[m].shape
+                    np.testing.assert_array_equal(za[m].view(np.uint32), zb[m].view(np.uint32))
