@@ -71,6 +71,15 @@ typedef struct mile_tune_cfg {
   float num_effective_samples;
 } mile_tune_cfg;
 
+/* Arguments of the NUTS branch: blackjax.nuts defaults (max_num_doublings 10, divergence_threshold 1000) and
+ * custom_window_adaptation's (src/training/warmup.py:27-36: initial_step_size 1.0, target_acceptance_rate 0.80). */
+typedef struct mile_nuts_cfg {
+  int32_t max_num_doublings;
+  float divergence_threshold;
+  float target_acceptance_rate;
+  float initial_step_size;
+} mile_nuts_cfg;
+
 typedef struct mile_ctx mile_ctx;
 
 const char* mile_last_error(void);
@@ -249,6 +258,33 @@ int mile_shard_mclmc_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, i
                             float* info_dev, void* stream);
 int mile_shard_mclmc_tune(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg,
                           const float* z_dev, uint64_t seed, float* tune_info_dev, void* stream);
+
+/* ---- NUTS branch of the sampling seam: src/training/sampling.py:70-81,107-210 (sampler = blackjax.nuts) and
+ * src/training/warmup.py:27-152 (`custom_window_adaptation`), called from `warmup_nuts` (sampling.py:220-262).  One
+ * persistent kernel per call runs whole transitions (momentum draw, trajectory doubling with the iterative U-turn
+ * checkpoints, progressive sampling, divergence test) for every chain; the warm-up call also applies `adapt_step`
+ * (dual averaging of the step size; Welford mass matrix in the slow windows) after every transition.
+ * schedule [n_steps] bytes: bit 0 = slow stage, bit 1 = end of a slow window (window_adaptation.build_schedule).
+ * z [n_steps,C,d] standard normals and uni [n_steps,C,2 D + 2^D] uniforms (directions | merge acceptances | per-leapfrog
+ * acceptances) replace the in-kernel Philox streams when given (trajectory-level tests against the oracle).
+ * info [n_steps,C,8] = num_integration_steps, acceptance_rate, num_trajectory_expansions, is_divergent, energy, is_turning
+ * (the NUTSInfo fields sampling.py:200-210 keeps), logdensity, step size used. */
+int mile_nuts_init(mile_ctx* ctx, const float* theta0_dev, const mile_nuts_cfg* cfg, void* stream);
+int mile_nuts_init_host(mile_ctx* ctx, const float* theta0, const mile_nuts_cfg* cfg);
+int mile_nuts_warmup(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const uint8_t* schedule_dev, const float* z_dev,
+                     const float* uni_dev, uint64_t seed, float* info_dev, void* stream);
+/* adapt_final: step_size = exp(averaged log step size) */
+int mile_nuts_finish_warmup(mile_ctx* ctx, void* stream);
+int mile_nuts_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
+                     const float* z_dev, const float* uni_dev, uint64_t seed, float* samples_dev, int64_t n_slots,
+                     float* info_dev, int32_t lppd, void* stream);
+/* host-buffer form of both: schedule != NULL = warm-up transitions, NULL = sampling transitions */
+int mile_nuts_run_host(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const uint8_t* schedule, int32_t n_thinning,
+                       const float* z, const float* uni, uint64_t seed, float* samples, int64_t n_slots, float* info,
+                       int32_t lppd);
+/* step_size [C], inverse_mass_matrix [C,d] (the `parameters` dict warmup_nuts returns); NULLs skipped */
+int mile_nuts_get_params_host(mile_ctx* ctx, float* step_size, float* inverse_mass_matrix);
+int mile_nuts_set_params_host(mile_ctx* ctx, const float* step_size, const float* inverse_mass_matrix);
 
 /* ---- bookkeeping ----------------------------------------------------------------- */
 /* Number of kernels this library has launched since mile_create (bench `gpu_launches`). */

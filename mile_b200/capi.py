@@ -21,6 +21,8 @@ SYMBOLS = [
     'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
+    'mile_nuts_init', 'mile_nuts_init_host', 'mile_nuts_warmup', 'mile_nuts_finish_warmup', 'mile_nuts_sample', 'mile_nuts_run_host',
+    'mile_nuts_get_params_host', 'mile_nuts_set_params_host',
     'mile_write_npz_batch', 'mile_set_frozen_mask_host', 'mile_precondition_from_moments', 'mile_set_sqrt_diag_cov_host', 'mile_get_sqrt_diag_cov_host',
     'mile_train_init', 'mile_train_epoch', 'mile_eval_metrics', 'mile_train_get_state',
     'mile_nccl_unique_id', 'mile_shard_init', 'mile_shard_p2p_handle', 'mile_shard_p2p_open', 'mile_shard_mclmc_init', 'mile_shard_mclmc_sample', 'mile_shard_mclmc_tune',
@@ -43,6 +45,11 @@ class TuneCfg(C.Structure):
         ('desired_energy_var_start', C.c_float), ('desired_energy_var_end', C.c_float),
         ('trust_in_estimate', C.c_float), ('num_effective_samples', C.c_float),
     ]
+
+
+class NutsCfg(C.Structure):
+    _fields_ = [('max_num_doublings', C.c_int32), ('divergence_threshold', C.c_float), ('target_acceptance_rate', C.c_float),
+                ('initial_step_size', C.c_float)]
 
 
 class OptCfg(C.Structure):
@@ -115,6 +122,14 @@ def load():
     lib.mile_train_epoch.argtypes = [vp, vp, i32, i32, C.POINTER(OptCfg), vp, fp, vp]
     lib.mile_eval_metrics.argtypes = [vp, fp, i32, i32, fp, vp]
     lib.mile_train_get_state.argtypes = [vp, fp, fp, fp, vp, vp]
+    lib.mile_nuts_init.argtypes = [vp, fp, C.POINTER(NutsCfg), vp]
+    lib.mile_nuts_init_host.argtypes = [vp, fp, C.POINTER(NutsCfg)]
+    lib.mile_nuts_warmup.argtypes = [vp, i32, i64, vp, fp, fp, u64, fp, vp]
+    lib.mile_nuts_finish_warmup.argtypes = [vp, vp]
+    lib.mile_nuts_sample.argtypes = [vp, i32, i64, i32, i64, fp, fp, u64, fp, i64, fp, i32, vp]
+    lib.mile_nuts_run_host.argtypes = [vp, i32, i64, vp, i32, fp, fp, u64, fp, i64, fp, i32]
+    lib.mile_nuts_get_params_host.argtypes = [vp, fp, fp]
+    lib.mile_nuts_set_params_host.argtypes = [vp, fp, fp]
     lib.mile_write_npz_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32]
     lib.mile_set_frozen_mask_host.argtypes = [vp, vp]
     lib.mile_precondition_from_moments.argtypes = [vp, vp]

@@ -5,6 +5,7 @@
 #include "mile_sharded.cuh"
 #include "mile_wide.cuh"
 #include "mile_train.cuh"
+#include "mile_nuts.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -88,6 +89,9 @@ struct mile_ctx {
   float* wp_out = nullptr; size_t wp_out_floats = 0;   // its [n, N, K] outputs when the caller wants them folded (LPPD)
   // tcgen05 v2: tf32 remainders of activations / deltas / weights + cached TMA tensor maps
   long w_part_per_chain = 0;
+  // NUTS branch (mile_nuts.cuh): inverse mass matrix / Welford moments [C,d], dual-averaging state [C,8], per-CTA scratch
+  float *nuts_imm = nullptr, *nuts_mean = nullptr, *nuts_m2 = nullptr, *nuts_da = nullptr, *nuts_scratch = nullptr;
+  size_t nuts_scratch_floats = 0; int nuts_max_doublings = 10; float nuts_div = 1000.f, nuts_target = 0.8f;
   float* pmask = nullptr; int pmask_on = 0, d_eff = 0;   // partition sampling: 1 = sampled / 0 = frozen per parameter
   float* sdc = nullptr; int sdc_on = 0;      // diagonal preconditioner [C][d] (warmup.py:391-393); used when sdc_on
   int integ_cluster = 8;      // cluster size of the large-d integrator kernel (16 = non-portable size: measured slower, 69 vs 55 us)
@@ -286,10 +290,11 @@ static int make_plan_impl(const mile_ctx* c, int n_chains, long nrows_for_split,
   return 0;
 }
 
-template <class GE, bool V2 = false>
+template <class GE, int V2 = 0>   // V2: 0 generic step loop, 1 restructured step loop of the tensor evaluator, 2 NUTS
 static int launch_t(const Plan& pl, int n_chains, cudaStream_t st) {
   void (*kern)(const KParams) = mile_mclmc_kernel<GE>;
-  if constexpr (V2) kern = mile_mma_step_kernel<GE>;   // restructured step loop of the tensor evaluator (mile_mma.cuh)
+  if constexpr (V2 == 1) kern = mile_mma_step_kernel<GE>;   // restructured step loop of the tensor evaluator (mile_mma.cuh)
+  if constexpr (V2 == 2) kern = mile_nuts_kernel<GE>;       // NUTS transitions (mile_nuts.cuh)
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   if (pl.G > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;
@@ -369,7 +374,12 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   if (pl.sync_mode) {
     const size_t nA = (size_t)n_chains * 2 * pl.G * (pl.kp.dS + 4), nB = (size_t)n_chains * 2 * (pl.kp.dS + 4);
     const size_t need = (nA + nB) * sizeof(float2);   // partials of every rank + the summed slices (reduce-scatter form)
-    const unsigned int adv = 2u * (unsigned int)(pl.kp.n_steps > 0 ? pl.kp.n_steps : 0) + 2u;
+    unsigned int adv = 2u * (unsigned int)(pl.kp.n_steps > 0 ? pl.kp.n_steps : 0) + 2u;
+    if (pl.kp.mode == MODE_NUTS) {   // at most 2^D gradient evaluations per transition
+      const unsigned long long ev = (unsigned long long)(pl.kp.n_steps > 0 ? pl.kp.n_steps : 0) << pl.kp.nuts.max_doublings;
+      if (ev > 0x40000000ull) return fail("too many NUTS transitions in one launch for the exchange flags: use smaller chunks");
+      adv = (unsigned int)ev + 2u;
+    }
     if (need > c->xchg_bytes || c->xepoch > 0xF0000000u - adv) {   // (re)allocate, or restart the flag epoch before it wraps
       if (need > c->xchg_bytes) {
         if (c->xchg) cudaFree(c->xchg);
@@ -385,12 +395,27 @@ static int launch(mile_ctx* c, Plan& pl, int n_chains, cudaStream_t st) {
   }
   const int NL = c->M.NL;
   int rc;
+  if (pl.kp.mode == MODE_NUTS) {   // NUTS: tensor evaluator or the generic tiles for the gradients (plans with fast = 1 are not made)
+    if (pl.fast == 2) {
+      if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, 2>(pl, n_chains, st);
+      else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, 2>(pl, n_chains, st);
+      else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, 2>(pl, n_chains, st);
+      else rc = launch_t<MmaGE<4, 16, 512>, 2>(pl, n_chains, st);
+    }
+    else if (pl.fast) return fail("internal: NUTS has no FFMA-pipeline plan");
+    else if (NL <= 2) rc = launch_t<GenericGE<2>, 2>(pl, n_chains, st);
+    else if (NL <= 4) rc = launch_t<GenericGE<4>, 2>(pl, n_chains, st);
+    else if (NL <= 8) rc = launch_t<GenericGE<8>, 2>(pl, n_chains, st);
+    else rc = launch_t<GenericGE<12>, 2>(pl, n_chains, st);
+    if (rc == 0) c->launches++;
+    return rc;
+  }
   // (the preconditioned dynamics live in the generic step loop; the tensor evaluator still computes the gradients)
   if (pl.fast == 2 && (pl.kp.mode == MODE_SAMPLE || pl.kp.mode == MODE_TUNE) && c->opt_steploop != 0 && !pl.kp.sdc && !pl.kp.pmask) {
-    if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, true>(pl, n_chains, st);
-    else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, true>(pl, n_chains, st);
-    else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, true>(pl, n_chains, st);
-    else rc = launch_t<MmaGE<4, 16, 512>, true>(pl, n_chains, st);
+    if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>, 1>(pl, n_chains, st);
+    else if (NL == 3) rc = launch_t<MmaGE<3, 16, 512>, 1>(pl, n_chains, st);
+    else if (pl.fast_fp == 8) rc = launch_t<MmaGE<4, 8, 512>, 1>(pl, n_chains, st);
+    else rc = launch_t<MmaGE<4, 16, 512>, 1>(pl, n_chains, st);
   }
   else if (pl.fast == 2) {
     if (NL == 3 && pl.fast_fp == 8) rc = launch_t<MmaGE<3, 8, 512>>(pl, n_chains, st);
@@ -550,7 +575,8 @@ void mile_destroy(mile_ctx* c) {
   void* ptrs[] = {c->X, c->y, c->Xt, c->yt, c->theta, c->u, c->grad, c->lp, c->t_time, c->t_xavg, c->t_epsmax,
                   c->t_eps, c->t_L, c->t_wtot, c->avg_x, c->avg_x2, c->lppd_m, c->lppd_s, c->carry,
                   c->gl, c->scal, c->thb, c->ub, c->gb, c->tr_m, c->tr_v, (float*)c->tr_t, (float*)c->xchg, c->w_act, c->w_delta[0], c->w_delta[1], c->w_part, c->w_llpart,
-                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin, c->sdc, c->pmask};
+                  c->w_ones, c->w_gl, c->wp_act, c->wp_out, c->w_wpk, c->w_wpk_lo, c->w_wpkT, c->w_wpkT_lo, c->w_arena, c->w_fin, c->sdc, c->pmask,
+                  c->nuts_imm, c->nuts_mean, c->nuts_m2, c->nuts_da, c->nuts_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : c->scratch) if (s.first) cudaFree(s.first);
   for (int r = 0; r < 8; ++r) if (c->xr_peer[r] && c->xr_peer[r] != c->xr) cudaIpcCloseMemHandle(c->xr_peer[r]);
@@ -1908,6 +1934,178 @@ int mile_debug_wide_gemm(int32_t device, int32_t core, int32_t M, int32_t N, int
   return 0;
 }
 #endif  // MILE_PROFILE
+
+// ---- NUTS branch of the sampling seam (mile_nuts.cuh) ---------------------------------------------------------------
+__global__ void nuts_adapt_init_kernel(float* imm, float* mean, float* m2, float* da, int C, int d, float eps0) {
+  const long n = (long)C * d;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    imm[i] = 1.f; mean[i] = 0.f; m2[i] = 0.f;
+  }
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float* a = da + (long)c * 8;   // window_adaptation.base.init: dual averaging at log(eps0), mu = log(10 eps0)
+    a[0] = logf(eps0); a[1] = 0.f; a[2] = 1.f; a[3] = 0.f; a[4] = logf(10.f * eps0); a[5] = 0.f; a[6] = eps0; a[7] = 0.f;
+  }
+}
+__global__ void nuts_adapt_final_kernel(float* da, int C) {   // adapt_final: step_size = exp(log_step_size_avg)
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) da[(long)c * 8 + 6] = expf(da[(long)c * 8 + 1]);
+}
+
+static int nuts_alloc(mile_ctx* c) {
+  if (c->nuts_imm) return 0;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  CK(cudaMalloc(&c->nuts_imm, Cd)); CK(cudaMalloc(&c->nuts_mean, Cd)); CK(cudaMalloc(&c->nuts_m2, Cd));
+  CK(cudaMalloc(&c->nuts_da, (size_t)c->C * 8 * 4));
+  return 0;
+}
+
+int mile_nuts_init(mile_ctx* c, const float* theta0_dev, const mile_nuts_cfg* cfg, void* stream) {
+  if (!c || !cfg) return fail("null ctx / cfg");
+  if (!c->X) return fail("mile_set_data has not been called");
+  if (c->wide) return fail("NUTS is not available on the wide path");
+  if (c->pmask_on || c->sdc_on) return fail("NUTS with a frozen-parameter mask or an MCLMC preconditioner is not supported");
+  if (cfg->max_num_doublings < 1 || cfg->max_num_doublings > 12) return fail("max_num_doublings must be in [1, 12]");
+  if (!(cfg->initial_step_size > 0.f)) return fail("initial_step_size must be positive");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nuts_alloc(c)) return -1;
+  c->nuts_max_doublings = cfg->max_num_doublings; c->nuts_div = cfg->divergence_threshold; c->nuts_target = cfg->target_acceptance_rate;
+  // hmc.init: position, logdensity, gradient
+  if (mile_logpost_value_and_grad(c, theta0_dev, c->C, c->lp, c->grad, stream)) return -1;
+  CK(cudaMemcpyAsync(c->theta, theta0_dev, (size_t)c->C * c->d * 4, cudaMemcpyDeviceToDevice, st));
+  nuts_adapt_init_kernel<<<64, 256, 0, st>>>(c->nuts_imm, c->nuts_mean, c->nuts_m2, c->nuts_da, c->C, c->d, cfg->initial_step_size);
+  CK(cudaGetLastError());
+  c->carry_valid = 0;
+  return 0;
+}
+
+static int nuts_launch(mile_ctx* c, int n_steps, long step_base, const unsigned char* schedule_dev, int thin, long sample_base,
+                       const float* z_dev, const float* uni_dev, uint64_t seed, float* samples_dev, long n_slots,
+                       float* info_dev, int lppd, cudaStream_t st) {
+  if (!c->nuts_imm) return fail("mile_nuts_init has not been called");
+  if (n_steps == 0) return 0;
+  Plan pl;
+  const int keep_fast = c->opt_fast;
+  if (c->opt_fast == 1) c->opt_fast = 0;   // (no NUTS instantiation of the FFMA layer pipeline)
+  const int prc = make_plan(c, c->C, c->N, true, pl);
+  c->opt_fast = keep_fast;
+  if (prc) return -1;
+  const int D = c->nuts_max_doublings;
+  const size_t need = (size_t)c->C * pl.G * (size_t)(10 + 2 * D) * pl.kp.dS;
+  if (need > c->nuts_scratch_floats) {
+    if (c->nuts_scratch) cudaFree(c->nuts_scratch);
+    c->nuts_scratch = nullptr; c->nuts_scratch_floats = 0;
+    CK(cudaMalloc(&c->nuts_scratch, need * 4));
+    c->nuts_scratch_floats = need;
+  }
+  fill_common(c, pl.kp);
+  KParams& k = pl.kp;
+  k.mode = MODE_NUTS; k.n_steps = n_steps; k.step_base = step_base; k.thin = thin; k.sample_base = sample_base;
+  k.n_slots = n_slots; k.z = z_dev; k.seed = seed; k.samples = samples_dev; k.do_lppd = lppd;
+  k.sdc = nullptr; k.pmask = nullptr;
+  NutsParams& q = k.nuts;
+  q.scratch = c->nuts_scratch; q.imm = c->nuts_imm; q.w_mean = c->nuts_mean; q.w_m2 = c->nuts_m2; q.da = c->nuts_da;
+  q.schedule = schedule_dev; q.uni = uni_dev; q.info = info_dev;
+  q.uni_len = 2 * D + (1 << D); q.max_doublings = D; q.divergence_threshold = c->nuts_div; q.target_accept = c->nuts_target;
+  return launch(c, pl, c->C, st);
+}
+
+int mile_nuts_warmup(mile_ctx* c, int32_t n_steps, int64_t step_base, const uint8_t* schedule_dev, const float* z_dev,
+                     const float* uni_dev, uint64_t seed, float* info_dev, void* stream) {
+  if (!c) return fail("null ctx");
+  if (n_steps < 0) return fail("n_steps must be >= 0");
+  if (!schedule_dev && n_steps > 0) return fail("the adaptation schedule is required");
+  CK(cudaSetDevice(c->device));
+  return nuts_launch(c, n_steps, step_base, schedule_dev, 1, 0, z_dev, uni_dev, seed, nullptr, 0, info_dev, 0, (cudaStream_t)stream);
+}
+
+int mile_nuts_finish_warmup(mile_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->nuts_imm) return fail("mile_nuts_init has not been called");
+  CK(cudaSetDevice(c->device));
+  nuts_adapt_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->nuts_da, c->C);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int mile_nuts_sample(mile_ctx* c, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base, const float* z_dev,
+                     const float* uni_dev, uint64_t seed, float* samples_dev, int64_t n_slots, float* info_dev, int32_t lppd,
+                     void* stream) {
+  if (!c) return fail("null ctx");
+  if (n_steps < 0 || n_thinning < 1) return fail("n_steps must be >= 0 and n_thinning >= 1");
+  if (lppd && !c->Xt) return fail("lppd requested but mile_set_test has not been called");
+  CK(cudaSetDevice(c->device));
+  if (lppd && !c->lppd_m && lppd_alloc(c, (cudaStream_t)stream)) return -1;
+  if (nuts_launch(c, n_steps, step_base, nullptr, n_thinning, sample_base, z_dev, uni_dev, seed, samples_dev, n_slots, info_dev,
+                  lppd, (cudaStream_t)stream)) return -1;
+  if (lppd && n_steps > 0) {
+    const long first = (step_base + n_thinning - 1) / n_thinning, last = (step_base + n_steps - 1) / n_thinning;
+    c->lppd_count += (last >= first) ? (last - first + 1) : 0;
+  }
+  return 0;
+}
+
+int mile_nuts_init_host(mile_ctx* c, const float* theta0, const mile_nuts_cfg* cfg) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  float* th = (float*)scratch(c, 2, Cd);
+  if (!th) return fail("cudaMalloc failed (staging)");
+  CK(cudaMemcpyAsync(th, theta0, Cd, cudaMemcpyHostToDevice, c->own_stream));
+  if (mile_nuts_init(c, th, cfg, c->own_stream)) return -1;
+  CK(cudaStreamSynchronize(c->own_stream));
+  return 0;
+}
+
+// schedule [n_steps] (warm-up) or NULL (sampling); z [n_steps,C,d] / uni [n_steps,C,2D+2^D] or NULL (in-kernel Philox)
+int mile_nuts_run_host(mile_ctx* c, int32_t n_steps, int64_t step_base, const uint8_t* schedule, int32_t n_thinning,
+                       const float* z, const float* uni, uint64_t seed, float* samples, int64_t n_slots, float* info,
+                       int32_t lppd) {
+  if (!c) return fail("null ctx");
+  if (n_steps < 0) return fail("n_steps must be >= 0");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->own_stream;
+  const size_t Cd = (size_t)c->C * c->d * 4;
+  const size_t ulen = (size_t)(2 * c->nuts_max_doublings + (1 << c->nuts_max_doublings));
+  const size_t ub = (size_t)n_steps * c->C * ulen * 4, ib = (size_t)n_steps * c->C * NUTS_INFO * 4;
+  unsigned char* sd = schedule ? (unsigned char*)scratch(c, 5, (size_t)n_steps + 4) : nullptr;
+  float* zd = z ? (float*)scratch(c, 7, (size_t)n_steps * Cd) : nullptr;
+  float* ud = uni ? (float*)scratch(c, 6, ub) : nullptr;
+  float* smp = samples ? (float*)scratch(c, 8, (size_t)n_slots * Cd) : nullptr;
+  float* id = info ? (float*)scratch(c, 9, ib) : nullptr;
+  if ((schedule && !sd) || (z && !zd) || (uni && !ud) || (samples && !smp) || (info && !id)) return fail("cudaMalloc failed (staging)");
+  if (schedule) CK(cudaMemcpyAsync(sd, schedule, (size_t)n_steps, cudaMemcpyHostToDevice, st));
+  if (z) CK(cudaMemcpyAsync(zd, z, (size_t)n_steps * Cd, cudaMemcpyHostToDevice, st));
+  if (uni) CK(cudaMemcpyAsync(ud, uni, ub, cudaMemcpyHostToDevice, st));
+  if (schedule) {
+    if (mile_nuts_warmup(c, n_steps, step_base, sd, zd, ud, seed, id, st)) return -1;
+  } else {
+    const int64_t sample_base = (step_base + n_thinning - 1) / n_thinning;
+    if (mile_nuts_sample(c, n_steps, step_base, n_thinning, sample_base, zd, ud, seed, smp, n_slots, id, lppd, st)) return -1;
+    if (samples) CK(cudaMemcpyAsync(samples, smp, (size_t)n_slots * Cd, cudaMemcpyDeviceToHost, st));
+  }
+  if (info) CK(cudaMemcpyAsync(info, id, ib, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mile_nuts_get_params_host(mile_ctx* c, float* step_size, float* inverse_mass_matrix) {
+  if (!c) return fail("null ctx");
+  if (!c->nuts_imm) return fail("mile_nuts_init has not been called");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  if (step_size) CK(cudaMemcpy2D(step_size, 4, c->nuts_da + 6, 32, 4, c->C, cudaMemcpyDeviceToHost));
+  if (inverse_mass_matrix) CK(cudaMemcpy(inverse_mass_matrix, c->nuts_imm, (size_t)c->C * c->d * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int mile_nuts_set_params_host(mile_ctx* c, const float* step_size, const float* inverse_mass_matrix) {
+  if (!c) return fail("null ctx");
+  if (!c->nuts_imm) return fail("mile_nuts_init has not been called");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  if (step_size) CK(cudaMemcpy2D(c->nuts_da + 6, 32, step_size, 4, 4, c->C, cudaMemcpyHostToDevice));
+  if (inverse_mass_matrix) CK(cudaMemcpy(c->nuts_imm, inverse_mass_matrix, (size_t)c->C * c->d * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
 int mile_synchronize(mile_ctx* c) {

@@ -17,6 +17,18 @@
 
 enum { MODE_EVAL = 0, MODE_INIT = 1, MODE_SAMPLE = 2, MODE_TUNE = 3, MODE_LPPD = 4, MODE_PREDICT = 5 };
 
+// NUTS branch (mile_nuts.cuh): adaptation state and per-CTA scratch; everything else comes from KParams
+struct NutsParams {
+  float* scratch;                 // [CTAs][(10 + 2 D) * dS]
+  float *imm, *w_mean, *w_m2;     // [C][d] inverse mass matrix (diagonal), Welford mean / m2 of the open window
+  float* da;                      // [C][8] log_x, log_x_avg, step, avg_error, mu, Welford count, step_size, -
+  const unsigned char* schedule;  // [n_steps] bit 0 = slow stage, bit 1 = window end; null = no adaptation (sampling)
+  const float* uni;               // [n_steps][C][uni_len] host-supplied uniforms or null (Philox)
+  float* info;                    // [n_steps][C][8] or null
+  int uni_len, max_doublings;
+  float divergence_threshold, target_accept;
+};
+
 struct KParams {
   DevModel M;
   // data: padded row-major copies [N][sA[0]]
@@ -65,6 +77,7 @@ struct KParams {
   const float* pmask; int d_eff;
   int mr_world, mr_rank; unsigned int mr_base;   // flag = mr_base + eval + 1 (advanced identically on every rank)
   float2* mr_sums[8];    // rank r's region [C][2 parities][world][dS+4] (own region for r == mr_rank)
+  NutsParams nuts;
 };
 
 struct Ctx {

@@ -292,6 +292,62 @@ class Ensemble:
         l = None if L is None else _f32(np.broadcast_to(L, (C_,)))
         capi.check(self.lib.mile_set_tuning_host(self.h, capi.host_ptr(e), capi.host_ptr(l)))
 
+    # ---- NUTS branch (sampling.py:70-81,107-210; warmup.py:27-152) ------------------------------
+    NUTS_INFO_FIELDS = ('num_integration_steps', 'acceptance_rate', 'num_trajectory_expansions', 'is_divergent', 'energy',
+                        'is_turning', 'logdensity', 'step_size')
+
+    def nuts_init(self, theta0, max_num_doublings: int = 10, divergence_threshold: float = 1000.0,
+                  target_acceptance_rate: float = 0.8, initial_step_size: float = 1.0):
+        """hmc.init (logdensity + gradient at theta0) and window_adaptation's init (unit metric, dual averaging at
+        initial_step_size)."""
+        theta0 = _f32(theta0).reshape(self.n_chains, self.d)
+        cfg = capi.NutsCfg(int(max_num_doublings), divergence_threshold, target_acceptance_rate, initial_step_size)
+        self._nuts_D = int(max_num_doublings)
+        capi.check(self.lib.mile_nuts_init_host(self.h, capi.host_ptr(theta0), C.byref(cfg)))
+
+    def nuts_uni_len(self) -> int:
+        return 2 * self._nuts_D + 2 ** self._nuts_D
+
+    def _nuts_run(self, n_steps, step_base, schedule, n_thinning, z, uni, seed, keep, info, lppd):
+        C_, d = self.n_chains, self.d
+        first = -(-step_base // n_thinning)
+        last = (step_base + n_steps - 1) // n_thinning
+        n_slots = max(0, last - first + 1) if keep and n_steps > 0 else 0
+        samples = np.empty((n_slots, C_, d), np.float32) if keep else None
+        inf = np.empty((n_steps, C_, 8), np.float32) if info else None
+        z = None if z is None else _f32(z).reshape(n_steps, C_, d)
+        uni = None if uni is None else _f32(uni).reshape(n_steps, C_, self.nuts_uni_len())
+        capi.check(self.lib.mile_nuts_run_host(self.h, n_steps, step_base, capi.host_ptr(schedule), n_thinning,
+                                               capi.host_ptr(z), capi.host_ptr(uni), seed, capi.host_ptr(samples), n_slots,
+                                               capi.host_ptr(inf), int(lppd)))
+        return samples, inf
+
+    def nuts_warmup(self, n_steps, schedule, *, step_base=0, z=None, uni=None, seed=0, info=False):
+        """n_steps warm-up transitions, each followed by adapt_step; schedule = [(stage, is_middle_window_end)] of THESE
+        steps (window_adaptation.build_schedule)."""
+        sched = np.ascontiguousarray([int(st) | (2 if end else 0) for st, end in schedule], dtype=np.uint8)
+        assert sched.shape == (n_steps,)
+        return self._nuts_run(n_steps, step_base, sched, 1, z, uni, seed, False, info, False)[1]
+
+    def nuts_finish_warmup(self):
+        capi.check(self.lib.mile_nuts_finish_warmup(self.h, None))
+        self.synchronize()
+
+    def nuts_sample(self, n_steps, *, step_base=0, n_thinning=1, z=None, uni=None, seed=0, keep=True, info=False, lppd=False):
+        """(samples [S,C,d] | None, info [n,C,8] | None): positions after every n_thinning-th transition."""
+        return self._nuts_run(n_steps, step_base, None, n_thinning, z, uni, seed, keep, info, lppd)
+
+    def nuts_params(self):
+        eps = np.empty(self.n_chains, np.float32)
+        imm = np.empty((self.n_chains, self.d), np.float32)
+        capi.check(self.lib.mile_nuts_get_params_host(self.h, capi.host_ptr(eps), capi.host_ptr(imm)))
+        return eps, imm
+
+    def set_nuts_params(self, step_size=None, inverse_mass_matrix=None):
+        e = None if step_size is None else _f32(np.broadcast_to(step_size, (self.n_chains,)))
+        m = None if inverse_mass_matrix is None else _f32(np.broadcast_to(inverse_mass_matrix, (self.n_chains, self.d)))
+        capi.check(self.lib.mile_nuts_set_params_host(self.h, capi.host_ptr(e), capi.host_ptr(m)))
+
     # ---- partition sampling (partition_sampling.py; trainer.py:613-659) ------------------------
     def set_frozen_mask(self, frozen):
         """frozen: bool [d] (True = the parameter keeps its value, sees no prior, gets no gradient / momentum / noise) or

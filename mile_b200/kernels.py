@@ -10,9 +10,9 @@ from typing import Callable
 import numpy as np
 
 from .probabilistic import unwrap_posterior
-from .types import IntegratorState, MCLMCInfo, SamplingAlgorithm, key_to_seed
+from .types import HMCState, IntegratorState, MCLMCInfo, SamplingAlgorithm, key_to_seed
 
-__all__ = ['mclmc', 'KERNELS']
+__all__ = ['mclmc', 'nuts', 'KERNELS']
 
 
 class _Bound:
@@ -74,6 +74,46 @@ def _state(b: _Bound, ens, batched) -> IntegratorState:
     return IntegratorState(b.tree(th, batched), b.tree(u, batched), lp if batched else lp[0], b.tree(g, batched))
 
 
+def nuts(logdensity_fn: Callable, step_size, inverse_mass_matrix, max_num_doublings: int = 10,
+         divergence_threshold: float = 1000.0) -> SamplingAlgorithm:
+    """blackjax.nuts(logdensity_fn, step_size, inverse_mass_matrix): init(position) / step(rng_key, state) -> (state, info)
+    with info = dict of the NUTSInfo fields the reference keeps (sampling.py:200-210).  Diagonal metric only."""
+    b = _Bound(logdensity_fn)
+
+    def _ensure(th):
+        fresh = b.ens is None or b.ens.n_chains != th.shape[0]
+        ens = b.ensure(th.shape[0])
+        if fresh:
+            ens.nuts_init(th, max_num_doublings, divergence_threshold)
+            ens.set_nuts_params(step_size, inverse_mass_matrix)
+        return ens
+
+    def init(position, rng_key=None) -> HMCState:
+        th, batched = b.flat(position)
+        ens = _ensure(th)
+        ens.nuts_init(th, max_num_doublings, divergence_threshold)
+        ens.set_nuts_params(step_size, inverse_mass_matrix)
+        b.step_counter = 0
+        return _hmc_state(b, ens, batched)
+
+    def step(rng_key, state: HMCState):
+        th, batched = b.flat(state.position)
+        ens = _ensure(th)
+        g, _ = b.flat(state.logdensity_grad)
+        ens.set_state(th, None, np.atleast_1d(np.asarray(state.logdensity, np.float32)), g)
+        _, info = ens.nuts_sample(1, step_base=b.step_counter, seed=key_to_seed(rng_key), keep=False, info=True)
+        b.step_counter += 1
+        inf = info[0] if batched else info[0, 0]
+        return _hmc_state(b, ens, batched), {k: inf[..., i] for i, k in enumerate(ens.NUTS_INFO_FIELDS)}
+
+    return SamplingAlgorithm(init, step)
+
+
+def _hmc_state(b: _Bound, ens, batched) -> HMCState:
+    th, _, lp, g = ens.get_state()
+    return HMCState(b.tree(th, batched), lp if batched else lp[0], b.tree(g, batched))
+
+
 def _not_on_cuda(name):
     def f(*a, **k):
         raise NotImplementedError(f"'{name}' is outside the accelerated hot path (SURVEY.md section 2, rows 12): "
@@ -81,5 +121,5 @@ def _not_on_cuda(name):
     return f
 
 
-KERNELS: dict = {'nuts': _not_on_cuda('nuts'), 'hmc': _not_on_cuda('hmc'), 'mclmc': mclmc}
+KERNELS: dict = {'nuts': nuts, 'hmc': _not_on_cuda('hmc'), 'mclmc': mclmc}
 WARMUP_KERNELS: dict = {}

@@ -20,6 +20,7 @@ from .warmup import run_warmup
 logger = logging.getLogger(__name__)
 
 CHUNK = 1000  # MCLMC steps per sampling launch (rounded to a multiple of n_thinning)
+NUTS_CHUNK = 500  # NUTS transitions per sampling launch
 # Where the kept positions go: 'npz' = the reference layout samples/{chain}/sample_{n}.npz (default: drop-in),
 # 'store' = one [C, S, d] array under <exp>/samples_store (sample_store.py; `python -m mile_b200.sample_store export`
 # reproduces the npz layout afterwards), 'both'.
@@ -36,8 +37,11 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     n_devices = len(step_ids)
     rng_key, warmup_key, sample_key = split(rng_key, 3)                      # sampling.py:65
     assert config.warmup_steps > 0, 'Number of warmup steps must be greater than 0.'
-    if config.name != Sampler.MCLMC:
+    if config.name not in (Sampler.MCLMC, Sampler.NUTS):
         raise NotImplementedError(f'{config.name} does not have a warmup implemented.')
+    nuts = config.name == Sampler.NUTS
+    if nuts and _frozen is not None:
+        raise NotImplementedError('partition sampling with NUTS is not implemented on the CUDA path')
     saving_path = Path(saving_path)
     model, x, y = unwrap_posterior(unnorm_log_posterior)
     spec = model.spec
@@ -52,17 +56,23 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
         ens.set_frozen_mask(_frozen)
     try:
         logger.info('> Starting Warmup sampling...')
-        eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens,
-                              _active=None if _frozen is None else np.flatnonzero(~np.asarray(_frozen, bool)))
-        saving_path.mkdir(parents=True, exist_ok=True)
-        with open(saving_path.parent / 'warmup_params.txt', 'w') as f:      # sampling.py:92-97
-            f.write(','.join(str(np.float32(v)) for v in eps) + '\n')
-            f.write(','.join(str(np.float32(v)) for v in L) + '\n')
+        if nuts:                                                             # sampling.py:70-81 (no warmup_params.txt)
+            warmup_nuts(None, config, warmup_key, init_params, step_ids, unnorm_log_posterior, n_devices, _ensemble=ens)
+            eps = L = None
+            saving_path.mkdir(parents=True, exist_ok=True)
+        else:
+            eps, L = warmup_mclmc(config, warmup_key, init_params, unnorm_log_posterior, n_devices, _ensemble=ens,
+                                  _active=None if _frozen is None else np.flatnonzero(~np.asarray(_frozen, bool)))
+            saving_path.mkdir(parents=True, exist_ok=True)
+            with open(saving_path.parent / 'warmup_params.txt', 'w') as f:      # sampling.py:92-97
+                f.write(','.join(str(np.float32(v)) for v in eps) + '\n')
+                f.write(','.join(str(np.float32(v)) for v in L) + '\n')
         logger.info('> Warmup sampling completed successfully.')
 
         logger.info(f'> Starting {config.name.value} Sampling...')
         thin = int(config.n_thinning)
-        chunk = max(thin, CHUNK // thin * thin)
+        chunk = max(thin, (NUTS_CHUNK if nuts else CHUNK) // thin * thin)
+        nuts_info = []
         fmt = SAMPLE_FORMAT
         if fmt not in ('npz', 'store', 'both'):
             raise ValueError(f'MILE_SAMPLE_FORMAT must be npz, store or both, not {fmt!r}')
@@ -79,7 +89,11 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
         done = 0
         while done < config.n_samples:                                       # HOT LOOP C, sampling.py:134-177
             n = min(chunk, config.n_samples - done)
-            samples, _ = ens.sample(n, eps, L, step_base=done, n_thinning=thin, seed=seed, lppd=fused_lppd)
+            if nuts:
+                samples, ninfo = ens.nuts_sample(n, step_base=done, n_thinning=thin, seed=seed, info=True, lppd=fused_lppd)
+                nuts_info.append(ninfo)
+            else:
+                samples, _ = ens.sample(n, eps, L, step_base=done, n_thinning=thin, seed=seed, lppd=fused_lppd)
             first = -(-done // thin)
             kept = [(first + k) * thin for k in range(samples.shape[0])]
             if writer is not None:
@@ -91,6 +105,11 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
             writer.close()
         if store is not None:
             store.close()
+        if nuts:                                                             # sampling.py:200-210: [n_devices, n_samples] each
+            ni = np.concatenate(nuts_info, axis=0).transpose(1, 0, 2)
+            info.update({'num_integration_steps': ni[..., 0].astype(np.int32), 'acceptance_rate': ni[..., 1],
+                         'num_trajectory_expansions': ni[..., 2].astype(np.int32), 'is_divergent': ni[..., 3] > 0.5,
+                         'energy': ni[..., 4], 'is_turning': ni[..., 5] > 0.5})
         if fused_lppd:
             m, s, cnt = ens.lppd_state()
             info['lppd'] = lppd_from_state(m, s, n_devices * cnt)
@@ -126,3 +145,20 @@ def warmup_mclmc(config: SamplerConfig, rng_key, init_params: dict, unnorm_log_p
     res = custom_mclmc_warmup(unnorm_log_posterior, diagonal_preconditioning=dp, **kw).run(
         rng_key, init_params, config.warmup_steps)
     return res.state, {'step_size': res.parameters.step_size, 'L': res.parameters.L}
+
+
+def warmup_nuts(kernel, config: SamplerConfig, rng_key, init_params: dict, step_ids, unnorm_log_posterior, n_devices: int,
+                saving_path=None, _ensemble=None):
+    """sampling.py:220-262: window adaptation of step size and diagonal mass matrix for every chain.  Returns
+    (warmup_state, parameters) like the reference; with `_ensemble` the state and the parameters stay on the device."""
+    from .nuts import custom_window_adaptation, run_window_adaptation
+    if saving_path:
+        raise NotImplementedError('saving the warm-up positions is not implemented on the CUDA path')
+    if _ensemble is not None:
+        model, x, y = unwrap_posterior(unnorm_log_posterior)
+        theta0 = model.spec.ravel(init_params).reshape(-1, model.spec.n_params)
+        eps, imm = run_window_adaptation(_ensemble, theta0, rng_key, config.warmup_steps)
+        return None, {'step_size': eps, 'inverse_mass_matrix': imm}
+    res = custom_window_adaptation(kernel, unnorm_log_posterior, progress_bar=True).run(
+        rng_key, init_params, None, config.warmup_steps, n_devices)
+    return res.state, res.parameters

@@ -17,6 +17,13 @@ class IntegratorState(NamedTuple):
     logdensity_grad: Any
 
 
+class HMCState(NamedTuple):
+    """blackjax.mcmc.hmc.HMCState (the state of the NUTS branch)."""
+    position: Any
+    logdensity: Any
+    logdensity_grad: Any
+
+
 class MCLMCInfo(NamedTuple):
     """blackjax.mcmc.mclmc.MCLMCInfo."""
     logdensity: Any
