@@ -63,7 +63,11 @@ def test_single_transitions_match_oracle(name, G, fast):
     ens.nuts_init(th.astype(np.float32), max_num_doublings=D)
     ens.set_nuts_params(eps, imm)
     kinds, mismatched = set(), 0
+    eps_base = eps.copy()
+    jit = 0.5 + np.random.default_rng(7).random((T, C)) if name == 'prior_only' else np.ones((T, C))
     for k in range(T):
+        eps = eps_base * jit[k]              # (prior_only: a different step size per transition varies how trajectories end)
+        ens.set_nuts_params(step_size=eps)
         ens.set_state(theta=th.astype(np.float32), lp=lp.astype(np.float32), grad=g.astype(np.float32))
         pos, info = ens.nuts_sample(1, step_base=k, z=z[k:k + 1], uni=uni[k:k + 1], info=True)
         th_g, _, lp_g, g_g = ens.get_state()
@@ -82,7 +86,8 @@ def test_single_transitions_match_oracle(name, G, fast):
                                     imm[c].astype(np.float32), z[k, c], uni[k, c], D)
                 wi = want[3]
                 assert got == (wi.num_integration_steps, wi.num_trajectory_expansions, wi.is_divergent, wi.is_turning), (k, c, got, wi)
-            kinds.add((wi.num_integration_steps == 2 ** D - 1, wi.is_divergent, wi.is_turning))
+            kinds.add((wi.num_integration_steps == 2 ** D - 1, wi.is_divergent, wi.is_turning,
+                       wi.is_turning and not wi.is_divergent and (wi.num_integration_steps & (wi.num_integration_steps + 1)) != 0))
             scale = np.linalg.norm(want[0])
             assert np.linalg.norm(th_g[c] - want[0]) <= 2e-5 * scale, (k, c, wi)
             assert abs(lp_g[c] - want[1]) <= 2e-5 * abs(want[1]), (k, c, wi)
@@ -100,7 +105,8 @@ def test_single_transitions_match_oracle(name, G, fast):
     assert mismatched <= (C * T) // 10, mismatched
     assert len(kinds) >= 2, kinds        # the cases exercised more than one way of ending a trajectory
     if name == 'prior_only':
-        assert any(k[2] and not k[1] for k in kinds), kinds      # ... among them the U-turn
+        assert any(k[2] and not k[1] for k in kinds), kinds      # ... among them the U-turn of the whole trajectory
+        assert any(k[3] for k in kinds), kinds                   # ... and of a sub-trajectory (tree size not 2^j - 1)
     ens.close()
 
 
