@@ -525,6 +525,47 @@ def measure(W, args, steps, warmup, rank, world, local, with_cpu, peaks):
     return line
 
 
+def measure_nuts(local: int, workload: str = DEFAULT_WORKLOAD, chains: int = 12, n_warm: int = 300, n_samp: int = 100):
+    """The NUTS branch (csrc/mile_nuts.cuh) on the default workload: window adaptation, then sampling transitions with
+    in-kernel Philox noise, timed through the host-buffer ABI call (wall clock around a synchronous call).  Reported as
+    gradient evaluations per second because a transition's length is data dependent."""
+    import numpy as np
+    from mile_b200 import Ensemble, FCNSpec
+    from mile_b200 import synthetic as syn
+    from mile_b200.nuts import build_schedule
+    spec = syn.workload_spec(workload)
+    X, y, _, _ = syn.synthetic_data(workload, seed=1234)
+    fs = FCNSpec(spec.n_features, spec.widths, spec.activation, spec.task)
+    ens = Ensemble(fs, chains, device=local)
+    try:
+        ens.set_data(X, y)
+        th0 = (0.3 * np.random.default_rng(0).standard_normal((chains, fs.n_params))).astype(np.float32)
+        ens.nuts_init(th0, max_num_doublings=10, initial_step_size=1.0)
+        sched = build_schedule(n_warm)
+        l0 = ens.launches
+        t0 = time.perf_counter()
+        done, ev_w = 0, 0
+        while done < n_warm:
+            n = min(100, n_warm - done)
+            ev_w += int(ens.nuts_warmup(n, sched[done:done + n], step_base=done, seed=1, info=True)[..., 0].sum())
+            done += n
+        ens.nuts_finish_warmup()
+        t_w = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        samples, info = ens.nuts_sample(n_samp, seed=2, info=True)
+        t_s = time.perf_counter() - t0
+        ev_s = int(info[..., 0].sum())
+        return {'workload': workload, 'chains': chains, 'kernel': 'mile_nuts_kernel (whole transitions per launch)',
+                'warmup': {'transitions': n_warm, 'grad_evals': ev_w, 'grad_evals_per_s': ev_w / t_w, 'seconds': t_w},
+                'sampling': {'transitions': n_samp, 'grad_evals': ev_s, 'grad_evals_per_s': ev_s / t_s, 'seconds': t_s,
+                             'mean_tree_size': float(info[..., 0].mean()), 'mean_acceptance': float(info[..., 1].mean()),
+                             'divergent_transitions': int(info[..., 3].sum())},
+                'gpu_launches': ens.launches - l0, 'samples_finite': bool(np.isfinite(samples).all()),
+                'note': 'host-buffer ABI calls, wall clock; MCLMC on this workload runs 2 gradient evaluations per chain-step'}
+    finally:
+        ens.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -571,10 +612,18 @@ def run_ours(args):
                     s['config'] = {k: sub['config'][k] for k in ('chains_per_gpu', 'inner_steps_per_launch', 'n_train', 'n_params',
                                                                  'cluster_size', 'kernel_path', 'parallelism')}
                 extra[W] = s
+    nuts = None
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == DEFAULT_WORKLOAD:
+        try:
+            nuts = measure_nuts(local)
+        except Exception as e:   # noqa: BLE001
+            nuts = {'error': repr(e)}
     if rank == 0:
         if extra:
             line['extra'] = {'workloads': extra,
                              'note': 'the other named shapes of BASELINE.json, same timing method on a shorter run (<= 3 steps)'}
+            if nuts is not None:
+                line['extra']['nuts'] = nuts
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -59,6 +59,25 @@ class _FastNpz:
                 zf.writestr(name, hdr + np.ascontiguousarray(leaf, dtype=self.dtype).tobytes())
 
 
+def write_npz_block(lib, paths, names, headers, sizes, block, n_threads, where=''):
+    """One call of the native writer (csrc/mile_npz.cu): file i = the members `names` (bytes, with '.npy') cut from row i of
+    `block` [n_files, sum(sizes)] float32 in order, each behind its prebuilt .npy header."""
+    import ctypes as C
+    from . import capi
+    nm = len(names)
+    assert block.dtype == np.float32 and block.flags['C_CONTIGUOUS'] and block.size == len(paths) * sum(sizes)
+    c_paths = (C.c_char_p * len(paths))(*paths)
+    c_names = (C.c_char_p * nm)(*names)
+    c_hdrs = (C.c_char_p * nm)(*headers)
+    c_hlen = (C.c_int32 * nm)(*[len(h) for h in headers])
+    c_size = (C.c_int64 * nm)(*sizes)
+    rc = lib.mile_write_npz_batch(C.cast(c_paths, C.c_void_p), len(paths), C.cast(c_names, C.c_void_p),
+                                  C.cast(c_hdrs, C.c_void_p), C.cast(c_hlen, C.c_void_p), C.cast(c_size, C.c_void_p),
+                                  nm, capi.host_ptr(block), int(n_threads))
+    if rc != 0:
+        raise OSError(f'mile_write_npz_batch failed ({rc}) under {where}')
+
+
 class SampleWriter:
     """Asynchronous batch writer of kept positions: every submitted block [S, C, d] becomes S x C npz files through ONE call
     of the native writer (`mile_write_npz_batch`: deflate + zip on a few host threads outside the GIL), issued from a
@@ -92,19 +111,7 @@ class SampleWriter:
         self.futures.append(self.pool.submit(self._write_block, block, paths))
 
     def _write_block(self, block, paths):
-        import ctypes as C
-        from . import capi
-        nm = len(self._names)
-        c_paths = (C.c_char_p * len(paths))(*paths)
-        c_names = (C.c_char_p * nm)(*self._names)
-        c_hdrs = (C.c_char_p * nm)(*self._headers)
-        c_hlen = (C.c_int32 * nm)(*[len(h) for h in self._headers])
-        c_size = (C.c_int64 * nm)(*self._sizes)
-        rc = self.lib.mile_write_npz_batch(C.cast(c_paths, C.c_void_p), len(paths), C.cast(c_names, C.c_void_p),
-                                           C.cast(c_hdrs, C.c_void_p), C.cast(c_hlen, C.c_void_p), C.cast(c_size, C.c_void_p),
-                                           nm, capi.host_ptr(block), self.n_threads)
-        if rc != 0:
-            raise OSError(f'mile_write_npz_batch failed ({rc}) under {self.base}')
+        write_npz_block(self.lib, paths, self._names, self._headers, self._sizes, block, self.n_threads, self.base)
 
     def close(self):
         for f in self.futures:

@@ -164,13 +164,30 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
         float g2, ug, nf;
         lp = cluster_reduce_grad<NT, 0>(c, gp, gslab, xflag, g2, ug, nf, use_ll, c.G);
         ++e;
-        float v[1] = {0.f};
+        // second half of the momentum update fused with everything that does not depend on the acceptance draw: kinetic
+        // energy, momentum sum of the sub-trajectory, the checkpoint of an even leaf, and -- on an odd leaf -- the first
+        // (innermost) U-turn check, so that one block reduction serves all of them
+        // (termination.iterative_uturn_numpyro: checkpoint on even leaves, check the open sub-trees on odd ones)
+        const int idx_max = __popc(k >> 1);
+        const int idx_min = idx_max - (__ffs(~k) - 1) + 1;
+        const bool even = (k & 1) == 0;
+        float* cp = ck_p + (size_t)idx_max * P.dS; float* cs = ck_s + (size_t)idx_max * P.dS;
+        float v[3] = {0.f, 0.f, 0.f};
         for (int i = tid; i < d; i += NT) {
           const float p = c.uu[i] + h * c.gg[i];
           c.uu[i] = p;
-          v[0] += imm[i] * p * p;
+          const float im = imm[i];
+          v[0] += im * p * p;
+          const float sm = k == 0 ? p : ssum[i] + p;
+          ssum[i] = sm;
+          if (even) { cp[i] = p; cs[i] = sm; }
+          else {
+            const float pl = cp[i];
+            const float rho = (sm - cs[i] + pl) - (p + pl) / 2.f;
+            v[1] += im * pl * rho; v[2] += im * p * rho;
+          }
         }
-        block_sum<1, NT, 0>(v, c.red, c.phase);
+        block_sum<3, NT, 0>(v, c.red, c.phase);
         // proposal.update: weight = initial energy - new energy (NaN -> -inf), divergence beyond the threshold
         const float new_e = -lp + 0.5f * v[0];
         float delta = e0 - new_e;
@@ -185,22 +202,14 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
           take = uni_at(2 * D + n_leap) < p_acc;
           sp_w = nuts_logaddexp(sp_w, n_w); sp_sl = nuts_logaddexp(sp_sl, n_sl);
         }
-        if (take) { sp_lp = lp; sp_e = new_e; }
-        // termination.iterative_uturn_numpyro: checkpoint on even leaves, check the open sub-trees on odd ones
-        const int idx_max = __popc(k >> 1);
-        const int idx_min = idx_max - (__ffs(~k) - 1) + 1;
-        const bool even = (k & 1) == 0;
-        float* cp = ck_p + (size_t)idx_max * P.dS; float* cs = ck_s + (size_t)idx_max * P.dS;
-        for (int i = tid; i < d; i += NT) {
-          const float p = c.uu[i];
-          const float sm = k == 0 ? p : ssum[i] + p;
-          ssum[i] = sm;
-          if (take) { sp_th[i] = c.th[i]; sp_g[i] = c.gg[i]; }
-          if (even) { cp[i] = p; cs[i] = sm; }
+        if (take) {
+          sp_lp = lp; sp_e = new_e;
+          for (int i = tid; i < d; i += NT) { sp_th[i] = c.th[i]; sp_g[i] = c.gg[i]; }
         }
         if (!even) {
+          s_term = (v[1] <= 0.f) || (v[2] <= 0.f);
 #pragma unroll 1
-          for (int j = idx_max; j >= idx_min && !s_term; --j) {
+          for (int j = idx_max - 1; j >= idx_min && !s_term; --j) {
             const float* qp = ck_p + (size_t)j * P.dS; const float* qs = ck_s + (size_t)j * P.dS;
             float w[2] = {0.f, 0.f};
             for (int i = tid; i < d; i += NT) {

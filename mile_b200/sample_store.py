@@ -98,20 +98,23 @@ class SampleStore:
     # ---- compatibility with the reference layout -----------------------------------------------------------
     def export_npz(self, samples_dir, max_workers: int = 8):
         """Writes samples/{chain}/sample_{n}.npz exactly like src/training/callbacks.py:36-43."""
+        import os
+        from . import capi
+        from .callbacks import _npy_header, write_npz_block
         samples_dir = Path(samples_dir)
         x, idx, leaves = self.samples, self.meta['sample_index'], self.meta['leaves']
-
-        def write_chain(c, cid):
-            cd = samples_dir / str(cid)
-            cd.mkdir(parents=True, exist_ok=True)
-            for k, n in enumerate(idx):
-                row = np.asarray(x[c, k])
-                members = {lf['name']: row[lf['offset']:lf['offset'] + int(np.prod(lf['shape']))].reshape(lf['shape'])
-                           for lf in leaves}
-                np.savez_compressed(cd / f'sample_{n}.npz', **members)
-
-        with ThreadPoolExecutor(max_workers=max_workers) as pool:
-            list(pool.map(lambda a: write_chain(*a), enumerate(self.meta['chains'])))
+        sizes = [int(np.prod(lf['shape'])) for lf in leaves]
+        # the members must tile a row in order (they do: the leaf table is in ravel order)
+        assert [lf['offset'] for lf in leaves] == [int(v) for v in np.cumsum([0] + sizes[:-1])] and sum(sizes) == x.shape[2]
+        names = [(lf['name'] + '.npy').encode() for lf in leaves]
+        headers = [_npy_header(lf['shape'], np.float32) for lf in leaves]
+        paths = []
+        for cid in self.meta['chains']:
+            (samples_dir / str(cid)).mkdir(parents=True, exist_ok=True)
+            paths += [str(samples_dir / str(cid) / f'sample_{n}.npz').encode() for n in idx]
+        block = np.ascontiguousarray(x, dtype=np.float32)            # [C, S, d]: row (c, k) -> file of chain c, position k
+        write_npz_block(capi.load(), paths, names, headers, sizes, block, max(1, min(max_workers, os.cpu_count() or 1)),
+                        samples_dir)
 
     @classmethod
     def from_npz_dir(cls, samples_dir, spec, out_path) -> 'SampleStore':

@@ -71,7 +71,8 @@ def test_unwrap_posterior_accepts_only_the_reference_closure():
         unwrap_posterior(functools.partial(pm.log_unnormalized_posterior, x=X))
     from mile_b200 import KERNELS
     with pytest.raises(NotImplementedError):
-        KERNELS['nuts'](None)
+        KERNELS['hmc'](None)
+    assert callable(KERNELS['nuts']) and callable(KERNELS['mclmc'])
 
 
 def test_param_io_layout_matches_reference(tmp_path):
