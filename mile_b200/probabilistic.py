@@ -99,18 +99,72 @@ def merge_partition(input_output_layers: dict, hidden_layers: dict) -> dict:
     return {'fcn': {**input_output_layers['fcn'], **hidden_layers['fcn']}}
 
 
+_ADOPTED = weakref.WeakKeyDictionary()     # reference ProbabilisticModel object -> (n_features, adapter)
+
+
+def _closure_vars(fn) -> dict:
+    code, cells = getattr(fn, '__code__', None), getattr(fn, '__closure__', None)
+    if code is None or not cells:
+        return {}
+    out = {}
+    for name, cell in zip(code.co_freevars, cells):
+        try:
+            out[name] = cell.cell_contents
+        except ValueError:
+            pass
+    return out
+
+
+def adopt_reference_model(owner, x) -> 'ProbabilisticModel':
+    """Describe the REFERENCE's own `src.training.probabilistic.ProbabilisticModel` (probabilistic.py:17-47) to the CUDA
+    library without importing it: `module.config.hidden_structure / activation / use_bias` (src/config/models/fcn.py:8-30),
+    `task`, `n_batches`, and the prior from `prior.name` plus the `loc` / `scale` its `log_prior` closure was built with
+    (src/training/priors.py:100-128).  Lets `inference_loop` take the closure the reference's trainer builds
+    (trainer.py:576-580) as it is."""
+    n_features = int(np.shape(x)[-1])
+    hit = _ADOPTED.get(owner)
+    if hit is not None and hit[0] == n_features:
+        return hit[1]
+    cfg = getattr(getattr(owner, 'module', None), 'config', None)
+    if cfg is None or not hasattr(cfg, 'hidden_structure') or not hasattr(cfg, 'activation'):
+        raise TypeError('the log-posterior closure belongs to a model whose `module.config` is not an FCN configuration '
+                        '(hidden_structure, activation): only the FCN of src/models/tabular/fcn.py runs on the CUDA path')
+    act = cfg.activation
+    module = FCN(tuple(cfg.hidden_structure), str(getattr(act, 'value', act)), bool(getattr(cfg, 'use_bias', True)))
+    pr = owner.prior
+    name = str(getattr(pr.name, 'value', pr.name))
+    cv = _closure_vars(pr.log_prior)
+    params = {} if name == 'StandardNormal' else {k: float(cv[k]) for k in ('loc', 'scale') if k in cv}
+    from .priors import PriorDist
+    prior = PriorDist(name).get_prior(**params)
+    hs = module.hidden_structure
+    dims = (n_features,) + hs
+    shape_tree = {'fcn': {f'layer{i}': {'kernel': np.zeros((dims[i], dims[i + 1]), np.float32),
+                                          'bias': np.zeros(dims[i + 1], np.float32)} for i in range(len(hs))}}
+    task = owner.task
+    pm = ProbabilisticModel(module, shape_tree, prior, task, n_batches=getattr(owner, 'n_batches', 1))
+    try:
+        _ADOPTED[owner] = (n_features, pm)
+    except TypeError:
+        pass
+    return pm
+
+
 def unwrap_posterior(fn):
     """Recognise `partial(prob_model.log_unnormalized_posterior, x=train_x, y=train_y)`
-    (src/training/trainer.py:576-580) and return (prob_model, x, y).  Anything else cannot be routed to the
-    fused CUDA kernel and is rejected loudly (there is no tracing / CPU fallback)."""
+    (src/training/trainer.py:576-580) and return (prob_model, x, y).  `prob_model` is this package's ProbabilisticModel, or
+    the reference's own one (recognised by its attributes and described through `adopt_reference_model`).  Anything else
+    cannot be routed to the fused CUDA kernel and is rejected loudly (there is no tracing / CPU fallback)."""
     if isinstance(fn, functools.partial):
         target = fn.func
         owner = getattr(target, '__self__', None)
-        if isinstance(owner, ProbabilisticModel) and getattr(target, '__name__', '') in (
-                'log_unnormalized_posterior', 'log_unnormalized_posterior_partition'):
-            kw = fn.keywords or {}
-            if 'x' in kw and 'y' in kw:
+        kw = fn.keywords or {}
+        if getattr(target, '__name__', '') in ('log_unnormalized_posterior', 'log_unnormalized_posterior_partition') \
+                and 'x' in kw and 'y' in kw:
+            if isinstance(owner, ProbabilisticModel):
                 return owner, kw['x'], kw['y']
+            if owner is not None and all(hasattr(owner, a) for a in ('module', 'prior', 'task', 'n_batches')):
+                return adopt_reference_model(owner, kw['x']), kw['x'], kw['y']
     raise TypeError('mile_b200 samplers need `functools.partial(prob_model.log_unnormalized_posterior, x=..., y=...)` '
-                    'of a mile_b200.probabilistic.ProbabilisticModel: arbitrary Python log-densities cannot run on '
-                    'the CUDA path and there is no CPU fallback')
+                    'of a ProbabilisticModel (this package\'s or the reference\'s): arbitrary Python log-densities cannot '
+                    'run on the CUDA path and there is no CPU fallback')

@@ -156,3 +156,68 @@ def test_synthetic_workloads_are_seeded_and_shaped():
         assert spec.n_features == F and tuple(spec.widths) == tuple(widths)
         th = syn.synthetic_theta0(spec.n_params, 3)
         assert th.shape == (3, spec.n_params) and not np.array_equal(th[0], th[1])
+
+
+def test_unwrap_posterior_adopts_the_reference_models_own_closure():
+    """The reference's trainer builds `partial(self.prob_model.log_unnormalized_posterior, x=..., y=...)` from ITS
+    ProbabilisticModel (trainer.py:576-580; probabilistic.py:17-47: attributes task, module, n_params, n_batches, prior;
+    module.config = FCNConfig(hidden_structure, activation enum, use_bias), src/config/models/fcn.py:8-30; prior =
+    NamedTuple(f_init, log_prior, name) whose log_prior closes over loc / scale, priors.py:60-128).  jax/flax are not
+    installable here, so stand-ins with exactly that attribute structure are adopted."""
+    import enum
+    from typing import Callable, NamedTuple
+    from mile_b200.probabilistic import ProbabilisticModel, unwrap_posterior
+
+    class Activation(str, enum.Enum):
+        RELU = 'relu'
+        TANH = 'tanh'
+
+    class PriorDist(str, enum.Enum):
+        NORMAL = 'Normal'
+        StandardNormal = 'StandardNormal'
+        LAPLACE = 'Laplace'
+
+    class Task(str, enum.Enum):
+        REGRESSION = 'regr'
+        CLASSIFICATION = 'class'
+
+    class RefPrior(NamedTuple):
+        f_init: Callable
+        log_prior: Callable
+        name: str
+
+    def log_prior_laplace(loc=0.0, scale=1.0):
+        def log_prior(params):
+            return loc + scale        # (the real one calls jax; only its closure matters here)
+        return log_prior
+
+    class FCNConfig:
+        def __init__(self, hs, act):
+            self.hidden_structure, self.activation, self.use_bias = hs, act, True
+
+    class RefFCN:
+        def __init__(self, config):
+            self.config = config
+
+    class RefProbabilisticModel:
+        def __init__(self, module, prior, task, n_batches=1):
+            self.task, self.module, self.n_params, self.n_batches, self.prior = task, module, 0, n_batches, prior
+
+        def log_unnormalized_posterior(self, position, x, y, **kwargs):
+            raise AssertionError('the JAX log-density must never be called by the CUDA path')
+
+    ref = RefProbabilisticModel(RefFCN(FCNConfig([16, 16, 2], Activation.TANH)),
+                                RefPrior(None, log_prior_laplace(loc=0.25, scale=1.5), PriorDist.LAPLACE), Task.REGRESSION)
+    X, y = np.zeros((7, 5), np.float32), np.zeros(7, np.float32)
+    pm, x2, y2 = unwrap_posterior(functools.partial(ref.log_unnormalized_posterior, x=X, y=y))
+    assert isinstance(pm, ProbabilisticModel) and x2 is X and y2 is y
+    spec = pm.spec
+    assert (spec.n_features, spec.widths, spec.activation, spec.task) == (5, (16, 16, 2), 'tanh', 'regr')
+    assert (spec.prior, spec.prior_loc, spec.prior_scale, spec.n_batches) == ('laplace', 0.25, 1.5, 1.0)
+    assert pm.n_params == 5 * 16 + 16 + 16 * 16 + 16 + 16 * 2 + 2
+    # adopted once per model object
+    assert unwrap_posterior(functools.partial(ref.log_unnormalized_posterior, x=X, y=y))[0] is pm
+    std = RefProbabilisticModel(RefFCN(FCNConfig([8, 3], Activation.RELU)),
+                                RefPrior(None, log_prior_laplace(), PriorDist.StandardNormal), Task.CLASSIFICATION)
+    s2 = unwrap_posterior(functools.partial(std.log_unnormalized_posterior, x=X, y=y))[0].spec
+    assert (s2.prior, s2.prior_loc, s2.prior_scale, s2.task, s2.widths) == ('normal', 0.0, 1.0, 'class', (8, 3))
