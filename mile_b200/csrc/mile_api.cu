@@ -1962,7 +1962,7 @@ int mile_nuts_init(mile_ctx* c, const float* theta0_dev, const mile_nuts_cfg* cf
   if (!c || !cfg) return fail("null ctx / cfg");
   if (!c->X) return fail("mile_set_data has not been called");
   if (c->wide) return fail("NUTS is not available on the wide path");
-  if (c->pmask_on || c->sdc_on) return fail("NUTS with a frozen-parameter mask or an MCLMC preconditioner is not supported");
+  if (c->sdc_on) return fail("NUTS with an MCLMC preconditioner (sqrt_diag_cov) set is not supported: clear it first");
   if (cfg->max_num_doublings < 1 || cfg->max_num_doublings > 12) return fail("max_num_doublings must be in [1, 12]");
   if (!(cfg->initial_step_size > 0.f)) return fail("initial_step_size must be positive");
   CK(cudaSetDevice(c->device));
@@ -2001,7 +2001,7 @@ static int nuts_launch(mile_ctx* c, int n_steps, long step_base, const unsigned 
   KParams& k = pl.kp;
   k.mode = MODE_NUTS; k.n_steps = n_steps; k.step_base = step_base; k.thin = thin; k.sample_base = sample_base;
   k.n_slots = n_slots; k.z = z_dev; k.seed = seed; k.samples = samples_dev; k.do_lppd = lppd;
-  k.sdc = nullptr; k.pmask = nullptr;
+  k.sdc = nullptr;
   NutsParams& q = k.nuts;
   q.scratch = c->nuts_scratch; q.imm = c->nuts_imm; q.w_mean = c->nuts_mean; q.w_m2 = c->nuts_m2; q.da = c->nuts_da;
   q.schedule = schedule_dev; q.uni = uni_dev; q.info = info_dev;

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
   c.xbuf = P.resident ? smem + P.off_x : c.xstream;
   c.aux = smem + P.off_aux;
   const int d = M.d, ch = c.chain, tid = threadIdx.x, D = Q.max_doublings;
+  c.pmask = P.pmask; c.deff = P.d_eff;   // partition sampling: frozen parameters keep their value (zero momentum and gradient)
   float* imm = c.avgx; float* ssum = c.avgx2; float* psum = c.ub; float* sp_th = c.thb; float* sp_g = c.gb;
   // this CTA's global scratch: (10 + 2 D) vectors of dS floats
   float* S = Q.scratch + (size_t)blockIdx.x * (size_t)(10 + 2 * D) * P.dS;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
     float v1[1] = {0.f};
     for (int i = tid; i < d; i += NT) {
       const float zz = zrow ? zrow[i] : philox_normal(P.seed, (uint32_t)(P.chain_base + ch), (uint64_t)tstep, 16u, (uint32_t)i);
-      const float p = zz / sqrtf(imm[i]);
+      const float p = pm_at(c, i) * zz / sqrtf(imm[i]);
       c.uu[i] = p; psum[i] = p;
       const float th = c.th[i], g = c.gg[i];
       L_th[i] = th; L_p[i] = p; L_g[i] = g; R_th[i] = th; R_p[i] = p; R_g[i] = g; P_th[i] = th; P_g[i] = g;

@@ -40,8 +40,6 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     if config.name not in (Sampler.MCLMC, Sampler.NUTS):
         raise NotImplementedError(f'{config.name} does not have a warmup implemented.')
     nuts = config.name == Sampler.NUTS
-    if nuts and _frozen is not None:
-        raise NotImplementedError('partition sampling with NUTS is not implemented on the CUDA path')
     saving_path = Path(saving_path)
     model, x, y = unwrap_posterior(unnorm_log_posterior)
     spec = model.spec

@@ -253,3 +253,68 @@ def test_nuts_seams_kernel_registry_and_inference_loop(tmp_path):
     assert abs(info['lppd'] - wl) <= 1e-4 * abs(wl)
     # the sampler moved and fits: the posterior-mean prediction beats the initial one
     assert np.isfinite(wl) and len({flat[0, s].tobytes() for s in range(60)}) > 20
+
+
+@pytest.mark.parametrize('name,widths', [('airfoil_3x16', None), ('airfoil_2x16', (16, 16, 16, 16, 16, 2))])
+def test_partition_nuts_matches_reduced_oracle(name, widths, tmp_path):
+    """NUTS with the frozen-parameter mask (experiments/replicate_uci/partition_NUTS.yaml: partition_sampling + sampler nuts;
+    src/training/partition_sampling.py:70-81,226-270): the transitions equal the oracle's on the REDUCED vector (sampled
+    parameters only; reduced log-density = prior of the sampled layers + likelihood of the merged network, trainer.py:651-659),
+    the frozen parameters keep their values bit for bit."""
+    from mile_b200 import Ensemble, FCNSpec
+    from tests.test_gpu_partition import reduced_logpost
+    ospec = o.make_spec(name)
+    if widths is not None:      # a deeper net runs on the generic evaluator (the shipped partition config has 9 layers)
+        ospec = o.ModelSpec(ospec.n_features, widths, 'relu', 'regr')
+    X, y, _, _ = o.synthetic_data(name, n_train=300)
+    C, T = 2, 5
+    spec = FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task)
+    frozen = spec.hidden_layer_mask()
+    active = np.flatnonzero(~frozen)
+    d = ospec.n_params
+    rng = np.random.default_rng(31)
+    th0 = o.synthetic_theta0(ospec, C)
+    imm = np.exp(0.5 * rng.standard_normal((C, d))).astype(np.float32)
+    eps = np.array([2e-3, 6e-3], np.float32)
+    z = rng.standard_normal((T, C, d)).astype(np.float32)
+    uni = rng.random((T, C, no.uni_len(D))).astype(np.float32)
+    ens = Ensemble(spec, C)
+    ens.set_data(X, y)
+    ens.set_frozen_mask(frozen)
+    ens.nuts_init(th0, max_num_doublings=D)
+    ens.set_nuts_params(eps, imm)
+    th_i, _, lp_i, g_i = ens.get_state()
+    pos, info = ens.nuts_sample(T, z=z, uni=uni, info=True)
+    th_g, _, lp_g, g_g = ens.get_state()
+    for c in range(C):
+        f64 = reduced_logpost(ospec, X, y, th0[c].astype(np.float64), active)
+        lp, g = f64(th0[c, active].astype(np.float64))
+        assert abs(lp_i[c] - lp) <= 1e-5 * abs(lp) and np.all(g_i[c, frozen] == 0)
+        assert np.linalg.norm(g_i[c, active] - g) <= 1e-5 * np.linalg.norm(g)
+        th = th0[c, active].astype(np.float64)
+        for k in range(T):
+            th, lp, g, wi = no.nuts_step(f64, th, lp, g, eps[c], imm[c, active].astype(np.float64), z[k, c, active], uni[k, c], D)
+            assert (int(info[k, c, 0]), int(info[k, c, 2]), bool(info[k, c, 3]), bool(info[k, c, 5])) == \
+                (wi.num_integration_steps, wi.num_trajectory_expansions, wi.is_divergent, wi.is_turning), (k, c, wi)
+            assert np.linalg.norm(pos[k, c, active] - th) <= 5e-5 * np.linalg.norm(th), (k, c)
+            np.testing.assert_array_equal(pos[k, c, frozen], th0[c, frozen])
+        assert abs(lp_g[c] - lp) <= 5e-5 * abs(lp)
+        assert np.all(g_g[c, frozen] == 0)
+    ens.close()
+    # the reference-facing seam: partition_inference_loop with sampler name 'nuts'
+    if widths is None:
+        from mile_b200 import FCN, PriorDist, ProbabilisticModel, SamplerConfig, partition_inference_loop
+        from mile_b200.utils import load_samples_from_dir
+        module = FCN(ospec.widths, ospec.activation)
+        pm = ProbabilisticModel(module, module.init(np.random.default_rng(0), ospec.n_features), PriorDist.StandardNormal.get_prior(), 'regr')
+        ps = [module.init(rng, ospec.n_features, scale=0.5) for _ in range(C)]
+        posb = {'fcn': {k: {kk: np.stack([p['fcn'][k][kk] for p in ps]) for kk in v} for k, v in ps[0]['fcn'].items()}}
+        cfg = SamplerConfig.from_dict({'name': 'nuts', 'warmup_steps': 40, 'n_chains': C, 'n_samples': 20, 'n_thinning': 1,
+                                       'partition_sampling': True})
+        log_post = functools.partial(pm.log_unnormalized_posterior_partition, x=X, y=y)
+        partition_inference_loop(log_post, cfg, 5, posb, np.arange(C), tmp_path / 'exp' / 'samples')
+        s = load_samples_from_dir(tmp_path / 'exp' / 'samples')
+        assert s['fcn']['layer1']['kernel'].shape == (C, 20, 16, 16)
+        for c in range(C):      # hidden layers frozen at their initial values, outer layers moved
+            np.testing.assert_array_equal(s['fcn']['layer1']['kernel'][c, -1], posb['fcn']['layer1']['kernel'][c])
+            assert np.any(s['fcn']['layer0']['kernel'][c, -1] != posb['fcn']['layer0']['kernel'][c])
