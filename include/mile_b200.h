@@ -259,6 +259,22 @@ int mile_shard_mclmc_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, i
 int mile_shard_mclmc_tune(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const mile_tune_cfg* cfg,
                           const float* z_dev, uint64_t seed, float* tune_info_dev, void* stream);
 
+/* ---- a12: phase 3 of the warmup on the device: src/training/warmup.py:408-465 (`make_adaptation_L`): n_steps sampling
+ * steps with every position kept in HBM, then blackjax.diagnostics.effective_sample_size of every (chain, parameter)
+ * series (one chain per series, as the reference calls it: `flat_samples[None, ...]`), by hand-written kernels: a tiled
+ * transpose to series-major order and one CTA per series (lazy direct autocovariance in shared memory + Geyer's initial
+ * positive / monotone sequence).  param_idx [n_params_sel] / sample_idx [n_samples_sel] (host, or NULL = all) are the
+ * reference's subsampling rules (> 2000 parameters: random subset; > 10000 samples: linspace).  ess_host [C, n_sel].
+ * The caller finishes with L = 0.4 * step_size * mean(n_steps / ess) (warmup.py:461-463). */
+int mile_mclmc_phase3_ess(mile_ctx* ctx, int32_t n_steps, const float* step_size_host, const float* L_host, uint64_t seed,
+                          const int32_t* param_idx, int32_t n_params_sel, const int32_t* sample_idx,
+                          int32_t n_samples_sel, float* ess_host);
+/* the same estimator on positions the caller holds: pos [n, C, d] on the device / on the host */
+int mile_ess_positions(mile_ctx* ctx, const float* pos_dev, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                       const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host, void* stream);
+int mile_ess_positions_host(mile_ctx* ctx, const float* pos, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                            const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host);
+
 /* ---- NUTS branch of the sampling seam: src/training/sampling.py:70-81,107-210 (sampler = blackjax.nuts) and
  * src/training/warmup.py:27-152 (`custom_window_adaptation`), called from `warmup_nuts` (sampling.py:220-262).  One
  * persistent kernel per call runs whole transitions (momentum draw, trajectory doubling with the iterative U-turn

@@ -6,6 +6,7 @@
 #include "mile_wide.cuh"
 #include "mile_train.cuh"
 #include "mile_nuts.cuh"
+#include "mile_ess.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -2105,6 +2106,86 @@ int mile_nuts_set_params_host(mile_ctx* c, const float* step_size, const float* 
   if (step_size) CK(cudaMemcpy2D(c->nuts_da + 6, 32, step_size, 4, 4, c->C, cudaMemcpyHostToDevice));
   if (inverse_mass_matrix) CK(cudaMemcpy(c->nuts_imm, inverse_mass_matrix, (size_t)c->C * c->d * 4, cudaMemcpyHostToDevice));
   return 0;
+}
+
+// ---- phase 3 of the warmup on the device (warmup.py:408-465): capture + effective sample size -----------------------
+static int ess_run(mile_ctx* c, const float* pos_dev, int n_total, const int32_t* param_idx, int n_sel, const int32_t* sample_idx,
+                   int n_samples_sel, float* ess_host, cudaStream_t st) {
+  const int d_sel = param_idx ? n_sel : c->d;
+  const int n = sample_idx ? n_samples_sel : n_total;
+  if (n < 4) return fail("effective sample size needs at least 4 samples");
+  if (d_sel < 1) return fail("no parameters selected");
+  const long n_series = (long)c->C * d_sel;
+  int* pidx_d = nullptr; int* sidx_d = nullptr;
+  if (param_idx) {
+    pidx_d = (int*)scratch(c, 10, (size_t)d_sel * 4);
+    if (!pidx_d) return fail("cudaMalloc failed (ess)");
+    for (int j = 0; j < d_sel; ++j) if (param_idx[j] < 0 || param_idx[j] >= c->d) return fail("parameter index out of range");
+    CK(cudaMemcpyAsync(pidx_d, param_idx, (size_t)d_sel * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (sample_idx) {
+    sidx_d = (int*)scratch(c, 11, (size_t)n * 4);
+    if (!sidx_d) return fail("cudaMalloc failed (ess)");
+    for (int i = 0; i < n; ++i) if (sample_idx[i] < 0 || sample_idx[i] >= n_total) return fail("sample index out of range");
+    CK(cudaMemcpyAsync(sidx_d, sample_idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  float* series = (float*)scratch(c, 12, (size_t)n_series * n * 4);
+  float* ess_d = (float*)scratch(c, 13, (size_t)n_series * 4);
+  if (!series || !ess_d) return fail("cudaMalloc failed (ess)");
+  EssParams E;
+  E.pos = pos_dev; E.series = series; E.pidx = pidx_d; E.sidx = sidx_d; E.ess = ess_d; E.n = n; E.C = c->C; E.d = c->d; E.d_sel = d_sel;
+  const size_t smem = ((size_t)n + (size_t)(n - (n & 1))) * 4;
+  if (smem > kSmemLimit) return fail("series too long for the on-device effective sample size (more than ~29000 samples): thin them first");
+  CK(cudaFuncSetAttribute(ess_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  dim3 tg((unsigned)((n_series + 31) / 32), (unsigned)((n + 31) / 32), 1);
+  if (tg.y > 65535) return fail("too many samples for the transpose grid");
+  ess_transpose_kernel<<<tg, dim3(32, 8, 1), 0, st>>>(E);
+  CK(cudaGetLastError());
+  ess_series_kernel<<<(unsigned)n_series, ESS_THREADS, smem, st>>>(E);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  CK(cudaMemcpyAsync(ess_host, ess_d, (size_t)n_series * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mile_ess_positions(mile_ctx* c, const float* pos_dev, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                       const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host, void* stream) {
+  if (!c || !pos_dev || !ess_host) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  return ess_run(c, pos_dev, n, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, (cudaStream_t)stream);
+}
+
+int mile_ess_positions_host(mile_ctx* c, const float* pos, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                            const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host) {
+  if (!c || !pos || !ess_host) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * c->C * c->d * 4;
+  float* pd = (float*)scratch(c, 14, bytes);
+  if (!pd) return fail("cudaMalloc failed (ess positions)");
+  CK(cudaMemcpyAsync(pd, pos, bytes, cudaMemcpyHostToDevice, c->own_stream));
+  return ess_run(c, pd, n, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, c->own_stream);
+}
+
+int mile_mclmc_phase3_ess(mile_ctx* c, int32_t n_steps, const float* step_size_host, const float* L_host, uint64_t seed,
+                          const int32_t* param_idx, int32_t n_params_sel, const int32_t* sample_idx, int32_t n_samples_sel,
+                          float* ess_host) {
+  if (!c || !step_size_host || !L_host || !ess_host) return fail("null argument");
+  if (n_steps < 4) return fail("phase 3 needs at least 4 steps");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->own_stream;
+  const size_t Cb = (size_t)c->C * 4;
+  float* e = (float*)scratch(c, 5, Cb); float* l = (float*)scratch(c, 6, Cb);
+  float* pos = (float*)scratch(c, 14, (size_t)n_steps * c->C * c->d * 4);
+  if (!e || !l || !pos) return fail("cudaMalloc failed (phase 3 positions)");
+  CK(cudaMemcpyAsync(e, step_size_host, Cb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(l, L_host, Cb, cudaMemcpyHostToDevice, st));
+  const int chunk = 10000;
+  for (int done = 0; done < n_steps; done += chunk) {     // HOT LOOP B: every position captured in HBM
+    const int n = n_steps - done < chunk ? n_steps - done : chunk;
+    if (mile_mclmc_sample(c, n, done, 1, 0, e, l, nullptr, seed, pos, n_steps, nullptr, 0, st)) return -1;
+  }
+  return ess_run(c, pos, n_steps, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, st);
 }
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }

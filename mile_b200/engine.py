@@ -292,6 +292,36 @@ class Ensemble:
         l = None if L is None else _f32(np.broadcast_to(L, (C_,)))
         capi.check(self.lib.mile_set_tuning_host(self.h, capi.host_ptr(e), capi.host_ptr(l)))
 
+    # ---- phase 3 of the warmup: capture + effective sample size on the device (warmup.py:408-465) --------
+    @staticmethod
+    def _idx(a):
+        return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+    def phase3_ess(self, n_steps, step_size, L, *, seed=0, param_idx=None, sample_idx=None):
+        """n_steps sampling steps from the current state with every position kept on the device, then the effective sample
+        size of every (chain, selected parameter) series -> [C, n_selected]."""
+        C_ = self.n_chains
+        eps = _f32(np.broadcast_to(step_size, (C_,)))
+        Ls = _f32(np.broadcast_to(L, (C_,)))
+        pi, si = self._idx(param_idx), self._idx(sample_idx)
+        out = np.empty((C_, self.d if pi is None else pi.size), np.float32)
+        capi.check(self.lib.mile_mclmc_phase3_ess(self.h, int(n_steps), capi.host_ptr(eps), capi.host_ptr(Ls), seed,
+                                                  capi.host_ptr(pi), 0 if pi is None else pi.size,
+                                                  capi.host_ptr(si), 0 if si is None else si.size, capi.host_ptr(out)))
+        return out
+
+    def ess_positions(self, positions, *, param_idx=None, sample_idx=None):
+        """The same estimator on host positions [n, C, d] (blackjax.diagnostics.effective_sample_size with one chain per
+        series) -> [C, n_selected]."""
+        pos = _f32(positions)
+        assert pos.ndim == 3 and pos.shape[1:] == (self.n_chains, self.d)
+        pi, si = self._idx(param_idx), self._idx(sample_idx)
+        out = np.empty((self.n_chains, self.d if pi is None else pi.size), np.float32)
+        capi.check(self.lib.mile_ess_positions_host(self.h, capi.host_ptr(pos), pos.shape[0], capi.host_ptr(pi),
+                                                    0 if pi is None else pi.size, capi.host_ptr(si),
+                                                    0 if si is None else si.size, capi.host_ptr(out)))
+        return out
+
     # ---- NUTS branch (sampling.py:70-81,107-210; warmup.py:27-152) ------------------------------
     NUTS_INFO_FIELDS = ('num_integration_steps', 'acceptance_rate', 'num_trajectory_expansions', 'is_divergent', 'energy',
                         'is_turning', 'logdensity', 'step_size')

@@ -58,8 +58,10 @@ class ProbabilisticModel:
     # ---- engine management ---------------------------------------------------------------------
     def make_ensemble(self, n_chains: int, x, y, device: int | None = None, **options) -> Ensemble:
         if device is None:
-            import torch
-            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            # torch's current device when torch is in use by the caller; a plain run never imports torch (seconds of start-up)
+            import sys
+            torch = sys.modules.get('torch')
+            device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
         ens = Ensemble(self.spec, n_chains, device=device, **options)
         ens.set_data(np.asarray(x, np.float32), np.asarray(y))
         if self._test is not None:

@@ -99,10 +99,12 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
             if store is not None:
                 store.append(samples, kept)
             done += n
+        logger.debug('sampling launches done')
         if writer is not None:
             writer.close()
         if store is not None:
             store.close()
+        logger.debug('sample files closed')
         if nuts:                                                             # sampling.py:200-210: [n_devices, n_samples] each
             ni = np.concatenate(nuts_info, axis=0).transpose(1, 0, 2)
             info.update({'num_integration_steps': ni[..., 0].astype(np.int32), 'acceptance_rate': ni[..., 1],

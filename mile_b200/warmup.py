@@ -1,7 +1,8 @@
 """MCLMC warmup (mirror of src/training/warmup.py:155-568: custom_mclmc_warmup, mclmc_find_L_and_step_size,
 make_L_step_size_adaptation, make_adaptation_L, handle_nans).  Phases 1+2 (HOT LOOP A) run inside the
 persistent CUDA kernel (mile_mclmc_tune); phase 3 (HOT LOOP B) is the sampling kernel capturing every
-position into an HBM buffer, followed by one FFT-based ESS (diagnostics.effective_sample_size)."""
+position into an HBM buffer, followed by the effective sample size of every series on the device (csrc/mile_ess.cuh;
+`phase3_L` keeps the torch.fft form for callers that hold the positions themselves)."""
 from __future__ import annotations
 
 import logging
@@ -23,10 +24,9 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
                desired_energy_var_end, trust_in_estimate, num_effective_samples, step_size_init,
                fft_params_limit: int = 2000, fft_samples_limit: int = 10000, diagonal_preconditioning: bool = False,
                active=None):
-    """custom_mclmc_warmup(...).run for all chains of `ens` at once.  Returns (step_size [C], L [C]); with
+    """custom_mclmc_warmup(...).run for all chains of `ens` at once (no torch on this path).  Returns (step_size [C], L [C]); with
     `diagonal_preconditioning` the preconditioner stays set on `ens` (read it with `ens.get_sqrt_diag_cov()`, clear it
     with `ens.set_sqrt_diag_cov(None)` -- the reference's sampling phase does not use it, sampling.py:291)."""
-    import torch
     seed = key_to_seed(rng_key)
     tune1, tune2, tune3 = (int(num_steps * r) for r in PHASE_RATIO)        # warmup.py:555-557
     # blackjax.mcmc.mclmc.init with the SAME key as the tuning (warmup.py:539-541,552)
@@ -40,6 +40,7 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
         n = min(CHUNK, tune1 + tune2 - done)
         ens.tune(n, done, cfg, seed=part1_key)
         done += n
+    logger.debug('warmup phases 1+2 done (%d steps)', tune1 + tune2)
     if tune2 != 0:
         ens.tune_finish_phase2()                                           # L = sqrt(sum var), warmup.py:387-390
         if diagonal_preconditioning:                                       # warmup.py:391-401
@@ -56,24 +57,20 @@ def run_warmup(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, de
                 ens.tune(steps, 0, cfg, seed=final_key)
     eps, L, _ = ens.get_tuning()
     if tune3 != 0:                                                         # HOT LOOP B, warmup.py:408-465
-        dev = torch.device(f'cuda:{ens.device}')
-        C, d = ens.n_chains, ens.d
-        pos = torch.empty((tune3, C, d), dtype=torch.float32, device=dev)
-        eps_d, L_d = torch.from_numpy(eps).to(dev), torch.from_numpy(L).to(dev)
-        with torch.cuda.device(dev):
-            done = 0
-            while done < tune3:
-                n = min(CHUNK, tune3 - done)
-                ens.sample_device(n, eps_d, L_d, step_base=done, n_thinning=1, sample_base=0, seed=part2_key,
-                                  samples_dev=pos, n_slots=tune3)
-                done += n
-            torch.cuda.synchronize(dev)
-            if active is not None:     # partition sampling: the ESS is taken over the sampled parameters only
-                pos = pos[:, :, torch.as_tensor(np.asarray(active), device=dev)]
-            L = phase3_L(pos, eps, seed=part2_key, fft_params_limit=fft_params_limit,
-                         fft_samples_limit=fft_samples_limit)
+        # every position stays in HBM; the effective sample size of every (chain, parameter) series is computed there
+        # (csrc/mile_ess.cuh) with the reference's subsampling rules (warmup.py:442-456)
+        sel = np.arange(ens.d, dtype=np.int32) if active is None else np.asarray(active, dtype=np.int32)
+        pidx = None if active is None else sel
+        if sel.size > fft_params_limit:
+            rng = np.random.default_rng(int(part2_key) & ((1 << 63) - 1))
+            pidx = np.sort(rng.permutation(sel)[:fft_params_limit]).astype(np.int32)
+        sidx = None
+        if tune3 > fft_samples_limit:
+            sidx = np.linspace(0, tune3 - 1, fft_samples_limit).astype(np.int32)
+        ess = ens.phase3_ess(tune3, eps, L, seed=part2_key, param_idx=pidx, sample_idx=sidx)     # [C, n_selected]
+        logger.debug('warmup phase 3 done (%d steps, ESS of %d series)', tune3, ess.size)
+        L = (LFACTOR * eps.astype(np.float64) * np.mean(float(tune3) / ess.astype(np.float64), axis=1)).astype(np.float32)
         ens.set_tuning(L=L)
-        del pos
     return eps.astype(np.float32), L.astype(np.float32)
 
 

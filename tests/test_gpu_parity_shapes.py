@@ -341,3 +341,57 @@ def test_wide_path_predict_and_lppd_match_oracle():
     want = o.lppd(o.pointwise_lppd(ospec, lv, yt.astype(np.float64)))
     assert abs(lppd_from_state(m, sst, C * 2) - want) <= 1e-5 * abs(want)
     ens.close()
+
+
+def test_device_ess_kernel_matches_oracle():
+    """csrc/mile_ess.cuh (transpose + one CTA per series: lazy direct autocovariance, Geyer initial positive / monotone
+    sequence) against the oracle's restatement of blackjax.diagnostics.effective_sample_size (FFT autocovariance, fp64),
+    one chain per series as warmup.py:457 calls it; with and without the reference's parameter / sample subsampling."""
+    from mile_b200 import Ensemble, FCNSpec
+    spec = FCNSpec(3, (4, 2), 'identity', 'regr')
+    C, d = 2, spec.n_params
+    ens = Ensemble(spec, C)
+    rng = np.random.default_rng(12)
+    for n in (601, 1200):
+        phi = np.concatenate([np.linspace(-0.6, 0.995, d - 1), [0.0]])
+        x = np.zeros((n, C, d))
+        e = rng.standard_normal((n, C, d))
+        for t in range(1, n):
+            x[t] = phi * x[t - 1] + e[t]
+        x = (x + 3.0 * rng.standard_normal((1, C, d))).astype(np.float32)
+        ess = ens.ess_positions(x)
+        assert ess.shape == (C, d)
+        for c in range(C):
+            want = o.effective_sample_size(x[:, c].astype(np.float64)[None])
+            assert np.all(np.abs(ess[c] - want) <= 2e-4 * want), (n, c, np.max(np.abs(ess[c] / want - 1)))
+        pidx = np.array([7, 0, 25, 3], np.int32)
+        sidx = np.linspace(0, n - 1, 400).astype(np.int32)
+        sub = ens.ess_positions(x, param_idx=pidx, sample_idx=sidx)
+        assert sub.shape == (C, 4)
+        for c in range(C):
+            want = o.effective_sample_size(x[sidx][:, c][:, pidx].astype(np.float64)[None])
+            assert np.all(np.abs(sub[c] - want) <= 2e-4 * want)
+    ens.close()
+
+
+def test_phase3_on_device_equals_oracle_L_on_the_same_positions():
+    """mile_mclmc_phase3_ess (capture in HBM + ESS kernels, no host copy of the positions) gives the L the oracle derives from
+    the very same positions (re-sampled from the same state with the same Philox key): warmup.py:408-465."""
+    name, C, n3 = 'airfoil_2x16', 3, 600
+    ospec, ens, X, y, _, _ = make(name, C)
+    th0 = o.synthetic_theta0(ospec, C)
+    ens.init(th0, seed=5)
+    ens.sample(200, 0.02, 8.0, seed=1, keep=False)
+    state = ens.get_state()
+    eps = np.asarray([0.02, 0.03, 0.015], np.float32)
+    Ls = np.asarray([8.0, 6.0, 9.0], np.float32)
+    ess = ens.phase3_ess(n3, eps, Ls, seed=9)
+    after = ens.get_state()
+    ens.set_state(*state)
+    pos, _ = ens.sample(n3, eps, Ls, n_thinning=1, seed=9)
+    np.testing.assert_array_equal(ens.get_state()[0], after[0])          # phase 3 advanced the chains by the same steps
+    for c in range(C):
+        want = o.adaptation_L(np.float64(eps[c]), pos[:, c].astype(np.float64))
+        got = 0.4 * eps[c] * np.mean(n3 / ess[c].astype(np.float64))
+        assert abs(got - want) <= 1e-3 * want, (c, got, want)
+    ens.close()

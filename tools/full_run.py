@@ -2,11 +2,12 @@
 of experiments/illustrative_example_readme/mclmc.yaml (12 chains, 50 000 warmup steps, 10 000 samples, thinning 10) on
 the synthetic airfoil problem, including the phase-3 ESS and the sample files.
 Usage: python tools/full_run.py [npz|store]"""
-import functools, os, sys, tempfile, time
+import functools, logging, os, sys, tempfile, time
 from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 fmt = sys.argv[1] if len(sys.argv) > 1 else 'npz'
+logging.basicConfig(level=logging.DEBUG, format='%(relativeCreated)8.0f ms %(name)s %(message)s')
 os.environ['MILE_SAMPLE_FORMAT'] = fmt
 from mile_b200 import FCN, PriorDist, ProbabilisticModel, inference_loop   # noqa: E402
 from mile_b200.config import SamplerConfig                                  # noqa: E402
