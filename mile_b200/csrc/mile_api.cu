@@ -2135,8 +2135,9 @@ static int ess_run(mile_ctx* c, const float* pos_dev, int n_total, const int32_t
   EssParams E;
   E.pos = pos_dev; E.series = series; E.pidx = pidx_d; E.sidx = sidx_d; E.ess = ess_d; E.n = n; E.C = c->C; E.d = c->d; E.d_sel = d_sel;
   const size_t smem = ((size_t)n + (size_t)(n - (n & 1))) * 4;
-  if (smem > kSmemLimit) return fail("series too long for the on-device effective sample size (more than ~29000 samples): thin them first");
-  CK(cudaFuncSetAttribute(ess_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  const size_t smem_max = kSmemLimit - 1024;   // (the kernel also holds a few static words)
+  if (smem > smem_max) return fail("series too long for the on-device effective sample size (more than ~28000 samples): thin them first");
+  CK(cudaFuncSetAttribute(ess_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   dim3 tg((unsigned)((n_series + 31) / 32), (unsigned)((n + 31) / 32), 1);
   if (tg.y > 65535) return fail("too many samples for the transpose grid");
   ess_transpose_kernel<<<tg, dim3(32, 8, 1), 0, st>>>(E);
