@@ -107,7 +107,9 @@ class SampleWriter:
     def submit(self, samples: np.ndarray, sample_indices):
         """samples [S, C, d]; sample_indices: the step index n of each kept position."""
         block = np.ascontiguousarray(np.transpose(samples, (1, 0, 2)), dtype=np.float32)        # [C, S, d]
-        paths = [str(self.base / f'{cid}/sample_{int(n)}.npz').encode() for cid in self.step_ids for n in sample_indices]
+        b = str(self.base)            # (plain string formatting: pathlib joins cost ~10 us each, 12 000 of them per run)
+        idx = [int(n) for n in sample_indices]
+        paths = [f'{b}/{cid}/sample_{n}.npz'.encode() for cid in self.step_ids for n in idx]
         self.futures.append(self.pool.submit(self._write_block, block, paths))
 
     def _write_block(self, block, paths):
