@@ -336,7 +336,8 @@ class Ensemble:
         capi.check(self.lib.mile_nuts_init_host(self.h, capi.host_ptr(theta0), C.byref(cfg)))
 
     def nuts_uni_len(self) -> int:
-        return 2 * self._nuts_D + 2 ** self._nuts_D
+        D = getattr(self, '_nuts_D', 10)
+        return 2 * D + 2 ** D
 
     def _nuts_run(self, n_steps, step_base, schedule, n_thinning, z, uni, seed, keep, info, lppd):
         C_, d = self.n_chains, self.d

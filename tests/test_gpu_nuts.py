@@ -318,3 +318,45 @@ def test_partition_nuts_matches_reduced_oracle(name, widths, tmp_path):
         for c in range(C):      # hidden layers frozen at their initial values, outer layers moved
             np.testing.assert_array_equal(s['fcn']['layer1']['kernel'][c, -1], posb['fcn']['layer1']['kernel'][c])
             assert np.any(s['fcn']['layer0']['kernel'][c, -1] != posb['fcn']['layer0']['kernel'][c])
+
+
+def test_nuts_and_mclmc_agree_on_the_posterior_predictive():
+    """Two samplers, one posterior: from the same warmed-up states, NUTS (window adaptation + sampling, in-kernel Philox) and
+    MCLMC (tuned step size / L) must give the same test-set LPPD and RMSE within the chain-to-chain spread (stated
+    tolerances: |dLPPD| <= 3 SE + 0.03, |dRMSE| <= 0.05) -- the 'matching LPPD' of the north star, between the two kernels."""
+    from mile_b200 import Ensemble, FCNSpec
+    from mile_b200.nuts import build_schedule
+    name, C = 'airfoil_2x16', 8
+    ospec = o.make_spec(name)
+    X, y, Xt, yt = o.synthetic_data(name, n_train=400, n_test=200)
+    fs = FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task)
+
+    def metrics(samples):      # [S, C, d]
+        S = samples.shape[0]
+        lv = np.stack([[o.forward(ospec, samples[s, c].astype(np.float64), Xt.astype(np.float64)) for s in range(S)]
+                       for c in range(C)])
+        pw = o.pointwise_lppd(ospec, lv, yt.astype(np.float64))
+        per_chain = np.array([o.lppd(pw[c:c + 1]) for c in range(C)])
+        return o.lppd(pw), per_chain, np.sqrt(np.mean((lv[..., 0].mean(axis=(0, 1)) - yt) ** 2))
+
+    ens = Ensemble(fs, C)
+    ens.set_data(X, y)
+    ens.init(o.synthetic_theta0(ospec, C), seed=1)
+    ens.tune_reset(0.01)
+    ens.tune(1800, 0, ens.tune_cfg(1600, 200, 0.5, 0.1, 1.5, 100), seed=2)
+    ens.tune_finish_phase2()
+    eps, L, _ = ens.get_tuning()
+    ens.sample(1500, eps, L, seed=3, keep=False)               # burn-in shared by both samplers
+    start = ens.get_state()
+    m_samples, _ = ens.sample(3000, eps, L, n_thinning=10, seed=4)
+    ens.nuts_init(start[0], max_num_doublings=7, initial_step_size=float(np.mean(eps)))
+    ens.nuts_warmup(150, build_schedule(150), seed=5)
+    ens.nuts_finish_warmup()
+    n_samples, info = ens.nuts_sample(300, seed=6, info=True)
+    ens.close()
+    assert np.mean(info[..., 3]) < 0.2                          # few divergent transitions
+    ml, mpc, mrmse = metrics(m_samples)
+    nl, npc, nrmse = metrics(n_samples)
+    se = np.sqrt(mpc.var(ddof=1) / C + npc.var(ddof=1) / C)
+    assert abs(ml - nl) <= 3 * se + 0.03, (ml, nl, se)
+    assert abs(mrmse - nrmse) <= 0.05, (mrmse, nrmse)
