@@ -395,3 +395,33 @@ def test_phase3_on_device_equals_oracle_L_on_the_same_positions():
         got = 0.4 * eps[c] * np.mean(n3 / ess[c].astype(np.float64))
         assert abs(got - want) <= 1e-3 * want, (c, got, want)
     ens.close()
+
+
+def test_wide_path_full_warmup_with_device_phase3():
+    """custom_mclmc_warmup on a model of the HBM-resident wide path (2 x 256, d = 69 890 > the 2000-parameter limit of
+    warmup.py:442-449): phases 1+2 in the tuning loop, phase 3 captured in HBM with the ESS kernels on a random subset of
+    2000 parameters; the L it returns is the oracle's L on the very same positions and parameter subset."""
+    from mile_b200 import Ensemble, FCNSpec
+    from mile_b200.warmup import run_warmup
+    F, N, C = 12, 700, 2
+    widths = (256, 256, 2)
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((N, F)).astype(np.float32); y = rng.standard_normal(N).astype(np.float32)
+    spec = FCNSpec(F, widths, 'relu', 'regr')
+    ens = Ensemble(spec, C)
+    ens.set_data(X, y)
+    assert ens.get_option('wide') == 1
+    th0 = (rng.standard_normal((C, spec.n_params)) * 0.04).astype(np.float32)
+    eps, L = run_warmup(ens, th0, 7, 400, desired_energy_var_start=0.5, desired_energy_var_end=0.1, trust_in_estimate=1.5,
+                        num_effective_samples=100, step_size_init=0.005)
+    assert eps.shape == L.shape == (C,) and np.all(np.isfinite(eps)) and np.all(eps > 0) and np.all(np.isfinite(L)) and np.all(L > 0)
+    # the ESS table of a fresh phase 3 against the oracle on the same positions / subset
+    state = ens.get_state()
+    pidx = np.sort(rng.permutation(spec.n_params)[:50]).astype(np.int32)
+    ess = ens.phase3_ess(40, eps, L, seed=3, param_idx=pidx)
+    ens.set_state(*state)
+    pos, _ = ens.sample(40, eps, L, n_thinning=1, seed=3)
+    for c in range(C):
+        want = o.effective_sample_size(pos[:, c][:, pidx].astype(np.float64)[None])
+        assert np.all(np.abs(ess[c] - want) <= 1e-3 * want), (c, np.max(np.abs(ess[c] / want - 1)))
+    ens.close()
