@@ -27,6 +27,7 @@ struct NutsParams {
   float* info;                    // [n_steps][C][8] or null
   int uni_len, max_doublings;
   float divergence_threshold, target_accept;
+  int smem_off;                   // float offset of the scratch inside dynamic shared memory, or -1 (global scratch)
 };
 
 struct KParams {

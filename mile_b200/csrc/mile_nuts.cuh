@@ -14,7 +14,7 @@
 //                                      avgx           inverse mass matrix (diagonal)
 //                                      avgx2, ub      momentum sums of the sub-trajectory / of the whole trajectory
 //                                      thb, gb        proposal of the sub-trajectory (position, gradient)
-//                       global (L2)    left / right end states, the transition's proposal, the U-turn checkpoints
+//                       shared memory when it fits, else global (L2):  left / right end states, the transition's proposal, the U-turn checkpoints
 //                                      [2][D][d], the Welford moments: element i is always touched by the same thread, so
 //                                      these need no barriers.
 #pragma once
@@ -37,6 +37,82 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t chain, u
                 (uint32_t)(seed >> 32) + chain, r);
   const uint32_t w = (idx & 2u) ? ((idx & 1u) ? r[3] : r[2]) : ((idx & 1u) ? r[1] : r[0]);
   return (float)(w >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+}
+
+// The gradient exchange of one leapfrog fused with everything that follows it element by element: sum of the G partials in rank
+// order + prior (as cluster_reduce_grad, mile_kernel.cuh), second half of the momentum update p += h g, kinetic energy,
+// momentum sum of the sub-trajectory, the checkpoint of an even leaf or the innermost U-turn check of an odd one -- one sweep
+// over d and ONE block reduction per leapfrog.  Returns the log-density; out = {p . M^-1 p, U-turn dots (left, right)}.
+template <int NT>
+__device__ __forceinline__ float nuts_reduce_half_step(Ctx& c, float* gpart, const float2* gslab, unsigned int flag, const bool use_ll,
+                                                       const float h, const float* imm, float* ssum, float* cp, float* cs,
+                                                       const bool first, const bool even, float (&out)[3]) {
+  const KParams& P = c.P;
+  const DevModel& M = P.M;
+  cg::cluster_group cluster = cg::this_cluster();
+  const float* rp[16];
+  const int stride_g = P.dS + 4;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) rp[r] = (!use_ll && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
+  float ll = 0.f;
+  if (!use_ll) {
+    float t[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ll += t[r];
+  }
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const float loc = M.prior_loc, sc = M.prior_scale, s2 = sc * sc;
+  const float lognorm = M.prior == MILE_PRIOR_NORMAL ? logf(6.283185307179586f * s2) : logf(2.f * sc);
+  auto consume = [&](int i, float s) {
+    const float dlt = c.th[i] - loc;
+    float pg, pv;
+    if (M.prior == MILE_PRIOR_NORMAL) { pv = (lognorm + dlt * dlt / s2) / -2.f; pg = -dlt / s2; }
+    else { pv = -lognorm - fabsf(dlt) / sc; pg = -((dlt > 0.f) - (dlt < 0.f)) / sc; }
+    const float mk = pm_at(c, i);
+    const float g = (s + pg * P.prior_weight) * mk;
+    c.gg[i] = g;
+    v[0] += pv * P.prior_weight * mk;
+    const float p = c.uu[i] + h * g;
+    c.uu[i] = p;
+    const float im = imm[i];
+    v[1] += im * p * p;
+    const float sm = first ? p : ssum[i] + p;
+    ssum[i] = sm;
+    if (even) { cp[i] = p; cs[i] = sm; }
+    else {
+      const float pl = cp[i];
+      const float rho = (sm - cs[i] + pl) - (p + pl) / 2.f;
+      v[2] += im * pl * rho; v[3] += im * p * rho;
+    }
+  };
+  if (use_ll) {
+    for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
+      const int i2 = i + NT;
+      if (i2 < M.d) {
+        float s0, s1;
+        ll_sum_pair(gslab + i, gslab + i2, stride_g, c.G, flag, s0, s1);
+        consume(i, s0); consume(i2, s1);
+      } else {
+        consume(i, ll_sum(gslab + i, stride_g, c.G, flag));
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < M.d; i += NT) {
+      float t[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][i] : 0.f;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += t[r];
+      consume(i, s);
+    }
+  }
+  if (use_ll && threadIdx.x == NT - 1) v[0] += ll_sum(gslab + P.dS, stride_g, c.G, flag);
+  block_sum<4, NT, 0>(v, c.red, c.phase);
+  out[0] = v[1]; out[1] = v[2]; out[2] = v[3];
+  return v[0] + ll;
 }
 
 template <class GE>
@@ -62,7 +138,8 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
   c.pmask = P.pmask; c.deff = P.d_eff;   // partition sampling: frozen parameters keep their value (zero momentum and gradient)
   float* imm = c.avgx; float* ssum = c.avgx2; float* psum = c.ub; float* sp_th = c.thb; float* sp_g = c.gb;
   // this CTA's global scratch: (10 + 2 D) vectors of dS floats
-  float* S = Q.scratch + (size_t)blockIdx.x * (size_t)(10 + 2 * D) * P.dS;
+  // (in shared memory behind the plan's carve-up when it fits -- the narrow MLPs -- else in this CTA's slice of the L2-resident scratch)
+  float* S = Q.smem_off >= 0 ? smem + Q.smem_off : Q.scratch + (size_t)blockIdx.x * (size_t)(10 + 2 * D) * P.dS;
   float *L_th = S, *L_p = S + P.dS, *L_g = S + 2 * P.dS, *R_th = S + 3 * P.dS, *R_p = S + 4 * P.dS, *R_g = S + 5 * P.dS;
   float *P_th = S + 6 * P.dS, *P_g = S + 7 * P.dS, *w_mean = S + 8 * P.dS, *w_m2 = S + 9 * P.dS;
   float* ck_p = S + 10 * (size_t)P.dS; float* ck_s = ck_p + (size_t)D * P.dS;
@@ -162,33 +239,14 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
         } else {
           __syncthreads();
         }
-        float g2, ug, nf;
-        lp = cluster_reduce_grad<NT, 0>(c, gp, gslab, xflag, g2, ug, nf, use_ll, c.G);
-        ++e;
-        // second half of the momentum update fused with everything that does not depend on the acceptance draw: kinetic
-        // energy, momentum sum of the sub-trajectory, the checkpoint of an even leaf, and -- on an odd leaf -- the first
-        // (innermost) U-turn check, so that one block reduction serves all of them
-        // (termination.iterative_uturn_numpyro: checkpoint on even leaves, check the open sub-trees on odd ones)
+        // termination.iterative_uturn_numpyro: checkpoint on even leaves, check the open sub-trees on odd ones
         const int idx_max = __popc(k >> 1);
         const int idx_min = idx_max - (__ffs(~k) - 1) + 1;
         const bool even = (k & 1) == 0;
         float* cp = ck_p + (size_t)idx_max * P.dS; float* cs = ck_s + (size_t)idx_max * P.dS;
-        float v[3] = {0.f, 0.f, 0.f};
-        for (int i = tid; i < d; i += NT) {
-          const float p = c.uu[i] + h * c.gg[i];
-          c.uu[i] = p;
-          const float im = imm[i];
-          v[0] += im * p * p;
-          const float sm = k == 0 ? p : ssum[i] + p;
-          ssum[i] = sm;
-          if (even) { cp[i] = p; cs[i] = sm; }
-          else {
-            const float pl = cp[i];
-            const float rho = (sm - cs[i] + pl) - (p + pl) / 2.f;
-            v[1] += im * pl * rho; v[2] += im * p * rho;
-          }
-        }
-        block_sum<3, NT, 0>(v, c.red, c.phase);
+        float v[3];
+        lp = nuts_reduce_half_step<NT>(c, gp, gslab, xflag, use_ll, h, imm, ssum, cp, cs, k == 0, even, v);
+        ++e;
         // proposal.update: weight = initial energy - new energy (NaN -> -inf), divergence beyond the threshold
         const float new_e = -lp + 0.5f * v[0];
         float delta = e0 - new_e;
