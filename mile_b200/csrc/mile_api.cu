@@ -92,7 +92,7 @@ struct mile_ctx {
   long w_part_per_chain = 0;
   // NUTS branch (mile_nuts.cuh): inverse mass matrix / Welford moments [C,d], dual-averaging state [C,8], per-CTA scratch
   float *nuts_imm = nullptr, *nuts_mean = nullptr, *nuts_m2 = nullptr, *nuts_da = nullptr, *nuts_scratch = nullptr;
-  size_t nuts_scratch_floats = 0; int opt_nuts_smem = 1, nuts_max_doublings = 10; float nuts_div = 1000.f, nuts_target = 0.8f;
+  size_t nuts_scratch_floats = 0; int opt_nuts_smem = 1, opt_nuts_push = 1, nuts_max_doublings = 10; float nuts_div = 1000.f, nuts_target = 0.8f;
   float* pmask = nullptr; int pmask_on = 0, d_eff = 0;   // partition sampling: 1 = sampled / 0 = frozen per parameter
   float* sdc = nullptr; int sdc_on = 0;      // diagonal preconditioner [C][d] (warmup.py:391-393); used when sdc_on
   int integ_cluster = 8;      // cluster size of the large-d integrator kernel (16 = non-portable size: measured slower, 69 vs 55 us)
@@ -597,6 +597,7 @@ int mile_set_option(mile_ctx* c, const char* key, int64_t v) {
   else if (!strcmp(key, "resident")) c->opt_resident = (int)v;
   else if (!strcmp(key, "fast")) c->opt_fast = (int)v;
   else if (!strcmp(key, "nuts_smem")) c->opt_nuts_smem = (int)v;
+  else if (!strcmp(key, "nuts_push")) c->opt_nuts_push = (int)v;
   else if (!strcmp(key, "tensor")) c->opt_tensor = (int)v;
   else if (!strcmp(key, "sync_mode")) c->opt_sync = (int)v;
   else if (!strcmp(key, "chain_base")) c->opt_chain_base = (int)v;
@@ -2010,7 +2011,7 @@ static int nuts_launch(mile_ctx* c, int n_steps, long step_base, const unsigned 
   q.uni_len = 2 * D + (1 << D); q.max_doublings = D; q.divergence_threshold = c->nuts_div; q.target_accept = c->nuts_target;
   // end states, proposal, checkpoints and Welford moments in shared memory when they fit behind the plan (1 CTA per SM either way)
   const size_t extra = (size_t)(10 + 2 * D) * pl.kp.dS * 4;
-  q.smem_off = -1;
+  q.smem_off = -1; q.push = c->opt_nuts_push;
   if (c->opt_nuts_smem && pl.smem + extra <= kSmemLimit) { q.smem_off = (int)(pl.smem / 4); pl.smem += extra; }
   return launch(c, pl, c->C, st);
 }

@@ -28,6 +28,7 @@ struct NutsParams {
   int uni_len, max_doublings;
   float divergence_threshold, target_accept;
   int smem_off;                   // float offset of the scratch inside dynamic shared memory, or -1 (global scratch)
+  int push;                       // 1 = DSMEM push exchange where the plan has its buffers (tensor-evaluator plans)
 };
 
 struct KParams {

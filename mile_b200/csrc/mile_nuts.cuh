@@ -46,7 +46,9 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t chain, u
 template <int NT>
 __device__ __forceinline__ float nuts_reduce_half_step(Ctx& c, float* gpart, const float2* gslab, unsigned int flag, const bool use_ll,
                                                        const float h, const float* imm, float* ssum, float* cp, float* cs,
-                                                       const bool first, const bool even, float (&out)[3]) {
+                                                       const bool first, const bool even, float (&out)[3],
+                                                       const float* gfull = nullptr) {
+  // gfull != null: the push exchange (mile_mma.cuh) has already delivered the rank-ordered sums [0, dS] to this CTA
   const KParams& P = c.P;
   const DevModel& M = P.M;
   cg::cluster_group cluster = cg::this_cluster();
@@ -55,7 +57,9 @@ __device__ __forceinline__ float nuts_reduce_half_step(Ctx& c, float* gpart, con
 #pragma unroll
   for (int r = 0; r < 16; ++r) rp[r] = (!use_ll && c.G > 1 && r < c.G) ? cluster.map_shared_rank(gpart, r) : gpart;
   float ll = 0.f;
-  if (!use_ll) {
+  if (gfull) {
+    ll = gfull[P.dS];
+  } else if (!use_ll) {
     float t[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) t[r] = r < c.G ? rp[r][P.dS] : 0.f;
@@ -87,7 +91,9 @@ __device__ __forceinline__ float nuts_reduce_half_step(Ctx& c, float* gpart, con
       v[2] += im * pl * rho; v[3] += im * p * rho;
     }
   };
-  if (use_ll) {
+  if (gfull) {
+    for (int i = threadIdx.x; i < M.d; i += NT) consume(i, gfull[i]);
+  } else if (use_ll) {
     for (int i = threadIdx.x; i < M.d; i += 2 * NT) {
       const int i2 = i + NT;
       if (i2 < M.d) {
@@ -166,6 +172,21 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
     for (long i = tid; i < np4; i += NT) d4[i] = i < nv4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  // DSMEM push exchange of the tensor evaluator's plans (mile_mma.cuh: reduce-scatter + all-gather with st.async + mbarrier
+  // transaction counts, no cluster.sync): recv[G][SL] + gfull[dS + 4] in the plan's gslice area, two mbarriers behind the
+  // reduction scratch.  Other plans keep the pull form (cluster.sync + remote loads) or the flagged words through L2.
+  const bool push = c.G > 1 && !P.sync_mode && P.off_gs > 0 && Q.push;
+  float* recv = smem + P.off_gs;
+  float* gfull = recv + (P.dS + 16);
+  const uint32_t xb1 = (uint32_t)__cvta_generic_to_shared(c.red + 160), xb2 = xb1 + 8;
+  if (push) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xb1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xb2));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();      // every CTA's barriers exist before the first remote store
+  }
   float lp = P.lp[ch];
   // adaptation state (window_adaptation.base): dual averaging + Welford count + the step size in use
   float* da = Q.da + (long)ch * 8;
@@ -234,6 +255,34 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
           __syncthreads();
           for (int i = tid; i <= P.dS; i += NT) ll_store(mine + i, gp[i], xflag);
           gslab = slab;
+        } else if (push) {
+          // hop 1: element i of this CTA's partial -> the owner's recv[rank][i - owner * SL]; the owner adds the G partials in
+          // rank order; hop 2: each sum -> every CTA's gfull[i].  (Buffer reuse across evaluations: argument in mile_mma.cuh.)
+          const int dS = P.dS;
+          const int SL = (dS + 1 + c.G - 1) / c.G;
+          const int my0 = c.rank * SL;
+          const int mySL = my0 > dS ? 0 : (my0 + SL > dS + 1 ? dS + 1 - my0 : SL);
+          const uint32_t par = e & 1u;
+          __syncthreads();                     // this CTA's partial is complete
+          if (tid == 0) { xbar_arm(xb1, (uint32_t)(c.G * mySL * 4)); xbar_arm(xb2, (uint32_t)((dS + 1) * 4)); }
+          const uint32_t recv_s = (uint32_t)__cvta_generic_to_shared(recv), gfull_s = (uint32_t)__cvta_generic_to_shared(gfull);
+          for (int i = tid; i <= dS; i += NT) {
+            const int owner = i / SL, off = i - owner * SL;
+            st_async_f32(mapa_u32(recv_s + (uint32_t)(c.rank * SL + off) * 4u, (uint32_t)owner), gp[i], mapa_u32(xb1, (uint32_t)owner));
+          }
+          xbar_wait(xb1, par);
+          for (int j = tid; j < mySL; j += NT) {
+            float tv[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) tv[r] = r < c.G ? recv[r * SL + j] : 0.f;
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) sum += tv[r];
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              if (r < c.G) st_async_f32(mapa_u32(gfull_s + (uint32_t)(my0 + j) * 4u, (uint32_t)r), sum, mapa_u32(xb2, (uint32_t)r));
+          }
+          xbar_wait(xb2, par);
         } else if (c.G > 1) {
           cluster.sync();
         } else {
@@ -245,7 +294,7 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
         const bool even = (k & 1) == 0;
         float* cp = ck_p + (size_t)idx_max * P.dS; float* cs = ck_s + (size_t)idx_max * P.dS;
         float v[3];
-        lp = nuts_reduce_half_step<NT>(c, gp, gslab, xflag, use_ll, h, imm, ssum, cp, cs, k == 0, even, v);
+        lp = nuts_reduce_half_step<NT>(c, gp, gslab, xflag, use_ll, h, imm, ssum, cp, cs, k == 0, even, v, push ? gfull : nullptr);
         ++e;
         // proposal.update: weight = initial energy - new energy (NaN -> -inf), divergence beyond the threshold
         const float new_e = -lp + 0.5f * v[0];

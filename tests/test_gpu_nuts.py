@@ -117,9 +117,11 @@ def test_multi_transition_launch_equals_single_launches():
     ospec, X, y, _, _, lg = problem()
     th, lp, g, eps, imm, z, uni = transition_cases(ospec, lg, C, T, seed=1, burn=25)
     outs = []
-    for chunks, opts in (([T], {}), ([1] * T, {}), ([4, 2], {}), ([T], {'nuts_smem': 0}), ([T], {'cluster_size': 12})):
-        # (nuts_smem 0: end states / checkpoints in the L2-resident scratch instead of shared memory; 12 CTAs per chain: the
-        #  flagged-word exchange -- a different summation tree of the partial gradients, so only the first four are compared bit for bit)
+    for chunks, opts in (([T], {}), ([1] * T, {}), ([4, 2], {}), ([T], {'nuts_smem': 0}), ([T], {'nuts_push': 0}),
+                         ([T], {'cluster_size': 12})):
+        # (nuts_smem 0: end states / checkpoints in the L2-resident scratch instead of shared memory; nuts_push 0: pull form of the
+        #  cluster exchange; 12 CTAs per chain: the flagged-word exchange with a different row split, so only the first five are
+        #  compared bit for bit)
         ens = Ensemble(FCNSpec(ospec.n_features, ospec.widths, ospec.activation, ospec.task), C, **opts)
         ens.set_data(X, y)
         ens.nuts_init(th.astype(np.float32), max_num_doublings=D)
@@ -131,11 +133,11 @@ def test_multi_transition_launch_equals_single_launches():
         outs.append((np.concatenate(pos), np.concatenate(infos), ens.get_state()[0]))
         ens.close()
     assert outs[0][0].shape == (T // 2, C, ospec.n_params)
-    for other in outs[1:4]:
+    for other in outs[1:5]:
         for a, b in zip(outs[0], other):
             np.testing.assert_array_equal(a, b)
-    np.testing.assert_array_equal(outs[4][1][..., [0, 2, 3, 5]], outs[0][1][..., [0, 2, 3, 5]])      # same trees
-    assert np.linalg.norm(outs[4][0] - outs[0][0]) <= 1e-4 * np.linalg.norm(outs[0][0])
+    np.testing.assert_array_equal(outs[5][1][..., [0, 2, 3, 5]], outs[0][1][..., [0, 2, 3, 5]])      # same trees
+    assert np.linalg.norm(outs[5][0] - outs[0][0]) <= 1e-4 * np.linalg.norm(outs[0][0])
 
 
 def test_window_adaptation_matches_oracle():
