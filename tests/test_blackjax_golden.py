@@ -127,3 +127,78 @@ def test_cuda_path_matches_blackjax():
         assert abs(lp[0] - G['step_logdensity'][s]) <= 1e-5 * scale
         assert abs(info[0, 0, 2] - G['step_info'][s, 2]) <= 1e-5 * scale
     ens.close()
+
+
+# ---- NUTS branch (present when the dump holds the nuts_* / wa_* arrays) -------------------------------------------------
+def _has_nuts():
+    return PATH.exists() and 'nuts_position' in np.load(PATH).files
+
+
+@pytest.mark.skipif(not _has_nuts(), reason='the golden file has no NUTS block')
+def test_nuts_oracle_matches_blackjax_transitions():
+    """oracle/nuts_oracle.py (fp64 and fp32) replays the dumped blackjax.nuts transitions with the replayed draws: first the
+    replay itself is judged (tree sizes / expansions / flags must agree: they depend on the direction and acceptance draws),
+    then the arithmetic (position, log-density, gradient, acceptance rate, energy)."""
+    from oracle import nuts_oracle as no
+    G, spec = _load()
+    D, eps = int(G['nuts_max_doublings']), float(G['nuts_step_size'])
+    for dt, tol in ((np.float64, 2e-5), (np.float32, 5e-5)):
+        X, y = G['X'].astype(dt), G['y'].astype(dt)
+        f = lambda t: o.logpost_value_and_grad(spec, t, X, y)
+        th = G['theta0'].astype(dt)
+        lp, g = f(th)
+        assert abs(lp - G['nuts_init_logdensity']) <= 1e-5 * abs(G['nuts_init_logdensity'])
+        assert rel(g, G['nuts_init_grad']) <= 1e-5
+        for k in range(G['nuts_position'].shape[0]):
+            th, lp, g, info = no.nuts_step(f, th, dt(lp), g, eps, G['nuts_imm'].astype(dt), G['nuts_z'][k], G['nuts_uni'][k], D)
+            want = G['nuts_info'][k]
+            assert (info.num_integration_steps, info.num_trajectory_expansions, info.is_divergent, info.is_turning) == \
+                (int(want[0]), int(want[2]), bool(want[3]), bool(want[5])), \
+                f'transition {k}: the replayed draws (or the tree logic) do not reproduce blackjax {G["blackjax_version"]}: {info} vs {want}'
+            assert rel(th, G['nuts_position'][k]) <= tol, (k, dt)
+            assert abs(lp - G['nuts_logdensity'][k]) <= tol * abs(G['nuts_logdensity'][k])
+            assert rel(g, G['nuts_grad'][k]) <= 10 * tol
+            assert abs(info.acceptance_rate - want[1]) <= 1e-4 and abs(info.energy - want[4]) <= tol * abs(want[4]) + 1e-3
+            # continue from blackjax's own state so that one flipped branch cannot cascade
+            th, lp, g = G['nuts_position'][k].astype(dt), dt(G['nuts_logdensity'][k]), G['nuts_grad'][k].astype(dt)
+
+
+@pytest.mark.skipif(not _has_nuts(), reason='the golden file has no NUTS block')
+def test_window_adaptation_matches_blackjax():
+    from oracle import nuts_oracle as no
+    from mile_b200.nuts import build_schedule
+    G, _ = _load()
+    want = [(int(a), bool(b)) for a, b in G['wa_schedule_1000']]
+    assert no.build_schedule(1000) == want and build_schedule(1000) == want
+    sched = no.build_schedule(60)
+    st = no.adapt_init(6, 0.1, np.float64)
+    for i in range(60):
+        st = no.adapt_step(st, sched[i], G['wa_positions'][i].astype(np.float64), float(G['wa_acceptance'][i]))
+        assert abs(st.step_size - G['wa_trace'][i, 0]) <= 1e-4 * G['wa_trace'][i, 0], i
+        np.testing.assert_allclose(st.imm, G['wa_trace'][i, 1:], rtol=1e-4, atol=1e-7)
+    e, m = no.adapt_final(st)
+    assert abs(e - G['wa_final_step_size']) <= 1e-4 * G['wa_final_step_size']
+    np.testing.assert_allclose(m, G['wa_final_imm'], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _has_nuts(), reason='the golden file has no NUTS block')
+def test_cuda_nuts_matches_blackjax_transitions():
+    from mile_b200 import Ensemble, FCNSpec
+    G, spec = _load()
+    D = int(G['nuts_max_doublings'])
+    ens = Ensemble(FCNSpec(spec.n_features, spec.widths, spec.activation, spec.task), 1)
+    ens.set_data(G['X'], G['y'])
+    ens.nuts_init(G['theta0'][None], max_num_doublings=D)
+    ens.set_nuts_params(float(G['nuts_step_size']), G['nuts_imm'][None])
+    for k in range(G['nuts_position'].shape[0]):
+        pos, info = ens.nuts_sample(1, step_base=k, z=G['nuts_z'][k][None, None], uni=G['nuts_uni'][k][None, None], info=True)
+        want = G['nuts_info'][k]
+        assert (int(info[0, 0, 0]), int(info[0, 0, 2]), bool(info[0, 0, 3]), bool(info[0, 0, 5])) == \
+            (int(want[0]), int(want[2]), bool(want[3]), bool(want[5])), (k, info[0, 0], want)
+        assert rel(pos[0, 0], G['nuts_position'][k]) <= 5e-5
+        th, _, lp, g = ens.get_state()
+        assert abs(lp[0] - G['nuts_logdensity'][k]) <= 5e-5 * abs(G['nuts_logdensity'][k])
+        assert abs(info[0, 0, 1] - want[1]) <= 1e-3
+        ens.set_state(theta=G['nuts_position'][k][None], lp=G['nuts_logdensity'][k:k + 1], grad=G['nuts_grad'][k][None])
+    ens.close()

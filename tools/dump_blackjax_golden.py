@@ -22,7 +22,15 @@ What is dumped (all float32, the reference's dtype; flat vectors in jax.flatten_
     FCN (src/training/probabilistic.py:115-138, src/models/tabular/fcn.py:11-28), and one
     `custom_mclmc_warmup(...).run(key, position, 200)` (src/training/warmup.py:486-568) with every normal draw it
     consumed; without it a pure-jax restatement of the log-density is used and the warmup block is skipped;
-  * `blackjax.diagnostics.effective_sample_size` on a fixed [1, 500, 7] array.
+  * `blackjax.diagnostics.effective_sample_size` on a fixed [1, 500, 7] array;
+  * the NUTS branch: `blackjax.mcmc.nuts.init` + four `nuts.build_kernel()` transitions (max_num_doublings 5, a fixed
+    diagonal inverse mass matrix) with their NUTSInfo, and the random draws of every transition REPLAYED from its key in the
+    layout of oracle/nuts_oracle.py (momentum normals; direction / merge / per-leapfrog uniforms): `jax.random.bernoulli(key,
+    p)` is `uniform(key) < p`, and blackjax 1.2.2 derives the keys as split(rng_key, 2) -> (momentum, integrator);
+    fold_in(integrator, expansion) -> split 3 -> (direction, trajectory, proposal); fold_in(trajectory, leaf).  If the
+    installed blackjax derives them differently, tests/test_blackjax_golden.py reports the mismatch of the replay itself
+    (tree sizes) before any arithmetic is judged.  Plus one `window_adaptation.base` trace (init / update / final over a
+    fixed sequence of positions and acceptance rates) and `build_schedule(1000)`.
 """
 from __future__ import annotations
 
@@ -181,6 +189,55 @@ def main():
         x[0, i] = rho * x[0, i - 1] + np.sqrt(1 - rho ** 2) * rng.standard_normal(7).astype(np.float32)
     out['ess_x'] = x
     out['ess'] = np.asarray(effective_sample_size(jnp.asarray(x)), np.float32)
+
+    # ---- NUTS branch (sampling.py:70-81,107-210; warmup.py:27-152) ----------------------------------------------
+    try:
+        from blackjax.mcmc import nuts as bj_nuts
+        from blackjax.adaptation.window_adaptation import base as wa_base, build_schedule
+        D = 5
+        imm = np.exp(0.3 * np.random.default_rng(9).standard_normal(d)).astype(np.float32)
+        n_eps = np.float32(2e-3)
+        nkernel = bj_nuts.build_kernel()
+        nstate = bj_nuts.init(position, logdensity_fn)
+        out['nuts_init_logdensity'] = np.float32(nstate.logdensity)
+        out['nuts_init_grad'] = flat(nstate.logdensity_grad)
+        n_len = 2 * D + 2 ** D
+        uniform = lambda k: np.float32(jax.random.uniform(k, (), jnp.float32))
+        zs, unis, npos, nlp, ngrad, ninfo = [], [], [], [], [], []
+        for k in jax.random.split(jax.random.PRNGKey(11), 4):
+            nstate, inf = nkernel(k, nstate, logdensity_fn, n_eps, jnp.asarray(imm), max_num_doublings=D)
+            km, ki = jax.random.split(k, 2)                                   # nuts.py kernel
+            zs.append(np.asarray(jax.random.normal(km, (d,), jnp.float32)))   # util.generate_gaussian_noise over the raveled position
+            u = np.zeros(n_len, np.float32)
+            for j in range(D):                                                # trajectory.dynamic_multiplicative_expansion
+                dk, tk, pk = jax.random.split(jax.random.fold_in(ki, j), 3)
+                u[j], u[D + j] = uniform(dk), uniform(pk)
+                for i in range(2 ** j):                                       # trajectory.dynamic_progressive_integration
+                    u[2 * D + 2 ** j - 1 + i] = uniform(jax.random.fold_in(tk, i))
+            unis.append(u)
+            npos.append(flat(nstate.position)); nlp.append(np.float32(nstate.logdensity)); ngrad.append(flat(nstate.logdensity_grad))
+            ninfo.append([np.float32(inf.num_integration_steps), np.float32(inf.acceptance_rate),
+                          np.float32(inf.num_trajectory_expansions), np.float32(inf.is_divergent), np.float32(inf.energy),
+                          np.float32(inf.is_turning)])
+        out.update(nuts_max_doublings=np.asarray(D), nuts_step_size=n_eps, nuts_imm=imm, nuts_z=np.stack(zs),
+                   nuts_uni=np.stack(unis), nuts_position=np.stack(npos), nuts_logdensity=np.asarray(nlp),
+                   nuts_grad=np.stack(ngrad), nuts_info=np.asarray(ninfo, np.float32))
+        # window adaptation arithmetic on a fixed input sequence (no sampler involved)
+        a_init, a_update, a_final = wa_base(True, target_acceptance_rate=0.8)
+        sched = build_schedule(60)
+        rng = np.random.default_rng(13)
+        xs = rng.standard_normal((60, 6)).astype(np.float32) * np.linspace(0.5, 2.0, 6).astype(np.float32)
+        accs = rng.uniform(0.3, 1.0, 60).astype(np.float32)
+        ast = a_init(jnp.zeros(6, jnp.float32), 0.1)
+        trace = []
+        for i in range(60):
+            ast = a_update(ast, (sched[i][0], sched[i][1]), jnp.asarray(xs[i]), accs[i])
+            trace.append(np.concatenate([[np.float32(ast.step_size)], np.asarray(ast.inverse_mass_matrix, np.float32)]))
+        fe, fm = a_final(ast)
+        out.update(wa_positions=xs, wa_acceptance=accs, wa_trace=np.stack(trace), wa_final_step_size=np.float32(fe),
+                   wa_final_imm=np.asarray(fm, np.float32), wa_schedule_1000=np.asarray(build_schedule(1000)).astype(np.int32))
+    except Exception as e:   # noqa: BLE001
+        print(f'[dump] NUTS block not dumped: {e!r}')
 
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(args.out, **out)
