@@ -7,7 +7,7 @@ nuts.custom_window_adaptation, probabilistic.ProbabilisticModel, ...).  There is
 """
 from .engine import Ensemble, FCNSpec, ShardedEnsemble, lppd_from_state  # noqa: F401
 from .config import PriorConfig, Sampler, SamplerConfig  # noqa: F401
-from .kernels import KERNELS, mclmc, nuts  # noqa: F401
+from .kernels import KERNELS, mclmc  # noqa: F401   (KERNELS['nuts']: the name `nuts` is the submodule mile_b200.nuts)
 from .models import FCN  # noqa: F401
 from .priors import Prior, PriorDist  # noqa: F401
 from .probabilistic import ProbabilisticModel  # noqa: F401
@@ -17,6 +17,6 @@ from .warmup import custom_mclmc_warmup  # noqa: F401
 from .partition_sampling import partition_inference_loop, partition_params  # noqa: F401
 from .evaluation import evaluate_bde, predict_bde  # noqa: F401
 
-__all__ = ['Ensemble', 'FCNSpec', 'ShardedEnsemble', 'lppd_from_state', 'PriorConfig', 'Sampler', 'SamplerConfig', 'KERNELS', 'mclmc', 'nuts',
+__all__ = ['Ensemble', 'FCNSpec', 'ShardedEnsemble', 'lppd_from_state', 'PriorConfig', 'Sampler', 'SamplerConfig', 'KERNELS', 'mclmc',
            'FCN', 'Prior', 'PriorDist', 'ProbabilisticModel', 'inference_loop', 'warmup_mclmc', 'warmup_nuts', 'custom_mclmc_warmup', 'custom_window_adaptation',
            'evaluate_bde', 'predict_bde', 'partition_inference_loop', 'partition_params']
