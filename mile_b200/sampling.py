@@ -55,6 +55,8 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     try:
         logger.info('> Starting Warmup sampling...')
         if nuts:                                                             # sampling.py:70-81 (no warmup_params.txt)
+            if saving_path_warmup is not None:
+                logger.warning('saving_path_warmup is ignored: the warm-up positions of the NUTS branch are not written on the CUDA path')
             warmup_nuts(None, config, warmup_key, init_params, step_ids, unnorm_log_posterior, n_devices, _ensemble=ens)
             eps = L = None
             saving_path.mkdir(parents=True, exist_ok=True)
