@@ -501,6 +501,13 @@ static void* scratch(mile_ctx* c, int slot, size_t bytes) {
   return s.first;
 }
 
+// give a large staging buffer back (the captured positions of phase 3 can be tens of GB for a wide model)
+static void scratch_release(mile_ctx* c, int slot, size_t keep_below) {
+  if ((int)c->scratch.size() <= slot) return;
+  auto& s = c->scratch[slot];
+  if (s.first && s.second > keep_below) { cudaFree(s.first); s.first = nullptr; s.second = 0; }
+}
+
 template <int NLMAX>
 static int launch_train(const TrainParams& T, int n_chains, size_t smem, cudaStream_t st) {
   CK(cudaFuncSetAttribute(mile_train_kernel<NLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -2192,7 +2199,10 @@ int mile_mclmc_phase3_ess(mile_ctx* c, int32_t n_steps, const float* step_size_h
     const int n = n_steps - done < chunk ? n_steps - done : chunk;
     if (mile_mclmc_sample(c, n, done, 1, 0, e, l, nullptr, seed, pos, n_steps, nullptr, 0, st)) return -1;
   }
-  return ess_run(c, pos, n_steps, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, st);
+  const int rc = ess_run(c, pos, n_steps, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, st);
+  scratch_release(c, 14, (size_t)256 << 20);     // positions and series-major copy: kept only when small
+  scratch_release(c, 12, (size_t)256 << 20);
+  return rc;
 }
 
 int64_t mile_launch_count(const mile_ctx* c) { return c ? c->launches : -1; }
