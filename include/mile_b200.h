@@ -287,14 +287,17 @@ int mile_ess_positions_host(mile_ctx* ctx, const float* pos, int32_t n, const in
  * (the NUTSInfo fields sampling.py:200-210 keeps), logdensity, step size used. */
 int mile_nuts_init(mile_ctx* ctx, const float* theta0_dev, const mile_nuts_cfg* cfg, void* stream);
 int mile_nuts_init_host(mile_ctx* ctx, const float* theta0, const mile_nuts_cfg* cfg);
+/* positions_dev [n_steps,C,d] or NULL: the position BEFORE each warm-up transition (what warmup.py:102-109 writes under
+ * saving_path when keep_warmup is set) */
 int mile_nuts_warmup(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const uint8_t* schedule_dev, const float* z_dev,
-                     const float* uni_dev, uint64_t seed, float* info_dev, void* stream);
+                     const float* uni_dev, uint64_t seed, float* positions_dev, float* info_dev, void* stream);
 /* adapt_final: step_size = exp(averaged log step size) */
 int mile_nuts_finish_warmup(mile_ctx* ctx, void* stream);
 int mile_nuts_sample(mile_ctx* ctx, int32_t n_steps, int64_t step_base, int32_t n_thinning, int64_t sample_base,
                      const float* z_dev, const float* uni_dev, uint64_t seed, float* samples_dev, int64_t n_slots,
                      float* info_dev, int32_t lppd, void* stream);
-/* host-buffer form of both: schedule != NULL = warm-up transitions, NULL = sampling transitions */
+/* host-buffer form of both: schedule != NULL = warm-up transitions (samples = the pre-transition positions, n_slots =
+ * n_steps), NULL = sampling transitions */
 int mile_nuts_run_host(mile_ctx* ctx, int32_t n_steps, int64_t step_base, const uint8_t* schedule, int32_t n_thinning,
                        const float* z, const float* uni, uint64_t seed, float* samples, int64_t n_slots, float* info,
                        int32_t lppd);

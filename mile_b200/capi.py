@@ -128,7 +128,7 @@ def load():
     lib.mile_ess_positions_host.argtypes = [vp, fp, i32, vp, i32, vp, i32, fp]
     lib.mile_nuts_init.argtypes = [vp, fp, C.POINTER(NutsCfg), vp]
     lib.mile_nuts_init_host.argtypes = [vp, fp, C.POINTER(NutsCfg)]
-    lib.mile_nuts_warmup.argtypes = [vp, i32, i64, vp, fp, fp, u64, fp, vp]
+    lib.mile_nuts_warmup.argtypes = [vp, i32, i64, vp, fp, fp, u64, fp, fp, vp]
     lib.mile_nuts_finish_warmup.argtypes = [vp, vp]
     lib.mile_nuts_sample.argtypes = [vp, i32, i64, i32, i64, fp, fp, u64, fp, i64, fp, i32, vp]
     lib.mile_nuts_run_host.argtypes = [vp, i32, i64, vp, i32, fp, fp, u64, fp, i64, fp, i32]

@@ -2024,12 +2024,12 @@ static int nuts_launch(mile_ctx* c, int n_steps, long step_base, const unsigned 
 }
 
 int mile_nuts_warmup(mile_ctx* c, int32_t n_steps, int64_t step_base, const uint8_t* schedule_dev, const float* z_dev,
-                     const float* uni_dev, uint64_t seed, float* info_dev, void* stream) {
+                     const float* uni_dev, uint64_t seed, float* positions_dev, float* info_dev, void* stream) {
   if (!c) return fail("null ctx");
   if (n_steps < 0) return fail("n_steps must be >= 0");
   if (!schedule_dev && n_steps > 0) return fail("the adaptation schedule is required");
   CK(cudaSetDevice(c->device));
-  return nuts_launch(c, n_steps, step_base, schedule_dev, 1, 0, z_dev, uni_dev, seed, nullptr, 0, info_dev, 0, (cudaStream_t)stream);
+  return nuts_launch(c, n_steps, step_base, schedule_dev, 1, 0, z_dev, uni_dev, seed, positions_dev, n_steps, info_dev, 0, (cudaStream_t)stream);
 }
 
 int mile_nuts_finish_warmup(mile_ctx* c, void* stream) {
@@ -2091,7 +2091,9 @@ int mile_nuts_run_host(mile_ctx* c, int32_t n_steps, int64_t step_base, const ui
   if (z) CK(cudaMemcpyAsync(zd, z, (size_t)n_steps * Cd, cudaMemcpyHostToDevice, st));
   if (uni) CK(cudaMemcpyAsync(ud, uni, ub, cudaMemcpyHostToDevice, st));
   if (schedule) {
-    if (mile_nuts_warmup(c, n_steps, step_base, sd, zd, ud, seed, id, st)) return -1;
+    if (samples && n_slots != n_steps) return fail("warm-up positions: n_slots must equal n_steps");
+    if (mile_nuts_warmup(c, n_steps, step_base, sd, zd, ud, seed, smp, id, st)) return -1;
+    if (samples) CK(cudaMemcpyAsync(samples, smp, (size_t)n_slots * Cd, cudaMemcpyDeviceToHost, st));
   } else {
     const int64_t sample_base = (step_base + n_thinning - 1) / n_thinning;
     if (mile_nuts_sample(c, n_steps, step_base, n_thinning, sample_base, zd, ud, seed, smp, n_slots, id, lppd, st)) return -1;

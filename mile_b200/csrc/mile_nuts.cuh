@@ -202,6 +202,9 @@ __global__ void __launch_bounds__(GE::NT, 1) mile_nuts_kernel(const __grid_const
     auto uni_at = [&](int idx) -> float {
       return urow ? urow[idx] : philox_uniform(P.seed, (uint32_t)(P.chain_base + ch), (uint64_t)tstep, 17u, (uint32_t)idx);
     };
+    // warm-up positions on request (warmup.py:102-109 saves the position BEFORE the transition of warm-up step n)
+    if (Q.schedule && P.samples && c.rank == 0)
+      for (int i = tid; i < d; i += NT) P.samples[((long)s * P.C + ch) * d + i] = c.th[i];
     // ---- momentum_generator + initial proposal / trajectory (nuts.py kernel, iterative_nuts_proposal.propose) ------
     float v1[1] = {0.f};
     for (int i = tid; i < d; i += NT) {

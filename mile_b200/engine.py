@@ -344,6 +344,8 @@ class Ensemble:
         first = -(-step_base // n_thinning)
         last = (step_base + n_steps - 1) // n_thinning
         n_slots = max(0, last - first + 1) if keep and n_steps > 0 else 0
+        if schedule is not None and keep:
+            n_slots = n_steps                      # warm-up: the position before every transition
         samples = np.empty((n_slots, C_, d), np.float32) if keep else None
         inf = np.empty((n_steps, C_, 8), np.float32) if info else None
         z = None if z is None else _f32(z).reshape(n_steps, C_, d)
@@ -353,12 +355,14 @@ class Ensemble:
                                                capi.host_ptr(inf), int(lppd)))
         return samples, inf
 
-    def nuts_warmup(self, n_steps, schedule, *, step_base=0, z=None, uni=None, seed=0, info=False):
+    def nuts_warmup(self, n_steps, schedule, *, step_base=0, z=None, uni=None, seed=0, info=False, keep=False):
         """n_steps warm-up transitions, each followed by adapt_step; schedule = [(stage, is_middle_window_end)] of THESE
-        steps (window_adaptation.build_schedule)."""
+        steps (window_adaptation.build_schedule).  Returns info [n,C,8] | None, or with keep=True (positions [n,C,d] BEFORE
+        each transition, info)."""
         sched = np.ascontiguousarray([int(st) | (2 if end else 0) for st, end in schedule], dtype=np.uint8)
         assert sched.shape == (n_steps,)
-        return self._nuts_run(n_steps, step_base, sched, 1, z, uni, seed, False, info, False)[1]
+        pos, inf = self._nuts_run(n_steps, step_base, sched, 1, z, uni, seed, keep, info, False)
+        return (pos, inf) if keep else inf
 
     def nuts_finish_warmup(self):
         capi.check(self.lib.mile_nuts_finish_warmup(self.h, None))

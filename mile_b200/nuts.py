@@ -43,17 +43,29 @@ def build_schedule(num_steps: int, initial_buffer_size: int = 75, final_buffer_s
 
 def run_window_adaptation(ens: Ensemble, theta0: np.ndarray, rng_key, num_steps: int, *, initial_step_size: float = 1.0,
                           target_acceptance_rate: float = 0.8, max_num_doublings: int = 10,
-                          divergence_threshold: float = 1000.0):
+                          divergence_threshold: float = 1000.0, saving_path=None, step_ids=None):
     """custom_window_adaptation(...).run (warmup.py:112-150) for all chains of `ens`.  Returns (step_size [C],
-    inverse_mass_matrix [C, d]); the warmed-up chain state and the adapted parameters stay in `ens`."""
+    inverse_mass_matrix [C, d]); the warmed-up chain state and the adapted parameters stay in `ens`.  With `saving_path`
+    the position before every warm-up step n is written to saving_path/{step_id}/sample_{n}.npz (warmup.py:102-109)."""
     seed = key_to_seed(rng_key)
     ens.nuts_init(theta0, max_num_doublings, divergence_threshold, target_acceptance_rate, initial_step_size)
     schedule = build_schedule(int(num_steps))
+    writer = None
+    if saving_path:
+        from .callbacks import SampleWriter
+        ids = list(range(ens.n_chains)) if step_ids is None else [int(s) for s in np.atleast_1d(np.asarray(step_ids))]
+        writer = SampleWriter(ens.spec, saving_path, ids)
     done = 0
     while done < num_steps:
         n = min(CHUNK, num_steps - done)
-        ens.nuts_warmup(n, schedule[done:done + n], step_base=done, seed=seed)
+        if writer is not None:
+            pos, _ = ens.nuts_warmup(n, schedule[done:done + n], step_base=done, seed=seed, keep=True)
+            writer.submit(pos, range(done, done + n))
+        else:
+            ens.nuts_warmup(n, schedule[done:done + n], step_base=done, seed=seed)
         done += n
+    if writer is not None:
+        writer.close()
     ens.nuts_finish_warmup()                                               # adapt_final, warmup.py:142
     return ens.nuts_params()
 
@@ -62,11 +74,9 @@ def custom_window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: 
                              target_acceptance_rate: float = 0.80, progress_bar: bool = False, saving_path=None,
                              **extra_parameters) -> AdaptationAlgorithm:
     """warmup.py:27-152 (same argument names and defaults).  `algorithm` is accepted for signature parity; the NUTS kernel
-    is the library's.  `saving_path` (warm-up positions on disk, off in every shipped config) is not written."""
+    is the library's."""
     if not is_mass_matrix_diagonal:
         raise NotImplementedError('only the diagonal mass matrix (the reference default) is adapted on the CUDA path')
-    if saving_path:
-        raise NotImplementedError('saving the warm-up positions is not implemented on the CUDA path')
     model, x, y = unwrap_posterior(logdensity_fn)
     spec = model.spec
 
@@ -77,8 +87,10 @@ def custom_window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: 
         theta0 = theta0.reshape(-1, spec.n_params)
         ens = model.make_ensemble(theta0.shape[0], x, y)
         try:
+            ids = None if device_id is None else np.unique(np.asarray(device_id).reshape(theta0.shape[0], -1)[:, 0])
             eps, imm = run_window_adaptation(ens, theta0, rng_key, num_steps, initial_step_size=initial_step_size,
-                                             target_acceptance_rate=target_acceptance_rate, **extra_parameters)
+                                             target_acceptance_rate=target_acceptance_rate, saving_path=saving_path,
+                                             step_ids=ids, **extra_parameters)
             th, _, lp, g = ens.get_state()
         finally:
             ens.close()

@@ -55,9 +55,8 @@ def inference_loop(unnorm_log_posterior, config: SamplerConfig, rng_key, init_pa
     try:
         logger.info('> Starting Warmup sampling...')
         if nuts:                                                             # sampling.py:70-81 (no warmup_params.txt)
-            if saving_path_warmup is not None:
-                logger.warning('saving_path_warmup is ignored: the warm-up positions of the NUTS branch are not written on the CUDA path')
-            warmup_nuts(None, config, warmup_key, init_params, step_ids, unnorm_log_posterior, n_devices, _ensemble=ens)
+            warmup_nuts(None, config, warmup_key, init_params, step_ids, unnorm_log_posterior, n_devices,
+                        saving_path=saving_path_warmup, _ensemble=ens)
             eps = L = None
             saving_path.mkdir(parents=True, exist_ok=True)
         else:
@@ -154,13 +153,13 @@ def warmup_nuts(kernel, config: SamplerConfig, rng_key, init_params: dict, step_
     """sampling.py:220-262: window adaptation of step size and diagonal mass matrix for every chain.  Returns
     (warmup_state, parameters) like the reference; with `_ensemble` the state and the parameters stay on the device."""
     from .nuts import custom_window_adaptation, run_window_adaptation
-    if saving_path:
-        raise NotImplementedError('saving the warm-up positions is not implemented on the CUDA path')
     if _ensemble is not None:
         model, x, y = unwrap_posterior(unnorm_log_posterior)
         theta0 = model.spec.ravel(init_params).reshape(-1, model.spec.n_params)
-        eps, imm = run_window_adaptation(_ensemble, theta0, rng_key, config.warmup_steps)
+        eps, imm = run_window_adaptation(_ensemble, theta0, rng_key, config.warmup_steps, saving_path=saving_path,
+                                         step_ids=step_ids)
         return None, {'step_size': eps, 'inverse_mass_matrix': imm}
-    res = custom_window_adaptation(kernel, unnorm_log_posterior, progress_bar=True).run(
-        rng_key, init_params, None, config.warmup_steps, n_devices)
+    ids = np.repeat(np.asarray(step_ids), config.warmup_steps).reshape(n_devices, -1)        # sampling.py:255
+    res = custom_window_adaptation(kernel, unnorm_log_posterior, progress_bar=True, saving_path=saving_path).run(
+        rng_key, init_params, ids, config.warmup_steps, n_devices)
     return res.state, res.parameters

@@ -244,8 +244,14 @@ def test_nuts_seams_kernel_registry_and_inference_loop(tmp_path):
     posb = {'fcn': {k: {kk: np.stack([p['fcn'][k][kk] for p in ps]) for kk in v} for k, v in ps[0]['fcn'].items()}}
     cfg = SamplerConfig.from_dict({'name': 'nuts', 'warmup_steps': 120, 'n_chains': C, 'n_samples': 60, 'n_thinning': 1})
     exp = tmp_path / 'exp'
-    info = inference_loop(log_post, cfg, 42, posb, np.array([0, 1, 2]), exp / 'samples')
+    info = inference_loop(log_post, cfg, 42, posb, np.array([0, 1, 2]), exp / 'samples', exp / 'warmup')
     assert not (exp / 'warmup_params.txt').exists()
+    # keep_warmup (trainer.py:324 -> saving_path_warmup; warmup.py:102-109): the position BEFORE warm-up step n of every chain
+    warm = load_samples_from_dir(exp / 'warmup')
+    assert warm['fcn']['layer0']['kernel'].shape == (C, 120, ospec.n_features, 16)
+    np.testing.assert_array_equal(warm['fcn']['layer1']['kernel'][:, 0], posb['fcn']['layer1']['kernel'])
+    # (the first transitions run at the initial step size 1.0 and are rejected: compare the end of the warm-up with its start)
+    assert np.any(warm['fcn']['layer1']['kernel'][:, -1] != warm['fcn']['layer1']['kernel'][:, 0])
     with open(exp / 'samples' / 'info.pkl', 'rb') as f:
         pk = pickle.load(f)
     assert set(pk) == {'num_integration_steps', 'acceptance_rate', 'num_trajectory_expansions', 'is_divergent', 'energy', 'is_turning'}
