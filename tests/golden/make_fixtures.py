@@ -1,8 +1,8 @@
 """Generates the committed fixtures under tests/golden/ from the read-only reference checkout.
 Run here (where /root/reference exists):  python tests/golden/make_fixtures.py
 
-  sampler_configs.json  the `training.sampler` / `model` / `data` blocks of the reference's MCLMC experiment
-                        YAMLs (experiments/**/mclmc.yaml, covertype.yaml ...): configuration DATA the host
+  sampler_configs.json  the `training.sampler` / `model` / `data` blocks of the reference's MCLMC and NUTS experiment
+                        YAMLs (experiments/**/mclmc.yaml, nuts.yaml, covertype.yaml ...): configuration DATA the host
                         mirror must parse unchanged.  (The reference holds no golden vectors for the
                         arithmetic itself -- SURVEY.md section 4.)
 """
@@ -22,7 +22,7 @@ for p in sorted(REF.rglob('*.yaml')):
     if not isinstance(y, dict) or 'training' not in y or 'sampler' not in (y.get('training') or {}):
         continue
     s = y['training']['sampler']
-    if s.get('name') != 'mclmc':
+    if s.get('name') not in ('mclmc', 'nuts'):
         continue
     cfgs[str(p.relative_to(REF))] = {'sampler': s, 'model': y.get('model'),
                                      'data': {k: y['data'].get(k) for k in ('path', 'task', 'train_split', 'valid_split', 'test_split')}}

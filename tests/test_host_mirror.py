@@ -14,17 +14,20 @@ GOLDEN = Path(__file__).resolve().parent / 'golden'
 
 
 def test_sampler_config_parses_every_reference_mclmc_yaml():
-    """tests/golden/sampler_configs.json = the `training.sampler` blocks of the reference's MCLMC YAMLs."""
+    """tests/golden/sampler_configs.json = the `training.sampler` blocks of the reference's MCLMC and NUTS YAMLs."""
     from mile_b200 import FCN, Sampler, SamplerConfig
     cfgs = json.loads((GOLDEN / 'sampler_configs.json').read_text())
     assert len(cfgs) >= 10
     for name, c in cfgs.items():
         sc = SamplerConfig.from_dict(c['sampler'])
-        assert sc.name == Sampler.MCLMC and sc.warmup_steps > 0 and sc.n_thinning >= 1
+        assert sc.name in (Sampler.MCLMC, Sampler.NUTS) and sc.warmup_steps > 0 and sc.n_thinning >= 1
         assert sc.prior.kind in ('normal', 'laplace')
         assert callable(sc.kernel)
         if c['model'] and c['model'].get('model') == 'FCN':
             FCN(tuple(c['model']['hidden_structure']), c['model']['activation'], c['model'].get('use_bias', True))
+    assert sum(SamplerConfig.from_dict(c['sampler']).name == Sampler.NUTS for c in cfgs.values()) == 9
+    nut = SamplerConfig.from_dict(cfgs['illustrative_example_readme/nuts.yaml']['sampler'])
+    assert (nut.warmup_steps, nut.n_chains, nut.n_samples, nut.n_thinning) == (100, 12, 1000, 1)
     ill = SamplerConfig.from_dict(cfgs['illustrative_example_readme/mclmc.yaml']['sampler'])
     assert (ill.warmup_steps, ill.n_chains, ill.n_samples, ill.n_thinning) == (50000, 12, 10000, 10)
     assert (ill.desired_energy_var_start, ill.desired_energy_var_end, ill.step_size_init) == (0.5, 0.1, 0.01)
