@@ -54,13 +54,22 @@ with tempfile.TemporaryDirectory() as tmp:
     info = inference_loop(log_post, cfg, 0, init, np.arange(C), exp / 'samples')
     t2 = time.perf_counter()
     out['sampling'] = {'seconds': t2 - t1, 'fused_lppd': float(info['lppd'])}
+    if 'is_divergent' in info:
+        out['sampling'].update(divergent_per_chain=[round(float(v), 3) for v in np.mean(info['is_divergent'], axis=1)],
+                               mean_tree=float(np.mean(info['num_integration_steps'])),
+                               acceptance_per_chain=[round(float(v), 3) for v in np.mean(info['acceptance_rate'], axis=1)])
     samples = load_samples_from_dir(exp / 'samples')                                      # what the report notebook reads
-    _, em = evaluate_bde(samples, module, Xt, yt, 'regr', verbose=False)
+    lv, em = evaluate_bde(samples, module, Xt, yt, 'regr', verbose=False)
+    # per-chain view: RMSE of the posterior-mean prediction (no predictive noise) and the largest predicted log-sigma
+    mean_rmse = [float(np.sqrt(np.mean((yt - lv[c, :, :, 0].mean(axis=0)) ** 2))) for c in range(C)]
+    max_logsig = [float(lv[c, :, :, 1].max()) for c in range(C)]
     flat = pm.spec.ravel(samples)                                                         # [C, S, d]
     rhat = np.asarray(M.split_chain_r_hat(flat, 4))
     ess = np.asarray(M.effective_sample_size(flat))
     t3 = time.perf_counter()
-    out['report'] = {'seconds': t3 - t2, 'lppd': float(em['lppd']), 'rmse': float(em['rmse']), 'samples_per_chain': int(flat.shape[1]),
+    out['report'] = {'seconds': t3 - t2, 'lppd': float(em['lppd']), 'rmse': float(em['rmse']),
+                     'rmse_of_mean_prediction_per_chain': [round(v, 4) for v in mean_rmse],
+                     'max_predicted_log_sigma_per_chain': [round(v, 2) for v in max_logsig], 'samples_per_chain': int(flat.shape[1]),
                      'split_rhat_median': float(np.median(rhat)), 'split_rhat_max': float(np.max(rhat)),
                      'ess_median': float(np.median(ess)), 'ess_min': float(np.min(ess))}
     out['total_seconds'] = t3 - t0
