@@ -563,6 +563,54 @@ def effective_sample_size(x: np.ndarray) -> np.ndarray:
     return (dt.type(ess_raw) / tau).squeeze()
 
 
+def effective_sample_size_direct(x: np.ndarray) -> float:
+    """The same estimator for ONE series [n], written the way csrc/mile_ess.cuh computes it: direct autocovariance lag by lag,
+    stopping at the first non-positive pair sum (Geyer's initial positive sequence never reads beyond it), then the
+    monotone-sequence pass over the kept pairs.  A second opinion for `effective_sample_size` (FFT, all lags) and the
+    statement of why the kernel may stop early."""
+    x = np.asarray(x)
+    dt = x.dtype.type
+    n = x.shape[0]
+    n_even = n - (n & 1)
+    T = n_even // 2
+    cen = x - x.mean(dtype=x.dtype)
+    fn = dt(n)
+    ac0 = np.dot(cen, cen) / fn
+    var0 = ac0 * fn / (fn - dt(1))
+    wvar = var0 * (fn - dt(1)) / fn
+    rho_cache = {0: dt(1)}
+
+    def rho(t):
+        if t not in rho_cache:
+            rho_cache[t] = dt(1) - (var0 - np.dot(cen[:n - t], cen[t:]) / fn) / wvar
+        return rho_cache[t]
+    n_pos = T
+    for k in range(T):
+        if not (rho(2 * k) + rho(2 * k + 1) > 0):
+            n_pos = k
+            break
+    sel = (n_pos - 1 if n_pos > 0 else 0) + 1
+    last_k = sel if sel < T else T - 1
+    run_min, total, last_even = dt(0), dt(0), dt(0)
+    for k in range(last_k + 1):
+        if k < n_pos:
+            re, ro = rho(2 * k), rho(2 * k + 1)
+        elif k == sel:
+            r = rho(2 * k)
+            re, ro = (r if r > 0 else dt(0)), dt(0)
+        else:
+            re, ro = dt(0), dt(0)
+        sm = re + ro
+        run_min = sm if k == 0 else min(run_min, sm)
+        if sm > run_min:
+            re = ro = run_min / dt(2)
+        total += re + ro
+        if k == last_k:
+            last_even = re
+    tau = max(dt(-1) + dt(2) * total - last_even, dt(1) / dt(np.log10(fn)))
+    return float(fn / tau), len(rho_cache)
+
+
 def adaptation_L(step_size, samples: np.ndarray, Lfactor=0.4):
     """warmup.py:442-463: L = Lfactor * eps * mean(n / ESS) over the tune3 positions
     ([tune3, d]; the >2000-parameter / >10000-sample subsampling is applied by the caller)."""

@@ -136,3 +136,23 @@ def test_run_warmup_gaussian_end_to_end():
         st, info = o.mclmc_step(gauss, st, eps, L, rng.standard_normal(d))
         des.append(info.energy_change)
     assert 0.5 * 5e-4 < np.var(des) / d < 2 * 5e-4
+
+
+def test_lazy_direct_ess_equals_the_fft_estimator():
+    """The estimator as the device kernel computes it (csrc/mile_ess.cuh: direct autocovariance, lags produced only up to the
+    first non-positive pair) against the restatement of blackjax.diagnostics.effective_sample_size (FFT, all lags), fp64 and
+    fp32, even / odd lengths, strongly and negatively correlated series; and the early stop really is early."""
+    rng = np.random.default_rng(0)
+    for n in (600, 601, 1500):
+        for phi in (0.0, 0.3, 0.9, 0.97, 0.995, -0.5):
+            x = np.zeros(n)
+            e = rng.standard_normal(n)
+            for t in range(1, n):
+                x[t] = phi * x[t - 1] + e[t]
+            want = float(o.effective_sample_size(x[None, :, None]))
+            got, lags = o.effective_sample_size_direct(x)
+            assert abs(got - want) <= 1e-9 * want, (n, phi, got, want)
+            got32, _ = o.effective_sample_size_direct(x.astype(np.float32))
+            assert abs(got32 - want) <= 1e-4 * want, (n, phi, got32, want)
+            if abs(phi) <= 0.9:
+                assert lags < n // 2, (n, phi, lags)      # far fewer than the n lags an FFT produces
