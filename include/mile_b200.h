@@ -274,6 +274,11 @@ int mile_ess_positions(mile_ctx* ctx, const float* pos_dev, int32_t n, const int
                        const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host, void* stream);
 int mile_ess_positions_host(mile_ctx* ctx, const float* pos, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
                             const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host);
+/* all chains pooled per parameter -- the report's ESS (src/inference/metrics.py:354-425 -> effective_sample_size on
+ * [chains, samples, dim]: autocovariance averaged over the chains, between-chain variance of the chain means in the
+ * normalisation, chains x samples in the numerator).  pos [n, C, d] on the host; ess_host [n_selected parameters]. */
+int mile_ess_pooled_host(mile_ctx* ctx, const float* pos, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                         const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host);
 
 /* ---- NUTS branch of the sampling seam: src/training/sampling.py:70-81,107-210 (sampler = blackjax.nuts) and
  * src/training/warmup.py:27-152 (`custom_window_adaptation`), called from `warmup_nuts` (sampling.py:220-262).  One

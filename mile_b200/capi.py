@@ -21,7 +21,7 @@ SYMBOLS = [
     'mile_tune_reset', 'mile_mclmc_tune', 'mile_mclmc_tune_host', 'mile_tune_finish_phase2', 'mile_get_tuning_host',
     'mile_set_tuning_host', 'mile_tuning_ptrs', 'mile_lppd_reset', 'mile_lppd_accumulate', 'mile_lppd_state_host',
     'mile_predict', 'mile_launch_count', 'mile_synchronize', 'mile_measure_fp32_peak',
-    'mile_mclmc_phase3_ess', 'mile_ess_positions', 'mile_ess_positions_host',
+    'mile_mclmc_phase3_ess', 'mile_ess_positions', 'mile_ess_positions_host', 'mile_ess_pooled_host',
     'mile_nuts_init', 'mile_nuts_init_host', 'mile_nuts_warmup', 'mile_nuts_finish_warmup', 'mile_nuts_sample', 'mile_nuts_run_host',
     'mile_nuts_get_params_host', 'mile_nuts_set_params_host',
     'mile_write_npz_batch', 'mile_set_frozen_mask_host', 'mile_precondition_from_moments', 'mile_set_sqrt_diag_cov_host', 'mile_get_sqrt_diag_cov_host',
@@ -126,6 +126,7 @@ def load():
     lib.mile_mclmc_phase3_ess.argtypes = [vp, i32, fp, fp, u64, vp, i32, vp, i32, fp]
     lib.mile_ess_positions.argtypes = [vp, fp, i32, vp, i32, vp, i32, fp, vp]
     lib.mile_ess_positions_host.argtypes = [vp, fp, i32, vp, i32, vp, i32, fp]
+    lib.mile_ess_pooled_host.argtypes = [vp, fp, i32, vp, i32, vp, i32, fp]
     lib.mile_nuts_init.argtypes = [vp, fp, C.POINTER(NutsCfg), vp]
     lib.mile_nuts_init_host.argtypes = [vp, fp, C.POINTER(NutsCfg)]
     lib.mile_nuts_warmup.argtypes = [vp, i32, i64, vp, fp, fp, u64, fp, fp, vp]

@@ -2125,7 +2125,7 @@ int mile_nuts_set_params_host(mile_ctx* c, const float* step_size, const float* 
 
 // ---- phase 3 of the warmup on the device (warmup.py:408-465): capture + effective sample size -----------------------
 static int ess_run(mile_ctx* c, const float* pos_dev, int n_total, const int32_t* param_idx, int n_sel, const int32_t* sample_idx,
-                   int n_samples_sel, float* ess_host, cudaStream_t st) {
+                   int n_samples_sel, float* ess_host, cudaStream_t st, bool pooled = false) {
   const int d_sel = param_idx ? n_sel : c->d;
   const int n = sample_idx ? n_samples_sel : n_total;
   if (n < 4) return fail("effective sample size needs at least 4 samples");
@@ -2157,10 +2157,20 @@ static int ess_run(mile_ctx* c, const float* pos_dev, int n_total, const int32_t
   if (tg.y > 65535) return fail("too many samples for the transpose grid");
   ess_transpose_kernel<<<tg, dim3(32, 8, 1), 0, st>>>(E);
   CK(cudaGetLastError());
-  ess_series_kernel<<<(unsigned)n_series, ESS_THREADS, smem, st>>>(E);
+  size_t n_out = (size_t)n_series;
+  if (pooled) {     // all chains of a parameter in one CTA: [C][n] + [n_even] floats of shared memory
+    if (c->C > 64) return fail("pooled effective sample size: at most 64 chains");
+    const size_t smem_p = ((size_t)c->C * n + (size_t)(n - (n & 1))) * 4;
+    if (smem_p > smem_max) return fail("pooled effective sample size: chains x samples do not fit in shared memory");
+    CK(cudaFuncSetAttribute(ess_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    ess_pooled_kernel<<<(unsigned)d_sel, ESS_THREADS, smem_p, st>>>(E);
+    n_out = (size_t)d_sel;
+  } else {
+    ess_series_kernel<<<(unsigned)n_series, ESS_THREADS, smem, st>>>(E);
+  }
   CK(cudaGetLastError());
   c->launches += 2;
-  CK(cudaMemcpyAsync(ess_host, ess_d, (size_t)n_series * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ess_host, ess_d, n_out * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -2181,6 +2191,17 @@ int mile_ess_positions_host(mile_ctx* c, const float* pos, int32_t n, const int3
   if (!pd) return fail("cudaMalloc failed (ess positions)");
   CK(cudaMemcpyAsync(pd, pos, bytes, cudaMemcpyHostToDevice, c->own_stream));
   return ess_run(c, pd, n, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, c->own_stream);
+}
+
+int mile_ess_pooled_host(mile_ctx* c, const float* pos, int32_t n, const int32_t* param_idx, int32_t n_params_sel,
+                         const int32_t* sample_idx, int32_t n_samples_sel, float* ess_host) {
+  if (!c || !pos || !ess_host) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * c->C * c->d * 4;
+  float* pd = (float*)scratch(c, 14, bytes);
+  if (!pd) return fail("cudaMalloc failed (ess positions)");
+  CK(cudaMemcpyAsync(pd, pos, bytes, cudaMemcpyHostToDevice, c->own_stream));
+  return ess_run(c, pd, n, param_idx, n_params_sel, sample_idx, n_samples_sel, ess_host, c->own_stream, true);
 }
 
 int mile_mclmc_phase3_ess(mile_ctx* c, int32_t n_steps, const float* step_size_host, const float* L_host, uint64_t seed,

@@ -141,3 +141,108 @@ __global__ void __launch_bounds__(ESS_THREADS) ess_series_kernel(const EssParams
   tau = fmaxf(tau, 1.f / log10f(fn));
   E.ess[blockIdx.x] = fn / tau;
 }
+
+// ---- all chains pooled per parameter (the report's ESS: src/inference/metrics.py -> blackjax / numpyro effective_sample_size on
+// [chains, samples, dim]): autocovariance averaged over the chains, between-chain variance of the chain means in the
+// normalisation, ess_raw = chains x samples.  One CTA per parameter; the C centred series of the parameter sit in shared
+// memory ([C][n] + [n_even] floats: up to ~4500 samples for 12 chains; longer runs use the torch form in diagnostics.py).
+__global__ void __launch_bounds__(ESS_THREADS) ess_pooled_kernel(const EssParams E) {
+  extern __shared__ float sm[];
+  const int n = E.n, C = E.C, n_even = n - (n & 1), T = n_even / 2;
+  float* xs = sm;                    // [C][n] centred series
+  float* ac = sm + (size_t)C * n;    // [n_even] mean autocovariance (filled lazily)
+  __shared__ float red[ESS_THREADS / 32];
+  __shared__ float cmean[64];
+  __shared__ int stop_pair;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;          // selected parameter
+  float q = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* src = E.series + ((long)c * E.d_sel + j) * n;
+    float* x = xs + (size_t)c * n;
+    float s = 0.f;
+    for (int i = tid; i < n; i += ESS_THREADS) { const float v = src[i]; x[i] = v; s += v; }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();                 // (red free again)
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float mean = 0.f;
+    for (int w = 0; w < ESS_THREADS / 32; ++w) mean += red[w];
+    mean /= (float)n;
+    if (tid == 0) cmean[c] = mean;
+    for (int i = tid; i < n; i += ESS_THREADS) { const float v = x[i] - mean; x[i] = v; q += v * v; }
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = q;
+  if (tid == 0) stop_pair = -1;
+  __syncthreads();
+  const float fn = (float)n, fc = (float)C;
+  float ac0 = 0.f;
+  for (int w = 0; w < ESS_THREADS / 32; ++w) ac0 += red[w];
+  ac0 = ac0 / fn / fc;                                   // mean over chains of acov_c[0]
+  float vb = 0.f;                                        // variance of the chain means (ddof = 1)
+  if (C > 1) {
+    float m = 0.f;
+    for (int c = 0; c < C; ++c) m += cmean[c];
+    m /= fc;
+    for (int c = 0; c < C; ++c) { const float dlt = cmean[c] - m; vb += dlt * dlt; }
+    vb /= (fc - 1.f);
+  }
+  const float var0 = ac0 * fn / (fn - 1.0f);
+  const float wvar = var0 * (fn - 1.0f) / fn + vb;
+  if (tid == 0 && n_even > 0) ac[0] = ac0;
+  int have = 1, first_bad = -1;
+  while (have < n_even) {
+    const int base = have;
+#pragma unroll 1
+    for (int u = 0; u < ESS_LAGS_PER_ROUND / (ESS_THREADS / 32); ++u) {
+      const int t = base + u * (ESS_THREADS / 32) + warp;
+      if (t < n_even) {
+        float a = 0.f;
+        const int m = n - t;
+        for (int c = 0; c < C; ++c) {
+          const float* x = xs + (size_t)c * n;
+          for (int i = lane; i < m; i += 32) a = fmaf(x[i], x[i + t], a);
+        }
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) ac[t] = a / fn / fc;
+      }
+    }
+    const int upto = min(n_even, base + ESS_LAGS_PER_ROUND);
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = base / 2; 2 * k + 1 < upto; ++k) {
+        const float re = k == 0 ? 1.f : 1.f - (var0 - ac[2 * k]) / wvar;
+        const float ro = 1.f - (var0 - ac[2 * k + 1]) / wvar;
+        if (!(re + ro > 0.f)) { stop_pair = k; break; }
+      }
+    }
+    __syncthreads();
+    have = upto;
+    first_bad = stop_pair;
+    if (first_bad >= 0) break;
+  }
+  if (tid != 0) return;
+  const int n_pos = first_bad >= 0 ? first_bad : T;
+  const int max_t = n_pos > 0 ? n_pos - 1 : 0;
+  const int sel = max_t + 1;
+  auto rho = [&](int t) -> float { return t == 0 ? 1.f : 1.f - (var0 - ac[t]) / wvar; };
+  const int last_k = sel < T ? sel : T - 1;
+  float run_min = 0.f, total = 0.f, last_even_f = 0.f;
+  for (int k = 0; k <= last_k; ++k) {
+    float re, ro;
+    if (k < n_pos) { re = rho(2 * k); ro = rho(2 * k + 1); }
+    else if (k == sel) { const float r = rho(2 * k); re = r > 0.f ? r : 0.f; ro = 0.f; }
+    else { re = 0.f; ro = 0.f; }
+    const float sum = re + ro;
+    if (k == 0) run_min = sum; else run_min = fminf(run_min, sum);
+    if (sum > run_min) { re = run_min / 2.f; ro = run_min / 2.f; }
+    total += re + ro;
+    if (k == last_k) last_even_f = re;
+  }
+  const float ess_raw = fn * fc;
+  float tau = -1.f + 2.f * total - last_even_f;
+  tau = fmaxf(tau, 1.f / log10f(ess_raw));
+  E.ess[j] = ess_raw / tau;
+}

@@ -310,16 +310,17 @@ class Ensemble:
                                                   capi.host_ptr(si), 0 if si is None else si.size, capi.host_ptr(out)))
         return out
 
-    def ess_positions(self, positions, *, param_idx=None, sample_idx=None):
-        """The same estimator on host positions [n, C, d] (blackjax.diagnostics.effective_sample_size with one chain per
-        series) -> [C, n_selected]."""
+    def ess_positions(self, positions, *, param_idx=None, sample_idx=None, pooled=False):
+        """The same estimator on host positions [n, C, d] (blackjax.diagnostics.effective_sample_size): one chain per series
+        -> [C, n_selected]; pooled=True: all chains of a parameter together, as the report computes it -> [n_selected]."""
         pos = _f32(positions)
         assert pos.ndim == 3 and pos.shape[1:] == (self.n_chains, self.d)
         pi, si = self._idx(param_idx), self._idx(sample_idx)
-        out = np.empty((self.n_chains, self.d if pi is None else pi.size), np.float32)
-        capi.check(self.lib.mile_ess_positions_host(self.h, capi.host_ptr(pos), pos.shape[0], capi.host_ptr(pi),
-                                                    0 if pi is None else pi.size, capi.host_ptr(si),
-                                                    0 if si is None else si.size, capi.host_ptr(out)))
+        nsel = self.d if pi is None else pi.size
+        out = np.empty(nsel if pooled else (self.n_chains, nsel), np.float32)
+        fn = self.lib.mile_ess_pooled_host if pooled else self.lib.mile_ess_positions_host
+        capi.check(fn(self.h, capi.host_ptr(pos), pos.shape[0], capi.host_ptr(pi), 0 if pi is None else pi.size,
+                      capi.host_ptr(si), 0 if si is None else si.size, capi.host_ptr(out)))
         return out
 
     # ---- NUTS branch (sampling.py:70-81,107-210; warmup.py:27-152) ------------------------------

@@ -364,6 +364,11 @@ def test_device_ess_kernel_matches_oracle():
         for c in range(C):
             want = o.effective_sample_size(x[:, c].astype(np.float64)[None])
             assert np.all(np.abs(ess[c] - want) <= 2e-4 * want), (n, c, np.max(np.abs(ess[c] / want - 1)))
+        # all chains pooled per parameter (the report's ESS, metrics.py:354-425): with and without chain-specific offsets
+        for xx in (x, x - x.mean(axis=0, keepdims=True) * 0.9):
+            pooled = ens.ess_positions(xx, pooled=True)
+            want = o.effective_sample_size(np.transpose(xx, (1, 0, 2)).astype(np.float64))
+            assert pooled.shape == (d,) and np.all(np.abs(pooled - want) <= 5e-4 * want), np.max(np.abs(pooled / want - 1))
         pidx = np.array([7, 0, 25, 3], np.int32)
         sidx = np.linspace(0, n - 1, 400).astype(np.int32)
         sub = ens.ess_positions(x, param_idx=pidx, sample_idx=sidx)
