@@ -10,7 +10,7 @@ from typing import Callable
 import numpy as np
 
 from .probabilistic import unwrap_posterior
-from .types import HMCState, IntegratorState, MCLMCInfo, SamplingAlgorithm, key_to_seed
+from .types import HMCState, IntegratorState, MCLMCInfo, NUTSInfo, SamplingAlgorithm, key_to_seed
 
 __all__ = ['mclmc', 'nuts', 'KERNELS']
 
@@ -77,7 +77,7 @@ def _state(b: _Bound, ens, batched) -> IntegratorState:
 def nuts(logdensity_fn: Callable, step_size, inverse_mass_matrix, max_num_doublings: int = 10,
          divergence_threshold: float = 1000.0) -> SamplingAlgorithm:
     """blackjax.nuts(logdensity_fn, step_size, inverse_mass_matrix): init(position) / step(rng_key, state) -> (state, info)
-    with info = dict of the NUTSInfo fields the reference keeps (sampling.py:200-210).  Diagonal metric only."""
+    with info = NUTSInfo (blackjax's field names; the fields the reference keeps, sampling.py:200-210, are filled).  Diagonal metric only."""
     b = _Bound(logdensity_fn)
 
     def _ensure(th):
@@ -104,7 +104,10 @@ def nuts(logdensity_fn: Callable, step_size, inverse_mass_matrix, max_num_doubli
         _, info = ens.nuts_sample(1, step_base=b.step_counter, seed=key_to_seed(rng_key), keep=False, info=True)
         b.step_counter += 1
         inf = info[0] if batched else info[0, 0]
-        return _hmc_state(b, ens, batched), {k: inf[..., i] for i, k in enumerate(ens.NUTS_INFO_FIELDS)}
+        f = {k: inf[..., i] for i, k in enumerate(ens.NUTS_INFO_FIELDS)}
+        return _hmc_state(b, ens, batched), NUTSInfo(None, f['is_divergent'] > 0.5, f['is_turning'] > 0.5, f['energy'], None, None,
+                                                     f['num_trajectory_expansions'].astype(np.int32),
+                                                     f['num_integration_steps'].astype(np.int32), f['acceptance_rate'])
 
     return SamplingAlgorithm(init, step)
 

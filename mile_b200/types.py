@@ -24,6 +24,19 @@ class HMCState(NamedTuple):
     logdensity_grad: Any
 
 
+class NUTSInfo(NamedTuple):
+    """blackjax.mcmc.nuts.NUTSInfo (field names and order).  The trajectory end states are not exported by the CUDA path."""
+    momentum: Any
+    is_divergent: Any
+    is_turning: Any
+    energy: Any
+    trajectory_leftmost_state: Any
+    trajectory_rightmost_state: Any
+    num_trajectory_expansions: Any
+    num_integration_steps: Any
+    acceptance_rate: Any
+
+
 class MCLMCInfo(NamedTuple):
     """blackjax.mcmc.mclmc.MCLMCInfo."""
     logdensity: Any

@@ -233,7 +233,8 @@ def test_nuts_seams_kernel_registry_and_inference_loop(tmp_path):
     want, gwant = o.logpost_value_and_grad(ospec, o.ravel_tree(ospec, pos).astype(np.float64), X.astype(np.float64), y)
     assert abs(st.logdensity - want) <= 1e-5 * abs(want)
     st2, info = sampler.step(4, st)
-    assert 1 <= int(info['num_integration_steps']) <= 15 and 0 <= float(info['acceptance_rate']) <= 1
+    assert 1 <= int(info.num_integration_steps) <= 15 and 0 <= float(info.acceptance_rate) <= 1
+    assert info.is_divergent in (True, False) and info._fields[6:] == ('num_trajectory_expansions', 'num_integration_steps', 'acceptance_rate')
     lp2, _ = o.logpost_value_and_grad(ospec, o.ravel_tree(ospec, st2.position).astype(np.float64), X.astype(np.float64), y)
     assert abs(st2.logdensity - lp2) <= 1e-5 * abs(lp2)
     # the whole loop
