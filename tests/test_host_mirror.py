@@ -224,3 +224,31 @@ def test_unwrap_posterior_adopts_the_reference_models_own_closure():
                                 RefPrior(None, log_prior_laplace(), PriorDist.StandardNormal), Task.CLASSIFICATION)
     s2 = unwrap_posterior(functools.partial(std.log_unnormalized_posterior, x=X, y=y))[0].spec
     assert (s2.prior, s2.prior_loc, s2.prior_scale, s2.task, s2.widths) == ('normal', 0.0, 1.0, 'class', (8, 3))
+
+
+def test_nuts_host_mirror_signatures_and_loud_failures():
+    """warmup.py:27-36 / sampling.py:220-229 argument names are kept; what the CUDA path does not implement fails loudly
+    before any device work (no CPU fallback)."""
+    import inspect
+    from mile_b200 import FCN, PriorDist, ProbabilisticModel, custom_window_adaptation, warmup_nuts
+    from mile_b200.probabilistic import unwrap_posterior
+    sig = list(inspect.signature(custom_window_adaptation).parameters)
+    assert sig[:7] == ['algorithm', 'logdensity_fn', 'is_mass_matrix_diagonal', 'initial_step_size', 'target_acceptance_rate',
+                       'progress_bar', 'saving_path']
+    assert list(inspect.signature(warmup_nuts).parameters)[:8] == ['kernel', 'config', 'rng_key', 'init_params', 'step_ids',
+                                                                    'unnorm_log_posterior', 'n_devices', 'saving_path']
+    module = FCN((16, 2), 'relu')
+    pm = ProbabilisticModel(module, module.init(np.random.default_rng(0), 5), PriorDist.StandardNormal.get_prior(), 'regr')
+    lp = functools.partial(pm.log_unnormalized_posterior, x=np.zeros((4, 5), np.float32), y=np.zeros(4, np.float32))
+    with pytest.raises(NotImplementedError):
+        custom_window_adaptation(None, lp, is_mass_matrix_diagonal=False)
+    assert callable(custom_window_adaptation(None, lp).run)
+
+    class NotAnFCN:
+        task, prior, n_batches = 'regr', None, 1
+        module = object()
+
+        def log_unnormalized_posterior(self, position, x, y):
+            return 0.0
+    with pytest.raises(TypeError):
+        unwrap_posterior(functools.partial(NotAnFCN().log_unnormalized_posterior, x=np.zeros((2, 3)), y=np.zeros(2)))
